@@ -1,0 +1,234 @@
+/*
+ * iswm_b200.h — C ABI of libiswm_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the ONE hot path of Alanlee0323/ISWM: the DeepLabV3+
+ * train / predict step, its weighted cross-entropy and its confusion matrix.
+ * The reference has no FFI of its own (pure Python); each entry
+ * point below names the reference Python call site it replaces (file:line
+ * relative to the reference tree).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch types;
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; the
+ *     library never frees or retains it (tensor-map caches key on the address);
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and
+ *     never synchronises;
+ *   - return 0 on success, non-zero on error; iswm_last_error() gives a
+ *     thread-local message; no C++ exception crosses the boundary;
+ *   - activations are NHWC bf16 unless stated, parameters handed over in the
+ *     reference's own layout (fp32 OIHW) and packed by iswm_pack_*.
+ */
+#ifndef ISWM_B200_H
+#define ISWM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------- */
+const char* iswm_last_error(void);
+int iswm_version(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t iswm_launch_count(void);
+void iswm_reset_launch_count(void);
+/* synchronising health check (tests / debug): code recorded by a tensor-core kernel whose
+ * bounded mbarrier wait timed out (0 = healthy); clears it. */
+int iswm_debug_abort_code(void);
+
+/* element type codes for label / prediction buffers */
+enum { ISWM_U8 = 0, ISWM_I32 = 1, ISWM_I64 = 2 };
+/* element type codes for floating tensors */
+enum { ISWM_F32 = 0, ISWM_BF16 = 1 };
+
+/* ---- loss / histogram / metric (HBM-bound) ----------------------------- */
+
+/* Per-class pixel counts: d_hist[c] += #{i : labels[i] == c}, 0 <= c < n_classes.
+ * Values outside [0,n_classes) (e.g. ignore 255) are counted nowhere.
+ * Replaces: train.py:401-402 `(labels == 0).sum()`, `(labels == 1).sum()` in
+ * calculate_class_weights, and the implicit per-class counts behind
+ * nn.CrossEntropyLoss's weighted-mean denominator (train.py:457-459).
+ * d_hist: int64[n_classes], ACCUMULATED into (zero it first for a fresh count). */
+int iswm_class_hist(const void* d_labels, int label_dtype, int64_t n,
+                    int n_classes, int64_t* d_hist, void* stream);
+
+/* Fused weighted softmax cross-entropy forward + backward, one HBM pass.
+ * Semantics = nn.CrossEntropyLoss(weight=w, ignore_index, reduction='mean')
+ * (train.py:454-459) called at train.py:1046 and differentiated at :1048.
+ *   d_logits : [B, C, HW] (NCHW), fp32 or bf16 (logit_dtype)
+ *   d_labels : [B, HW]
+ *   d_weight : float[C] or NULL (all ones)
+ *   d_hist   : int64[C] per-class counts of THIS loss's batch (global batch
+ *              when data-parallel), from iswm_class_hist; gives the
+ *              denominator D = sum_c w_c * hist[c] (c != ignore_index)
+ *   d_grad   : same shape/dtype as logits, = grad_scale * dL/dlogits, or NULL
+ *   d_loss_num: double[1], ACCUMULATES sum_i w[y_i] * nll_i (zero it first)
+ *   d_loss   : float[1] or NULL; if non-NULL a last-block epilogue writes
+ *              loss = loss_num / D
+ */
+int iswm_wce_fwd_bwd(const void* d_logits, int logit_dtype, const void* d_labels,
+                     int label_dtype, const float* d_weight, const int64_t* d_hist,
+                     int64_t B, int C, int64_t HW, int ignore_index,
+                     float grad_scale, void* d_grad, double* d_loss_num,
+                     float* d_loss, void* stream);
+
+/* Confusion matrix: cm[t*n + p] += 1 for every i with 0 <= t=true[i] < n
+ * (pred p outside [0,n) is dropped and counted in d_cm[n*n], one extra slot).
+ * Replaces: metrics/stream_metrics.py:24-31 `_fast_hist` + :122 accumulation.
+ * d_cm: int64[n*n + 1], ACCUMULATED into. */
+int iswm_confusion(const void* d_true, int true_dtype, const void* d_pred,
+                   int pred_dtype, int64_t n, int n_classes, int64_t* d_cm,
+                   void* stream);
+
+/* argmax / threshold fused with the confusion matrix.
+ * Replaces: train.py:644,659 `logits.max(1)[1]` (mode 0: first maximum wins,
+ * ties -> lowest class) and predict.py:264-275 / evaluate_quantization.py:265-269
+ * `softmax(logits,1)[:,1] > threshold` (mode 1, C must be >= 2), followed by
+ * `_fast_hist`.
+ *   d_pred_out: optional uint8[B*HW] class map (NULL to skip)
+ *   d_conf_out: optional uint8[B*HW] `uint8(prob1*255)` map, mode 1 only
+ *               (predict.py:285-288), NULL to skip
+ *   d_true may be NULL (no confusion matrix, predictions only). */
+int iswm_argmax_confusion(const void* d_logits, int logit_dtype, const void* d_true,
+                          int true_dtype, int64_t B, int C, int64_t HW, int mode,
+                          float threshold, uint8_t* d_pred_out, uint8_t* d_conf_out,
+                          int64_t* d_cm, void* stream);
+
+/* ---- convolution as implicit GEMM on tcgen05 / TMEM / TMA -------------- */
+
+#define ISWM_MAX_TAPS 16
+
+/* epilogue flags */
+enum {
+  ISWM_EPI_AFFINE   = 1,  /* y = acc * scale[c] + shift[c] (eval BN folded / bias) */
+  ISWM_EPI_RELU     = 2,
+  ISWM_EPI_RESIDUAL = 4,  /* y += residual (bf16, same geometry, own ld)      */
+  ISWM_EPI_STATS    = 8,  /* accumulate per-channel sum / sum^2 of acc (fp32) */
+  ISWM_EPI_OUT_F32  = 16  /* write fp32 instead of bf16                       */
+};
+
+/* Geometry of one implicit-GEMM convolution over NHWC bf16 activations.
+ * out[b,ho,wo,n] = sum_t sum_c in[img(t,b), ho + dh[t], wo + dw[t], c] * wgt[n, t, c]
+ * with zero fill outside [0,Hi)x[0,Wi). Strided convolutions are expressed
+ * over the 4 parity phases of the input (phase-major [4][B][Hi][Wi][C]),
+ * img(t,b) = phase[t]*B + b.
+ * Replaces nn.Conv2d at network/backbone/resnet.py:27-35 (conv3x3/conv1x1),
+ * network/_deeplab.py:37,45,48,51,124,134,149,162 and, with transposed packed
+ * weights and negated taps, their input gradients. */
+typedef struct {
+  int32_t B, Hi, Wi, Cin;     /* input images (per phase), spatial, channels  */
+  int32_t in_ld;              /* input row pitch in elements (>= Cin)          */
+  int32_t n_img;              /* images in the input tensor (B * n_phases)     */
+  int32_t Ho, Wo, Cout;
+  int32_t out_ld;             /* output row pitch in elements                  */
+  int32_t res_ld;             /* residual row pitch in elements                */
+  int32_t ntaps;
+  int8_t  dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
+  int32_t flags;
+} iswm_conv_desc;
+
+/* d_in: bf16 activations; d_wgt: packed bf16 [Cout][ntaps][Cin_pad] (Cin_pad =
+ * Cin rounded up to 64, zero padded) from iswm_pack_weight*; d_out bf16/fp32;
+ * d_scale/d_shift float[Cout] (AFFINE); d_res bf16 (RESIDUAL); d_stats
+ * float[2*Cout] accumulated (STATS). */
+int iswm_conv_igemm(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt,
+                    void* d_out, const float* d_scale, const float* d_shift,
+                    const void* d_res, float* d_stats, void* stream);
+
+/* Weight gradient: dW[n, t, c] += sum_{b,ho,wo} dy[b,ho,wo,n] * in[img(t,b), ho+dh[t], wo+dw[t], c]
+ * desc as for the forward conv (Cout = channels of dy). d_dw: float [Cout][ntaps][Cin],
+ * ACCUMULATED into with fp32 reductions (zero it first). dy row pitch = out_ld. */
+int iswm_conv_wgrad(const iswm_conv_desc* desc, const void* d_in, const void* d_dy,
+                    float* d_dw, void* stream);
+
+/* fp32 OIHW [Cout][Cin][R*S] -> bf16 rows of row_ld elements, element (t*cin_pad + c) = w[o][c][t],
+ * zero elsewhere. Forward operand: cin_pad = Cin rounded up to 64, row_ld = R*S*cin_pad.
+ * Stem (7x7 over the im2col matrix): cin_pad = Cin, row_ld = 49*Cin rounded up to 64. */
+int iswm_pack_weight_fwd(const float* d_w, int Cout, int Cin, int RS, int cin_pad, int row_ld,
+                         void* d_out, void* stream);
+/* fp32 OIHW -> bf16 [Cin][R*S][cout_pad] (dgrad operand, taps kept in forward order) */
+int iswm_pack_weight_dgrad(const float* d_w, int Cout, int Cin, int RS, int cout_pad, void* d_out,
+                           void* stream);
+/* wgrad accumulator (fp32 rows of row_ld, element t*cin_stride + c) -> fp32 OIHW grad,
+ * dst = beta*dst + src. Normal: cin_stride = Cin, row_ld = R*S*Cin. */
+int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stride, int row_ld,
+                      float beta, float* d_grad_oihw, void* stream);
+
+/* ---- HBM-bound glue kernels (see src for reference citations) ---------- */
+
+/* BatchNorm2d training forward, second half (network/backbone/resnet.py:92-110 bn1..bn3,
+ * network/_deeplab.py:38,46,49,125,135,150,163): from per-channel sum/sum^2
+ * (conv epilogue STATS) compute batch mean / biased var, write
+ * out = [relu]( gamma*(x-mean)*invstd + beta [+ residual] ) with optional dropout,
+ * save mean/invstd for backward, update running stats (momentum, unbiased var). */
+int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_stats, int64_t M, int C,
+                        const float* d_gamma, const float* d_beta, float eps, float momentum,
+                        float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
+                        float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld, int relu,
+                        float drop_p, uint64_t drop_seed, void* d_out, int out_ld, void* stream);
+
+/* eval-mode BN folding: scale = gamma / sqrt(running_var + eps), shift = beta - mean*scale */
+int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean, const float* d_var,
+                 float eps, int C, float* d_scale, float* d_shift, void* stream);
+
+/* BatchNorm backward, pass 1: dz = dout * [out>0 if relu] * dropmask;
+ * sums[c] = sum dz, sums[C+c] = sum dz * xhat. d_out_act = post-activation output (for the ReLU mask). */
+int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
+                       const void* d_out_act, int act_ld, int64_t M, int C,
+                       const float* d_save_mean, const float* d_save_invstd, int relu,
+                       float drop_p, uint64_t drop_seed, float* d_sums, void* stream);
+/* pass 2: dx = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); dgamma += , dbeta += ;
+ * optionally writes dz (the pre-activation gradient, used by the residual identity path). */
+int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
+                      const void* d_out_act, int act_ld, int64_t M, int C,
+                      const float* d_gamma, const float* d_save_mean, const float* d_save_invstd,
+                      const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                      void* d_dx, int dx_ld, void* d_dz, int dz_ld,
+                      float* d_dgamma, float* d_dbeta, void* stream);
+
+/* NCHW fp32 image -> stem im2col matrix bf16 [B*Ho*Wo][Kpad] for the 7x7/s2/p3 conv
+ * (network/backbone/resnet.py:144); column = (r*7+s)*Cin + c, zero padded to Kpad. */
+int iswm_stem_im2col(const float* d_img, int B, int Cin, int H, int W, int Ho, int Wo,
+                     int Kpad, void* d_out, void* stream);
+/* MaxPool2d(3,2,1) (resnet.py:148), NHWC bf16; d_idx uint8 window argmax (first max wins) */
+int iswm_maxpool_fwd(const void* d_x, int B, int H, int W, int C, int Ho, int Wo,
+                     void* d_out, uint8_t* d_idx, void* stream);
+int iswm_maxpool_bwd(const void* d_dout, const uint8_t* d_idx, int B, int H, int W, int C,
+                     int Ho, int Wo, void* d_dx, void* stream);
+/* AdaptiveAvgPool2d(1) (network/_deeplab.py:133): [B,HW,C] bf16 -> [B,C] bf16 */
+int iswm_gap_fwd(const void* d_x, int x_ld, int B, int64_t HW, int C, void* d_out, void* stream);
+/* broadcast [B,C] over HW into a channel slice (the bilinear upsample of a 1x1 map, _deeplab.py:141) */
+int iswm_broadcast_hw(const void* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream);
+/* adjoint of broadcast (sum over HW) and of GAP (scale 1/HW, broadcast add) */
+int iswm_sum_hw(const void* d_x, int x_ld, int B, int64_t HW, int C, void* d_out, void* stream);
+int iswm_gap_bwd_add(const void* d_dpool, int B, int64_t HW, int C, void* d_dx, int dx_ld, void* stream);
+/* F.interpolate(bilinear, align_corners=False) on NHWC bf16 (network/_deeplab.py:58) and its adjoint */
+int iswm_bilinear_fwd(const void* d_x, int x_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                      void* d_out, int out_ld, void* stream);
+int iswm_bilinear_bwd(const void* d_dout, int dout_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                      void* d_dx, int dx_ld, void* stream);
+/* final upsample (network/utils.py:22): NHWC fp32 [B,h,w,C] logits -> NCHW fp32 [B,C,H,W]; and adjoint
+ * NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels C..dx_ld-1 zero-filled) */
+int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C, int Ho, int Wo, float* d_out, void* stream);
+int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld, void* stream);
+/* strided helpers for stride-2 convolutions */
+int iswm_phase_split(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream);   /* -> [4][B][ceil(H/2)][ceil(W/2)][C], phase = (h&1)*2 + (w&1) */
+int iswm_subsample2(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream);    /* -> [B][ceil(H/2)][ceil(W/2)][C] */
+int iswm_zero_stuff2(const void* d_x, int B, int Ho, int Wo, int C, int H, int W, void* d_out, void* stream); /* out[b,2i,2j]=x[b,i,j], else 0 */
+int iswm_scatter2_add(const void* d_x, int B, int Ho, int Wo, int C, int H, int W, void* d_inout, void* stream); /* inout[b,2i,2j]+=x */
+/* elementwise bf16: out = a + b */
+int iswm_add_bf16(const void* d_a, const void* d_b, int64_t n, void* d_out, void* stream);
+/* NHWC bf16 -> NCHW fp32 (feature export for tests / API) and back */
+int iswm_nhwc_to_nchw_f32(const void* d_x, int x_ld, int B, int64_t HW, int C, float* d_out, void* stream);
+int iswm_nchw_f32_to_nhwc(const float* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream);
+
+/* fused multi-tensor SGD(momentum, nesterov, weight decay) step (train.py:421-431, :1049) on a flat fp32 buffer */
+int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr, float momentum,
+                  float weight_decay, int nesterov, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISWM_B200_H */

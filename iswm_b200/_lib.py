@@ -1,0 +1,106 @@
+"""ctypes binding of libiswm_b200.so (the C ABI declared in include/iswm_b200.h).
+
+The library is the product; there is no fallback. Importing this module never fails
+(so CPU-only tooling can import the package), but the first call that needs the
+library raises if the shared object is missing, and every op raises on a non-zero
+return code with the library's own error text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiswm_b200.so")
+
+MAX_TAPS = 16
+U8, I32, I64 = 0, 1, 2
+F32, BF16 = 0, 1
+EPI_AFFINE, EPI_RELU, EPI_RESIDUAL, EPI_STATS, EPI_OUT_F32 = 1, 2, 4, 8, 16
+
+
+class ConvDesc(C.Structure):
+    """Mirror of iswm_conv_desc."""
+
+    _fields_ = [
+        ("B", C.c_int32), ("Hi", C.c_int32), ("Wi", C.c_int32), ("Cin", C.c_int32),
+        ("in_ld", C.c_int32), ("n_img", C.c_int32),
+        ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
+        ("out_ld", C.c_int32), ("res_ld", C.c_int32), ("ntaps", C.c_int32),
+        ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS), ("phase", C.c_int8 * MAX_TAPS),
+        ("flags", C.c_int32),
+    ]
+
+
+_p, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+
+# name -> (restype, argtypes); kept in the order of include/iswm_b200.h
+SIGNATURES = {
+    "iswm_last_error": (C.c_char_p, []),
+    "iswm_version": (_i, []),
+    "iswm_launch_count": (_i64, []),
+    "iswm_reset_launch_count": (None, []),
+    "iswm_debug_abort_code": (_i, []),
+    "iswm_class_hist": (_i, [_p, _i, _i64, _i, _p, _p]),
+    "iswm_wce_fwd_bwd": (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _i64, _i, _f, _p, _p, _p, _p]),
+    "iswm_confusion": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p]),
+    "iswm_argmax_confusion": (_i, [_p, _i, _p, _i, _i64, _i, _i64, _i, _f, _p, _p, _p, _p]),
+    "iswm_conv_igemm": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p]),
+    "iswm_conv_wgrad": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p]),
+    "iswm_pack_weight_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_pack_weight_dgrad": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "iswm_unpack_wgrad": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
+    "iswm_bn_train_apply": (_i, [_p, _i, _p, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _i, _p]),
+    "iswm_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
+    "iswm_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _i, _f, _u64, _p, _p]),
+    "iswm_bn_bwd_apply": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _u64, _p, _i, _p, _i, _p, _p, _p]),
+    "iswm_stem_im2col": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_maxpool_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "iswm_maxpool_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_gap_fwd": (_i, [_p, _i, _i, _i64, _i, _p, _p]),
+    "iswm_broadcast_hw": (_i, [_p, _i, _i64, _i, _p, _i, _p]),
+    "iswm_sum_hw": (_i, [_p, _i, _i, _i64, _i, _p, _p]),
+    "iswm_gap_bwd_add": (_i, [_p, _i, _i64, _i, _p, _i, _p]),
+    "iswm_bilinear_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "iswm_bilinear_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "iswm_logits_up_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_logits_up_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "iswm_phase_split": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_subsample2": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_zero_stuff2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_scatter2_add": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_add_bf16": (_i, [_p, _p, _i64, _p, _p]),
+    "iswm_nhwc_to_nchw_f32": (_i, [_p, _i, _i, _i64, _i, _p, _p]),
+    "iswm_nchw_f32_to_nhwc": (_i, [_p, _i, _i64, _i, _p, _i, _p]),
+    "iswm_sgd_step": (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). iswm_b200 has no CPU or PyTorch fallback."
+            )
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().iswm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libiswm_b200 {what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().iswm_launch_count())

@@ -1,0 +1,387 @@
+// conv_igemm.cu — convolution as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[pixel, cout] = sum_tap sum_cin  A_tap[pixel, cin] * W[cout, tap, cin]
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0   TMA producer: per (tap, 64-channel slice) one 4-D box load of the NHWC
+//            activations shifted by the tap offset (out-of-image elements arrive as
+//            zeros = the convolution padding, so no im2col buffer exists anywhere)
+//            plus one 2-D box of the packed weights, into a multi-stage smem ring;
+//   warp 1   one thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32) into a
+//            double-buffered TMEM accumulator and commits stage/accumulator barriers;
+//   warp 2   TMEM allocator;
+//   warps 4-7 epilogue: tcgen05.ld the accumulator, then any of: per-channel affine
+//            (folded eval BatchNorm / bias), residual add, ReLU, per-channel sum and
+//            sum-of-squares for training BatchNorm, bf16 or fp32 NHWC store.
+//
+// Forward convs of network/backbone/resnet.py:27-35 (conv3x3 / conv1x1, all dilations)
+// and network/_deeplab.py:37-51,124,134,149,162; their data gradients run through the
+// same kernel with transposed packed weights and negated tap offsets.
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace iswm {
+
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+constexpr int kKBlock = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kABytes = kTileM * 128;       // 16 KiB
+constexpr int kTmemCols = 512;
+constexpr int kSmemBudget = 196608;         // ring budget (bytes)
+
+struct ConvKParams {
+  int B, Ho, Wo, Cout;
+  int lgBW, lgBH;                // log2 of the pixel-tile box (BW*BH*BB == 128)
+  int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
+  int BN, kchunks, cin_pad, ntaps, stages, flags;
+  int n_img_per_phase;
+  int out_ld, res_ld;
+  int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
+  void* out;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;
+  float* stats;
+  int* abort_flag;
+};
+
+template <int N>
+__device__ __forceinline__ void bfly_step(float (&v)[16], int lane, int mask) {
+  const bool up = (lane & mask) != 0;
+#pragma unroll
+  for (int i = 0; i < N / 2; i++) {
+    const float send = up ? v[i] : v[i + N / 2];
+    const float keep = up ? v[i + N / 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+  }
+}
+// column sums of a 32x16 block held one row per lane; result for column (lane>>1)&15 in v[0]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+  bfly_step<16>(v, lane, 16);
+  bfly_step<8>(v, lane, 8);
+  bfly_step<4>(v, lane, 4);
+  bfly_step<2>(v, lane, 2);
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_b, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = tc::smem_u32(smem_raw);
+  const uint32_t ring = (raw_addr + 1023u) & ~1023u;     // swizzle-128B tiles need 1 KiB alignment
+  uint8_t* smem = smem_raw + (ring - raw_addr);
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[8] empty[8] tfull[2] tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* s_scale = reinterpret_cast<float*>(tail + 256);
+  float* s_shift = s_scale + 256;
+
+  const uint32_t bar_full = tc::smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; s++) {
+      tc::mbar_init(bar_full + 8 * s, 1);
+      tc::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      tc::mbar_init(bar_tfull + 8 * s, 1);
+      tc::mbar_init(bar_tempty + 8 * s, 4);   // one arrival per epilogue warp
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tc::smem_u32(tmem_slot), kTmemCols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = p.ntaps * p.kchunks;
+  const int BW = 1 << p.lgBW, BH = 1 << p.lgBH;
+  const int BB = kTileM >> (p.lgBW + p.lgBH);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h,
+                  tb = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB, n0 = nt * p.BN;
+        for (int t = 0; t < p.ntaps && ok; t++) {
+          const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
+          for (int kc = 0; kc < p.kchunks; kc++) {
+            if (!tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 1)) { ok = false; break; }
+            const uint32_t a_dst = ring + stage * stage_bytes;
+            tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
+            tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, kc * kKBlock, cw, ch, cb);
+            tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage,
+                            t * p.cin_pad + kc * kKBlock, n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+        if (!tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 2)) break;
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        for (int kb = 0; kb < kblocks; kb++) {
+          if (!tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 3)) { ok = false; break; }
+          tc::tc_fence_after();
+          const uint32_t a_addr = ring + stage * stage_bytes;
+          const uint64_t da = tc::make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = tc::make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kKBlock / 16; k++)
+            tc::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc::umma_commit(bar_empty + 8 * stage);     // frees this smem stage when the MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        tc::umma_commit(bar_tfull + 8 * as);          // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;                          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int row = ew * 32 + lane;
+    const int bb = row >> (p.lgBW + p.lgBH);
+    const int hh = (row >> p.lgBW) & (BH - 1);
+    const int ww = row & (BW - 1);
+    const bool f_aff = p.flags & ISWM_EPI_AFFINE, f_relu = p.flags & ISWM_EPI_RELU,
+               f_res = p.flags & ISWM_EPI_RESIDUAL, f_stats = p.flags & ISWM_EPI_STATS,
+               f_f32 = p.flags & ISWM_EPI_OUT_F32;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h,
+                tb = mt / (p.tiles_w * p.tiles_h);
+      const int w = tw * BW + ww, h = th * BH + hh, b = tb * BB + bb, n0 = nt * p.BN;
+      const bool valid = (b < p.B) && (h < p.Ho) && (w < p.Wo);
+      const size_t pix = ((size_t)b * p.Ho + h) * p.Wo + w;
+      if (f_aff) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done
+        for (int i = threadIdx.x - 128; i < p.BN; i += 128) {
+          const int n = n0 + i;
+          s_scale[i] = (n < p.Cout) ? p.scale[n] : 0.f;
+          s_shift[i] = (n < p.Cout) ? p.shift[n] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (!tc::mbar_wait(bar_tfull + 8 * as, aphase, p.abort_flag, 4)) break;
+      tc::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * p.BN);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(t_row + c, v);
+        tc::tmem_ld_wait();
+        const int n = n0 + c;
+        if (n >= p.Cout) continue;                    // warp-uniform
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
+        if (f_stats) {
+          float s[16], q[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float x = valid ? f[j] : 0.f;
+            s[j] = x;
+            q[j] = x * x;
+          }
+          const float cs = warp_colsum16(s, lane);
+          const float cq = warp_colsum16(q, lane);
+          const int col = n + ((lane >> 1) & 15);
+          if ((lane & 1) == 0 && col < p.Cout) {
+            atomicAdd(p.stats + col, cs);
+            atomicAdd(p.stats + p.Cout + col, cq);
+          }
+        }
+        if (f_aff) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) f[j] = fmaf(f[j], s_scale[c + j], s_shift[c + j]);
+        }
+        const bool full16 = (n + 16 <= p.Cout);
+        if (f_res && valid) {
+          const __nv_bfloat16* rp = p.res + pix * (size_t)p.res_ld + n;
+          if (full16 && (p.res_ld & 7) == 0) {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+            const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              float lo, hi;
+              unpack_bf16x2(rr[j], lo, hi);
+              f[2 * j] += lo;
+              f[2 * j + 1] += hi;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (n + j < p.Cout) f[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (f_relu) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          if (f_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + n;
+            if (full16 && (p.out_ld & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if (n + j < p.Cout) op[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + n;
+            if (full16 && (p.out_ld & 7) == 0) {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+              o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+              o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+              *reinterpret_cast<uint4*>(op) = o0;
+              *reinterpret_cast<uint4*>(op + 8) = o1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if (n + j < p.Cout) op[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * as);   // accumulator buffer drained
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+static int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) l++;
+  return l;
+}
+
+}  // namespace iswm
+
+using namespace iswm;
+
+extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const void* d_wgt,
+                               void* d_out, const float* d_scale, const float* d_shift,
+                               const void* d_res, float* d_stats, void* stream) {
+  ISWM_REQUIRE(d && d_in && d_wgt && d_out, "conv_igemm: null argument");
+  ISWM_REQUIRE(d->ntaps >= 1 && d->ntaps <= ISWM_MAX_TAPS, "conv_igemm: ntaps=%d", d->ntaps);
+  ISWM_REQUIRE(d->Cin >= 1 && d->Cout >= 1 && d->B >= 1 && d->Ho >= 1 && d->Wo >= 1, "conv_igemm: bad dims");
+  ISWM_REQUIRE((d->in_ld % 8) == 0 && d->in_ld >= d->Cin, "conv_igemm: in_ld=%d must be a multiple of 8 and >= Cin=%d", d->in_ld, d->Cin);
+  ISWM_REQUIRE((reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_wgt) & 15) == 0, "conv_igemm: operands must be 16-byte aligned");
+  ISWM_REQUIRE(!(d->flags & ISWM_EPI_AFFINE) || (d_scale && d_shift), "conv_igemm: AFFINE needs scale/shift");
+  ISWM_REQUIRE(!(d->flags & ISWM_EPI_RESIDUAL) || d_res, "conv_igemm: RESIDUAL needs d_res");
+  ISWM_REQUIRE(!(d->flags & ISWM_EPI_STATS) || d_stats, "conv_igemm: STATS needs d_stats");
+  int* abort_flag = abort_flag_ptr();
+  ISWM_REQUIRE(abort_flag, "conv_igemm: cannot allocate abort flag");
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  int B = d->B, Hi = d->Hi, Wi = d->Wi, Ho = d->Ho, Wo = d->Wo, n_img = d->n_img;
+  bool pointwise = (d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->phase[0] == 0 &&
+                    Hi == Ho && Wi == Wo && n_img == B);
+  if (pointwise) {  // a 1x1 convolution is a plain GEMM over all pixels: no tile-edge waste
+    const int64_t M = (int64_t)B * Ho * Wo;
+    if (M < (1ll << 31)) {
+      Wo = Wi = (int)M;
+      Ho = Hi = 1;
+      B = n_img = 1;
+    }
+  }
+  p.lgBW = std::min(7, ilog2_ceil(Wo));
+  p.lgBH = std::min(7 - p.lgBW, ilog2_ceil(Ho));
+  const int BW = 1 << p.lgBW, BH = 1 << p.lgBH, BB = kTileM / (BW * BH);
+  p.B = B; p.Ho = Ho; p.Wo = Wo; p.Cout = d->Cout;
+  p.tiles_w = (Wo + BW - 1) / BW;
+  p.tiles_h = (Ho + BH - 1) / BH;
+  p.tiles_b = (B + BB - 1) / BB;
+  int BN = std::min(256, ((d->Cout + 15) / 16) * 16);
+  p.BN = BN;
+  p.tiles_n = (d->Cout + BN - 1) / BN;
+  const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+  ISWM_REQUIRE(total < (1ll << 31), "conv_igemm: too many tiles");
+  p.total_tiles = (int)total;
+  p.kchunks = (d->Cin + kKBlock - 1) / kKBlock;
+  p.cin_pad = p.kchunks * kKBlock;
+  p.ntaps = d->ntaps;
+  const int stage_bytes = kABytes + BN * 128;
+  p.stages = std::max(2, std::min(kMaxStages, kSmemBudget / stage_bytes));
+  p.flags = d->flags;
+  p.n_img_per_phase = B;
+  p.out_ld = d->out_ld;
+  p.res_ld = d->res_ld;
+  for (int t = 0; t < d->ntaps; t++) { p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t]; }
+  p.out = d_out; p.scale = d_scale; p.shift = d_shift;
+  p.res = static_cast<const __nv_bfloat16*>(d_res);
+  p.stats = d_stats;
+  p.abort_flag = abort_flag;
+
+  CUtensorMap tmap_a, tmap_b;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)n_img};
+    const uint64_t str[4] = {1, (uint64_t)d->in_ld, (uint64_t)Wi * d->in_ld, (uint64_t)Hi * Wi * d->in_ld};
+    const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};
+    if (int rc = encode_tmap_bf16(&tmap_a, d_in, 4, dims, str, box)) return rc;
+  }
+  {
+    const uint64_t ktot = (uint64_t)d->ntaps * p.cin_pad;
+    const uint64_t dims[2] = {ktot, (uint64_t)d->Cout};
+    const uint64_t str[2] = {1, ktot};
+    const uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)BN};
+    if (int rc = encode_tmap_bf16(&tmap_b, d_wgt, 2, dims, str, box)) return rc;
+  }
+  const int smem_bytes = p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*scale,shift*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    ISWM_REQUIRE(e == cudaSuccess, "conv_igemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, num_sms());
+  conv_igemm_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, p);
+  return check_launch("conv_igemm");
+}

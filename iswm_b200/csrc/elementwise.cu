@@ -1,0 +1,915 @@
+// elementwise.cu — the HBM-bound glue between the tensor-core convolutions: BatchNorm
+// (training statistics -> normalise, backward), pooling, bilinear resampling, layout and
+// stride helpers, weight packing, optimiser step. Activations are NHWC bf16 and every
+// kernel moves 16 bytes (8 channels) per thread access, rows addressed through an explicit
+// pitch (ld) so that channel slices of a concat buffer are read and written in place —
+// torch.cat (network/_deeplab.py:59, :171) never materialises.
+#include "common.cuh"
+#include <algorithm>
+
+namespace iswm {
+
+constexpr int kT = 256;
+
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  F8 o;
+  unpack_bf16x2(r.x, o.v[0], o.v[1]);
+  unpack_bf16x2(r.y, o.v[2], o.v[3]);
+  unpack_bf16x2(r.z, o.v[4], o.v[5]);
+  unpack_bf16x2(r.w, o.v[6], o.v[7]);
+  return o;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& f) {
+  uint4 r;
+  r.x = pack_bf16x2(f.v[0], f.v[1]);
+  r.y = pack_bf16x2(f.v[2], f.v[3]);
+  r.z = pack_bf16x2(f.v[4], f.v[5]);
+  r.w = pack_bf16x2(f.v[6], f.v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+static inline int grid_for(int64_t work, int per_block = kT, int waves = 8) {
+  int64_t g = (work + per_block - 1) / per_block;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)num_sms() * waves));
+}
+
+// ---------------------------------------------------------------------------
+// weight packing
+__global__ void pack_weight_fwd_kernel(const float* __restrict__ w, int Cout, int Cin, int RS,
+                                       int cin_pad, int row_ld, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)Cout * row_ld;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int o = (int)(i / row_ld), k = (int)(i % row_ld);
+    const int t = k / cin_pad, c = k % cin_pad;
+    float v = 0.f;
+    if (t < RS && c < Cin) v = w[((int64_t)o * Cin + c) * RS + t];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int RS,
+                                         int cout_pad, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)Cin * RS * cout_pad;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int o = (int)(i % cout_pad);
+    const int t = (int)((i / cout_pad) % RS);
+    const int c = (int)(i / ((int64_t)cout_pad * RS));
+    float v = 0.f;
+    if (o < Cout) v = w[((int64_t)o * Cin + c) * RS + t];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int Cin, int RS,
+                                    int cin_stride, int row_ld, float beta, float* __restrict__ g) {
+  const int64_t total = (int64_t)Cout * Cin * RS;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int t = (int)(i % RS);
+    const int c = (int)((i / RS) % Cin);
+    const int o = (int)(i / ((int64_t)RS * Cin));
+    const float v = dw[(int64_t)o * row_ld + (int64_t)t * cin_stride + c];
+    g[i] = (beta == 0.f) ? v : fmaf(beta, g[i], v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BatchNorm training forward: stats -> normalise (+residual, ReLU, dropout)
+__global__ void __launch_bounds__(kT)
+bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float* __restrict__ stats,
+                      int64_t M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float eps, float momentum, float* running_mean, float* running_var,
+                      long long* nbt, float* save_mean, float* save_invstd,
+                      const __nv_bfloat16* __restrict__ res, int res_ld, int relu, float drop_p,
+                      uint64_t drop_seed, __nv_bfloat16* __restrict__ out, int out_ld) {
+  extern __shared__ float s_par[];  // scale[C], shift[C]
+  float* s_scale = s_par;
+  float* s_shift = s_par + C;
+  const float invM = 1.0f / (float)M;
+  for (int c = threadIdx.x; c < C; c += kT) {
+    const float mean = stats[c] * invM;
+    const float var = fmaxf(stats[C + c] * invM - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * invstd;
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - mean * sc;
+    if (blockIdx.x == 0) {
+      if (save_mean) save_mean[c] = mean;
+      if (save_invstd) save_invstd[c] = invstd;
+      if (running_mean) {
+        const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+  __syncthreads();
+  const int nvec = C >> 3;
+  const int64_t total = M * nvec;
+  const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t row = i / nvec;
+    const int c0 = (int)(i - row * nvec) << 3;
+    F8 f = load8(x + row * x_ld + c0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], s_scale[c0 + j], s_shift[c0 + j]);
+    if (res) {
+      const F8 r = load8(res + row * res_ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) f.v[j] = fmaxf(f.v[j], 0.f);
+    }
+    if (drop_p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        f.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? f.v[j] * keep_scale : 0.f;
+    }
+    store8(out + row * out_ld + c0, f);
+  }
+}
+
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean,
+                               const float* var, float eps, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * kT + threadIdx.x;
+  if (c < C) {
+    const float sc = gamma[c] / sqrtf(var[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - mean[c] * sc;
+  }
+}
+
+// BatchNorm backward pass 1: per-channel sum(dz), sum(dz * xhat)
+__global__ void __launch_bounds__(kT)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
+                     const __nv_bfloat16* __restrict__ x, int x_ld,
+                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                     float drop_p, uint64_t drop_seed, float* __restrict__ sums, int nx, int ny,
+                     int rows_per_block) {
+  __shared__ float s_red[kT * 16];
+  const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
+  const int nvec = C >> 3;
+  const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  for (int cg = tx; cg < nvec; cg += nx) {
+    const int c0 = cg << 3;
+    float a[8], b[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { a[j] = 0.f; b[j] = 0.f; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+    if (ty < ny) {
+      for (int64_t row = r0 + ty; row < r1; row += ny) {
+        F8 g = load8(dout + row * dout_ld + c0);
+        const F8 xv = load8(x + row * x_ld + c0);
+        if (relu) {
+          const F8 o = load8(act + row * act_ld + c0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+        }
+        if (drop_p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            g.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? g.v[j] * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          a[j] += g.v[j];
+          b[j] = fmaf(g.v[j], (xv.v[j] - mu[j]) * is[j], b[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      s_red[threadIdx.x * 16 + j] = a[j];
+      s_red[threadIdx.x * 16 + 8 + j] = b[j];
+    }
+    __syncthreads();
+    if (ty == 0) {
+      for (int j = 0; j < 16; j++) {
+        float t = 0.f;
+        for (int y = 0; y < ny; y++) t += s_red[(y * nx + tx) * 16 + j];
+        const int c = c0 + (j & 7);
+        atomicAdd(sums + (j < 8 ? c : C + c), t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// BatchNorm backward pass 2
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
+                    const __nv_bfloat16* __restrict__ x, int x_ld,
+                    const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
+                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ sums, int relu,
+                    float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
+                    __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta) {
+  extern __shared__ float s_par[];  // k1[C] = gamma*invstd, mean[C], invstd[C], m_dz[C], m_dzx[C]
+  float* s_k = s_par;
+  float* s_mu = s_par + C;
+  float* s_is = s_par + 2 * C;
+  float* s_a = s_par + 3 * C;
+  float* s_b = s_par + 4 * C;
+  const float invM = 1.0f / (float)M;
+  for (int c = threadIdx.x; c < C; c += kT) {
+    s_k[c] = gamma[c] * invstd[c];
+    s_mu[c] = mean[c];
+    s_is[c] = invstd[c];
+    s_a[c] = sums[c] * invM;
+    s_b[c] = sums[C + c] * invM;
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[c] += sums[c];
+      if (dgamma) dgamma[c] += sums[C + c];
+    }
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const int64_t total = M * nvec;
+  const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t row = i / nvec;
+    const int c0 = (int)(i - row * nvec) << 3;
+    F8 g = load8(dout + row * dout_ld + c0);
+    const F8 xv = load8(x + row * x_ld + c0);
+    if (relu) {
+      const F8 o = load8(act + row * act_ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+    }
+    if (drop_p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        g.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? g.v[j] * keep_scale : 0.f;
+    }
+    if (dz) store8(dz + row * dz_ld + c0, g);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = c0 + j;
+      const float xh = (xv.v[j] - s_mu[c]) * s_is[c];
+      o.v[j] = s_k[c] * (g.v[j] - s_a[c] - xh * s_b[c]);
+    }
+    store8(dx + row * dx_ld + c0, o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stem im2col: NCHW fp32 image -> [B*Ho*Wo][Kpad] bf16, col = (r*7+s)*Cin + c
+__global__ void __launch_bounds__(kT)
+stem_im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int Ho, int Wo,
+                   int Kpad, __nv_bfloat16* __restrict__ out) {
+  const int koct = Kpad >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * koct;
+  const int K = 49 * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int ko = (int)(i % koct);
+    const int64_t m = i / koct;
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    F8 f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int k = ko * 8 + j;
+      float v = 0.f;
+      if (k < K) {
+        const int c = k % Cin, t = k / Cin;
+        const int r = t / 7, s = t % 7;
+        const int hi = 2 * ho + r - 3, wi = 2 * wo + s - 3;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+          v = __ldg(img + (((int64_t)b * Cin + c) * H + hi) * W + wi);
+      }
+      f.v[j] = v;
+    }
+    store8(out + m * Kpad + ko * 8, f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// MaxPool2d(3, 2, 1)
+__global__ void __launch_bounds__(kT)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    const int64_t m = i / nvec;
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { best[j] = -INFINITY; arg[j] = 0; }
+    for (int r = 0; r < 3; r++) {
+      const int hi = 2 * ho + r - 1;
+      if (hi < 0 || hi >= H) continue;
+      for (int s = 0; s < 3; s++) {
+        const int wi = 2 * wo + s - 1;
+        if (wi < 0 || wi >= W) continue;
+        const F8 v = load8(x + (((int64_t)b * H + hi) * W + wi) * C + cg * 8);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (v.v[j] > best[j]) { best[j] = v.v[j]; arg[j] = r * 3 + s; }
+      }
+    }
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = best[j];
+    store8(out + m * C + cg * 8, o);
+    if (idx) {
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(idx + m * C + cg * 8) = pk;
+    }
+  }
+}
+__global__ void __launch_bounds__(kT)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx, int B,
+                   int H, int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)B * H * W * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    const int64_t m = i / nvec;
+    const int wi = (int)(m % W), hi = (int)((m / W) % H), b = (int)(m / ((int64_t)W * H));
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc.v[j] = 0.f;
+    // output windows containing (hi, wi): ho in {floor((hi+1)/2) - ?}: 2*ho + r - 1 == hi, r in 0..2
+    for (int r = 0; r < 3; r++) {
+      const int hnum = hi + 1 - r;
+      if (hnum < 0 || (hnum & 1)) continue;
+      const int ho = hnum >> 1;
+      if (ho >= Ho) continue;
+      for (int s = 0; s < 3; s++) {
+        const int wnum = wi + 1 - s;
+        if (wnum < 0 || (wnum & 1)) continue;
+        const int wo = wnum >> 1;
+        if (wo >= Wo) continue;
+        const int64_t om = ((int64_t)b * Ho + ho) * Wo + wo;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + om * C + cg * 8);
+        const F8 g = load8(dout + om * C + cg * 8);
+        const int code = r * 3 + s;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int a = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
+          if (a == code) acc.v[j] += g.v[j];
+        }
+      }
+    }
+    store8(dx + m * C + cg * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// reductions / broadcasts over the spatial axis: [B, HW, C] <-> [B, C]
+__global__ void __launch_bounds__(kT)
+reduce_hw_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int64_t HW, int C, float scale,
+                 __nv_bfloat16* __restrict__ out, int nx, int ny) {
+  __shared__ float s_red[kT * 8];
+  const int b = blockIdx.y;
+  const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
+  const int cg = blockIdx.x * nx + tx;
+  const int nvec = C >> 3;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) a[j] = 0.f;
+  if (cg < nvec && ty < ny) {
+    const __nv_bfloat16* xp = x + (int64_t)b * HW * x_ld + cg * 8;
+    for (int64_t r = ty; r < HW; r += ny) {
+      const F8 v = load8(xp + r * x_ld);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] += v.v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) s_red[threadIdx.x * 8 + j] = a[j];
+  __syncthreads();
+  if (ty == 0 && cg < nvec) {
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float t = 0.f;
+      for (int y = 0; y < ny; y++) t += s_red[(y * nx + tx) * 8 + j];
+      o.v[j] = t * scale;
+    }
+    store8(out + (int64_t)b * C + cg * 8, o);
+  }
+}
+__global__ void __launch_bounds__(kT)
+broadcast_hw_kernel(const __nv_bfloat16* __restrict__ x, int B, int64_t HW, int C,
+                    __nv_bfloat16* __restrict__ out, int out_ld, float scale, int accumulate) {
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)B * HW * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    const int64_t m = i / nvec;
+    const int b = (int)(m / HW);
+    F8 v = load8(x + (int64_t)b * C + cg * 8);
+    __nv_bfloat16* op = out + m * out_ld + cg * 8;
+    if (accumulate) {
+      const F8 o = load8(op);
+#pragma unroll
+      for (int j = 0; j < 8; j++) v.v[j] = fmaf(v.v[j], scale, o.v[j]);
+    } else if (scale != 1.f) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v.v[j] *= scale;
+    }
+    store8(op, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bilinear, align_corners=False (ATen upsample_bilinear2d index rule)
+__device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int& i1, float& l1) {
+  float src = ((float)o + 0.5f) * scale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(kT)
+bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int Hi, int Wi, int C,
+                    int Ho, int Wo, __nv_bfloat16* __restrict__ out, int out_ld) {
+  const int nvec = C >> 3;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const int64_t total = (int64_t)B * Ho * Wo * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    const int64_t m = i / nvec;
+    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(ho, sh, Hi, y0, y1, ly);
+    bil_src(wo, sw, Wi, x0, x1, lx);
+    const __nv_bfloat16* base = x + (int64_t)b * Hi * Wi * x_ld + cg * 8;
+    const F8 v00 = load8(base + ((int64_t)y0 * Wi + x0) * x_ld);
+    const F8 v01 = load8(base + ((int64_t)y0 * Wi + x1) * x_ld);
+    const F8 v10 = load8(base + ((int64_t)y1 * Wi + x0) * x_ld);
+    const F8 v11 = load8(base + ((int64_t)y1 * Wi + x1) * x_ld);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = w00 * v00.v[j] + w01 * v01.v[j] + w10 * v10.v[j] + w11 * v11.v[j];
+    store8(out + m * out_ld + cg * 8, o);
+  }
+}
+
+// candidate output range that can touch input index i
+__device__ __forceinline__ void bil_range(int i, float rscale, int out, int& lo, int& hi) {
+  lo = (int)floorf(((float)i - 0.5f) * rscale - 0.5f) - 1;
+  hi = (int)ceilf(((float)i + 1.5f) * rscale - 0.5f) + 1;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > out - 1 ? out - 1 : hi;
+}
+
+__global__ void __launch_bounds__(kT)
+bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, int Hi, int Wi,
+                    int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, int dx_ld) {
+  const int nvec = C >> 3;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
+  const int64_t total = (int64_t)B * Hi * Wi * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    const int64_t m = i / nvec;
+    const int xi = (int)(m % Wi), yi = (int)((m / Wi) % Hi), b = (int)(m / ((int64_t)Wi * Hi));
+    int ylo, yhi, xlo, xhi;
+    bil_range(yi, rh, Ho, ylo, yhi);
+    bil_range(xi, rw, Wo, xlo, xhi);
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc.v[j] = 0.f;
+    const __nv_bfloat16* base = dout + (int64_t)b * Ho * Wo * dout_ld + cg * 8;
+    for (int oy = ylo; oy <= yhi; oy++) {
+      int y0, y1; float ly;
+      bil_src(oy, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = xlo; ox <= xhi; ox++) {
+        int x0, x1; float lx;
+        bil_src(ox, sw, Wi, x0, x1, lx);
+        const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+        if (wx == 0.f) continue;
+        const F8 g = load8(base + ((int64_t)oy * Wo + ox) * dout_ld);
+        const float w = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc.v[j] = fmaf(w, g.v[j], acc.v[j]);
+      }
+    }
+    store8(dx + m * dx_ld + cg * 8, acc);
+  }
+}
+
+// final logits upsample: NHWC fp32 [B,h,w,C] -> NCHW fp32 [B,C,H,W]
+__global__ void __launch_bounds__(kT)
+logits_up_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                     float* __restrict__ out) {
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int wo = (int)(i % Wo), ho = (int)((i / Wo) % Ho), b = (int)(i / ((int64_t)Wo * Ho));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(ho, sh, Hi, y0, y1, ly);
+    bil_src(wo, sw, Wi, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float* base = x + (int64_t)b * Hi * Wi * C;
+    const float* p00 = base + ((int64_t)y0 * Wi + x0) * C;
+    const float* p01 = base + ((int64_t)y0 * Wi + x1) * C;
+    const float* p10 = base + ((int64_t)y1 * Wi + x0) * C;
+    const float* p11 = base + ((int64_t)y1 * Wi + x1) * C;
+    for (int c = 0; c < C; c++) {
+      const float v = w00 * __ldg(p00 + c) + w01 * __ldg(p01 + c) + w10 * __ldg(p10 + c) + w11 * __ldg(p11 + c);
+      out[(((int64_t)b * C + c) * Ho + ho) * Wo + wo] = v;
+    }
+  }
+}
+// adjoint: NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels >= C zero-filled)
+__global__ void __launch_bounds__(kT)
+logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                     __nv_bfloat16* __restrict__ dx, int dx_ld) {
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
+  const int64_t total = (int64_t)B * Hi * Wi * C;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int c = (int)(i % C);
+    const int64_t m = i / C;
+    const int xi = (int)(m % Wi), yi = (int)((m / Wi) % Hi), b = (int)(m / ((int64_t)Wi * Hi));
+    int ylo, yhi, xlo, xhi;
+    bil_range(yi, rh, Ho, ylo, yhi);
+    bil_range(xi, rw, Wo, xlo, xhi);
+    const float* base = dout + ((int64_t)b * C + c) * Ho * Wo;
+    float acc = 0.f;
+    for (int oy = ylo; oy <= yhi; oy++) {
+      int y0, y1; float ly;
+      bil_src(oy, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+      if (wy == 0.f) continue;
+      float rowacc = 0.f;
+      for (int ox = xlo; ox <= xhi; ox++) {
+        int x0, x1; float lx;
+        bil_src(ox, sw, Wi, x0, x1, lx);
+        const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+        if (wx != 0.f) rowacc = fmaf(wx, __ldg(base + (int64_t)oy * Wo + ox), rowacc);
+      }
+      acc = fmaf(wy, rowacc, acc);
+    }
+    dx[m * dx_ld + c] = __float2bfloat16_rn(acc);
+    if (c == C - 1)
+      for (int cc = C; cc < dx_ld; cc++) dx[m * dx_ld + cc] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stride-2 helpers
+// phase split: out[(p*2+q)][b][i][j][c] = x[b][2i+p][2j+q][c]  (zero beyond the image)
+__global__ void __launch_bounds__(kT)
+phase_split_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int H, int W, int C,
+                   int Hp, int Wp, __nv_bfloat16* __restrict__ out) {
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)4 * B * Hp * Wp * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    int64_t m = i / nvec;
+    const int j = (int)(m % Wp); m /= Wp;
+    const int ii = (int)(m % Hp); m /= Hp;
+    const int b = (int)(m % B);
+    const int ph = (int)(m / B);
+    const int h = 2 * ii + (ph >> 1), w = 2 * j + (ph & 1);
+    F8 v;
+    if (h < H && w < W) v = load8(x + (((int64_t)b * H + h) * W + w) * x_ld + cg * 8);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) v.v[k] = 0.f;
+    }
+    store8(out + (i / nvec) * C + cg * 8, v);
+  }
+}
+// subsample: out[b][i][j] = x[b][2i][2j]
+__global__ void __launch_bounds__(kT)
+subsample2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int H, int W, int C,
+                  int Ho, int Wo, __nv_bfloat16* __restrict__ out) {
+  const int nvec = C >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(i % nvec);
+    const int64_t m = i / nvec;
+    const int j = (int)(m % Wo), ii = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    const F8 v = load8(x + (((int64_t)b * H + 2 * ii) * W + 2 * j) * x_ld + cg * 8);
+    store8(out + m * C + cg * 8, v);
+  }
+}
+// zero stuff: out[b][h][w] = (h,w even and in range) ? x[b][h/2][w/2] : 0 ; mode 1: out += at even sites
+__global__ void __launch_bounds__(kT)
+stuff2_kernel(const __nv_bfloat16* __restrict__ x, int B, int Ho, int Wo, int C, int H, int W,
+              __nv_bfloat16* __restrict__ out, int accumulate) {
+  const int nvec = C >> 3;
+  if (accumulate) {
+    const int64_t total = (int64_t)B * Ho * Wo * nvec;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+      const int cg = (int)(i % nvec);
+      const int64_t m = i / nvec;
+      const int j = (int)(m % Wo), ii = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+      if (2 * ii >= H || 2 * j >= W) continue;
+      __nv_bfloat16* op = out + (((int64_t)b * H + 2 * ii) * W + 2 * j) * C + cg * 8;
+      F8 o = load8(op);
+      const F8 v = load8(x + m * C + cg * 8);
+#pragma unroll
+      for (int k = 0; k < 8; k++) o.v[k] += v.v[k];
+      store8(op, o);
+    }
+  } else {
+    const int64_t total = (int64_t)B * H * W * nvec;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+      const int cg = (int)(i % nvec);
+      const int64_t m = i / nvec;
+      const int w = (int)(m % W), h = (int)((m / W) % H), b = (int)(m / ((int64_t)W * H));
+      F8 v;
+      if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+        v = load8(x + (((int64_t)b * Ho + (h >> 1)) * Wo + (w >> 1)) * C + cg * 8);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v.v[k] = 0.f;
+      }
+      store8(out + m * C + cg * 8, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t nvec8,
+                __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nvec8; i += (int64_t)gridDim.x * kT) {
+    F8 x = load8(a + i * 8);
+    const F8 y = load8(b + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.v[k] += y.v[k];
+    store8(out + i * 8, x);
+  }
+}
+
+// layout converters (API boundary / tests)
+__global__ void __launch_bounds__(kT)
+nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int64_t HW, int C,
+                        float* __restrict__ out) {
+  const int64_t total = (int64_t)B * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t p = i % HW;
+    const int c = (int)((i / HW) % C);
+    const int64_t b = i / (HW * C);
+    out[i] = __bfloat162float(x[(b * HW + p) * x_ld + c]);
+  }
+}
+__global__ void __launch_bounds__(kT)
+nchw_f32_to_nhwc_kernel(const float* __restrict__ x, int B, int64_t HW, int C,
+                        __nv_bfloat16* __restrict__ out, int out_ld) {
+  const int64_t total = (int64_t)B * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int c = (int)(i % C);
+    const int64_t p = (i / C) % HW;
+    const int64_t b = i / ((int64_t)C * HW);
+    out[(b * HW + p) * out_ld + c] = __float2bfloat16_rn(x[(b * C + c) * HW + p]);
+  }
+}
+
+// fused SGD(momentum, nesterov, weight decay) over a flat fp32 buffer (torch.optim.SGD rule)
+__global__ void __launch_bounds__(kT)
+sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, int64_t n,
+                float lr, float momentum, float wd, int nesterov, int first) {
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+    float grad = g[i];
+    const float w = p[i];
+    if (wd != 0.f) grad = fmaf(wd, w, grad);
+    if (momentum != 0.f) {
+      const float buf = first ? grad : fmaf(momentum, mom[i], grad);
+      mom[i] = buf;
+      grad = nesterov ? fmaf(momentum, buf, grad) : buf;
+    }
+    p[i] = fmaf(-lr, grad, w);
+  }
+}
+
+}  // namespace iswm
+
+// ---------------------------------------------------------------------------
+using namespace iswm;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) static_cast<const __nv_bfloat16*>(p)
+#define BFW(p) static_cast<__nv_bfloat16*>(p)
+#define REQ_C8(C, what) ISWM_REQUIRE(((C) % 8) == 0 && (C) > 0, what ": channel count %d must be a positive multiple of 8", (int)(C))
+#define REQ_LD8(ld, what) ISWM_REQUIRE(((ld) % 8) == 0, what ": row pitch %d must be a multiple of 8", (int)(ld))
+
+extern "C" int iswm_pack_weight_fwd(const float* d_w, int Cout, int Cin, int RS, int cin_pad,
+                                    int row_ld, void* d_out, void* stream) {
+  ISWM_REQUIRE(d_w && d_out && cin_pad >= Cin && row_ld >= RS * cin_pad, "pack_weight_fwd: bad args");
+  pack_weight_fwd_kernel<<<grid_for((int64_t)Cout * row_ld), kT, 0, ST(stream)>>>(d_w, Cout, Cin, RS, cin_pad, row_ld, BFW(d_out));
+  return check_launch("pack_weight_fwd");
+}
+extern "C" int iswm_pack_weight_dgrad(const float* d_w, int Cout, int Cin, int RS, int cout_pad,
+                                      void* d_out, void* stream) {
+  ISWM_REQUIRE(d_w && d_out && cout_pad >= Cout, "pack_weight_dgrad: bad args");
+  pack_weight_dgrad_kernel<<<grid_for((int64_t)Cin * RS * cout_pad), kT, 0, ST(stream)>>>(d_w, Cout, Cin, RS, cout_pad, BFW(d_out));
+  return check_launch("pack_weight_dgrad");
+}
+extern "C" int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stride,
+                                 int row_ld, float beta, float* d_grad_oihw, void* stream) {
+  ISWM_REQUIRE(d_dw && d_grad_oihw, "unpack_wgrad: null");
+  unpack_wgrad_kernel<<<grid_for((int64_t)Cout * Cin * RS), kT, 0, ST(stream)>>>(d_dw, Cout, Cin, RS, cin_stride, row_ld, beta, d_grad_oihw);
+  return check_launch("unpack_wgrad");
+}
+
+extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_stats, int64_t M, int C,
+                                   const float* d_gamma, const float* d_beta, float eps, float momentum,
+                                   float* d_running_mean, float* d_running_var, int64_t* d_nbt,
+                                   float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld,
+                                   int relu, float drop_p, uint64_t drop_seed, void* d_out, int out_ld,
+                                   void* stream) {
+  REQ_C8(C, "bn_train_apply"); REQ_LD8(x_ld, "bn_train_apply"); REQ_LD8(out_ld, "bn_train_apply");
+  ISWM_REQUIRE(d_x && d_stats && d_gamma && d_beta && d_out && M > 0, "bn_train_apply: null/empty");
+  ISWM_REQUIRE(!d_res || (res_ld % 8) == 0, "bn_train_apply: res_ld");
+  ISWM_REQUIRE(C <= 4096, "bn_train_apply: C too large");
+  bn_train_apply_kernel<<<grid_for(M * (C / 8)), kT, 2 * C * sizeof(float), ST(stream)>>>(
+      BF(d_x), x_ld, d_stats, M, C, d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var,
+      reinterpret_cast<long long*>(d_nbt), d_save_mean, d_save_invstd, BF(d_res), res_ld, relu,
+      drop_p, drop_seed, BFW(d_out), out_ld);
+  return check_launch("bn_train_apply");
+}
+extern "C" int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean,
+                            const float* d_var, float eps, int C, float* d_scale, float* d_shift,
+                            void* stream) {
+  ISWM_REQUIRE(d_gamma && d_beta && d_mean && d_var && d_scale && d_shift && C > 0, "bn_fold: null");
+  bn_fold_kernel<<<(C + kT - 1) / kT, kT, 0, ST(stream)>>>(d_gamma, d_beta, d_mean, d_var, eps, C, d_scale, d_shift);
+  return check_launch("bn_fold");
+}
+
+static void bn_red_shape(int C, int& nx, int& ny) {
+  const int nvec = C / 8;
+  nx = std::min(nvec, kT);
+  ny = std::max(1, kT / nx);
+}
+
+extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
+                                  const void* d_out_act, int act_ld, int64_t M, int C,
+                                  const float* d_save_mean, const float* d_save_invstd, int relu,
+                                  float drop_p, uint64_t drop_seed, float* d_sums, void* stream) {
+  REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
+  ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
+  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_reduce: relu needs the activation");
+  int nx, ny;
+  bn_red_shape(C, nx, ny);
+  int64_t want_blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)num_sms() * 4, (M + ny * 4 - 1) / (ny * 4)));
+  const int rows_per_block = (int)((M + want_blocks - 1) / want_blocks);
+  const int blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+  bn_bwd_reduce_kernel<<<blocks, kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
+                                                      M, C, d_save_mean, d_save_invstd, relu, drop_p,
+                                                      drop_seed, d_sums, nx, ny, rows_per_block);
+  return check_launch("bn_bwd_reduce");
+}
+extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
+                                 const void* d_out_act, int act_ld, int64_t M, int C,
+                                 const float* d_gamma, const float* d_save_mean, const float* d_save_invstd,
+                                 const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                                 void* d_dx, int dx_ld, void* d_dz, int dz_ld, float* d_dgamma,
+                                 float* d_dbeta, void* stream) {
+  REQ_C8(C, "bn_bwd_apply"); REQ_LD8(dout_ld, "bn_bwd_apply"); REQ_LD8(x_ld, "bn_bwd_apply"); REQ_LD8(dx_ld, "bn_bwd_apply");
+  ISWM_REQUIRE(d_dout && d_x && d_gamma && d_save_mean && d_save_invstd && d_sums && d_dx && M > 0, "bn_bwd_apply: null/empty");
+  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_apply: relu needs the activation");
+  ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd_apply: dz_ld");
+  ISWM_REQUIRE(C <= 4096, "bn_bwd_apply: C too large");
+  bn_bwd_apply_kernel<<<grid_for(M * (C / 8)), kT, 5 * C * sizeof(float), ST(stream)>>>(
+      BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_save_mean,
+      d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta);
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int iswm_stem_im2col(const float* d_img, int B, int Cin, int H, int W, int Ho, int Wo,
+                                int Kpad, void* d_out, void* stream) {
+  ISWM_REQUIRE(d_img && d_out && (Kpad % 8) == 0 && Kpad >= 49 * Cin, "stem_im2col: bad args");
+  stem_im2col_kernel<<<grid_for((int64_t)B * Ho * Wo * (Kpad / 8)), kT, 0, ST(stream)>>>(d_img, B, Cin, H, W, Ho, Wo, Kpad, BFW(d_out));
+  return check_launch("stem_im2col");
+}
+extern "C" int iswm_maxpool_fwd(const void* d_x, int B, int H, int W, int C, int Ho, int Wo,
+                                void* d_out, uint8_t* d_idx, void* stream) {
+  REQ_C8(C, "maxpool_fwd");
+  ISWM_REQUIRE(d_x && d_out, "maxpool_fwd: null");
+  maxpool_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, H, W, C, Ho, Wo, BFW(d_out), d_idx);
+  return check_launch("maxpool_fwd");
+}
+extern "C" int iswm_maxpool_bwd(const void* d_dout, const uint8_t* d_idx, int B, int H, int W, int C,
+                                int Ho, int Wo, void* d_dx, void* stream) {
+  REQ_C8(C, "maxpool_bwd");
+  ISWM_REQUIRE(d_dout && d_idx && d_dx, "maxpool_bwd: null");
+  maxpool_bwd_kernel<<<grid_for((int64_t)B * H * W * (C / 8)), kT, 0, ST(stream)>>>(BF(d_dout), d_idx, B, H, W, C, Ho, Wo, BFW(d_dx));
+  return check_launch("maxpool_bwd");
+}
+
+static int launch_reduce_hw(const void* d_x, int x_ld, int B, int64_t HW, int C, float scale, void* d_out, void* stream) {
+  const int nvec = C / 8;
+  const int nx = std::min(nvec, 16);
+  const int ny = kT / nx;
+  dim3 grid((nvec + nx - 1) / nx, B);
+  reduce_hw_kernel<<<grid, kT, 0, ST(stream)>>>(BF(d_x), x_ld, HW, C, scale, BFW(d_out), nx, ny);
+  return check_launch("reduce_hw");
+}
+extern "C" int iswm_gap_fwd(const void* d_x, int x_ld, int B, int64_t HW, int C, void* d_out, void* stream) {
+  REQ_C8(C, "gap_fwd"); REQ_LD8(x_ld, "gap_fwd");
+  ISWM_REQUIRE(d_x && d_out && HW > 0, "gap_fwd: null/empty");
+  return launch_reduce_hw(d_x, x_ld, B, HW, C, 1.0f / (float)HW, d_out, stream);
+}
+extern "C" int iswm_sum_hw(const void* d_x, int x_ld, int B, int64_t HW, int C, void* d_out, void* stream) {
+  REQ_C8(C, "sum_hw"); REQ_LD8(x_ld, "sum_hw");
+  ISWM_REQUIRE(d_x && d_out && HW > 0, "sum_hw: null/empty");
+  return launch_reduce_hw(d_x, x_ld, B, HW, C, 1.0f, d_out, stream);
+}
+extern "C" int iswm_broadcast_hw(const void* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream) {
+  REQ_C8(C, "broadcast_hw"); REQ_LD8(out_ld, "broadcast_hw");
+  ISWM_REQUIRE(d_x && d_out, "broadcast_hw: null");
+  broadcast_hw_kernel<<<grid_for((int64_t)B * HW * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, HW, C, BFW(d_out), out_ld, 1.f, 0);
+  return check_launch("broadcast_hw");
+}
+extern "C" int iswm_gap_bwd_add(const void* d_dpool, int B, int64_t HW, int C, void* d_dx, int dx_ld, void* stream) {
+  REQ_C8(C, "gap_bwd_add"); REQ_LD8(dx_ld, "gap_bwd_add");
+  ISWM_REQUIRE(d_dpool && d_dx && HW > 0, "gap_bwd_add: null/empty");
+  broadcast_hw_kernel<<<grid_for((int64_t)B * HW * (C / 8)), kT, 0, ST(stream)>>>(BF(d_dpool), B, HW, C, BFW(d_dx), dx_ld, 1.0f / (float)HW, 1);
+  return check_launch("gap_bwd_add");
+}
+extern "C" int iswm_bilinear_fwd(const void* d_x, int x_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                                 void* d_out, int out_ld, void* stream) {
+  REQ_C8(C, "bilinear_fwd"); REQ_LD8(x_ld, "bilinear_fwd"); REQ_LD8(out_ld, "bilinear_fwd");
+  ISWM_REQUIRE(d_x && d_out, "bilinear_fwd: null");
+  bilinear_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_out), out_ld);
+  return check_launch("bilinear_fwd");
+}
+extern "C" int iswm_bilinear_bwd(const void* d_dout, int dout_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                                 void* d_dx, int dx_ld, void* stream) {
+  REQ_C8(C, "bilinear_bwd"); REQ_LD8(dout_ld, "bilinear_bwd"); REQ_LD8(dx_ld, "bilinear_bwd");
+  ISWM_REQUIRE(d_dout && d_dx, "bilinear_bwd: null");
+  bilinear_bwd_kernel<<<grid_for((int64_t)B * Hi * Wi * (C / 8)), kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  return check_launch("bilinear_bwd");
+}
+extern "C" int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C, int Ho, int Wo, float* d_out, void* stream) {
+  ISWM_REQUIRE(d_x && d_out && C >= 1, "logits_up_fwd: null");
+  logits_up_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo), kT, 0, ST(stream)>>>(d_x, B, Hi, Wi, C, Ho, Wo, d_out);
+  return check_launch("logits_up_fwd");
+}
+extern "C" int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld, void* stream) {
+  ISWM_REQUIRE(d_dout && d_dx && C >= 1 && dx_ld >= C, "logits_up_bwd: bad args");
+  logits_up_bwd_kernel<<<grid_for((int64_t)B * Hi * Wi * C), kT, 0, ST(stream)>>>(d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  return check_launch("logits_up_bwd");
+}
+extern "C" int iswm_phase_split(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream) {
+  REQ_C8(C, "phase_split"); REQ_LD8(x_ld, "phase_split");
+  ISWM_REQUIRE(d_x && d_out, "phase_split: null");
+  const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
+  phase_split_kernel<<<grid_for((int64_t)4 * B * Hp * Wp * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, H, W, C, Hp, Wp, BFW(d_out));
+  return check_launch("phase_split");
+}
+extern "C" int iswm_subsample2(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream) {
+  REQ_C8(C, "subsample2"); REQ_LD8(x_ld, "subsample2");
+  ISWM_REQUIRE(d_x && d_out, "subsample2: null");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  subsample2_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, H, W, C, Ho, Wo, BFW(d_out));
+  return check_launch("subsample2");
+}
+extern "C" int iswm_zero_stuff2(const void* d_x, int B, int Ho, int Wo, int C, int H, int W, void* d_out, void* stream) {
+  REQ_C8(C, "zero_stuff2");
+  ISWM_REQUIRE(d_x && d_out, "zero_stuff2: null");
+  stuff2_kernel<<<grid_for((int64_t)B * H * W * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, Ho, Wo, C, H, W, BFW(d_out), 0);
+  return check_launch("zero_stuff2");
+}
+extern "C" int iswm_scatter2_add(const void* d_x, int B, int Ho, int Wo, int C, int H, int W, void* d_inout, void* stream) {
+  REQ_C8(C, "scatter2_add");
+  ISWM_REQUIRE(d_x && d_inout, "scatter2_add: null");
+  stuff2_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, Ho, Wo, C, H, W, BFW(d_inout), 1);
+  return check_launch("scatter2_add");
+}
+extern "C" int iswm_add_bf16(const void* d_a, const void* d_b, int64_t n, void* d_out, void* stream) {
+  ISWM_REQUIRE(d_a && d_b && d_out && (n % 8) == 0, "add_bf16: n must be a multiple of 8");
+  if (n == 0) return 0;
+  add_bf16_kernel<<<grid_for(n / 8), kT, 0, ST(stream)>>>(BF(d_a), BF(d_b), n / 8, BFW(d_out));
+  return check_launch("add_bf16");
+}
+extern "C" int iswm_nhwc_to_nchw_f32(const void* d_x, int x_ld, int B, int64_t HW, int C, float* d_out, void* stream) {
+  ISWM_REQUIRE(d_x && d_out, "nhwc_to_nchw_f32: null");
+  nhwc_to_nchw_f32_kernel<<<grid_for((int64_t)B * HW * C), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, HW, C, d_out);
+  return check_launch("nhwc_to_nchw_f32");
+}
+extern "C" int iswm_nchw_f32_to_nhwc(const float* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream) {
+  ISWM_REQUIRE(d_x && d_out, "nchw_f32_to_nhwc: null");
+  nchw_f32_to_nhwc_kernel<<<grid_for((int64_t)B * HW * C), kT, 0, ST(stream)>>>(d_x, B, HW, C, BFW(d_out), out_ld);
+  return check_launch("nchw_f32_to_nhwc");
+}
+extern "C" int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr,
+                             float momentum, float weight_decay, int nesterov, int first_step, void* stream) {
+  ISWM_REQUIRE(d_param && d_grad && (momentum == 0.f || d_mom), "sgd_step: null");
+  if (n == 0) return 0;
+  sgd_step_kernel<<<grid_for(n), kT, 0, ST(stream)>>>(d_param, d_grad, d_mom, n, lr, momentum, weight_decay, nesterov, first_step);
+  return check_launch("sgd_step");
+}

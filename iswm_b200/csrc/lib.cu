@@ -1,0 +1,21 @@
+// lib.cu — process-wide plumbing of libiswm_b200.so: thread-local error text,
+// launch counter, version.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace iswm {
+static thread_local char t_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace iswm
+
+extern "C" const char* iswm_last_error(void) { return iswm::t_err; }
+extern "C" int iswm_version(void) { return 100; }
+extern "C" int64_t iswm_launch_count(void) { return iswm::g_launches.load(); }
+extern "C" void iswm_reset_launch_count(void) { iswm::g_launches.store(0); }

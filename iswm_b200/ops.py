@@ -1,0 +1,197 @@
+"""Tensor-level wrappers over the C ABI (include/iswm_b200.h).
+
+Each function takes CUDA torch tensors, passes raw device pointers + sizes + the current
+CUDA stream to libiswm_b200.so, and raises on any error. PyTorch is used for memory and
+streams only. There is no fallback path: a CPU tensor or a missing library is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+_LABEL_CODE = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64}
+_FLOAT_CODE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("iswm_b200 ops need CUDA tensors (no CPU fallback exists)")
+    return t.data_ptr()
+
+
+def _label_code(t: torch.Tensor) -> int:
+    try:
+        return _LABEL_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"label dtype {t.dtype} not supported (uint8/int32/int64)") from None
+
+
+# ----------------------------------------------------------------------------- loss / metric
+
+def class_hist(labels: torch.Tensor, n_classes: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int64[n_classes] pixel counts; accumulates into `out` when given (train.py:401-402)."""
+    labels = labels.contiguous()
+    if out is None:
+        out = torch.zeros(n_classes, dtype=torch.int64, device=labels.device)
+    check(_lib.lib().iswm_class_hist(_ptr(labels), _label_code(labels), labels.numel(), n_classes,
+                                     _ptr(out), _stream()), "class_hist")
+    return out
+
+
+def wce_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, weight: Optional[torch.Tensor],
+                hist: torch.Tensor, ignore_index: int = 255, grad_scale: float = 1.0,
+                want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Fused weighted CE forward(+backward). Returns (loss[0-dim fp32], dlogits or None)."""
+    assert logits.dim() >= 2
+    logits = logits.contiguous()
+    labels = labels.contiguous()
+    B, Cc = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // max(1, B * Cc)
+    if labels.numel() != B * HW:
+        raise ValueError(f"labels {tuple(labels.shape)} do not match logits {tuple(logits.shape)}")
+    grad = torch.empty_like(logits) if want_grad else None
+    num = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    w = None if weight is None else weight.to(device=logits.device, dtype=torch.float32).contiguous()
+    check(_lib.lib().iswm_wce_fwd_bwd(_ptr(logits), _FLOAT_CODE[logits.dtype], _ptr(labels),
+                                      _label_code(labels), _ptr(w), _ptr(hist), B, Cc, HW,
+                                      ignore_index, grad_scale, _ptr(grad), _ptr(num), _ptr(loss),
+                                      _stream()), "wce_fwd_bwd")
+    return loss, grad
+
+
+def confusion(true: torch.Tensor, pred: torch.Tensor, n_classes: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int64[n*n+1] confusion counts (last slot: predictions outside [0,n))."""
+    true = true.contiguous()
+    pred = pred.contiguous()
+    if true.numel() != pred.numel():
+        raise ValueError("true / pred size mismatch")
+    if out is None:
+        out = torch.zeros(n_classes * n_classes + 1, dtype=torch.int64, device=true.device)
+    check(_lib.lib().iswm_confusion(_ptr(true), _label_code(true), _ptr(pred), _label_code(pred),
+                                    true.numel(), n_classes, _ptr(out), _stream()), "confusion")
+    return out
+
+
+def argmax_confusion(logits: torch.Tensor, true: Optional[torch.Tensor], mode: int = 0,
+                     threshold: float = 0.5, want_pred: bool = False, want_conf: bool = False,
+                     out: Optional[torch.Tensor] = None):
+    logits = logits.contiguous()
+    B, Cc = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // max(1, B * Cc)
+    dev = logits.device
+    pred = torch.empty((B,) + tuple(logits.shape[2:]), dtype=torch.uint8, device=dev) if want_pred else None
+    conf = torch.empty((B,) + tuple(logits.shape[2:]), dtype=torch.uint8, device=dev) if want_conf else None
+    if true is not None:
+        true = true.contiguous()
+        if out is None:
+            out = torch.zeros(Cc * Cc + 1, dtype=torch.int64, device=dev)
+    check(_lib.lib().iswm_argmax_confusion(_ptr(logits), _FLOAT_CODE[logits.dtype], _ptr(true),
+                                           _label_code(true) if true is not None else _lib.I64,
+                                           B, Cc, HW, mode, threshold, _ptr(pred), _ptr(conf),
+                                           _ptr(out) if true is not None else None, _stream()),
+          "argmax_confusion")
+    return out, pred, conf
+
+
+# ----------------------------------------------------------------------------- convolution
+
+def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,
+                   Cout: int, out_ld: int, taps: Sequence[Tuple[int, int, int]], flags: int = 0,
+                   res_ld: int = 0) -> ConvDesc:
+    d = ConvDesc()
+    d.B, d.Hi, d.Wi, d.Cin, d.in_ld, d.n_img = B, Hi, Wi, Cin, in_ld, n_img
+    d.Ho, d.Wo, d.Cout, d.out_ld, d.res_ld = Ho, Wo, Cout, out_ld, res_ld
+    d.ntaps = len(taps)
+    if d.ntaps > _lib.MAX_TAPS:
+        raise ValueError("too many taps")
+    for i, (dh, dw, ph) in enumerate(taps):
+        d.dh[i], d.dw[i], d.phase[i] = dh, dw, ph
+    d.flags = flags
+    return d
+
+
+def conv_igemm(desc: ConvDesc, x: torch.Tensor, wgt: torch.Tensor, out: torch.Tensor,
+               scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+               res: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
+    check(_lib.lib().iswm_conv_igemm(C.byref(desc), _ptr(x), _ptr(wgt), _ptr(out), _ptr(scale),
+                                     _ptr(shift), _ptr(res), _ptr(stats), _stream()), "conv_igemm")
+
+
+def conv_wgrad(desc: ConvDesc, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor) -> None:
+    check(_lib.lib().iswm_conv_wgrad(C.byref(desc), _ptr(x), _ptr(dy), _ptr(dw), _stream()), "conv_wgrad")
+
+
+def pack_weight_fwd(w: torch.Tensor, out: Optional[torch.Tensor] = None, stem: bool = False) -> torch.Tensor:
+    """fp32 OIHW -> packed bf16 forward operand [Cout][R*S][cin_pad] (or the stem's [Cout][K192])."""
+    w = w.contiguous()
+    Cout, Cin, R, S = w.shape
+    RS = R * S
+    if stem:
+        cin_pad, row_ld = Cin, ((RS * Cin + 63) // 64) * 64
+    else:
+        cin_pad = ((Cin + 63) // 64) * 64
+        row_ld = RS * cin_pad
+    if out is None:
+        out = torch.empty(Cout * row_ld, dtype=torch.bfloat16, device=w.device)
+    check(_lib.lib().iswm_pack_weight_fwd(_ptr(w), Cout, Cin, RS, cin_pad, row_ld, _ptr(out), _stream()),
+          "pack_weight_fwd")
+    return out
+
+
+def pack_weight_dgrad(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 OIHW -> packed bf16 dgrad operand [Cin][R*S][cout_pad]."""
+    w = w.contiguous()
+    Cout, Cin, R, S = w.shape
+    cout_pad = ((Cout + 63) // 64) * 64
+    if out is None:
+        out = torch.empty(Cin * R * S * cout_pad, dtype=torch.bfloat16, device=w.device)
+    check(_lib.lib().iswm_pack_weight_dgrad(_ptr(w), Cout, Cin, R * S, cout_pad, _ptr(out), _stream()),
+          "pack_weight_dgrad")
+    return out
+
+
+def unpack_wgrad(dw: torch.Tensor, grad_oihw: torch.Tensor, beta: float = 0.0, stem_row_ld: int = 0) -> None:
+    Cout, Cin, R, S = grad_oihw.shape
+    RS = R * S
+    if stem_row_ld:
+        cin_stride, row_ld = Cin, stem_row_ld
+    else:
+        cin_stride, row_ld = Cin, RS * Cin
+    check(_lib.lib().iswm_unpack_wgrad(_ptr(dw), Cout, Cin, RS, cin_stride, row_ld, beta,
+                                       _ptr(grad_oihw), _stream()), "unpack_wgrad")
+
+
+def conv_taps(k: int, dilation: int) -> list:
+    """Tap offsets of a stride-1 k x k convolution with padding = dilation*(k//2)."""
+    h = k // 2
+    return [((r - h) * dilation, (s - h) * dilation, 0) for r in range(k) for s in range(k)]
+
+
+def conv_taps_s2_3x3() -> list:
+    """Taps of a 3x3 / stride 2 / pad 1 convolution over the 4 parity phases of its input."""
+    def split(r):  # input row 2i + r - 1 -> (phase parity, offset in the phase image)
+        return (1, -1) if r == 0 else ((0, 0) if r == 1 else (1, 0))
+    taps = []
+    for r in range(3):
+        p, dh = split(r)
+        for s in range(3):
+            q, dw = split(s)
+            taps.append((dh, dw, p * 2 + q))
+    return taps
+
+
+def abort_code() -> int:
+    return int(_lib.lib().iswm_debug_abort_code())

@@ -1,0 +1,159 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (forward, data gradient, weight gradient)
+against torch.nn.functional.conv2d in fp32 on the same bf16-rounded operands.
+Tolerance: bf16 inputs, fp32 accumulation -> relative error ~1e-2 on bf16 outputs (north_star)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from iswm_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _mk(B, Cin, H, W, Cout, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((B, Cin, H, W), generator=g).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, k, k), generator=g) * (2.0 / (Cin * k * k)) ** 0.5)
+    return x, w
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _assert_healthy():
+    torch.cuda.synchronize()
+    code = ops.abort_code()
+    assert code == 0, f"tensor-core kernel timed out on an mbarrier (code {code})"
+
+
+CASES = [
+    # B, Cin, H, W, Cout, k, dilation
+    (2, 64, 16, 16, 64, 1, 1),
+    (2, 256, 16, 16, 64, 1, 1),
+    (1, 64, 32, 32, 256, 1, 1),
+    (2, 64, 16, 16, 64, 3, 1),
+    (2, 128, 32, 32, 128, 3, 1),
+    (2, 512, 8, 8, 512, 3, 2),
+    (1, 2048, 8, 8, 256, 3, 6),
+    (1, 2048, 8, 8, 256, 3, 12),
+    (2, 304, 16, 16, 256, 3, 1),
+    (2, 256, 13, 13, 48, 1, 1),
+    (2, 256, 9, 11, 2, 1, 1),
+    (3, 64, 25, 25, 128, 3, 1),
+    (2, 1024, 8, 8, 2048, 1, 1),
+]
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", CASES)
+def test_conv_fwd_raw_and_stats(B, Cin, H, W, Cout, k, dil):
+    x, w = _mk(B, Cin, H, W, Cout, k)
+    xd = _nhwc(x).to(DEV)
+    wp = ops.pack_weight_fwd(w.to(DEV))
+    out_ld = ((Cout + 7) // 8) * 8
+    out = torch.zeros((B, H, W, out_ld), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2 * Cout, dtype=torch.float32, device=DEV)
+    d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, out_ld, ops.conv_taps(k, dil), flags=_lib.EPI_STATS)
+    ops.conv_igemm(d, xd, wp, out, stats=stats)
+    _assert_healthy()
+    ref = F.conv2d(x.float(), w.to(torch.bfloat16).float(), padding=dil * (k // 2), dilation=dil)
+    got = out[..., :Cout].float().cpu().permute(0, 3, 1, 2)
+    assert _rel_err(got, ref) < 1e-2
+    s = stats.cpu()
+    np.testing.assert_allclose(s[:Cout].numpy(), ref.sum((0, 2, 3)).numpy(), rtol=2e-3, atol=2e-2)
+    np.testing.assert_allclose(s[Cout:].numpy(), (ref * ref).sum((0, 2, 3)).numpy(), rtol=2e-3, atol=2e-2)
+
+
+def test_conv_fwd_affine_relu_residual_f32():
+    B, Cin, H, W, Cout = 2, 128, 16, 16, 256
+    x, w = _mk(B, Cin, H, W, Cout, 1, seed=3)
+    g = torch.Generator().manual_seed(4)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g)
+    res = torch.randn((B, Cout, H, W), generator=g).to(torch.bfloat16)
+    ref = F.relu(F.conv2d(x.float(), w.to(torch.bfloat16).float()) * scale[None, :, None, None] + shift[None, :, None, None] + res.float())
+    xd, wp = _nhwc(x).to(DEV), ops.pack_weight_fwd(w.to(DEV))
+    for f32 in (False, True):
+        out = torch.zeros((B, H, W, Cout), dtype=torch.float32 if f32 else torch.bfloat16, device=DEV)
+        flags = _lib.EPI_AFFINE | _lib.EPI_RELU | _lib.EPI_RESIDUAL | (_lib.EPI_OUT_F32 if f32 else 0)
+        d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, Cout, ops.conv_taps(1, 1), flags=flags, res_ld=Cout)
+        ops.conv_igemm(d, xd, wp, out, scale=scale.to(DEV), shift=shift.to(DEV), res=_nhwc(res).to(DEV))
+        _assert_healthy()
+        got = out.float().cpu().permute(0, 3, 1, 2)
+        assert _rel_err(got, ref) < (2e-3 if f32 else 1e-2)
+
+
+def test_conv_fwd_channel_slices():
+    """input read from, and output written into, channel slices of wider buffers (concat in place)."""
+    B, H, W = 2, 16, 16
+    x, w = _mk(B, 64, H, W, 48, 1, seed=5)
+    big_in = torch.randn((B, H, W, 128)).to(torch.bfloat16).to(DEV)
+    big_in[..., 64:128] = _nhwc(x).to(DEV)
+    big_out = torch.full((B, H, W, 304), 7.0, dtype=torch.bfloat16, device=DEV)
+    d = ops.make_conv_desc(B, H, W, 64, 128, B, H, W, 48, 304, ops.conv_taps(1, 1))
+    ops.conv_igemm(d, big_in[..., 64:], ops.pack_weight_fwd(w.to(DEV)), big_out[..., 8:])
+    _assert_healthy()
+    ref = F.conv2d(x.float(), w.to(torch.bfloat16).float())
+    assert _rel_err(big_out[..., 8:56].float().cpu().permute(0, 3, 1, 2), ref) < 1e-2
+    assert float(big_out[..., :8].float().min()) == 7.0 and float(big_out[..., 56:].float().min()) == 7.0
+
+
+def test_conv_stride2_via_phases():
+    B, Cin, H, W, Cout = 2, 128, 16, 16, 128
+    x, w = _mk(B, Cin, H, W, Cout, 3, seed=6)
+    ref = F.conv2d(x.float(), w.to(torch.bfloat16).float(), stride=2, padding=1)
+    xn = _nhwc(x)
+    phases = torch.stack([xn[:, p::2, q::2, :] for p in (0, 1) for q in (0, 1)], 0).contiguous().to(DEV)  # [4,B,H/2,W/2,C]
+    Ho, Wo = H // 2, W // 2
+    out = torch.zeros((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=DEV)
+    d = ops.make_conv_desc(B, Ho, Wo, Cin, Cin, 4 * B, Ho, Wo, Cout, Cout, ops.conv_taps_s2_3x3())
+    ops.conv_igemm(d, phases, ops.pack_weight_fwd(w.to(DEV)), out)
+    _assert_healthy()
+    assert _rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", [(2, 64, 16, 16, 128, 3, 1), (1, 256, 8, 8, 512, 3, 2), (2, 256, 16, 16, 64, 1, 1), (2, 256, 9, 11, 2, 1, 1)])
+def test_conv_dgrad(B, Cin, H, W, Cout, k, dil):
+    x, w = _mk(B, Cin, H, W, Cout, k, seed=7)
+    g = torch.Generator().manual_seed(8)
+    dy = torch.randn((B, Cout, H, W), generator=g).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    F.conv2d(xr, w.to(torch.bfloat16).float(), padding=dil * (k // 2), dilation=dil).backward(dy.float())
+    dy_ld = ((Cout + 7) // 8) * 8
+    dyd = torch.zeros((B, H, W, dy_ld), dtype=torch.bfloat16, device=DEV)
+    dyd[..., :Cout] = _nhwc(dy).to(DEV)
+    wd = ops.pack_weight_dgrad(w.to(DEV))
+    dx = torch.zeros((B, H, W, Cin), dtype=torch.bfloat16, device=DEV)
+    taps = [(-a, -b, 0) for (a, b, _) in ops.conv_taps(k, dil)]
+    d = ops.make_conv_desc(B, H, W, Cout, dy_ld, B, H, W, Cin, Cin, taps)
+    ops.conv_igemm(d, dyd, wd, dx)
+    _assert_healthy()
+    assert _rel_err(dx.float().cpu().permute(0, 3, 1, 2), xr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", [(2, 64, 16, 16, 64, 1, 1), (2, 64, 16, 16, 128, 3, 1), (1, 512, 8, 8, 256, 3, 2),
+                                                   (2, 304, 16, 16, 256, 3, 1), (2, 256, 9, 11, 2, 1, 1), (4, 2048, 8, 8, 256, 3, 6),
+                                                   (2, 256, 32, 32, 48, 1, 1)])
+def test_conv_wgrad(B, Cin, H, W, Cout, k, dil):
+    x, w = _mk(B, Cin, H, W, Cout, k, seed=9)
+    g = torch.Generator().manual_seed(10)
+    dy = torch.randn((B, Cout, H, W), generator=g).to(torch.bfloat16)
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(x.float(), wr, padding=dil * (k // 2), dilation=dil).backward(dy.float())
+    dy_ld = ((Cout + 7) // 8) * 8
+    dyd = torch.zeros((B, H, W, dy_ld), dtype=torch.bfloat16, device=DEV)
+    dyd[..., :Cout] = _nhwc(dy).to(DEV)
+    dw = torch.zeros((Cout, k * k, Cin), dtype=torch.float32, device=DEV)
+    d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, dy_ld, ops.conv_taps(k, dil))
+    ops.conv_wgrad(d, _nhwc(x).to(DEV), dyd, dw)
+    _assert_healthy()
+    grad = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=DEV)
+    ops.unpack_wgrad(dw, grad)
+    torch.cuda.synchronize()
+    assert _rel_err(grad.cpu(), wr.grad) < 5e-3
