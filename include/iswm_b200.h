@@ -224,6 +224,12 @@ int iswm_add_bf16(const void* d_a, const void* d_b, int64_t n, void* d_out, void
 int iswm_nhwc_to_nchw_f32(const void* d_x, int x_ld, int B, int64_t HW, int C, float* d_out, void* stream);
 int iswm_nchw_f32_to_nhwc(const float* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream);
 
+/* classifier bias gradient (network/_deeplab.py:51 Conv2d(256, C, 1) bias): out[c] += sum_{b,p} d[b,c,p], NCHW fp32 */
+int iswm_bias_grad_nchw(const float* d_dout, int B, int C, int64_t HW, float* d_out, void* stream);
+/* x *= *d_scalar in place; a no-op pass when the device scalar is exactly 1.0 (criterion backward
+ * under the implicit grad_output of loss.backward(), train.py:1048) */
+int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, const float* d_scalar, void* stream);
+
 /* fused multi-tensor SGD(momentum, nesterov, weight decay) step (train.py:421-431, :1049) on a flat fp32 buffer */
 int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr, float momentum,
                   float weight_decay, int nesterov, int first_step, void* stream);

@@ -72,6 +72,8 @@ SIGNATURES = {
     "iswm_add_bf16": (_i, [_p, _p, _i64, _p, _p]),
     "iswm_nhwc_to_nchw_f32": (_i, [_p, _i, _i, _i64, _i, _p, _p]),
     "iswm_nchw_f32_to_nhwc": (_i, [_p, _i, _i64, _i, _p, _i, _p]),
+    "iswm_bias_grad_nchw": (_i, [_p, _i, _i, _i64, _p, _p]),
+    "iswm_scale_by_device_scalar": (_i, [_p, _i, _i64, _p, _p]),
     "iswm_sgd_step": (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _p]),
 }
 

@@ -696,6 +696,38 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
   }
 }
 
+// per-channel sum of an NCHW fp32 tensor (classifier bias gradient): out[c] += sum_{b,p} d[b,c,p]
+__global__ void __launch_bounds__(kT)
+bias_grad_nchw_kernel(const float* __restrict__ d, int B, int C, int64_t HW, float* __restrict__ out) {
+  __shared__ float s_red[kT / 32];
+  const int c = blockIdx.y;
+  float acc = 0.f;
+  const int64_t total = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t b = i / HW, p = i - b * HW;
+    acc += __ldg(d + (b * C + c) * HW + p);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kT / 32; w++) t += s_red[w];
+    atomicAdd(out + c, t);
+  }
+}
+
+// x *= *scalar, skipped entirely when the device scalar is exactly 1 (the loss.backward() case)
+template <typename T>
+__global__ void __launch_bounds__(kT)
+scale_by_device_scalar_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ scalar) {
+  const float s = *scalar;
+  if (s == 1.0f) return;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT)
+    x[i] = (T)((float)x[i] * s);
+}
+
 }  // namespace iswm
 
 // ---------------------------------------------------------------------------
@@ -762,6 +794,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
   REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_reduce: relu needs the activation");
+  ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny;
   bn_red_shape(C, nx, ny);
   int64_t want_blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)num_sms() * 4, (M + ny * 4 - 1) / (ny * 4)));
@@ -912,4 +945,22 @@ extern "C" int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, 
   if (n == 0) return 0;
   sgd_step_kernel<<<grid_for(n), kT, 0, ST(stream)>>>(d_param, d_grad, d_mom, n, lr, momentum, weight_decay, nesterov, first_step);
   return check_launch("sgd_step");
+}
+
+extern "C" int iswm_bias_grad_nchw(const float* d_dout, int B, int C, int64_t HW, float* d_out, void* stream) {
+  ISWM_REQUIRE(d_dout && d_out && C >= 1, "bias_grad_nchw: null");
+  if ((int64_t)B * HW == 0) return 0;
+  dim3 grid(grid_for((int64_t)B * HW, kT * 8, 2), C);
+  bias_grad_nchw_kernel<<<grid, kT, 0, ST(stream)>>>(d_dout, B, C, HW, d_out);
+  return check_launch("bias_grad_nchw");
+}
+extern "C" int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, const float* d_scalar, void* stream) {
+  ISWM_REQUIRE(d_x && d_scalar, "scale_by_device_scalar: null");
+  if (n == 0) return 0;
+  if (dtype == ISWM_F32)
+    scale_by_device_scalar_kernel<float><<<grid_for(n), kT, 0, ST(stream)>>>(static_cast<float*>(d_x), n, d_scalar);
+  else if (dtype == ISWM_BF16)
+    scale_by_device_scalar_kernel<__nv_bfloat16><<<grid_for(n), kT, 0, ST(stream)>>>(BFW(d_x), n, d_scalar);
+  else { set_error("scale_by_device_scalar: bad dtype %d", dtype); return 2; }
+  return check_launch("scale_by_device_scalar");
 }

@@ -1,0 +1,572 @@
+"""Whole-network executor for the DeepLabV3+ (ResNet-50/101) hot path.
+
+The nn.Module tree (iswm_b200/network) only OWNS parameters under the reference's state_dict
+names; this module RUNS them: it walks the known graph (network/utils.py:16-25 forward,
+network/backbone/resnet.py:99-120 bottleneck, network/_deeplab.py:55-61, :167-172 head/ASPP),
+launching libiswm_b200.so kernels on the current CUDA stream through raw pointers. Activations
+are NHWC bf16; concat buffers are written in place through channel slices. In training mode each
+op records a closure on a tape and `backward()` replays it in reverse — a hand-written reverse
+sweep, not torch.autograd — writing fp32 OIHW parameter gradients into one flat buffer that the
+data-parallel layer all-reduces in buckets.
+
+No op here has a PyTorch / cuDNN fallback: torch is used for allocation, memsets and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Act:
+    """NHWC bf16 activation: `t` is a [B,H,W,C] view whose row pitch is `ld` elements."""
+
+    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad")
+
+    def __init__(self, t: torch.Tensor, B: int, H: int, W: int, Cc: int, ld: int):
+        self.t, self.B, self.H, self.W, self.C, self.ld = t, B, H, W, Cc, ld
+        self.grad: Optional["Act"] = None             # gradient w.r.t. this activation (same geometry)
+
+    @property
+    def M(self) -> int:
+        return self.B * self.H * self.W
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    @staticmethod
+    def new(B, H, W, Cc, device) -> "Act":
+        return Act(torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=device), B, H, W, Cc, Cc)
+
+    def slice(self, off: int, Cc: int) -> "Act":
+        return Act(self.t[..., off:off + Cc], self.B, self.H, self.W, Cc, self.ld)
+
+    def new_grad(self) -> "Act":
+        """Allocate a dense gradient buffer of this activation's geometry and attach it."""
+        self.grad = Act.new(self.B, self.H, self.W, self.C, self.t.device)
+        return self.grad
+
+
+class ConvSpec:
+    """Static description of one convolution + its packed-weight cache."""
+
+    def __init__(self, name, conv, bn, k, stride, dilation):
+        self.name, self.conv, self.bn = name, conv, bn
+        self.k, self.stride, self.dilation = k, stride, dilation
+        self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+        self.packed_fwd = None
+        self.packed_dgrad = None
+        self.version = -1
+        self.fold_scale = None
+        self.fold_shift = None
+        self.fold_version = None
+        self.is_stem = False
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self.specs: List[ConvSpec] = []
+        self._build_specs()
+        self.tape: List[Callable[[], None]] = []
+        self.step = 0
+        self.flat_g = None            # fp32 flat gradient buffer (all parameters, registration order)
+        self.grad_views = {}
+        self.wacc = None              # fp32 scratch for k>1 weight gradients
+        self.grad_ready_hook: Optional[Callable[[torch.nn.Parameter], None]] = None
+        self.dropout_p = 0.1
+        self.seed = 0x5EED
+        self._logits_lo = None
+        self._saved = None
+
+    # ------------------------------------------------------------------ graph description
+    def _build_specs(self):
+        m = self.model
+        bb, head = m.backbone, m.classifier
+        S = self._spec
+        self.stem = S("backbone.conv1", bb.conv1, bb.bn1, 7, 2, 1)
+        self.stem.is_stem = True
+        self.layers = []
+        for lname in ("layer1", "layer2", "layer3", "layer4"):
+            blocks = []
+            for bi, blk in enumerate(getattr(bb, lname)):
+                p = f"backbone.{lname}.{bi}"
+                c1 = S(p + ".conv1", blk.conv1, blk.bn1, 1, 1, 1)
+                c2 = S(p + ".conv2", blk.conv2, blk.bn2, 3, blk.stride, blk.dilation)
+                c3 = S(p + ".conv3", blk.conv3, blk.bn3, 1, 1, 1)
+                ds = None
+                if blk.downsample is not None:
+                    ds = S(p + ".downsample.0", blk.downsample[0], blk.downsample[1], 1, blk.stride, 1)
+                blocks.append((c1, c2, c3, ds))
+            self.layers.append(blocks)
+        self.low_proj = S("classifier.project.0", head.project[0], head.project[1], 1, 1, 1)
+        aspp = head.aspp
+        self.aspp_branches = [S("classifier.aspp.convs.0.0", aspp.convs[0][0], aspp.convs[0][1], 1, 1, 1)]
+        for i, r in enumerate(aspp.rates):
+            self.aspp_branches.append(S(f"classifier.aspp.convs.{i + 1}.0", aspp.convs[i + 1][0], aspp.convs[i + 1][1], 3, 1, r))
+        self.aspp_pool = S("classifier.aspp.convs.4.1", aspp.convs[4][1], aspp.convs[4][2], 1, 1, 1)
+        self.aspp_proj = S("classifier.aspp.project.0", aspp.project[0], aspp.project[1], 1, 1, 1)
+        cl = head.classifier
+        self.dec1 = S("classifier.classifier.0", cl[0], cl[1], 3, 1, 1)
+        self.dec2 = S("classifier.classifier.3", cl[3], cl[4], 3, 1, 1)
+        self.cls = S("classifier.classifier.6", cl[6], None, 1, 1, 1)
+
+    def _spec(self, name, conv, bn, k, stride, dilation) -> ConvSpec:
+        s = ConvSpec(name, conv, bn, k, stride, dilation)
+        self.specs.append(s)
+        return s
+
+    # ------------------------------------------------------------------ parameters / packing
+    def _check_device(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("iswm_b200 runs on CUDA only: move the model and the input to a B200 (no CPU fallback)")
+        for p in self.model.parameters():
+            if p.device != x.device:
+                raise RuntimeError(f"parameter on {p.device} but input on {x.device}: call model.to(device) first")
+            break
+        self.device = x.device
+
+    def _pack(self, s: ConvSpec, need_dgrad: bool):
+        w = s.conv.weight
+        v = w._version
+        if s.packed_fwd is None or s.version != v or s.packed_fwd.device != w.device:
+            s.packed_fwd = ops.pack_weight_fwd(w.detach(), out=s.packed_fwd if (s.packed_fwd is not None and s.packed_fwd.device == w.device) else None, stem=s.is_stem)
+            s.packed_dgrad = None
+            s.version = v
+        if need_dgrad and s.packed_dgrad is None and not s.is_stem:
+            s.packed_dgrad = ops.pack_weight_dgrad(w.detach())
+
+    def _ensure_grad_buffers(self):
+        params = [p for p in self.model.parameters()]
+        total = sum(p.numel() for p in params)
+        if self.flat_g is None or self.flat_g.numel() != total or self.flat_g.device != self.device:
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.grad_views = {}
+            off = 0
+            for p in params:
+                self.grad_views[id(p)] = self.flat_g[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            wsz = 0
+            self.wacc_off = {}
+            for s in self.specs:
+                if s.k > 1:
+                    n = s.cout * (160 if s.is_stem else s.k * s.k * s.cin)
+                    self.wacc_off[s.name] = (wsz, n)
+                    wsz += n
+            self.wacc = torch.zeros(wsz, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ low-level launches
+    def _conv(self, s: ConvSpec, x: Act, out_t: torch.Tensor, out_ld: int, Ho: int, Wo: int, taps, n_img: int,
+              flags: int = 0, scale=None, shift=None, res: Optional[torch.Tensor] = None, res_ld: int = 0,
+              stats=None, wgt=None, cin=None, cout=None, Hi=None, Wi=None, B=None):
+        d = ops.make_conv_desc(B if B is not None else x.B, Hi if Hi is not None else x.H, Wi if Wi is not None else x.W,
+                               cin if cin is not None else x.C, x.ld, n_img, Ho, Wo,
+                               cout if cout is not None else s.cout, out_ld, taps, flags, res_ld)
+        check(_lib.lib().iswm_conv_igemm(C.byref(d), x.ptr, (wgt if wgt is not None else s.packed_fwd).data_ptr(),
+                                         out_t.data_ptr(), None if scale is None else scale.data_ptr(),
+                                         None if shift is None else shift.data_ptr(),
+                                         None if res is None else res.data_ptr(),
+                                         None if stats is None else stats.data_ptr(), _st()), "conv_igemm " + s.name)
+
+    def _prep_input(self, s: ConvSpec, x: Act):
+        """Returns (conv input Act, taps, n_img, Ho, Wo) handling stride 2 by phase split / subsampling."""
+        L = _lib.lib()
+        if s.stride == 1:
+            return x, ops.conv_taps(s.k, s.dilation), x.B, x.H, x.W
+        assert s.stride == 2 and s.dilation == 1
+        Ho, Wo = (x.H + 1) // 2, (x.W + 1) // 2
+        if s.k == 1:
+            xs = Act.new(x.B, Ho, Wo, x.C, self.device)
+            check(L.iswm_subsample2(x.ptr, x.ld, x.B, x.H, x.W, x.C, xs.ptr, _st()), "subsample2")
+            return xs, ops.conv_taps(1, 1), x.B, Ho, Wo
+        ph = torch.empty((4 * x.B, Ho, Wo, x.C), dtype=torch.bfloat16, device=self.device)
+        check(L.iswm_phase_split(x.ptr, x.ld, x.B, x.H, x.W, x.C, ph.data_ptr(), _st()), "phase_split")
+        xa = Act(ph, x.B, Ho, Wo, x.C, x.C)
+        return xa, ops.conv_taps_s2_3x3(), 4 * x.B, Ho, Wo
+
+    # ------------------------------------------------------------------ eval-mode unit: conv + folded BN (+res, relu)
+    def _fold(self, s: ConvSpec):
+        bn = s.bn
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
+        if s.fold_scale is None or s.fold_version != key or s.fold_scale.device != self.device:
+            s.fold_scale = torch.empty(s.cout, dtype=torch.float32, device=self.device)
+            s.fold_shift = torch.empty(s.cout, dtype=torch.float32, device=self.device)
+            check(_lib.lib().iswm_bn_fold(bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                                          bn.running_var.data_ptr(), BN_EPS, s.cout, s.fold_scale.data_ptr(),
+                                          s.fold_shift.data_ptr(), _st()), "bn_fold")
+            s.fold_version = key
+
+    def _unit_eval(self, s: ConvSpec, x: Act, relu=True, residual: Optional[Act] = None, out: Optional[Act] = None) -> Act:
+        self._pack(s, False)
+        self._fold(s)
+        xin, taps, n_img, Ho, Wo = self._prep_input(s, x)
+        if out is None:
+            out = Act.new(x.B, Ho, Wo, s.cout, self.device)
+        flags = _lib.EPI_AFFINE | (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RESIDUAL if residual is not None else 0)
+        self._conv(s, xin, out.t, out.ld, Ho, Wo, taps, n_img, flags, s.fold_scale, s.fold_shift,
+                   None if residual is None else residual.t, 0 if residual is None else residual.ld)
+        return out
+
+    # ------------------------------------------------------------------ train-mode unit: conv(+stats) -> BN apply, taped
+    def _unit_train(self, s: ConvSpec, x: Act, relu=True, residual: Optional[Act] = None, out: Optional[Act] = None,
+                    drop_p: float = 0.0, need_dx: bool = True) -> Act:
+        L = _lib.lib()
+        self._pack(s, need_dx)
+        xin, taps, n_img, Ho, Wo = self._prep_input(s, x)
+        B = x.B
+        M = B * Ho * Wo
+        Cout = s.cout
+        raw = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
+        stats = self._stats_slot(2 * Cout)
+        self._conv(s, xin, raw, Cout, Ho, Wo, taps, n_img, _lib.EPI_STATS, stats=stats)
+        if out is None:
+            out = Act.new(B, Ho, Wo, Cout, self.device)
+        save = self._save_slot(2 * Cout)
+        bn = s.bn
+        seed = (self.seed + self.step * 1000003 + len(self.tape)) & 0xFFFFFFFFFFFF
+        check(L.iswm_bn_train_apply(raw.data_ptr(), Cout, stats.data_ptr(), M, Cout, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                    BN_EPS, BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                    bn.num_batches_tracked.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(),
+                                    None if residual is None else residual.ptr, 0 if residual is None else residual.ld,
+                                    1 if relu else 0, drop_p, seed, out.ptr, out.ld, _st()), "bn_train_apply " + s.name)
+
+        def backward():
+            dout = out.grad
+            assert dout is not None, f"no gradient reached {s.name}"
+            use_mask = relu  # residual units: the mask comes from the block output (post add + ReLU)
+            sums = self._stats_slot(2 * Cout)
+            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, out.ptr, out.ld, M, Cout,
+                                       save.data_ptr(), save[Cout:].data_ptr(), 1 if use_mask else 0, drop_p, seed,
+                                       sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+            dy = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
+            dz_ptr, dz_ld, dz_tmp = None, 0, None
+            if residual is not None:
+                if residual.grad is None:
+                    residual.new_grad()
+                    dz_ptr, dz_ld = residual.grad.ptr, residual.C
+                else:
+                    assert residual.grad.ld == residual.C
+                    dz_tmp = torch.empty_like(residual.grad.t)
+                    dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
+            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, out.ptr, out.ld, M, Cout,
+                                      bn.weight.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
+                                      1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                      self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
+                  "bn_bwd_apply " + s.name)
+            if dz_tmp is not None:
+                check(L.iswm_add_bf16(residual.grad.ptr, dz_tmp.data_ptr(), dz_tmp.numel(), residual.grad.ptr, _st()), "add_bf16")
+            out.grad = None
+            self._conv_backward(s, x, xin, taps, n_img, Ho, Wo, dy, need_dx)
+            self._notify(bn.weight)
+            self._notify(bn.bias)
+
+        self.tape.append(backward)
+        return out
+
+    def _conv_backward(self, s: ConvSpec, x: Act, xin: Act, taps, n_img, Ho, Wo, dy: torch.Tensor, need_dx: bool):
+        """Weight gradient into the flat fp32 buffer and data gradient into x.grad (assign or accumulate)."""
+        L = _lib.lib()
+        B, Cout = x.B, s.cout
+        dy_ld = dy.shape[-1]
+        gview = self.grad_views[id(s.conv.weight)]
+        d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps)
+        if s.k == 1:
+            check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), gview.data_ptr(), _st()), "conv_wgrad " + s.name)
+        else:
+            off, n = self.wacc_off[s.name]
+            acc = self.wacc[off:off + n]
+            check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
+            check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
+        self._notify(s.conv.weight)
+        if not need_dx:
+            return
+        Cin = s.cin
+        if s.stride == 1:
+            dtaps = [(-a, -b, 0) for (a, b, _) in taps]
+            self._dgrad_into(s, x, dy, dy_ld, x.H, x.W, dtaps, x.H, x.W)
+        elif s.k == 3:
+            dyz = torch.empty((B, x.H, x.W, Cout), dtype=torch.bfloat16, device=self.device)
+            check(L.iswm_zero_stuff2(dy.data_ptr(), B, Ho, Wo, Cout, x.H, x.W, dyz.data_ptr(), _st()), "zero_stuff2")
+            dtaps = [(-a, -b, 0) for (a, b, _) in ops.conv_taps(3, 1)]
+            self._dgrad_into(s, x, dyz, Cout, x.H, x.W, dtaps, x.H, x.W)
+        else:
+            dsub = torch.empty((B, Ho, Wo, Cin), dtype=torch.bfloat16, device=self.device)
+            dd = ops.make_conv_desc(B, Ho, Wo, Cout, dy_ld, B, Ho, Wo, Cin, Cin, [(0, 0, 0)])
+            check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), dsub.data_ptr(), None, None, None, None, _st()), "dgrad " + s.name)
+            if x.grad is None:
+                x.new_grad()
+                check(L.iswm_zero_stuff2(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "zero_stuff2")
+            else:
+                assert x.grad.ld == Cin
+                check(L.iswm_scatter2_add(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "scatter2_add")
+
+    def _dgrad_into(self, s: ConvSpec, x: Act, dy: torch.Tensor, dy_ld: int, Hi, Wi, dtaps, Ho, Wo):
+        L = _lib.lib()
+        B, Cin, Cout = x.B, s.cin, s.cout
+        flags, res = 0, None
+        if x.grad is None:
+            x.new_grad()
+        else:
+            flags, res = _lib.EPI_RESIDUAL, x.grad
+        g = x.grad
+        dd = ops.make_conv_desc(B, Hi, Wi, Cout, dy_ld, B, Ho, Wo, Cin, g.ld, dtaps, flags, g.ld)
+        check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, None, None,
+                                None if res is None else res.ptr, None, _st()), "dgrad " + s.name)
+
+    def _notify(self, p):
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(p)
+
+    # per-step scratch (fp32), carved from one zeroed buffer
+    def _begin_scratch(self):
+        need = 0
+        for s in self.specs:
+            if s.bn is not None:
+                need += 8 * s.cout        # fwd stats, bwd sums, save mean/invstd (+ slack)
+        need += 4096
+        if getattr(self, "_scratch", None) is None or self._scratch.numel() < need or self._scratch.device != self.device:
+            self._scratch = torch.empty(need, dtype=torch.float32, device=self.device)
+        self._scratch.zero_()
+        self._scratch_off = 0
+
+    def _stats_slot(self, n: int) -> torch.Tensor:
+        n_al = (n + 63) // 64 * 64
+        t = self._scratch[self._scratch_off:self._scratch_off + n]
+        self._scratch_off += n_al
+        assert self._scratch_off <= self._scratch.numel(), "scratch exhausted"
+        return t
+
+    _save_slot = _stats_slot
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
+        """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]."""
+        self._check_device(x)
+        if x.dim() != 4 or x.shape[1] != self.stem.cin:
+            raise ValueError(f"expected [B,{self.stem.cin},H,W] input, got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        L = _lib.lib()
+        self.tape = []
+        self._begin_scratch()
+        if train:
+            self._ensure_grad_buffers()
+            self.step += 1
+        unit = self._unit_train if train else self._unit_eval
+        B, _, H, W = x.shape
+        dev = self.device
+
+        # ---- stem: 7x7/s2 conv as im2col GEMM -> BN -> ReLU -> maxpool 3x3/s2 (resnet.py:144-148)
+        H1, W1 = (H + 1) // 2, (W + 1) // 2
+        Kp = 160
+        col = torch.empty((B * H1 * W1, Kp), dtype=torch.bfloat16, device=dev)
+        check(L.iswm_stem_im2col(x.data_ptr(), B, 3, H, W, H1, W1, Kp, col.data_ptr(), _st()), "stem_im2col")
+        colA = Act(col.view(1, 1, B * H1 * W1, Kp), 1, 1, B * H1 * W1, Kp, Kp)
+        stem_out = self._stem_unit(colA, B, H1, W1, train)
+        H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
+        pooled = Act.new(B, H2, W2, 64, dev)
+        idx = torch.empty((B, H2, W2, 64), dtype=torch.uint8, device=dev) if train else None
+        check(L.iswm_maxpool_fwd(stem_out.ptr, B, H1, W1, 64, H2, W2, pooled.ptr, None if idx is None else idx.data_ptr(), _st()), "maxpool_fwd")
+        if train:
+            def pool_bwd():
+                g = pooled.grad
+                assert g.ld == 64
+                stem_out.new_grad()
+                check(L.iswm_maxpool_bwd(g.ptr, idx.data_ptr(), B, H1, W1, 64, H2, W2, stem_out.grad.ptr, _st()), "maxpool_bwd")
+                pooled.grad = None
+            self.tape.append(pool_bwd)
+
+        # ---- residual layers (resnet.py:99-120, :176-198)
+        a = pooled
+        low_level = None
+        for li, blocks in enumerate(self.layers):
+            for (c1, c2, c3, ds) in blocks:
+                idt = a if ds is None else unit(ds, a, relu=False)
+                y = unit(c1, a)
+                y = unit(c2, y)
+                a = unit(c3, y, relu=True, residual=idt)
+            if li == 0:
+                low_level = a
+        feat = a
+
+        # ---- head (_deeplab.py:55-61): low-level projection and ASPP write straight into concat buffers
+        h4, w4 = low_level.H, low_level.W
+        cat2 = Act.new(B, h4, w4, 304, dev)
+        low_slice = cat2.slice(0, 48)
+        unit(self.low_proj, low_level, out=low_slice)
+        hf, wf = feat.H, feat.W
+        cat1 = Act.new(B, hf, wf, 1280, dev)
+        br_slices = [cat1.slice(256 * i, 256) for i in range(5)]
+        for i, s in enumerate(self.aspp_branches):
+            unit(s, feat, out=br_slices[i])
+        self._aspp_pool(feat, br_slices[4], train)
+        if train:
+            self._slice_grad_split(cat1, [(br_slices[i], 256 * i) for i in range(5)])
+            aspp_out = self._unit_train(self.aspp_proj, cat1, drop_p=self.dropout_p)
+        else:
+            aspp_out = self._unit_eval(self.aspp_proj, cat1)
+        up = cat2.slice(48, 256)
+        check(L.iswm_bilinear_fwd(aspp_out.ptr, aspp_out.ld, B, hf, wf, 256, h4, w4, up.ptr, up.ld, _st()), "bilinear_fwd")
+        if train:
+            def up_bwd():
+                g = up.grad
+                aspp_out.new_grad()
+                check(L.iswm_bilinear_bwd(g.ptr, g.ld, B, hf, wf, 256, h4, w4, aspp_out.grad.ptr, 256, _st()), "bilinear_bwd")
+                up.grad = None
+            self.tape.append(up_bwd)
+            self._slice_grad_split(cat2, [(low_slice, 0), (up, 48)])
+        y = unit(self.dec1, cat2)
+        y = unit(self.dec2, y)
+
+        # ---- classifier 1x1 (+bias) -> fp32 NHWC low-res logits -> bilinear to input size (utils.py:22)
+        ncls = self.cls.cout
+        self._pack(self.cls, train)
+        bias = self.cls.conv.bias
+        ones = self._ones(ncls)
+        lo = torch.empty((B, h4, w4, ncls), dtype=torch.float32, device=dev)
+        self._conv(self.cls, y, lo, ncls, h4, w4, ops.conv_taps(1, 1), B, _lib.EPI_AFFINE | _lib.EPI_OUT_F32, ones, bias.detach())
+        logits = torch.empty((B, ncls, H, W), dtype=torch.float32, device=dev)
+        check(L.iswm_logits_up_fwd(lo.data_ptr(), B, h4, w4, ncls, H, W, logits.data_ptr(), _st()), "logits_up_fwd")
+        if train:
+            self._saved = (y, B, h4, w4, H, W, ncls)
+        return logits
+
+    def _ones(self, n):
+        t = getattr(self, "_ones_t", None)
+        if t is None or t.numel() < n or t.device != self.device:
+            t = torch.ones(max(n, 64), dtype=torch.float32, device=self.device)
+            self._ones_t = t
+        return t
+
+    def _stem_unit(self, colA: Act, B, H1, W1, train) -> Act:
+        """The stem conv runs as a 1-tap GEMM over the im2col matrix; output viewed as [B,H1,W1,64]."""
+        L = _lib.lib()
+        s = self.stem
+        self._pack(s, False)
+        M = B * H1 * W1
+        dev = self.device
+        out = Act.new(B, H1, W1, 64, dev)
+        taps = [(0, 0, 0)]
+        if not train:
+            self._fold(s)
+            self._conv(s, colA, out.t, 64, 1, M, taps, 1, _lib.EPI_AFFINE | _lib.EPI_RELU, s.fold_scale, s.fold_shift, cin=colA.C)
+            return out
+        raw = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
+        stats = self._stats_slot(128)
+        self._conv(s, colA, raw, 64, 1, M, taps, 1, _lib.EPI_STATS, stats=stats, cin=colA.C)
+        save = self._save_slot(128)
+        bn = s.bn
+        check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
+                                    BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
+                                    save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, out.ptr, 64, _st()), "bn_train_apply stem")
+
+        def backward():
+            dout = out.grad
+            sums = self._stats_slot(128)
+            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), 64, out.ptr, 64, M, 64, save.data_ptr(), save[64:].data_ptr(),
+                                       1, 0.0, 0, sums.data_ptr(), _st()), "bn_bwd_reduce stem")
+            dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
+            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), 64, out.ptr, 64, M, 64, bn.weight.data_ptr(), save.data_ptr(),
+                                      save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, dy.data_ptr(), 64, None, 0,
+                                      self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd_apply stem")
+            out.grad = None
+            off, n = self.wacc_off[s.name]
+            acc = self.wacc[off:off + n]
+            d = ops.make_conv_desc(1, 1, M, colA.C, colA.ld, 1, 1, M, 64, 64, taps)
+            check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
+            gview = self.grad_views[id(s.conv.weight)]
+            check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
+            self._notify(s.conv.weight)
+            self._notify(bn.weight)
+            self._notify(bn.bias)
+
+        self.tape.append(backward)
+        return out
+
+    def _aspp_pool(self, feat: Act, dst: Act, train: bool):
+        """ASPPPooling (_deeplab.py:130-141): GAP -> 1x1 -> BN -> ReLU -> broadcast (bilinear from 1x1)."""
+        L = _lib.lib()
+        B, HW, dev = feat.B, feat.H * feat.W, self.device
+        pooled = Act.new(B, 1, 1, feat.C, dev)
+        check(L.iswm_gap_fwd(feat.ptr, feat.ld, B, HW, feat.C, pooled.ptr, _st()), "gap_fwd")
+        if train:
+            def gap_bwd():
+                g = pooled.grad
+                assert g.ld == feat.C
+                if feat.grad is None:
+                    feat.new_grad()
+                    feat.grad.t.zero_()
+                check(L.iswm_gap_bwd_add(g.ptr, B, HW, feat.C, feat.grad.ptr, feat.grad.ld, _st()), "gap_bwd_add")
+                pooled.grad = None
+            self.tape.append(gap_bwd)
+            v = self._unit_train(self.aspp_pool, pooled)
+        else:
+            v = self._unit_eval(self.aspp_pool, pooled)
+        check(L.iswm_broadcast_hw(v.ptr, B, HW, 256, dst.ptr, dst.ld, _st()), "broadcast_hw")
+        if train:
+            def bc_bwd():
+                g = dst.grad
+                v.new_grad()
+                check(L.iswm_sum_hw(g.ptr, g.ld, B, HW, 256, v.grad.ptr, _st()), "sum_hw")
+                dst.grad = None
+            self.tape.append(bc_bwd)
+
+    def _slice_grad_split(self, cat: Act, parts):
+        """After the consumer of a concat buffer produced cat.grad, hand each producer its channel slice
+        (a strided view of cat.grad: no copy)."""
+        def split():
+            g = cat.grad
+            for act, off in parts:
+                act.grad = g.slice(off, act.C)
+            cat.grad = None
+        self.tape.append(split)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dlogits: torch.Tensor):
+        """dlogits: fp32 NCHW gradient of the loss w.r.t. the logits returned by forward(train=True)."""
+        L = _lib.lib()
+        y, B, h4, w4, H, W, ncls = self._saved
+        dev = self.device
+        dlogits = dlogits.contiguous().float()
+        params = list(self.model.parameters())
+        fresh = all(p.grad is None for p in params)
+        if fresh:
+            self.flat_g.zero_()
+            for p in params:
+                p.grad = self.grad_views[id(p)]
+        else:
+            for p in params:
+                if p.grad is None:
+                    self.grad_views[id(p)].zero_()
+                    p.grad = self.grad_views[id(p)]
+                elif p.grad.data_ptr() != self.grad_views[id(p)].data_ptr():
+                    raise RuntimeError("parameter .grad was replaced by a foreign tensor; call optimizer.zero_grad(set_to_none=True)")
+        self.wacc.zero_()
+        # classifier: bias grad, low-res logits gradient, weight grad, data grad
+        cls = self.cls
+        check(L.iswm_bias_grad_nchw(dlogits.data_ptr(), B, ncls, H * W, self.grad_views[id(cls.conv.bias)].data_ptr(), _st()), "bias_grad")
+        self._notify(cls.conv.bias)
+        ldp = 8 * ((ncls + 7) // 8)
+        dlo = torch.empty((B, h4, w4, ldp), dtype=torch.bfloat16, device=dev)
+        check(L.iswm_logits_up_bwd(dlogits.data_ptr(), B, h4, w4, ncls, H, W, dlo.data_ptr(), ldp, _st()), "logits_up_bwd")
+        d = ops.make_conv_desc(B, h4, w4, y.C, y.ld, B, h4, w4, ncls, ldp, [(0, 0, 0)])
+        check(L.iswm_conv_wgrad(C.byref(d), y.ptr, dlo.data_ptr(), self.grad_views[id(cls.conv.weight)].data_ptr(), _st()), "conv_wgrad cls")
+        self._notify(cls.conv.weight)
+        self._dgrad_into(cls, y, dlo, ldp, h4, w4, [(0, 0, 0)], h4, w4)
+        # reverse sweep
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        self._saved = None

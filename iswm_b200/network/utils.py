@@ -1,0 +1,52 @@
+"""Top-level segmentation module (reference: network/utils.py:8-25 _SimpleSegmentationModel).
+
+forward(x: float32 [B,3,H,W]) -> float32 [B,num_classes,H,W], differentiable w.r.t. every
+parameter; .train()/.eval() switch BatchNorm and Dropout behaviour. The computation is the CUDA
+engine's (iswm_b200/engine.py); this class only bridges it to torch.autograd so that
+`loss.backward()` (train.py:1048) and torch.optim (train.py:424-442) work unchanged."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+class _EngineFn(torch.autograd.Function):
+    """One autograd node for the whole network. Parameter gradients are written by the engine
+    straight into its flat buffer (exposed as each parameter's .grad), so backward returns None
+    for them instead of 374 temporaries."""
+
+    @staticmethod
+    def forward(ctx, x, engine, anchor, *params):
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        return engine.forward(x, train=True)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.engine.backward(dlogits)
+        return (None, None, None) + (None,) * ctx.n_params
+
+
+class _SimpleSegmentationModel(nn.Module):
+    def __init__(self, backbone, classifier):
+        super().__init__()
+        self.backbone = backbone
+        self.classifier = classifier
+        self._engine_obj = None
+
+    def engine(self):
+        if self._engine_obj is None:
+            from ..engine import Engine
+            self._engine_obj = Engine(self)
+        return self._engine_obj
+
+    def forward(self, x):
+        eng = self.engine()
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.training:
+            if needs_grad:
+                anchor = next(self.parameters())
+                return _EngineFn.apply(x, eng, anchor, *self.parameters())
+            return eng.forward(x, train=True)          # BN batch statistics, no tape kept for backward
+        with torch.no_grad():                          # eval: BatchNorm folded into the conv epilogues
+            return eng.forward(x, train=False)

@@ -1,0 +1,224 @@
+"""GPU parity of the HBM-bound glue kernels against stock torch ops in fp32 on the same
+bf16-rounded inputs (tolerances: one bf16 rounding of the output, 2^-8 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from iswm_b200 import _lib
+from iswm_b200._lib import check
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+L = _lib.lib
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def close(a, b, rtol=1e-2, atol=1e-2):
+    np.testing.assert_allclose(a.float().cpu().numpy(), b.float().cpu().numpy(), rtol=rtol, atol=atol)
+
+
+def rnd(shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,C,H,W,relu,with_res", [(2, 64, 9, 7, True, False), (3, 48, 8, 8, True, True), (2, 256, 5, 5, False, False), (2, 2048, 4, 4, True, True)])
+def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
+    x = rnd((B, C, H, W), 1, 2.0)
+    res = rnd((B, C, H, W), 2) if with_res else None
+    g = torch.Generator().manual_seed(3)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    dout = rnd((B, C, H, W), 4)
+    # torch reference
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y = F.batch_norm(xr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    resr = res.float().requires_grad_(True) if with_res else None
+    if with_res:
+        y = y + resr
+    if relu:
+        y = F.relu(y)
+    y.backward(dout.float())
+    # ours
+    M = B * H * W
+    xd = nhwc(x).to(DEV)
+    stats = torch.stack([x.float().sum((0, 2, 3)), (x.float() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    save = torch.empty(2 * C, dtype=torch.float32, device=DEV)
+    rmd, rvd = rm.to(DEV), rv.to(DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    gd, bd = gamma.to(DEV), beta.to(DEV)
+    resd = nhwc(res).to(DEV) if with_res else None
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, rmd.data_ptr(), rvd.data_ptr(),
+                                  nbt.data_ptr(), save.data_ptr(), save[C:].data_ptr(), None if resd is None else resd.data_ptr(), C,
+                                  1 if relu else 0, 0.0, 0, out.data_ptr(), C, st()))
+    close(nchw(out), y.detach(), 1e-2, 2e-2)
+    close(rmd, rm_ref, 1e-4, 1e-5)
+    close(rvd, rv_ref, 1e-3, 1e-4)
+    assert nbt.item() == 1
+    dd = nhwc(dout).to(DEV)
+    sums = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, save.data_ptr(), save[C:].data_ptr(),
+                                 1 if relu else 0, 0.0, 0, sums.data_ptr(), st()))
+    dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    dg = torch.zeros(C, dtype=torch.float32, device=DEV)
+    db = torch.zeros(C, dtype=torch.float32, device=DEV)
+    check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, gd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
+                                sums.data_ptr(), 1 if relu else 0, 0.0, 0, dx.data_ptr(), C, dz.data_ptr(), C, dg.data_ptr(), db.data_ptr(), st()))
+    scale = float(xr.grad.abs().max())
+    close(nchw(dx), xr.grad, 2e-2, 2e-2 * scale)
+    close(dg, gr.grad, 2e-2, 5e-2)
+    close(db, br.grad, 2e-2, 5e-2)
+    if with_res:
+        close(nchw(dz), resr.grad, 1e-2, 1e-2)
+
+
+def test_maxpool_fwd_bwd():
+    B, C, H, W = 2, 64, 13, 18
+    x = rnd((B, C, H, W), 5)
+    xr = x.float().requires_grad_(True)
+    y = F.max_pool2d(xr, 3, 2, 1)
+    dout = rnd(tuple(y.shape), 6)
+    y.backward(dout.float())
+    Ho, Wo = y.shape[2:]
+    out = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=DEV)
+    idx = torch.empty((B, Ho, Wo, C), dtype=torch.uint8, device=DEV)
+    xd = nhwc(x).to(DEV)
+    check(L().iswm_maxpool_fwd(xd.data_ptr(), B, H, W, C, Ho, Wo, out.data_ptr(), idx.data_ptr(), st()))
+    assert torch.equal(nchw(out).float().cpu(), y.detach())
+    dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_maxpool_bwd(nhwc(dout).to(DEV).data_ptr(), idx.data_ptr(), B, H, W, C, Ho, Wo, dx.data_ptr(), st()))
+    close(nchw(dx), xr.grad, 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(4, 4, 16, 16), (13, 13, 50, 50), (8, 6, 17, 23), (1, 1, 5, 5)])
+def test_bilinear_fwd_bwd(Hi, Wi, Ho, Wo):
+    B, C = 2, 16
+    x = rnd((B, C, Hi, Wi), 7)
+    xr = x.float().requires_grad_(True)
+    y = F.interpolate(xr, size=(Ho, Wo), mode="bilinear", align_corners=False)
+    dout = rnd((B, C, Ho, Wo), 8)
+    y.backward(dout.float())
+    out = torch.full((B, Ho, Wo, 24), 3.0, dtype=torch.bfloat16, device=DEV)
+    xd = nhwc(x).to(DEV)
+    check(L().iswm_bilinear_fwd(xd.data_ptr(), C, B, Hi, Wi, C, Ho, Wo, out[..., 8:].data_ptr(), 24, st()))
+    close(nchw(out[..., 8:]), y.detach(), 1e-2, 1e-2)
+    assert float(out[..., :8].float().min()) == 3.0
+    dx = torch.empty((B, Hi, Wi, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_bilinear_bwd(nhwc(dout).to(DEV).data_ptr(), C, B, Hi, Wi, C, Ho, Wo, dx.data_ptr(), C, st()))
+    close(nchw(dx), xr.grad, 1e-2, 2e-2 * float(xr.grad.abs().max()))
+
+
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo,C", [(16, 16, 64, 64, 2), (13, 11, 50, 41, 3)])
+def test_logits_up_fwd_bwd(Hi, Wi, Ho, Wo, C):
+    B = 2
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((B, C, Hi, Wi), generator=g)
+    xr = x.clone().requires_grad_(True)
+    y = F.interpolate(xr, size=(Ho, Wo), mode="bilinear", align_corners=False)
+    dout = torch.randn((B, C, Ho, Wo), generator=g)
+    y.backward(dout)
+    out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=DEV)
+    check(L().iswm_logits_up_fwd(nhwc(x).to(DEV).data_ptr(), B, Hi, Wi, C, Ho, Wo, out.data_ptr(), st()))
+    close(out, y.detach(), 1e-5, 1e-5)
+    dx = torch.empty((B, Hi, Wi, 8), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_logits_up_bwd(dout.to(DEV).data_ptr(), B, Hi, Wi, C, Ho, Wo, dx.data_ptr(), 8, st()))
+    close(nchw(dx[..., :C]), xr.grad, 1e-2, 1e-2 * float(xr.grad.abs().max()))
+    assert torch.count_nonzero(dx[..., C:]).item() == 0
+    bias = torch.zeros(C, dtype=torch.float32, device=DEV)
+    check(L().iswm_bias_grad_nchw(dout.to(DEV).data_ptr(), B, C, Ho * Wo, bias.data_ptr(), st()))
+    close(bias, dout.sum((0, 2, 3)), 1e-4, 1e-3)
+
+
+def test_gap_broadcast_sum():
+    B, C, H, W = 3, 2048, 5, 7
+    x = rnd((B, C, H, W), 10)
+    xd = nhwc(x).to(DEV)
+    out = torch.empty((B, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_gap_fwd(xd.data_ptr(), C, B, H * W, C, out.data_ptr(), st()))
+    close(out, x.float().mean((2, 3)), 1e-2, 1e-2)
+    s = torch.empty((B, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_sum_hw(xd.data_ptr(), C, B, H * W, C, s.data_ptr(), st()))
+    close(s, x.float().sum((2, 3)), 1e-2, 5e-2)
+    v = rnd((B, 256), 11).to(DEV)
+    cat = torch.zeros((B, H, W, 1280), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_broadcast_hw(v.data_ptr(), B, H * W, 256, cat[..., 1024:].data_ptr(), 1280, st()))
+    assert torch.equal(cat[..., 1024:], v[:, None, None, :].expand(B, H, W, 256))
+    assert torch.count_nonzero(cat[..., :1024]).item() == 0
+    dx = torch.ones((B, H, W, 256), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_gap_bwd_add(v.data_ptr(), B, H * W, 256, dx.data_ptr(), 256, st()))
+    close(dx, 1.0 + v.float()[:, None, None, :].expand(B, H, W, 256) / (H * W), 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (9, 7)])
+def test_stride2_helpers(H, W):
+    B, C = 2, 16
+    x = rnd((B, C, H, W), 12)
+    xn = nhwc(x).to(DEV)
+    Hp, Wp = (H + 1) // 2, (W + 1) // 2
+    ph = torch.empty((4, B, Hp, Wp, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_phase_split(xn.data_ptr(), C, B, H, W, C, ph.data_ptr(), st()))
+    for p in (0, 1):
+        for q in (0, 1):
+            ref = torch.zeros((B, Hp, Wp, C), dtype=torch.bfloat16, device=DEV)
+            sub = xn[:, p::2, q::2, :]
+            ref[:, :sub.shape[1], :sub.shape[2]] = sub
+            assert torch.equal(ph[p * 2 + q], ref)
+    ss = torch.empty((B, Hp, Wp, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_subsample2(xn.data_ptr(), C, B, H, W, C, ss.data_ptr(), st()))
+    assert torch.equal(ss, xn[:, ::2, ::2, :])
+    z = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_zero_stuff2(ss.data_ptr(), B, Hp, Wp, C, H, W, z.data_ptr(), st()))
+    ref = torch.zeros_like(z)
+    ref[:, ::2, ::2, :] = ss
+    assert torch.equal(z, ref)
+    acc = torch.ones((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_scatter2_add(ss.data_ptr(), B, Hp, Wp, C, H, W, acc.data_ptr(), st()))
+    close(acc, 1.0 + ref.float(), 1e-2, 1e-2)
+
+
+def test_stem_im2col_and_pack():
+    B, H, W = 2, 18, 22
+    g = torch.Generator().manual_seed(13)
+    img = torch.randn((B, 3, H, W), generator=g)
+    w = torch.randn((64, 3, 7, 7), generator=g) * 0.1
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    col = torch.empty((B * Ho * Wo, 160), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_stem_im2col(img.to(DEV).data_ptr(), B, 3, H, W, Ho, Wo, 160, col.data_ptr(), st()))
+    from iswm_b200 import ops
+    wp = ops.pack_weight_fwd(w.to(DEV), stem=True).view(64, 192)
+    got = (col.float() @ wp[:, :160].float().t()).view(B, Ho, Wo, 64)
+    ref = F.conv2d(img.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=3)
+    close(nchw(got), ref, 1e-3, 1e-3)
+    assert torch.count_nonzero(col[:, 147:]).item() == 0
+
+
+def test_sgd_step_matches_torch():
+    g = torch.Generator().manual_seed(14)
+    p0 = torch.randn(10007, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([p_ref], lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    p = p0.clone().to(DEV)
+    mom = torch.zeros_like(p)
+    for step in range(3):
+        grad = torch.randn(10007, generator=g)
+        p_ref.grad = grad.clone()
+        opt.step()
+        check(L().iswm_sgd_step(p.data_ptr(), grad.to(DEV).data_ptr(), mom.data_ptr(), p.numel(), 1e-3, 0.9, 1e-4, 1, 1 if step == 0 else 0, st()))
+    close(p, p_ref.detach(), 1e-6, 1e-7)
