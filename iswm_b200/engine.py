@@ -89,8 +89,9 @@ class Engine:
         self.grad_ready_hook: Optional[Callable[[torch.nn.Parameter], None]] = None
         self.dropout_p = 0.1
         self.seed = 0x5EED
-        self._logits_lo = None
         self._saved = None
+        self.debug_taps = None        # dict name -> NCHW fp32 copy of each unit's output (tools/layer_diff.py)
+        self.debug_units = None       # list of per-unit records of the engine's own tensors (tests/test_unit_replay_gpu.py)
 
     # ------------------------------------------------------------------ graph description
     def _build_specs(self):
@@ -218,6 +219,7 @@ class Engine:
         flags = _lib.EPI_AFFINE | (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RESIDUAL if residual is not None else 0)
         self._conv(s, xin, out.t, out.ld, Ho, Wo, taps, n_img, flags, s.fold_scale, s.fold_shift,
                    None if residual is None else residual.t, 0 if residual is None else residual.ld)
+        self._tap(s.name, out)
         return out
 
     # ------------------------------------------------------------------ train-mode unit: conv(+stats) -> BN apply, taped
@@ -242,11 +244,22 @@ class Engine:
                                     bn.num_batches_tracked.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(),
                                     None if residual is None else residual.ptr, 0 if residual is None else residual.ld,
                                     1 if relu else 0, drop_p, seed, out.ptr, out.ld, _st()), "bn_train_apply " + s.name)
+        self._tap(s.name, out)
+        if self.debug_taps is not None:
+            self.debug_taps[s.name + ":raw"] = raw.float().permute(0, 3, 1, 2).cpu()
 
         def backward():
             dout = out.grad
             assert dout is not None, f"no gradient reached {s.name}"
             use_mask = relu  # residual units: the mask comes from the block output (post add + ReLU)
+            rec = None
+            if self.debug_units is not None:
+                rec = dict(name=s.name, k=s.k, stride=s.stride, dilation=s.dilation, relu=relu, x=x.t.clone(), raw=raw.clone(),
+                           out=out.t.clone(), dout=dout.t.clone(), mean=save[:Cout].clone(), invstd=save[Cout:2 * Cout].clone(),
+                           gamma=bn.weight.detach().clone(), beta=bn.bias.detach().clone(), w=s.conv.weight.detach().clone(),
+                           residual=None if residual is None else residual.t.clone(),
+                           xgrad_before=None if x.grad is None else x.grad.t.clone(),
+                           resgrad_before=None if (residual is None or residual.grad is None) else residual.grad.t.clone())
             sums = self._stats_slot(2 * Cout)
             check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, out.ptr, out.ld, M, Cout,
                                        save.data_ptr(), save[Cout:].data_ptr(), 1 if use_mask else 0, drop_p, seed,
@@ -270,6 +283,11 @@ class Engine:
                 check(L.iswm_add_bf16(residual.grad.ptr, dz_tmp.data_ptr(), dz_tmp.numel(), residual.grad.ptr, _st()), "add_bf16")
             out.grad = None
             self._conv_backward(s, x, xin, taps, n_img, Ho, Wo, dy, need_dx)
+            if rec is not None:
+                rec.update(dy=dy.clone(), dW=self.grad_views[id(s.conv.weight)].clone(), dgamma=self.grad_views[id(bn.weight)].clone(),
+                           dbeta=self.grad_views[id(bn.bias)].clone(), xgrad_after=None if x.grad is None else x.grad.t.clone(),
+                           resgrad_after=None if residual is None else residual.grad.t.clone())
+                self.debug_units.append(rec)
             self._notify(bn.weight)
             self._notify(bn.bias)
 
@@ -326,6 +344,10 @@ class Engine:
         check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, None, None,
                                 None if res is None else res.ptr, None, _st()), "dgrad " + s.name)
 
+    def _tap(self, name: str, a: Act):
+        if self.debug_taps is not None:
+            self.debug_taps[name] = a.t.float().permute(0, 3, 1, 2).cpu()
+
     def _notify(self, p):
         if self.grad_ready_hook is not None:
             self.grad_ready_hook(p)
@@ -358,6 +380,7 @@ class Engine:
         if x.dim() != 4 or x.shape[1] != self.stem.cin:
             raise ValueError(f"expected [B,{self.stem.cin},H,W] input, got {tuple(x.shape)}")
         x = x.contiguous().float()
+        self._image = x if self.debug_units is not None else None
         L = _lib.lib()
         self.tape = []
         self._begin_scratch()
@@ -462,6 +485,7 @@ class Engine:
         if not train:
             self._fold(s)
             self._conv(s, colA, out.t, 64, 1, M, taps, 1, _lib.EPI_AFFINE | _lib.EPI_RELU, s.fold_scale, s.fold_shift, cin=colA.C)
+            self._tap(s.name, out)
             return out
         raw = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
         stats = self._stats_slot(128)
@@ -471,6 +495,7 @@ class Engine:
         check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                     BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
                                     save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, out.ptr, 64, _st()), "bn_train_apply stem")
+        self._tap(s.name, out)
 
         def backward():
             dout = out.grad
@@ -488,6 +513,13 @@ class Engine:
             check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
             gview = self.grad_views[id(s.conv.weight)]
             check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
+            if self.debug_units is not None:
+                self.debug_units.append(dict(name=s.name, k=7, stride=2, dilation=1, relu=True, x=None, image=self._image, raw=raw.view(B, H1, W1, 64).clone(),
+                                             out=out.t.clone(), dout=dout.t.clone(), mean=save[:64].clone(), invstd=save[64:128].clone(),
+                                             gamma=bn.weight.detach().clone(), beta=bn.bias.detach().clone(), w=s.conv.weight.detach().clone(),
+                                             residual=None, xgrad_before=None, resgrad_before=None, dy=dy.view(B, H1, W1, 64).clone(),
+                                             dW=gview.clone(), dgamma=self.grad_views[id(bn.weight)].clone(), dbeta=self.grad_views[id(bn.bias)].clone(),
+                                             xgrad_after=None, resgrad_after=None))
             self._notify(s.conv.weight)
             self._notify(bn.weight)
             self._notify(bn.bias)
@@ -565,6 +597,10 @@ class Engine:
         check(L.iswm_conv_wgrad(C.byref(d), y.ptr, dlo.data_ptr(), self.grad_views[id(cls.conv.weight)].data_ptr(), _st()), "conv_wgrad cls")
         self._notify(cls.conv.weight)
         self._dgrad_into(cls, y, dlo, ldp, h4, w4, [(0, 0, 0)], h4, w4)
+        if self.debug_units is not None:
+            self.debug_units.append(dict(name=cls.name, kind="cls", x=y.t.clone(), dlogits=dlogits.clone(), dlo=dlo.clone(),
+                                         w=cls.conv.weight.detach().clone(), dW=self.grad_views[id(cls.conv.weight)].clone(),
+                                         dbias=self.grad_views[id(cls.conv.bias)].clone(), xgrad_after=y.grad.t.clone()))
         # reverse sweep
         for fn in reversed(self.tape):
             fn()
