@@ -90,6 +90,9 @@ class Engine:
         self.dropout_p = 0.1
         self.seed = 0x5EED
         self._saved = None
+        self.weights_epoch = 0        # bumped by optimisers that update parameters behind autograd's back
+        self.flat_w = None            # fp32 flat master weights (parameters become views of it)
+        self.profile = None           # list of (kernel, algorithmic_flops, start_event, end_event) when profiling
         self.debug_taps = None        # dict name -> NCHW fp32 copy of each unit's output (tools/layer_diff.py)
         self.debug_units = None       # list of per-unit records of the engine's own tensors (tests/test_unit_replay_gpu.py)
 
@@ -142,13 +145,45 @@ class Engine:
 
     def _pack(self, s: ConvSpec, need_dgrad: bool):
         w = s.conv.weight
-        v = w._version
+        v = (w._version, self.weights_epoch, w.data_ptr())
         if s.packed_fwd is None or s.version != v or s.packed_fwd.device != w.device:
             s.packed_fwd = ops.pack_weight_fwd(w.detach(), out=s.packed_fwd if (s.packed_fwd is not None and s.packed_fwd.device == w.device) else None, stem=s.is_stem)
             s.packed_dgrad = None
             s.version = v
         if need_dgrad and s.packed_dgrad is None and not s.is_stem:
             s.packed_dgrad = ops.pack_weight_dgrad(w.detach())
+
+    def flatten_parameters(self):
+        """Re-point every parameter at a view of ONE flat fp32 buffer (same registration order as the flat
+        gradient buffer) so the optimiser step and the gradient all-reduce are single passes over
+        contiguous memory. Parameter objects keep their identity; state_dict / checkpoints are unchanged."""
+        params = [p for p in self.model.parameters()]
+        total = sum(p.numel() for p in params)
+        dev = params[0].device
+        if self.flat_w is not None and self.flat_w.device == dev and self.flat_w.numel() == total:
+            off = 0
+            ok = True
+            for p in params:
+                if p.data_ptr() != self.flat_w.data_ptr() + 4 * off:
+                    ok = False
+                    break
+                off += p.numel()
+            if ok:
+                return self.flat_w
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                v = flat[off:off + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+                off += p.numel()
+        self.flat_w = flat
+        self.weights_epoch += 1
+        return flat
+
+    def invalidate_packed(self):
+        self.weights_epoch += 1
 
     def _ensure_grad_buffers(self):
         params = [p for p in self.model.parameters()]
@@ -176,11 +211,13 @@ class Engine:
         d = ops.make_conv_desc(B if B is not None else x.B, Hi if Hi is not None else x.H, Wi if Wi is not None else x.W,
                                cin if cin is not None else x.C, x.ld, n_img, Ho, Wo,
                                cout if cout is not None else s.cout, out_ld, taps, flags, res_ld)
+        ev = self._prof_begin()
         check(_lib.lib().iswm_conv_igemm(C.byref(d), x.ptr, (wgt if wgt is not None else s.packed_fwd).data_ptr(),
                                          out_t.data_ptr(), None if scale is None else scale.data_ptr(),
                                          None if shift is None else shift.data_ptr(),
                                          None if res is None else res.data_ptr(),
                                          None if stats is None else stats.data_ptr(), _st()), "conv_igemm " + s.name)
+        self._prof_end(ev, "conv_igemm", 2.0 * d.B * Ho * Wo * d.Cout * (147 if s.is_stem else d.Cin * d.ntaps))
 
     def _prep_input(self, s: ConvSpec, x: Act):
         """Returns (conv input Act, taps, n_img, Ho, Wo) handling stride 2 by phase split / subsampling."""
@@ -301,12 +338,15 @@ class Engine:
         dy_ld = dy.shape[-1]
         gview = self.grad_views[id(s.conv.weight)]
         d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps)
+        ev = self._prof_begin()
         if s.k == 1:
             check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), gview.data_ptr(), _st()), "conv_wgrad " + s.name)
+            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin)
         else:
             off, n = self.wacc_off[s.name]
             acc = self.wacc[off:off + n]
             check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
+            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k)
             check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
         self._notify(s.conv.weight)
         if not need_dx:
@@ -323,7 +363,9 @@ class Engine:
         else:
             dsub = torch.empty((B, Ho, Wo, Cin), dtype=torch.bfloat16, device=self.device)
             dd = ops.make_conv_desc(B, Ho, Wo, Cout, dy_ld, B, Ho, Wo, Cin, Cin, [(0, 0, 0)])
+            ev = self._prof_begin()
             check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), dsub.data_ptr(), None, None, None, None, _st()), "dgrad " + s.name)
+            self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin)
             if x.grad is None:
                 x.new_grad()
                 check(L.iswm_zero_stuff2(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "zero_stuff2")
@@ -341,8 +383,27 @@ class Engine:
             flags, res = _lib.EPI_RESIDUAL, x.grad
         g = x.grad
         dd = ops.make_conv_desc(B, Hi, Wi, Cout, dy_ld, B, Ho, Wo, Cin, g.ld, dtaps, flags, g.ld)
+        ev = self._prof_begin()
         check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, None, None,
                                 None if res is None else res.ptr, None, _st()), "dgrad " + s.name)
+        # algorithmic FLOPs of a data gradient = those of the forward conv it differentiates (no credit
+        # for the zero-stuffed positions of the stride-2 case)
+        fwd_pix = B * (Ho // s.stride if s.stride > 1 else Ho) * (Wo // s.stride if s.stride > 1 else Wo)
+        self._prof_end(ev, "conv_igemm", 2.0 * fwd_pix * Cout * Cin * len(dtaps))
+
+    def _prof_begin(self):
+        if self.profile is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def _prof_end(self, ev0, kernel: str, flops: float):
+        if ev0 is None:
+            return
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        self.profile.append((kernel, flops, ev0, ev1))
 
     def _tap(self, name: str, a: Act):
         if self.debug_taps is not None:
