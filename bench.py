@@ -224,7 +224,7 @@ def run_ours(args):
     for _ in range(args.steps):
         xs = x_host.to(dev, non_blocking=True)
         ys = y_host.to(dev, non_blocking=True)
-        last = float(step(xs, ys))                      # device -> host read of the step's loss, every step
+        last = float(step(xs, ys).detach())             # device -> host read of the step's loss, every step
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -240,9 +240,16 @@ def run_ours(args):
         step(x_dev, y_dev)
         torch.cuda.synchronize()
         agg = {}
-        for k, fl, a, b in eng.profile:
+        detail = []
+        for k, fl, a, b, tag in eng.profile:
             t_, f_, n_ = agg.get(k, (0.0, 0.0, 0))
-            agg[k] = (t_ + a.elapsed_time(b), f_ + fl, n_ + 1)
+            dt = a.elapsed_time(b)
+            agg[k] = (t_ + dt, f_ + fl, n_ + 1)
+            detail.append((tag, fl, dt))
+        if args.profile_detail:
+            with open(args.profile_detail, "w") as f:
+                for tag, fl, dt in detail:
+                    f.write(f"{tag:55s} {fl / 1e9:10.2f} GF {dt * 1e3:9.1f} us {fl / (dt * 1e-3) / 1e12:8.1f} TF/s\n")
         eng.profile = None
         pk = peaks()
         peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
@@ -296,6 +303,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-detail", default="", help="write the per-launch table of the instrumented step here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -28,9 +28,12 @@ struct WgradKParams {
   int Cout, Cin, ntaps;
   int lgBW, lgBH;                 // pixel box: BW*BH*BB == 64
   int tiles_w, tiles_h, tiles_b;  // pixel blocks
-  int pix_blocks, blocks_per_split, splits;
+  int pix_blocks;
   int tiles_m, tiles_n, BN, nchunks_b, stages;
-  int total_units;
+  int n_tiles;                    // output tiles = tiles_m * ntaps * tiles_n
+  long long total_kblocks;        // n_tiles * pix_blocks, split evenly over the CTAs (stream-K)
+  long long kblocks_per_cta;
+  int vec_red;
   int n_img_per_phase;
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   float* dwgt;
@@ -83,26 +86,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
   const int BW = 1 << p.lgBW, BH = 1 << p.lgBH;
   const int BB = kPixBlock >> (p.lgBW + p.lgBH);
 
-  // unit -> (split, m tile, tap, n tile); consecutive units share the pixel range (L2 reuse)
-  auto decode = [&](int unit, int& split, int& mt, int& tap, int& nt) {
-    nt = unit % p.tiles_n;
-    int r = unit / p.tiles_n;
+  // Stream-K: the (output tile, pixel block) space is linearised and cut into equal contiguous
+  // ranges, one per CTA; a CTA flushes its partial tile with fp32 reductions whenever its range
+  // crosses a tile boundary. tile -> (m tile, tap, n tile), n fastest (neighbours share dy in L2).
+  auto decode = [&](int tile, int& mt, int& tap, int& nt) {
+    nt = tile % p.tiles_n;
+    const int r = tile / p.tiles_n;
     tap = r % p.ntaps;
-    r /= p.ntaps;
-    mt = r % p.tiles_m;
-    split = r / p.tiles_m;
+    mt = r / p.ntaps;
   };
+  const long long range_lo = (long long)blockIdx.x * p.kblocks_per_cta;
+  const long long range_hi = min(range_lo + p.kblocks_per_cta, p.total_kblocks);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int unit = blockIdx.x; unit < p.total_units && ok; unit += gridDim.x) {
-        int split, mt, tap, nt;
-        decode(unit, split, mt, tap, nt);
-        const int pb0 = split * p.blocks_per_split;
-        const int pb1 = min(pb0 + p.blocks_per_split, p.pix_blocks);
+      for (long long cur = range_lo; cur < range_hi && ok;) {
+        const int tile = (int)(cur / p.pix_blocks);
+        const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+        const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+        int mt, tap, nt;
+        decode(tile, mt, tap, nt);
         const int m0 = mt * kWTileM, n0 = nt * p.BN;
         for (int pb = pb0; pb < pb1; pb++) {
           const int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h,
@@ -120,6 +126,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
             tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, n0 + 64 * j, xw, xh, xb);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        cur += pb1 - pb0;
       }
     }
   } else if (warp == 1) {
@@ -128,11 +135,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       bool ok = true;
-      for (int unit = blockIdx.x; unit < p.total_units && ok; unit += gridDim.x) {
-        int split, mt, tap, nt;
-        decode(unit, split, mt, tap, nt);
-        const int pb0 = split * p.blocks_per_split;
-        const int pb1 = min(pb0 + p.blocks_per_split, p.pix_blocks);
+      for (long long cur = range_lo; cur < range_hi && ok;) {
+        const int tile = (int)(cur / p.pix_blocks);
+        const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+        const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
         if (!tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 12)) break;
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
@@ -153,6 +159,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
         tc::umma_commit(bar_tfull + 8 * as);
         as ^= 1;
         if (as == 0) aphase ^= 1;
+        cur += pb1 - pb0;
       }
     }
   } else if (warp >= 4) {
@@ -160,9 +167,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
     const int row = ew * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-      int split, mt, tap, nt;
-      decode(unit, split, mt, tap, nt);
+    for (long long cur = range_lo; cur < range_hi;) {
+      const int tile = (int)(cur / p.pix_blocks);
+      const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+      const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+      int mt, tap, nt;
+      decode(tile, mt, tap, nt);
       const int m = mt * kWTileM + row, n0 = nt * p.BN;
       if (!tc::mbar_wait(bar_tfull + 8 * as, aphase, p.abort_flag, 14)) break;
       tc::tc_fence_after();
@@ -174,9 +184,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
         tc::tmem_ld_wait();
         const int n = n0 + c;
         if (m < p.Cout) {
+          if (p.vec_red && n + 16 <= p.Cin) {
 #pragma unroll
-          for (int j = 0; j < 16; j++)
-            if (n + j < p.Cin) atomicAdd(orow + n + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + n + j),
+                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (n + j < p.Cin) atomicAdd(orow + n + j, __uint_as_float(v[j]));
+          }
         }
       }
       tc::tc_fence_before();
@@ -184,6 +203,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
       if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * as);
       as ^= 1;
       if (as == 0) aphase ^= 1;
+      cur += pb1 - pb0;
     }
   }
 
@@ -239,14 +259,15 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
   p.BN = std::min(256, (((d->Cin + n_split_n - 1) / n_split_n + 15) / 16) * 16);
   p.tiles_n = (d->Cin + p.BN - 1) / p.BN;
   p.nchunks_b = (p.BN + 63) / 64;
-  const int64_t base_units = (int64_t)p.tiles_m * p.ntaps * p.tiles_n;
-  int64_t splits = (2 * num_sms() + base_units - 1) / base_units;
-  splits = std::max<int64_t>(1, std::min<int64_t>(splits, std::max<int64_t>(1, pbs / 4)));
-  p.blocks_per_split = (int)((pbs + splits - 1) / splits);
-  p.splits = (int)((pbs + p.blocks_per_split - 1) / p.blocks_per_split);
-  const int64_t total = base_units * p.splits;
-  ISWM_REQUIRE(total < (1ll << 31), "conv_wgrad: too many work units");
-  p.total_units = (int)total;
+  const int64_t n_tiles = (int64_t)p.tiles_m * p.ntaps * p.tiles_n;
+  ISWM_REQUIRE(n_tiles < (1ll << 31), "conv_wgrad: too many output tiles");
+  p.n_tiles = (int)n_tiles;
+  p.total_kblocks = n_tiles * pbs;
+  // stream-K: equal k-block ranges per CTA; at least ~4 k-blocks each so a flush is amortised
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms(), p.total_kblocks / 4));
+  p.kblocks_per_cta = (p.total_kblocks + grid - 1) / grid;
+  grid = (int)((p.total_kblocks + p.kblocks_per_cta - 1) / p.kblocks_per_cta);
+  p.vec_red = ((reinterpret_cast<uintptr_t>(d_dw) & 15) == 0 && (d->Cin % 4) == 0) ? 1 : 0;
   const int stage_bytes = (2 + p.nchunks_b) * kChunkBytes;
   p.stages = std::max(2, std::min(kWStages, kWSmemBudget / stage_bytes));
   p.n_img_per_phase = B;
@@ -274,7 +295,6 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
     ISWM_REQUIRE(e == cudaSuccess, "conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = std::min(p.total_units, num_sms());
   conv_wgrad_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_dy, tmap_x, p);
   return check_launch("conv_wgrad");
 }

@@ -31,6 +31,16 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& f) {
   *reinterpret_cast<uint4*>(p) = r;
 }
 
+__device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ F8 unpack8(const uint4& r) {
+  F8 o;
+  unpack_bf16x2(r.x, o.v[0], o.v[1]);
+  unpack_bf16x2(r.y, o.v[2], o.v[3]);
+  unpack_bf16x2(r.z, o.v[4], o.v[5]);
+  unpack_bf16x2(r.w, o.v[6], o.v[7]);
+  return o;
+}
+
 static inline int grid_for(int64_t work, int per_block = kT, int waves = 8) {
   int64_t g = (work + per_block - 1) / per_block;
   return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)num_sms() * waves));
@@ -74,26 +84,33 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int 
 }
 
 // ---------------------------------------------------------------------------
+// BatchNorm kernels share one thread layout: blockDim = 256 = nx * ny (+ idle), tx = channel group
+// (8 channels = 16 bytes), ty = row lane. Per-channel constants live in registers; a block walks
+// its row range with several rows in flight per thread, so there is no per-element index math.
+
 // BatchNorm training forward: stats -> normalise (+residual, ReLU, dropout)
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 3)
 bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float* __restrict__ stats,
                       int64_t M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float eps, float momentum, float* running_mean, float* running_var,
                       long long* nbt, float* save_mean, float* save_invstd,
                       const __nv_bfloat16* __restrict__ res, int res_ld, int relu, float drop_p,
-                      uint64_t drop_seed, __nv_bfloat16* __restrict__ out, int out_ld) {
-  extern __shared__ float s_par[];  // scale[C], shift[C]
-  float* s_scale = s_par;
-  float* s_shift = s_par + C;
+                      uint64_t drop_seed, __nv_bfloat16* __restrict__ out, int out_ld, int nx, int ny,
+                      int rows_per_block) {
+  const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
+  if (ty >= ny) return;
+  const int c0 = tx << 3;
   const float invM = 1.0f / (float)M;
-  for (int c = threadIdx.x; c < C; c += kT) {
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = c0 + j;
     const float mean = stats[c] * invM;
     const float var = fmaxf(stats[C + c] * invM - mean * mean, 0.f);
     const float invstd = rsqrtf(var + eps);
-    const float sc = gamma[c] * invstd;
-    s_scale[c] = sc;
-    s_shift[c] = beta[c] - mean * sc;
-    if (blockIdx.x == 0) {
+    sc[j] = gamma[c] * invstd;
+    sh[j] = beta[c] - mean * sc[j];
+    if (blockIdx.x == 0 && ty == 0) {
       if (save_mean) save_mean[c] = mean;
       if (save_invstd) save_invstd[c] = invstd;
       if (running_mean) {
@@ -104,31 +121,43 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
-  __syncthreads();
-  const int nvec = C >> 3;
-  const int64_t total = M * nvec;
   const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int64_t row = i / nvec;
-    const int c0 = (int)(i - row * nvec) << 3;
-    F8 f = load8(x + row * x_ld + c0);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  constexpr int U = 4;
+  for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
+    uint4 fr[U], rr[U];
 #pragma unroll
-    for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], s_scale[c0 + j], s_shift[c0 + j]);
-    if (res) {
-      const F8 r = load8(res + row * res_ld + c0);
-#pragma unroll
-      for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
+    for (int u = 0; u < U; u++) {
+      const int64_t row = base + (int64_t)u * ny;
+      if (row < r1) {
+        fr[u] = load_raw(x + row * x_ld + c0);
+        if (res) rr[u] = load_raw(res + row * res_ld + c0);
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) f.v[j] = fmaxf(f.v[j], 0.f);
-    }
-    if (drop_p > 0.f) {
+    for (int u = 0; u < U; u++) {
+      const int64_t row = base + (int64_t)u * ny;
+      if (row >= r1) continue;
+      F8 f = unpack8(fr[u]);
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        f.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? f.v[j] * keep_scale : 0.f;
+      for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
+      if (res) {
+        const F8 r = unpack8(rr[u]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) f.v[j] = fmaxf(f.v[j], 0.f);
+      }
+      if (drop_p > 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          f.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? f.v[j] * keep_scale : 0.f;
+      }
+      store8(out + row * out_ld + c0, f);
     }
-    store8(out + row * out_ld + c0, f);
   }
 }
 
@@ -143,7 +172,7 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 }
 
 // BatchNorm backward pass 1: per-channel sum(dz), sum(dz * xhat)
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      const __nv_bfloat16* __restrict__ x, int x_ld,
                      const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
@@ -152,21 +181,34 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      int rows_per_block) {
   __shared__ float s_red[kT * 16];
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
-  const int nvec = C >> 3;
   const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
-  for (int cg = tx; cg < nvec; cg += nx) {
-    const int c0 = cg << 3;
-    float a[8], b[8], mu[8], is[8];
+  const int c0 = tx << 3;
+  float a[8], b[8], mu[8], is[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { a[j] = 0.f; b[j] = 0.f; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
-    if (ty < ny) {
-      for (int64_t row = r0 + ty; row < r1; row += ny) {
-        F8 g = load8(dout + row * dout_ld + c0);
-        const F8 xv = load8(x + row * x_ld + c0);
+  for (int j = 0; j < 8; j++) { a[j] = 0.f; b[j] = 0.f; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+  if (ty < ny) {
+    constexpr int U = 2;
+    for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
+      uint4 gr[U], xr[U], orr[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int64_t row = base + (int64_t)u * ny;
+        if (row < r1) {
+          gr[u] = load_raw(dout + row * dout_ld + c0);
+          xr[u] = load_raw(x + row * x_ld + c0);
+          if (relu) orr[u] = load_raw(act + row * act_ld + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int64_t row = base + (int64_t)u * ny;
+        if (row >= r1) continue;
+        F8 g = unpack8(gr[u]);
+        const F8 xv = unpack8(xr[u]);
         if (relu) {
-          const F8 o = load8(act + row * act_ld + c0);
+          const F8 o = unpack8(orr[u]);
 #pragma unroll
           for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
         }
@@ -182,79 +224,90 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
         }
       }
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      s_red[threadIdx.x * 16 + j] = a[j];
-      s_red[threadIdx.x * 16 + 8 + j] = b[j];
-    }
-    __syncthreads();
-    if (ty == 0) {
-      for (int j = 0; j < 16; j++) {
-        float t = 0.f;
-        for (int y = 0; y < ny; y++) t += s_red[(y * nx + tx) * 16 + j];
-        const int c = c0 + (j & 7);
-        atomicAdd(sums + (j < 8 ? c : C + c), t);
-      }
-    }
-    __syncthreads();
+  for (int j = 0; j < 8; j++) {
+    s_red[threadIdx.x * 16 + j] = a[j];
+    s_red[threadIdx.x * 16 + 8 + j] = b[j];
+  }
+  __syncthreads();
+  // one thread per (channel group, component): 16 * nx outputs per block
+  for (int o = threadIdx.x; o < nx * 16; o += kT) {
+    const int gx = o >> 4, j = o & 15;
+    float t = 0.f;
+    for (int y = 0; y < ny; y++) t += s_red[(y * nx + gx) * 16 + j];
+    const int c = (gx << 3) + (j & 7);
+    atomicAdd(sums + (j < 8 ? c : C + c), t);
   }
 }
 
 // BatchNorm backward pass 2
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     const __nv_bfloat16* __restrict__ x, int x_ld,
                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                     const float* __restrict__ gamma, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ sums, int relu,
                     float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
-                    __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta) {
-  extern __shared__ float s_par[];  // k1[C] = gamma*invstd, mean[C], invstd[C], m_dz[C], m_dzx[C]
-  float* s_k = s_par;
-  float* s_mu = s_par + C;
-  float* s_is = s_par + 2 * C;
-  float* s_a = s_par + 3 * C;
-  float* s_b = s_par + 4 * C;
+                    __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta, int nx,
+                    int ny, int rows_per_block) {
+  const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
+  if (ty >= ny) return;
+  const int c0 = tx << 3;
   const float invM = 1.0f / (float)M;
-  for (int c = threadIdx.x; c < C; c += kT) {
-    s_k[c] = gamma[c] * invstd[c];
-    s_mu[c] = mean[c];
-    s_is[c] = invstd[c];
-    s_a[c] = sums[c] * invM;
-    s_b[c] = sums[C + c] * invM;
-    if (blockIdx.x == 0) {
+  // dx = k*dz + p*x + q  with  k = gamma*invstd, p = -k*invstd*mean(dz*xhat), q = -k*mean(dz) - p*mu
+  float kk[8], pp[8], qq[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = c0 + j;
+    const float is = invstd[c], mu = mean[c];
+    const float k = gamma[c] * is;
+    const float ma = sums[c] * invM, mb = sums[C + c] * invM;
+    kk[j] = k;
+    pp[j] = -k * is * mb;
+    qq[j] = -k * ma - pp[j] * mu;
+    if (blockIdx.x == 0 && ty == 0) {
       if (dbeta) dbeta[c] += sums[c];
       if (dgamma) dgamma[c] += sums[C + c];
     }
   }
-  __syncthreads();
-  const int nvec = C >> 3;
-  const int64_t total = M * nvec;
   const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int64_t row = i / nvec;
-    const int c0 = (int)(i - row * nvec) << 3;
-    F8 g = load8(dout + row * dout_ld + c0);
-    const F8 xv = load8(x + row * x_ld + c0);
-    if (relu) {
-      const F8 o = load8(act + row * act_ld + c0);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  constexpr int U = 2;
+  for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
+    uint4 gr[U], xr[U], orr[U];
 #pragma unroll
-      for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+    for (int u = 0; u < U; u++) {
+      const int64_t row = base + (int64_t)u * ny;
+      if (row < r1) {
+        gr[u] = load_raw(dout + row * dout_ld + c0);
+        xr[u] = load_raw(x + row * x_ld + c0);
+        if (relu) orr[u] = load_raw(act + row * act_ld + c0);
+      }
     }
-    if (drop_p > 0.f) {
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        g.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? g.v[j] * keep_scale : 0.f;
-    }
-    if (dz) store8(dz + row * dz_ld + c0, g);
-    F8 o;
+    for (int u = 0; u < U; u++) {
+      const int64_t row = base + (int64_t)u * ny;
+      if (row >= r1) continue;
+      F8 g = unpack8(gr[u]);
+      const F8 xv = unpack8(xr[u]);
+      if (relu) {
+        const F8 o = unpack8(orr[u]);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int c = c0 + j;
-      const float xh = (xv.v[j] - s_mu[c]) * s_is[c];
-      o.v[j] = s_k[c] * (g.v[j] - s_a[c] - xh * s_b[c]);
+        for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+      }
+      if (drop_p > 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          g.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? g.v[j] * keep_scale : 0.f;
+      }
+      if (dz) store8(dz + row * dz_ld + c0, g);
+      F8 r;
+#pragma unroll
+      for (int j = 0; j < 8; j++) r.v[j] = fmaf(kk[j], g.v[j], fmaf(pp[j], xv.v[j], qq[j]));
+      store8(dx + row * dx_ld + c0, r);
     }
-    store8(dx + row * dx_ld + c0, o);
   }
 }
 
@@ -757,6 +810,20 @@ extern "C" int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, i
   return check_launch("unpack_wgrad");
 }
 
+static void bn_red_shape(int C, int& nx, int& ny) {
+  const int nvec = C / 8;
+  nx = std::min(nvec, kT);
+  ny = std::max(1, kT / nx);
+}
+// rows per block so that every thread walks >= rows_per_thread rows, capped at 8 blocks per SM
+static void bn_row_grid(int C, int64_t M, int rows_per_thread, int& nx, int& ny, int& rows_per_block, int& blocks) {
+  bn_red_shape(C, nx, ny);
+  int64_t want = (M + (int64_t)ny * rows_per_thread - 1) / ((int64_t)ny * rows_per_thread);
+  want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * 8));
+  rows_per_block = (int)((M + want - 1) / want);
+  blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+}
+
 extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_stats, int64_t M, int C,
                                    const float* d_gamma, const float* d_beta, float eps, float momentum,
                                    float* d_running_mean, float* d_running_var, int64_t* d_nbt,
@@ -766,11 +833,13 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_sta
   REQ_C8(C, "bn_train_apply"); REQ_LD8(x_ld, "bn_train_apply"); REQ_LD8(out_ld, "bn_train_apply");
   ISWM_REQUIRE(d_x && d_stats && d_gamma && d_beta && d_out && M > 0, "bn_train_apply: null/empty");
   ISWM_REQUIRE(!d_res || (res_ld % 8) == 0, "bn_train_apply: res_ld");
-  ISWM_REQUIRE(C <= 4096, "bn_train_apply: C too large");
-  bn_train_apply_kernel<<<grid_for(M * (C / 8)), kT, 2 * C * sizeof(float), ST(stream)>>>(
+  ISWM_REQUIRE(C <= 2048, "bn_train_apply: C=%d > 2048 not supported", C);
+  int nx, ny, rpb, blocks;
+  bn_row_grid(C, M, 16, nx, ny, rpb, blocks);
+  bn_train_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
       BF(d_x), x_ld, d_stats, M, C, d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var,
       reinterpret_cast<long long*>(d_nbt), d_save_mean, d_save_invstd, BF(d_res), res_ld, relu,
-      drop_p, drop_seed, BFW(d_out), out_ld);
+      drop_p, drop_seed, BFW(d_out), out_ld, nx, ny, rpb);
   return check_launch("bn_train_apply");
 }
 extern "C" int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean,
@@ -781,12 +850,6 @@ extern "C" int iswm_bn_fold(const float* d_gamma, const float* d_beta, const flo
   return check_launch("bn_fold");
 }
 
-static void bn_red_shape(int C, int& nx, int& ny) {
-  const int nvec = C / 8;
-  nx = std::min(nvec, kT);
-  ny = std::max(1, kT / nx);
-}
-
 extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                                   const void* d_out_act, int act_ld, int64_t M, int C,
                                   const float* d_save_mean, const float* d_save_invstd, int relu,
@@ -795,11 +858,8 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_reduce: relu needs the activation");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
-  int nx, ny;
-  bn_red_shape(C, nx, ny);
-  int64_t want_blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)num_sms() * 4, (M + ny * 4 - 1) / (ny * 4)));
-  const int rows_per_block = (int)((M + want_blocks - 1) / want_blocks);
-  const int blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+  int nx, ny, rows_per_block, blocks;
+  bn_row_grid(C, M, 16, nx, ny, rows_per_block, blocks);
   bn_bwd_reduce_kernel<<<blocks, kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
                                                       M, C, d_save_mean, d_save_invstd, relu, drop_p,
                                                       drop_seed, d_sums, nx, ny, rows_per_block);
@@ -815,10 +875,13 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   ISWM_REQUIRE(d_dout && d_x && d_gamma && d_save_mean && d_save_invstd && d_sums && d_dx && M > 0, "bn_bwd_apply: null/empty");
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_apply: relu needs the activation");
   ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd_apply: dz_ld");
-  ISWM_REQUIRE(C <= 4096, "bn_bwd_apply: C too large");
-  bn_bwd_apply_kernel<<<grid_for(M * (C / 8)), kT, 5 * C * sizeof(float), ST(stream)>>>(
+  ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
+  int nx, ny, rpb, blocks;
+  bn_row_grid(C, M, 8, nx, ny, rpb, blocks);
+  bn_bwd_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
       BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_save_mean,
-      d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta);
+      d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta,
+      nx, ny, rpb);
   return check_launch("bn_bwd_apply");
 }
 

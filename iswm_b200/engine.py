@@ -217,7 +217,7 @@ class Engine:
                                          None if shift is None else shift.data_ptr(),
                                          None if res is None else res.data_ptr(),
                                          None if stats is None else stats.data_ptr(), _st()), "conv_igemm " + s.name)
-        self._prof_end(ev, "conv_igemm", 2.0 * d.B * Ho * Wo * d.Cout * (147 if s.is_stem else d.Cin * d.ntaps))
+        self._prof_end(ev, "conv_igemm", 2.0 * d.B * Ho * Wo * d.Cout * (147 if s.is_stem else d.Cin * d.ntaps), "fwd " + s.name)
 
     def _prep_input(self, s: ConvSpec, x: Act):
         """Returns (conv input Act, taps, n_img, Ho, Wo) handling stride 2 by phase split / subsampling."""
@@ -341,12 +341,12 @@ class Engine:
         ev = self._prof_begin()
         if s.k == 1:
             check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), gview.data_ptr(), _st()), "conv_wgrad " + s.name)
-            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin)
+            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin, "wgrad " + s.name)
         else:
             off, n = self.wacc_off[s.name]
             acc = self.wacc[off:off + n]
             check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
-            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k)
+            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k, "wgrad " + s.name)
             check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
         self._notify(s.conv.weight)
         if not need_dx:
@@ -365,7 +365,7 @@ class Engine:
             dd = ops.make_conv_desc(B, Ho, Wo, Cout, dy_ld, B, Ho, Wo, Cin, Cin, [(0, 0, 0)])
             ev = self._prof_begin()
             check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), dsub.data_ptr(), None, None, None, None, _st()), "dgrad " + s.name)
-            self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin)
+            self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin, "dgrad " + s.name)
             if x.grad is None:
                 x.new_grad()
                 check(L.iswm_zero_stuff2(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "zero_stuff2")
@@ -389,7 +389,7 @@ class Engine:
         # algorithmic FLOPs of a data gradient = those of the forward conv it differentiates (no credit
         # for the zero-stuffed positions of the stride-2 case)
         fwd_pix = B * (Ho // s.stride if s.stride > 1 else Ho) * (Wo // s.stride if s.stride > 1 else Wo)
-        self._prof_end(ev, "conv_igemm", 2.0 * fwd_pix * Cout * Cin * len(dtaps))
+        self._prof_end(ev, "conv_igemm", 2.0 * fwd_pix * Cout * Cin * len(dtaps), "dgrad " + s.name)
 
     def _prof_begin(self):
         if self.profile is None:
@@ -398,12 +398,12 @@ class Engine:
         ev.record()
         return ev
 
-    def _prof_end(self, ev0, kernel: str, flops: float):
+    def _prof_end(self, ev0, kernel: str, flops: float, tag: str = ""):
         if ev0 is None:
             return
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
-        self.profile.append((kernel, flops, ev0, ev1))
+        self.profile.append((kernel, flops, ev0, ev1, tag))
 
     def _tap(self, name: str, a: Act):
         if self.debug_taps is not None:
