@@ -151,6 +151,16 @@ int iswm_pack_weight_fwd(const float* d_w, int Cout, int Cin, int RS, int cin_pa
 /* fp32 OIHW -> bf16 [Cin][R*S][cout_pad] (dgrad operand, taps kept in forward order) */
 int iswm_pack_weight_dgrad(const float* d_w, int Cout, int Cin, int RS, int cout_pad, void* d_out,
                            void* stream);
+/* One launch for many weight tensors (after an optimiser step): d_jobs is a DEVICE array of n_jobs
+ * records; mode 0 = forward operand (as iswm_pack_weight_fwd, pad = cin_pad), mode 1 = dgrad operand
+ * (as iswm_pack_weight_dgrad, pad = cout_pad, row_ld unused). */
+typedef struct {
+  const float* w;      /* fp32 OIHW source (device) */
+  void* dst;           /* bf16 destination (device) */
+  int32_t Cout, Cin, RS, pad, row_ld, mode;
+} iswm_pack_job;
+int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, void* stream);
+
 /* wgrad accumulator (fp32 rows of row_ld, element t*cin_stride + c) -> fp32 OIHW grad,
  * dst = beta*dst + src. Normal: cin_stride = Cin, row_ld = R*S*Cin. */
 int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stride, int row_ld,

@@ -32,6 +32,13 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """Mirror of iswm_pack_job."""
+
+    _fields_ = [("w", C.c_void_p), ("dst", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32), ("RS", C.c_int32),
+                ("pad", C.c_int32), ("row_ld", C.c_int32), ("mode", C.c_int32)]
+
+
 _p, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 
 # name -> (restype, argtypes); kept in the order of include/iswm_b200.h
@@ -49,6 +56,7 @@ SIGNATURES = {
     "iswm_conv_wgrad": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p]),
     "iswm_pack_weight_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weight_dgrad": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "iswm_pack_weights_batched": (_i, [_p, _i, _p]),
     "iswm_unpack_wgrad": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
     "iswm_bn_train_apply": (_i, [_p, _i, _p, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _i, _p]),
     "iswm_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),

@@ -83,6 +83,38 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int 
   }
 }
 
+// all convolutions' weights packed in ONE launch: blockIdx.y = job, blockIdx.x strides the job's output
+struct PackJob {
+  const float* w;
+  __nv_bfloat16* dst;
+  int Cout, Cin, RS, pad, row_ld, mode;   // mode 0: forward operand (pad = cin_pad), 1: dgrad operand (pad = cout_pad)
+};
+__global__ void __launch_bounds__(kT)
+pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  if (j.mode == 0) {
+    const int64_t total = (int64_t)j.Cout * j.row_ld;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += stride) {
+      const int o = (int)(i / j.row_ld), k = (int)(i % j.row_ld);
+      const int t = k / j.pad, c = k % j.pad;
+      float v = 0.f;
+      if (t < j.RS && c < j.Cin) v = j.w[((int64_t)o * j.Cin + c) * j.RS + t];
+      j.dst[i] = __float2bfloat16_rn(v);
+    }
+  } else {
+    const int64_t total = (int64_t)j.Cin * j.RS * j.pad;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += stride) {
+      const int o = (int)(i % j.pad);
+      const int t = (int)((i / j.pad) % j.RS);
+      const int c = (int)(i / ((int64_t)j.pad * j.RS));
+      float v = 0.f;
+      if (o < j.Cout) v = j.w[((int64_t)o * j.Cin + c) * j.RS + t];
+      j.dst[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // BatchNorm kernels share one thread layout: blockDim = 256 = nx * ny (+ idle), tx = channel group
 // (8 channels = 16 bytes), ty = row lane. Per-channel constants live in registers; a block walks
@@ -1026,4 +1058,12 @@ extern "C" int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, cons
     scale_by_device_scalar_kernel<__nv_bfloat16><<<grid_for(n), kT, 0, ST(stream)>>>(BFW(d_x), n, d_scalar);
   else { set_error("scale_by_device_scalar: bad dtype %d", dtype); return 2; }
   return check_launch("scale_by_device_scalar");
+}
+
+extern "C" int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, void* stream) {
+  static_assert(sizeof(PackJob) == 40, "PackJob layout is part of the C ABI (iswm_pack_job)");
+  ISWM_REQUIRE(d_jobs && n_jobs >= 1 && n_jobs <= 65535, "pack_weights_batched: bad args");
+  dim3 grid(96, n_jobs);
+  pack_weights_batched_kernel<<<grid, kT, 0, ST(stream)>>>(static_cast<const PackJob*>(d_jobs));
+  return check_launch("pack_weights_batched");
 }

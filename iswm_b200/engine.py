@@ -92,6 +92,7 @@ class Engine:
         self._saved = None
         self.weights_epoch = 0        # bumped by optimisers that update parameters behind autograd's back
         self.flat_w = None            # fp32 flat master weights (parameters become views of it)
+        self.batched_pack = True      # repack all weights in one launch when any changed
         self.profile = None           # list of (kernel, algorithmic_flops, start_event, end_event) when profiling
         self.debug_taps = None        # dict name -> NCHW fp32 copy of each unit's output (tools/layer_diff.py)
         self.debug_units = None       # list of per-unit records of the engine's own tensors (tests/test_unit_replay_gpu.py)
@@ -143,15 +144,58 @@ class Engine:
             break
         self.device = x.device
 
+    def pack_all(self, need_dgrad: bool = True):
+        """Repack every convolution's weights (both operand layouts) in ONE kernel launch; called when the
+        parameters changed (optimiser step, load_state_dict) instead of 2 small launches per layer."""
+        import numpy as np
+        sig = tuple((s.conv.weight.data_ptr(), tuple(s.conv.weight.shape)) for s in self.specs) + (need_dgrad, str(self.device))
+        if getattr(self, "_pack_sig", None) != sig:
+            jobs = []
+            for s in self.specs:
+                w = s.conv.weight
+                Cout, Cin, R, S = w.shape
+                RS = R * S
+                if s.is_stem:
+                    cin_pad, row_ld = Cin, ((RS * Cin + 63) // 64) * 64
+                else:
+                    cin_pad = ((Cin + 63) // 64) * 64
+                    row_ld = RS * cin_pad
+                if s.packed_fwd is None or s.packed_fwd.numel() != Cout * row_ld or s.packed_fwd.device != w.device:
+                    s.packed_fwd = torch.empty(Cout * row_ld, dtype=torch.bfloat16, device=w.device)
+                jobs.append((w.data_ptr(), s.packed_fwd.data_ptr(), Cout, Cin, RS, cin_pad, row_ld, 0))
+                if need_dgrad and not s.is_stem:
+                    cout_pad = ((Cout + 63) // 64) * 64
+                    n = Cin * RS * cout_pad
+                    if s.packed_dgrad is None or s.packed_dgrad.numel() != n or s.packed_dgrad.device != w.device:
+                        s.packed_dgrad = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                    jobs.append((w.data_ptr(), s.packed_dgrad.data_ptr(), Cout, Cin, RS, cout_pad, 0, 1))
+            arr = (_lib.PackJob * len(jobs))()
+            for i, j in enumerate(jobs):
+                arr[i].w, arr[i].dst, arr[i].Cout, arr[i].Cin, arr[i].RS, arr[i].pad, arr[i].row_ld, arr[i].mode = j
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            self._pack_jobs = host.to(self.device)
+            self._pack_njobs = len(jobs)
+            self._pack_sig = sig
+        check(_lib.lib().iswm_pack_weights_batched(self._pack_jobs.data_ptr(), self._pack_njobs, _st()), "pack_weights_batched")
+        for s in self.specs:
+            w = s.conv.weight
+            s.version = (w._version, self.weights_epoch, w.data_ptr())
+            s.has_dgrad = need_dgrad and not s.is_stem
+
     def _pack(self, s: ConvSpec, need_dgrad: bool):
         w = s.conv.weight
         v = (w._version, self.weights_epoch, w.data_ptr())
+        if self.batched_pack and (s.packed_fwd is None or s.version != v or (need_dgrad and not s.is_stem and not getattr(s, "has_dgrad", False))):
+            self.pack_all(need_dgrad or self.model.training)
+            return
         if s.packed_fwd is None or s.version != v or s.packed_fwd.device != w.device:
             s.packed_fwd = ops.pack_weight_fwd(w.detach(), out=s.packed_fwd if (s.packed_fwd is not None and s.packed_fwd.device == w.device) else None, stem=s.is_stem)
             s.packed_dgrad = None
+            s.has_dgrad = False
             s.version = v
-        if need_dgrad and s.packed_dgrad is None and not s.is_stem:
+        if need_dgrad and (s.packed_dgrad is None or not getattr(s, "has_dgrad", False)) and not s.is_stem:
             s.packed_dgrad = ops.pack_weight_dgrad(w.detach())
+            s.has_dgrad = True
 
     def flatten_parameters(self):
         """Re-point every parameter at a view of ONE flat fp32 buffer (same registration order as the flat
