@@ -25,7 +25,10 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-TRAIN_GFLOP_PER_IMG = {("resnet50", 16, 512): 413.64}     # 3*fwd - stem fwd
+TRAIN_GFLOP_PER_IMG = {("resnet50", 16, 512): 413.64, ("resnet50", 16, 1024): 1654.52,
+                       ("resnet101", 8, 1024): 6236.69}   # 3*fwd - stem fwd
+FWD_GFLOP_PER_IMG = {("resnet50", 16, 512): 138.29, ("resnet50", 16, 1024): 553.15, ("resnet50", 16, 2048): 2212.58,
+                     ("resnet101", 8, 1024): 2080.54}
 PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -105,14 +108,14 @@ def synth_batch(B, H, W, seed, device=None, pinned=False):
 
 
 # ----------------------------------------------------------------------------- CPU arms
-def cpu_train_step_rate(B, H, W, steps, warmup, threads=None):
+def cpu_train_step_rate(B, H, W, steps, warmup, threads=None, backbone="resnet50", output_stride=16):
     """The reference algorithm on the host: fp32 torch oracle (oracle/torch_model.py), zero_grad ->
     forward -> weighted CE -> backward -> SGD step (train.py:1045-1049), all host threads."""
     from oracle import torch_model as TM
     n = threads or os.cpu_count() or 1
     torch.set_num_threads(n)
     torch.manual_seed(0)
-    model = TM.oracle_model("resnet50", 2, 16).train()
+    model = TM.oracle_model(backbone, 2, output_stride).train()
     opt = torch.optim.SGD(model.parameters(), momentum=0.9, weight_decay=1e-4, nesterov=True)   # lr: torch default, as train.py:424-431
     crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 7.0]), ignore_index=255, reduction="mean")
     x, y = synth_batch(B, H, W, 0)
@@ -124,31 +127,275 @@ def cpu_train_step_rate(B, H, W, steps, warmup, threads=None):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        float(loss)
+        float(loss.detach())
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     per = sum(times) / len(times)
     return B / per, per, n
 
 
+def train_workload_name(backbone, output_stride, H, W, B):
+    cfgname = "cfg2" if (backbone, output_stride, H, B) == ("resnet50", 16, 512, 16) else ("cfg3" if backbone == "resnet101" else "custom")
+    bbname = {"resnet50": "ResNet-50", "resnet101": "ResNet-101"}[backbone]
+    return (f"{cfgname}: DeepLabV3+ {bbname} OS{output_stride}, 2 classes, synthetic {H}x{W}, batch {B} per GPU, one step = forward + "
+            "adaptive weighted CE + backward + fused SGD(momentum 0.9, nesterov, wd 1e-4)")
+
+
 def run_reference(args):
+    """CPU arm: the reference algorithm (fp32 torch oracle = restatement of the reference modules, pinned to the
+    reference's own outputs by tests/golden; /root/reference does not exist on the GPU box) on all host threads,
+    on a BOUNDED sample of our arm's workload (batch 2 per step instead of 16: img/s is per image)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B, H, W = 2, 512, 512
+    H = W = args.size
     steps, warmup = max(1, min(args.steps, 3)), 1
-    rate, per, n = cpu_train_step_rate(B, H, W, steps, warmup)
+    if args.workload == "predict":
+        Hs = min(H, 1024)
+        rate, per, n = cpu_predict_rate(1, Hs, Hs, steps, warmup)
+        metric = f"predict img/s DeepLabV3+ R50 {H}^2"
+        workload = f"cfg4: predict.py path, DeepLabV3+ ResNet-50 OS16 eval forward on synthetic {H}x{W} tiles, batch {args.batch} per GPU, softmax[:,1] > 0.5 fused with the confusion matrix, mIoU read per step (e2e)"
+        sample = f"{warmup} warm-up + {steps} timed steps of batch 1 at {Hs}x{Hs} (img/s scaled by area {Hs * Hs}/{H * W} is NOT applied), fp32"
+        if Hs != H:
+            rate = rate * (Hs * Hs) / (H * W)
+            sample = f"{warmup} warm-up + {steps} timed steps of batch 1 at {Hs}x{Hs}, img/s scaled to {H}x{W} by pixel count (convolutions are linear in pixels), fp32"
+    else:
+        B = 2
+        rate, per, n = cpu_train_step_rate(B, min(H, 512), min(W, 512), steps, warmup, backbone=args.backbone, output_stride=args.output_stride)
+        if H > 512:
+            rate = rate * (512 * 512) / (H * W)
+        metric = f"train img/s DeepLabV3+ {'R50' if args.backbone == 'resnet50' else 'R101'} {H}^2"
+        workload = train_workload_name(args.backbone, args.output_stride, H, W, args.batch)
+        sample = (f"{warmup} warm-up + {steps} timed steps, batch {B} (of the workload's {args.batch}), {min(H, 512)}x{min(W, 512)}"
+                  + (f" scaled to {H}x{W} by pixel count" if H > 512 else "") + f", {args.backbone}-OS{args.output_stride} fwd+CE+bwd+SGD, fp32, torch {torch.__version__}")
     line = {
-        "impl": "reference", "metric": "train img/s DeepLabV3+ R50 512^2", "value": rate, "unit": "img/s",
+        "impl": "reference", "metric": metric, "value": rate, "unit": "img/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: DeepLabV3+ ResNet-50 OS16 train step (fwd + weighted CE + bwd + SGD), synthetic 512x512",
-                   "note": f"CPU arm: fp32 torch oracle (restatement of the reference modules; /root/reference is absent on the GPU box), bounded sample of batch {B} per step"},
-        "cpu_baseline": {"value": rate, "unit": "img/s", "cores": n, "kind": "port",
-                         "sample": f"{warmup} warm-up + {steps} timed steps, batch {B}, 512x512, R50-OS16 fwd+CE+bwd+SGD, fp32, torch {torch.__version__}"},
+        "config": {"workload": workload,
+                   "note": "CPU arm: fp32 torch oracle (restatement of the reference modules; /root/reference is absent on the GPU box) on the host cores, bounded sample"},
+        "cpu_baseline": {"value": rate, "unit": "img/s", "cores": n, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def traffic_from_profiles(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full
+    capture summary (profiles/traffic.json, written by tools/ncu_summary.py); None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def _time_region(fn, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), w0, time.time(), out
+
+
+def _max_over_ranks(vals, dev, world):
+    if world == 1:
+        return vals
+    import torch.distributed as dist
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def cpu_predict_rate(B, H, W, steps, warmup, threads=None):
+    """predict.py:262-278 + evaluate_quantization.py:265-270 on the host: no_grad forward, softmax[:,1] > 0.5,
+    StreamMetrics._fast_hist (numpy oracle), fp32 torch oracle network."""
+    from oracle import oracle_np as O
+    from oracle import torch_model as TM
+    n = threads or os.cpu_count() or 1
+    torch.set_num_threads(n)
+    torch.manual_seed(0)
+    model = TM.oracle_model("resnet50", 2, 16).eval()
+    x, y = synth_batch(B, H, W, 0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            prob = torch.softmax(model(x), dim=1)
+        pred = (prob[:, 1] > 0.5).long().numpy()
+        O.fast_hist(y.numpy().reshape(-1), pred.reshape(-1), 2)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    return B / per, per, n
+
+
+def run_predict(args, dev, world, rank, local):
+    """cfg4: predict.py's forward -> softmax[:,1] > 0.5 -> StreamMetrics confusion matrix -> mIoU, batched."""
+    import torch.distributed as dist
+    from iswm_b200 import _lib
+    from iswm_b200.metrics import StreamMetrics
+    from iswm_b200.network import modeling
+    B, H, W = args.batch, args.size, args.size
+    torch.manual_seed(0)
+    model = modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(dev).eval()
+    metrics = StreamMetrics(2, device=dev)
+    x_dev, y_dev = synth_batch(B, H, W, rank, device=dev)
+    x_host, y_host = synth_batch(B, H, W, rank, pinned=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x, y):
+        logits = model(x)
+        metrics.update_cuda(y, logits, threshold=0.5)
+        return logits
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = _lib.launch_count()
+    ms, w0, w1, _ = _time_region(lambda: step(x_dev, y_dev), args.steps, barrier)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    metrics.reset()
+
+    def e2e_step():
+        step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+        return metrics.get_results()["MIoU"]            # device -> host read of the int64 counters every step
+
+    ms_e2e, _, _, miou = _time_region(e2e_step, args.steps, barrier)
+    ms, ms_e2e = _max_over_ranks([ms, ms_e2e], dev, world)
+    roof = None
+    if rank == 0:
+        eng = model.engine()
+        eng.profile = []
+        step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        t_ms = sum(a.elapsed_time(b) for k, fl, a, b, tag in eng.profile if k == "conv_igemm")
+        fl = sum(fl for k, fl, a, b, tag in eng.profile if k == "conv_igemm")
+        n = sum(1 for k, *_ in eng.profile if k == "conv_igemm")
+        eng.profile = None
+        pk = peaks()
+        peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        ach = fl / (t_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward implicit GEMMs, BN folded into the epilogue)", "achieved": ach,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic_from_profiles("conv_igemm_kernel"),
+                "launches_per_step": n, "kernel_ms_per_step": t_ms, "peak_source": pk["_source"] + " bf16_tflops_sustained"}
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    imgs = B * world * args.steps
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, per, n = cpu_predict_rate(1, min(H, 1024), min(W, 1024), 1, 1)
+        cpu = {"value": rate, "unit": "img/s", "cores": n, "kind": "port",
+               "sample": f"1 warm-up + 1 timed forward+threshold+fast_hist of batch 1 at {min(H, 1024)}x{min(W, 1024)}, fp32 torch oracle on the host"}
+    print(json.dumps({
+        "metric": f"predict img/s DeepLabV3+ R50 {H}^2", "value": imgs / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"cfg4: predict.py path, DeepLabV3+ ResNet-50 OS16 eval forward on synthetic {H}x{W} tiles, batch {B} per GPU, softmax[:,1] > 0.5 fused with the confusion matrix, mIoU read per step (e2e)",
+                   "parallelism": f"dp{world}", "global_batch": B * world, "l2": "inputs and activations >> 126 MB L2", "miou": miou},
+        "clocks": clocks,
+        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8) * world,
+                "d2h_bytes_per_step": 8 * 5 * world, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}))
+
+
+def run_lossmetric(args, dev, world, rank, local):
+    """cfg5: class histogram, fused weighted CE fwd+bwd and argmax+confusion matrix on [B,2,S,S] logits."""
+    from iswm_b200 import _lib, ops
+    B, H, W = args.batch, args.size, args.size
+    g = torch.Generator().manual_seed(rank)
+    logits = torch.randn((B, 2, H, W), generator=g).to(dev)
+    u = torch.rand((B, H, W), generator=g)
+    labels = (u < 0.02).long()
+    labels[torch.rand((B, H, W), generator=g) < 0.01] = 255
+    labels = labels.to(dev)
+    w = torch.tensor([1.0, 7.0], device=dev)
+    N = B * H * W
+    algo = {"class_hist": N * 8, "wce_fwd_bwd": 2 * N * 2 * 4 + N * 8, "argmax_confusion": N * 2 * 4 + N * 8}
+    hist = ops.class_hist(labels, 2)
+    cm = torch.zeros(5, dtype=torch.int64, device=dev)
+    fns = {"class_hist": lambda: ops.class_hist(labels, 2, out=hist),
+           "wce_fwd_bwd": lambda: ops.wce_fwd_bwd(logits, labels, w, hist),
+           "argmax_confusion": lambda: ops.argmax_confusion(logits, labels, mode=1, threshold=0.5, out=cm)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    res = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    w0 = time.time()
+    launches0 = _lib.launch_count()
+    for name, fn in fns.items():
+        for _ in range(args.warmup):
+            fn()
+        ts = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        res[name] = {"us": ts[len(ts) // 2] * 1e3, "algorithmic_bytes": algo[name]}
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop(w0, time.time())
+    pk = peaks()
+    for name, r in res.items():
+        r["GB/s"] = r["algorithmic_bytes"] / (r["us"] * 1e-6) / 1e9
+        r["frac_of_hbm_peak"] = r["GB/s"] / pk["hbm_gbs"]
+    # e2e: host logits + labels -> loss scalar on the host, through the criterion API
+    from iswm_b200.utils.loss import CrossEntropyLoss
+    crit = CrossEntropyLoss(weight=w).to(dev)
+    lh, yh = logits.cpu().pin_memory(), labels.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        v = float(crit(lh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)))
+    e2e_s = (time.perf_counter() - t0) / 3
+    total_us = sum(r["us"] for r in res.values())
+    k = "wce_fwd_bwd"
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle_np as O
+        ln, yn, wn = logits[:2].cpu().numpy(), labels[:2].cpu().numpy(), w.cpu().numpy()
+        t0 = time.perf_counter()
+        O.class_hist(yn, 2)
+        O.weighted_ce(ln, yn, wn)
+        O.fast_hist(yn.reshape(-1), O.threshold_pred(ln)[0].reshape(-1), 2)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 2 * H * W / dt / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port", "sample": f"numpy oracle, histogram + weighted CE fwd/bwd + threshold + fast_hist on 2 of the {B} images"}
+    print(json.dumps({
+        "metric": "loss+metric Mpx/s (class histogram + weighted CE fwd/bwd + argmax confusion matrix)", "value": N / (total_us * 1e-6) / 1e6, "unit": "Mpx/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_us * 1e-3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg5: loss+metrics microbench on {B}x2x{H}x{W} fp32 logits, int64 labels (2 % foreground, 1 % ignore)", "l2": "256 MB flush write between timed launches",
+                   "kernels": res, "loss": v},
+        "clocks": clocks,
+        "e2e": {"value": N / e2e_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": lh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "wce2_kernel (fused weighted softmax-CE forward + backward)", "achieved": res[k]["GB/s"], "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": res[k]["frac_of_hbm_peak"], "traffic": traffic_from_profiles("wce2_kernel"), "peak_source": pk["_source"] + " hbm_gbs"},
+        "cpu_baseline": cpu}))
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -168,9 +415,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "predict":
+        return run_predict(args, dev, world, rank, local)
+    if args.workload == "lossmetric":
+        return run_lossmetric(args, dev, world, rank, local)
     B, H, W = args.batch, args.size, args.size
     torch.manual_seed(0)
-    model = modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(dev).train()
+    ctor = modeling.deeplabv3plus_resnet50 if args.backbone == "resnet50" else modeling.deeplabv3plus_resnet101
+    model = ctor(num_classes=2, output_stride=args.output_stride, pretrained_backbone=False).to(dev).train()
     crit = CrossEntropyLoss(weight=torch.tensor([1.0, 7.0]), ignore_index=255).to(dev)      # [1, sqrt(0.98/0.02)]
     opt = FusedSGD(model, lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
     dp = None
@@ -257,7 +509,7 @@ def run_ours(args):
         t_ms, fl, n = agg[k]
         ach = fl / (t_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient implicit GEMMs)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic_from_profiles("conv_igemm_kernel"),
                 "launches_per_step": n, "kernel_ms_per_step": t_ms, "peak_source": pk["_source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "other_kernels": {kk: {"ms_per_step": v[0], "TFLOP/s": v[1] / (v[0] * 1e-3) / 1e12, "launches": v[2]} for kk, v in agg.items() if kk != k}}
     if rank != 0:
@@ -269,15 +521,15 @@ def run_ours(args):
     e2e_value = imgs / (ms_e2e * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, per, n = cpu_train_step_rate(2, H, W, 2, 1)
+        rate, per, n = cpu_train_step_rate(2, min(H, 512), min(W, 512), 2, 1)
         cpu = {"value": rate, "unit": "img/s", "cores": n, "kind": "port",
                "sample": f"1 warm-up + 2 timed steps of batch 2, {H}x{W}, R50-OS16 fwd+CE+bwd+SGD, fp32 torch oracle on the host"}
-    gflop = TRAIN_GFLOP_PER_IMG.get(("resnet50", 16, H))
+    gflop = TRAIN_GFLOP_PER_IMG.get((args.backbone, args.output_stride, H))
     line = {
-        "metric": "train img/s DeepLabV3+ R50 512^2", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "metric": f"train img/s DeepLabV3+ {'R50' if args.backbone == 'resnet50' else 'R101'} {H}^2", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"cfg2: DeepLabV3+ ResNet-50 OS16, 2 classes, synthetic {H}x{W}, batch {B} per GPU, one step = forward + adaptive weighted CE + backward + fused SGD(momentum 0.9, nesterov, wd 1e-4)",
+        "config": {"workload": train_workload_name(args.backbone, args.output_stride, H, W, B),
                    "parallelism": f"dp{world}", "global_batch": B * world,
                    "l2": "no explicit flush: each step streams > 2 GB of activations (>> 126 MB L2)",
                    "whole_step_tensor_frac": (gflop * 1e9 * B * world * args.steps / (ms * 1e-3) / 1e12 / world / peaks().get("bf16_tflops_sustained", 1400.0)) if gflop else None,
@@ -300,12 +552,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--workload", default="train", choices=["train", "predict", "lossmetric"],
+                    help="train = cfg2 (the headline; cfg3 with --backbone resnet101 --output-stride 8 --size 1024 --batch 4); "
+                         "predict = cfg4 (R50 eval forward + threshold + confusion matrix); lossmetric = cfg5 microbench")
+    ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "resnet101"])
+    ap.add_argument("--output-stride", type=int, default=16, choices=[8, 16])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 16 train, 8 predict, 16 lossmetric)")
+    ap.add_argument("--size", type=int, default=0, help="tile edge (default: 512 train, 2048 predict, 1024 lossmetric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-detail", default="", help="write the per-launch table of the instrumented step here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.batch = args.batch or {"train": 16, "predict": 8, "lossmetric": 16}[args.workload]
+    args.size = args.size or {"train": 512, "predict": 2048, "lossmetric": 1024}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:
