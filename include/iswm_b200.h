@@ -184,17 +184,20 @@ int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean,
                  float eps, int C, float* d_scale, float* d_shift, void* stream);
 
 /* BatchNorm backward, pass 1: dz = dout * [out>0 if relu] * dropmask;
- * sums[c] = sum dz, sums[C+c] = sum dz * xhat. d_out_act = post-activation output (for the ReLU mask). */
+ * sums[c] = sum dz, sums[C+c] = sum dz * xhat. d_out_act = post-activation output (for the ReLU mask);
+ * pass NULL for a unit WITHOUT a residual add and the mask is recomputed from d_x with the forward
+ * kernel's own arithmetic, gamma*invstd*x + (beta - mean*gamma*invstd) > 0 (one tensor read less). */
 int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                        const void* d_out_act, int act_ld, int64_t M, int C,
-                       const float* d_save_mean, const float* d_save_invstd, int relu,
+                       const float* d_save_mean, const float* d_save_invstd,
+                       const float* d_gamma, const float* d_beta, int relu,
                        float drop_p, uint64_t drop_seed, float* d_sums, void* stream);
 /* pass 2: dx = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); dgamma += , dbeta += ;
  * optionally writes dz (the pre-activation gradient, used by the residual identity path). */
 int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                       const void* d_out_act, int act_ld, int64_t M, int C,
-                      const float* d_gamma, const float* d_save_mean, const float* d_save_invstd,
-                      const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                      const float* d_gamma, const float* d_beta, const float* d_save_mean,
+                      const float* d_save_invstd, const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
                       void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                       float* d_dgamma, float* d_dbeta, void* stream);
 

@@ -10,12 +10,15 @@
 //   warp 1   one thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32) into a
 //            double-buffered TMEM accumulator and commits stage/accumulator barriers;
 //   warp 2   TMEM allocator;
-//   warps 4-7 epilogue: tcgen05.ld the accumulator, then any of: per-channel affine
-//            (folded eval BatchNorm / bias), residual add, ReLU, per-channel sum and
-//            sum-of-squares for training BatchNorm; bf16 results are staged in 128B-swizzled
-//            smem 64 channels at a time and written with TMA tensor stores (coalesced, edge
-//            clipping by the hardware), residual tiles arrive the same way by TMA loads;
-//            fp32 / unaligned outputs use direct stores.
+//   warps 4-11 epilogue, two warpgroups that take alternate 64-channel chunks of the
+//            accumulator: one tcgen05.ld of 64 columns per thread (= one output pixel), then
+//            any of: per-channel affine (folded eval BatchNorm / bias), residual add (the
+//            thread's 128 contiguous bytes, loaded under the TMEM read), ReLU; bf16 results are
+//            staged in 128B-swizzled smem and written with TMA tensor stores (coalesced, edge
+//            clipping by the hardware). Training BatchNorm statistics (per-channel sum and
+//            sum of squares of the bf16 values BatchNorm will read back) are column sums of the
+//            staged tile, kept in registers across the CTA's tiles and flushed with one fp32
+//            atomic per channel per CTA. fp32 / unaligned outputs use direct stores.
 //
 // Forward convs of network/backbone/resnet.py:27-35 (conv3x3 / conv1x1, all dilations)
 // and network/_deeplab.py:37-51,124,134,149,162; their data gradients run through the
@@ -50,46 +53,23 @@ struct ConvKParams {
   int* abort_flag;
 };
 
-template <int N>
-__device__ __forceinline__ void bfly_step(float (&v)[16], int lane, int mask) {
-  const bool up = (lane & mask) != 0;
-#pragma unroll
-  for (int i = 0; i < N / 2; i++) {
-    const float send = up ? v[i] : v[i + N / 2];
-    const float keep = up ? v[i + N / 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-  }
-}
-// column sums of a 32x16 block held one row per lane; result for column (lane>>1)&15 in v[0]
-__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
-  bfly_step<16>(v, lane, 16);
-  bfly_step<8>(v, lane, 8);
-  bfly_step<4>(v, lane, 4);
-  bfly_step<2>(v, lane, 2);
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_out,
-                  const __grid_constant__ CUtensorMap tmap_res, const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap tmap_out, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
   const uint32_t ring = (raw_addr + 1023u) & ~1023u;     // swizzle-128B tiles need 1 KiB alignment
   uint8_t* smem = smem_raw + (ring - raw_addr);
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  // [ring stages][out staging 2x16K if TMA out][residual staging 2x16K if TMA out + residual][barriers][scale, shift]
+  // [ring stages][out staging: one 16K tile per epilogue warpgroup, if TMA out][barriers][scale, shift]
   const bool tma_out = p.use_tma_out != 0;
-  const bool tma_res = tma_out && (p.flags & ISWM_EPI_RESIDUAL);
   uint32_t off = (uint32_t)p.stages * stage_bytes;
   const uint32_t obuf = ring + off;
   if (tma_out) off += 2 * kStageBuf;
-  const uint32_t rbuf = ring + off;
-  if (tma_res) off += 2 * kStageBuf;
   uint8_t* tail = smem + off;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[8] empty[8] tfull[2] tempty[2] rfull[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[8] empty[8] tfull[2] tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
   float* s_scale = reinterpret_cast<float*>(tail + 256);
   float* s_shift = s_scale + 256;
@@ -98,7 +78,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  const uint32_t bar_rfull = bar_tempty + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -106,7 +85,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc::tma_prefetch_desc(&tmap_a);
     tc::tma_prefetch_desc(&tmap_b);
     if (tma_out) tc::tma_prefetch_desc(&tmap_out);
-    if (tma_res) tc::tma_prefetch_desc(&tmap_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; s++) {
@@ -115,8 +93,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; s++) {
       tc::mbar_init(bar_tfull + 8 * s, 1);
-      tc::mbar_init(bar_tempty + 8 * s, 4);   // one arrival per epilogue warp
-      tc::mbar_init(bar_rfull + 8 * s, 1);
+      tc::mbar_init(bar_tempty + 8 * s, 8);   // one arrival per epilogue warp
     }
     tc::fence_barrier_init();
   }
@@ -188,199 +165,188 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;                          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int row = ew * 32 + lane;
+    // ===================== epilogue: two warpgroups, 64-channel chunks alternate between them =====================
+    const int wg = (warp - 4) >> 2;                     // warpgroup 0 / 1
+    const int q = warp & 3;                             // TMEM lane quadrant of this warp (warp % 4)
+    const int row = q * 32 + lane;                      // accumulator row = thread index inside the warpgroup
     const int bb = row >> (p.lgBW + p.lgBH);
     const int hh = (row >> p.lgBW) & (BH - 1);
     const int ww = row & (BW - 1);
     const bool f_aff = p.flags & ISWM_EPI_AFFINE, f_relu = p.flags & ISWM_EPI_RELU,
                f_res = p.flags & ISWM_EPI_RESIDUAL, f_stats = p.flags & ISWM_EPI_STATS,
                f_f32 = p.flags & ISWM_EPI_OUT_F32;
-    const bool issuer = (threadIdx.x == 128);           // issues the epilogue's TMA loads / stores
+    const bool issuer = (row == 0);                     // issues this warpgroup's TMA stores
     const int nchunk64 = (p.BN + 63) >> 6;
-    const uint32_t row_off = (uint32_t)row * 128u;      // this thread's row inside a staging tile
+    const uint32_t ob = obuf + (uint32_t)wg * kStageBuf; // this warpgroup's 128 x 64 bf16 staging tile
+    const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);            // 128B swizzle: 16-byte chunk index ^= row % 8
-    int as = 0;
+    const int bar_wg = 1 + wg;                          // named barrier of this warpgroup
+    // BatchNorm statistics: thread (q, lane) owns channel pair `lane` of rows [32q, 32q+32) of each staged
+    // chunk; partial sums stay in registers across this CTA's tiles while the channel tile is unchanged.
+    float st[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) st[i][j] = 0.f;
+    auto flush_stats = [&](int n0f) {
+#pragma unroll
+      for (int slot = 0; slot < 2; slot++) {
+        const int c64 = (nchunk64 == 1) ? 0 : 2 * slot + wg;
+        if (c64 >= nchunk64) continue;
+        const int col = n0f + c64 * 64 + 2 * lane;
+        if (col < p.Cout) {
+          atomicAdd(p.stats + col, st[slot][0]);
+          atomicAdd(p.stats + p.Cout + col, st[slot][2]);
+        }
+        if (col + 1 < p.Cout) {
+          atomicAdd(p.stats + col + 1, st[slot][1]);
+          atomicAdd(p.stats + p.Cout + col + 1, st[slot][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) st[slot][j] = 0.f;
+      }
+    };
+    int as = 0, it = 0, cur_n0 = -1;
     uint32_t aphase = 0;
-    uint32_t cc = 0;                                    // running 64-channel chunk counter (staging parity)
-    auto tile_coords = [&](int tile, int& w0, int& h0, int& b0, int& n0) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-      w0 = tw * BW; h0 = th * BH; b0 = tb * BB; n0 = nt * p.BN;
-    };
-    if (tma_res && issuer && (int)blockIdx.x < p.total_tiles) {   // residual chunk 0 of the first tile
-      int w0, h0, b0, n0;
-      tile_coords(blockIdx.x, w0, h0, b0, n0);
-      tc::mbar_expect_tx(bar_rfull, kStageBuf);
-      tc::tma_load_4d(rbuf, &tmap_res, bar_rfull, n0, w0, h0, b0);
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int w0, h0, b0, n0;
-      tile_coords(tile, w0, h0, b0, n0);
+      const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB, n0 = nt * p.BN;
       const int w = w0 + ww, h = h0 + hh, b = b0 + bb;
       const bool valid = (b < p.B) && (h < p.Ho) && (w < p.Wo);
       const size_t pix = ((size_t)b * p.Ho + h) * p.Wo + w;
-      if (f_aff) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done
-        for (int i = threadIdx.x - 128; i < p.BN; i += 128) {
-          const int n = n0 + i;
-          s_scale[i] = (n < p.Cout) ? p.scale[n] : 0.f;
-          s_shift[i] = (n < p.Cout) ? p.shift[n] : 0.f;
+      if (n0 != cur_n0) {
+        if (f_stats && cur_n0 >= 0) flush_stats(cur_n0);
+        if (f_aff) {
+          asm volatile("bar.sync 3, 256;" ::: "memory");   // every reader of the previous channel tile is done
+          for (int i = threadIdx.x - 128; i < p.BN; i += 256) {
+            const int n = n0 + i;
+            s_scale[i] = (n < p.Cout) ? p.scale[n] : 0.f;
+            s_shift[i] = (n < p.Cout) ? p.shift[n] : 0.f;
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_n0 = n0;
       }
       if (!tc::mbar_wait(bar_tfull + 8 * as, aphase, p.abort_flag, 4)) break;
       tc::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * p.BN);
-      bool dead = false;
-      for (int c64 = 0; c64 < nchunk64 && !dead; c64++, cc++) {
-        const uint32_t ob = obuf + (cc & 1) * kStageBuf;
-        const uint32_t rb = rbuf + (cc & 1) * kStageBuf;
-        if (tma_out) {
-          // the store issued two chunks ago has finished reading this staging buffer
-          if (issuer) tc::tma_store_wait_read<1>();
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (tma_res) {
-            if (!tc::mbar_wait(bar_rfull + 8 * (cc & 1), (cc >> 1) & 1, p.abort_flag, 5)) { dead = true; break; }
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+      for (int c64 = 0; c64 < nchunk64; c64++) {
+        if (((it * nchunk64 + c64) & 1) != wg) continue;
+        const int nc = n0 + c64 * 64;                   // first output channel of this chunk
+        if (nc >= p.Cout) continue;
+        const int ncols = min(64, min(p.BN - c64 * 64, p.Cout - nc));
+        uint32_t v[64];
+        tc::tmem_ld64(t_row + c64 * 64, v);
+        // residual: this thread's row of the chunk is 128 contiguous bytes; issue the loads under the TMEM read
+        uint4 rr[8];
+        const bool res_vec = f_res && valid && ncols == 64 && (p.res_ld & 7) == 0;
+        if (res_vec) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * (size_t)p.res_ld + nc);
+#pragma unroll
+          for (int j = 0; j < 8; j++) rr[j] = rp[j];
+        }
+        tc::tmem_ld_wait();
+        float f[64];
+#pragma unroll
+        for (int j = 0; j < 64; j++) f[j] = __uint_as_float(v[j]);
+        if (f_aff) {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c64 * 64);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c64 * 64);
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float4 a = sc4[j], c = sh4[j];
+            f[4 * j] = fmaf(f[4 * j], a.x, c.x);
+            f[4 * j + 1] = fmaf(f[4 * j + 1], a.y, c.y);
+            f[4 * j + 2] = fmaf(f[4 * j + 2], a.z, c.z);
+            f[4 * j + 3] = fmaf(f[4 * j + 3], a.w, c.w);
           }
         }
-        const int cend = min(p.BN, (c64 + 1) * 64);
-        for (int c = c64 * 64; c < cend; c += 16) {
-          uint32_t v[16];
-          tc::tmem_ld16(t_row + c, v);
-          tc::tmem_ld_wait();
-          const int n = n0 + c;
-          if (n >= p.Cout) continue;                    // warp-uniform
-          float f[16];
+        if (f_res) {
+          if (res_vec) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]);
-          if (f_stats) {
-            float s[16], q[16];
+            for (int j = 0; j < 8; j++) {
+              const uint32_t r4[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const float x = valid ? f[j] : 0.f;
-              s[j] = x;
-              q[j] = x * x;
-            }
-            const float cs = warp_colsum16(s, lane);
-            const float cq = warp_colsum16(q, lane);
-            const int col = n + ((lane >> 1) & 15);
-            if ((lane & 1) == 0 && col < p.Cout) {
-              atomicAdd(p.stats + col, cs);
-              atomicAdd(p.stats + p.Cout + col, cq);
-            }
-          }
-          if (f_aff) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) f[j] = fmaf(f[j], s_scale[c + j], s_shift[c + j]);
-          }
-          const bool full16 = (n + 16 <= p.Cout);
-          const uint32_t q0 = (uint32_t)((c & 63) >> 3);          // first of this thread's two 16-byte chunks
-          if (f_res) {
-            if (tma_res) {
-              uint32_t rr[8];
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3])
-                           : "r"(rb + row_off + ((q0 ^ sw) << 4)));
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
-                           : "r"(rb + row_off + (((q0 + 1) ^ sw) << 4)));
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
+              for (int k = 0; k < 4; k++) {
                 float lo, hi;
-                unpack_bf16x2(rr[j], lo, hi);
-                f[2 * j] += lo;
-                f[2 * j + 1] += hi;
-              }
-            } else if (valid) {
-              const __nv_bfloat16* rp = p.res + pix * (size_t)p.res_ld + n;
-              if (full16 && (p.res_ld & 7) == 0) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                  float lo, hi;
-                  unpack_bf16x2(rr[j], lo, hi);
-                  f[2 * j] += lo;
-                  f[2 * j + 1] += hi;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                  if (n + j < p.Cout) f[j] += __bfloat162float(rp[j]);
+                unpack_bf16x2(r4[k], lo, hi);
+                f[8 * j + 2 * k] += lo;
+                f[8 * j + 2 * k + 1] += hi;
               }
             }
-          }
-          if (f_relu) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (tma_out) {
-            const uint32_t a0 = ob + row_off + ((q0 ^ sw) << 4);
-            const uint32_t a1 = ob + row_off + (((q0 + 1) ^ sw) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pack_bf16x2(f[0], f[1])),
-                         "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pack_bf16x2(f[8], f[9])),
-                         "r"(pack_bf16x2(f[10], f[11])), "r"(pack_bf16x2(f[12], f[13])), "r"(pack_bf16x2(f[14], f[15])) : "memory");
           } else if (valid) {
-            if (f_f32) {
-              float* op = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + n;
-              if (full16 && (p.out_ld & 3) == 0) {
+            const __nv_bfloat16* rp = p.res + pix * (size_t)p.res_ld + nc;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                  *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                  if (n + j < p.Cout) op[j] = f[j];
-              }
-            } else {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + n;
-              if (full16 && (p.out_ld & 7) == 0) {
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                *reinterpret_cast<uint4*>(op) = o0;
-                *reinterpret_cast<uint4*>(op + 8) = o1;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                  if (n + j < p.Cout) op[j] = __float2bfloat16_rn(f[j]);
-              }
-            }
+            for (int j = 0; j < 64; j++)
+              if (j < ncols) f[j] += __bfloat162float(rp[j]);
           }
         }
+        if (f_relu) {
+#pragma unroll
+          for (int j = 0; j < 64; j++) f[j] = fmaxf(f[j], 0.f);
+        }
         if (tma_out) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+          // the previous store of this warpgroup has finished reading the staging tile (and so have the
+          // statistics readers, who arrive at this barrier after their loop)
+          if (issuer) tc::tma_store_wait_read<0>();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ob + row_off + ((((uint32_t)j) ^ sw) << 4)),
+                         "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
           tc::fence_proxy_async();                        // staging writes -> visible to the TMA engine
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
           if (issuer) {
-            if (n0 + c64 * 64 < p.Cout) {
-              tc::tma_store_4d(&tmap_out, ob, n0 + c64 * 64, w0, h0, b0);
-            }
+            tc::tma_store_4d(&tmap_out, ob, nc, w0, h0, b0);
             tc::tma_store_commit();
-            if (tma_res) {                               // prefetch the next residual chunk into the other buffer
-              int nt_tile = tile, nc = c64 + 1;
-              if (nc == nchunk64) { nt_tile = tile + gridDim.x; nc = 0; }
-              if (nt_tile < p.total_tiles) {
-                int w1, h1, b1, n1;
-                tile_coords(nt_tile, w1, h1, b1, n1);
-                const uint32_t nb = (cc + 1) & 1;
-                tc::mbar_expect_tx(bar_rfull + 8 * nb, kStageBuf);
-                tc::tma_load_4d(rbuf + nb * kStageBuf, &tmap_res, bar_rfull + 8 * nb, n1 + nc * 64, w1, h1, b1);
-              }
+          }
+          if (f_stats) {
+            const int slot = c64 >> 1;
+            const uint32_t base = ob + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
+            const uint32_t ch = (uint32_t)(lane >> 2);
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+              uint32_t wv;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(base + (uint32_t)r * 128u + ((ch ^ (uint32_t)(r & 7)) << 4)));
+              float lo, hi;
+              unpack_bf16x2(wv, lo, hi);
+              s0 += lo; s1 += hi;
+              q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
             }
+            st[slot][0] += s0; st[slot][1] += s1; st[slot][2] += q0; st[slot][3] += q1;
+          }
+        } else if (valid) {
+          if (f_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + nc;
+            if (ncols == 64 && (p.out_ld & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; j++)
+                if (j < ncols) op[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + nc;
+#pragma unroll
+            for (int j = 0; j < 64; j++)
+              if (j < ncols) op[j] = __float2bfloat16_rn(f[j]);
           }
         }
       }
-      if (dead) break;
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * as);   // accumulator buffer drained
+      if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * as);   // this warp has drained its part of the accumulator
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (f_stats && cur_n0 >= 0) flush_stats(cur_n0);
     if (tma_out && issuer) tc::tma_store_wait_all();         // staging smem must outlive the last store
   }
 
@@ -444,10 +410,12 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   p.ntaps = d->ntaps;
   const int stage_bytes = kABytes + BN * 128;
   p.use_tma_out = (!(d->flags & ISWM_EPI_OUT_F32) && (d->out_ld % 8) == 0 &&
-                   (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
-                   (!(d->flags & ISWM_EPI_RESIDUAL) || ((d->res_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d_res) & 15) == 0))) ? 1 : 0;
+                   (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
+  ISWM_REQUIRE(!(d->flags & ISWM_EPI_RESIDUAL) || (reinterpret_cast<uintptr_t>(d_res) & 15) == 0 || (d->res_ld & 7) != 0,
+               "conv_igemm: a residual with res_ld %% 8 == 0 must be 16-byte aligned");
+  ISWM_REQUIRE(!(d->flags & ISWM_EPI_STATS) || p.use_tma_out, "conv_igemm: STATS needs a bf16 output with out_ld %% 8 == 0 and a 16-byte aligned base");
   int fixed = 1024 /*align*/ + 256 /*barriers*/ + ((d->flags & ISWM_EPI_AFFINE) ? 2048 : 0);
-  if (p.use_tma_out) fixed += 2 * kStageBuf + ((d->flags & ISWM_EPI_RESIDUAL) ? 2 * kStageBuf : 0);
+  if (p.use_tma_out) fixed += 2 * kStageBuf;
   p.stages = std::max(2, std::min(kMaxStages, (kSmemMax - fixed) / stage_bytes));
   p.flags = d->flags;
   p.n_img_per_phase = B;
@@ -473,16 +441,12 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
     const uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)BN};
     if (int rc = encode_tmap_bf16(&tmap_b, d_wgt, 2, dims, str, box)) return rc;
   }
-  CUtensorMap tmap_out = tmap_a, tmap_res = tmap_a;      // placeholders when unused
+  CUtensorMap tmap_out = tmap_a;                         // placeholder when unused
   if (p.use_tma_out) {
     const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
     const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};
     const uint64_t str[4] = {1, (uint64_t)d->out_ld, (uint64_t)Wo * d->out_ld, (uint64_t)Ho * Wo * d->out_ld};
     if (int rc = encode_tmap_bf16(&tmap_out, d_out, 4, dims, str, box)) return rc;
-    if (d->flags & ISWM_EPI_RESIDUAL) {
-      const uint64_t rstr[4] = {1, (uint64_t)d->res_ld, (uint64_t)Wo * d->res_ld, (uint64_t)Ho * Wo * d->res_ld};
-      if (int rc = encode_tmap_bf16(&tmap_res, d_res, 4, dims, rstr, box)) return rc;
-    }
   }
   const int smem_bytes = p.stages * stage_bytes + fixed;
   static bool attr_set = false;
@@ -493,6 +457,6 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, num_sms());
-  conv_igemm_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, tmap_out, tmap_res, p);
+  conv_igemm_kernel<<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, tmap_out, p);
   return check_launch("conv_igemm");
 }

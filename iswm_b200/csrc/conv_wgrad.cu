@@ -31,8 +31,9 @@ struct WgradKParams {
   int pix_blocks;
   int tiles_m, tiles_n, BN, nchunks_b, stages;
   int n_tiles;                    // output tiles = tiles_m * ntaps * tiles_n
-  long long total_kblocks;        // n_tiles * pix_blocks, split evenly over the CTAs (stream-K)
-  long long kblocks_per_cta;
+  long long total_kblocks;        // n_tiles * pix_blocks
+  long long kblocks_per_cta;      // stream-K mode: equal contiguous ranges of the linearised (tile, pixel block) space
+  int splits, split_len;          // split mode (splits > 0): CTA = (tile, split); same-split CTAs walk the same pixels
   int vec_red;
   int n_img_per_phase;
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
@@ -95,8 +96,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
     tap = r % p.ntaps;
     mt = r / p.ntaps;
   };
-  const long long range_lo = (long long)blockIdx.x * p.kblocks_per_cta;
-  const long long range_hi = min(range_lo + p.kblocks_per_cta, p.total_kblocks);
+  long long range_lo, range_hi;
+  if (p.splits > 0) {
+    // every CTA of one split index reads the SAME pixel blocks at the same time (different output tiles), so dy / x
+    // stream from HBM once and are shared through L2; partial tiles are reduced with fp32 atomics at the end
+    const int t = (int)(blockIdx.x % (unsigned)p.n_tiles), sp = (int)(blockIdx.x / (unsigned)p.n_tiles);
+    range_lo = (long long)t * p.pix_blocks + (long long)sp * p.split_len;
+    range_hi = min(range_lo + p.split_len, (long long)(t + 1) * p.pix_blocks);
+  } else {
+    range_lo = (long long)blockIdx.x * p.kblocks_per_cta;
+    range_hi = min(range_lo + p.kblocks_per_cta, p.total_kblocks);
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -263,10 +273,27 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
   ISWM_REQUIRE(n_tiles < (1ll << 31), "conv_wgrad: too many output tiles");
   p.n_tiles = (int)n_tiles;
   p.total_kblocks = n_tiles * pbs;
-  // stream-K: equal k-block ranges per CTA; at least ~4 k-blocks each so a flush is amortised
-  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms(), p.total_kblocks / 4));
-  p.kblocks_per_cta = (p.total_kblocks + grid - 1) / grid;
-  grid = (int)((p.total_kblocks + p.kblocks_per_cta - 1) / p.kblocks_per_cta);
+  int grid;
+  const int sms = num_sms();
+  if (n_tiles <= 2 * sms) {
+    // split mode: pick the split count (each split >= ~4 pixel blocks) that fills whole waves of SMs best
+    const int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(pbs / 4, (4 * sms) / n_tiles));
+    int best = 1;
+    double best_eff = 0.0;
+    for (int sp = 1; sp <= max_splits; sp++) {
+      const int64_t ctas = n_tiles * sp;
+      const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms) - 1e-4 * sp;
+      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+    }
+    p.split_len = (int)((pbs + best - 1) / best);
+    p.splits = (int)((pbs + p.split_len - 1) / p.split_len);
+    grid = (int)(n_tiles * p.splits);
+  } else {
+    // stream-K: equal k-block ranges per CTA; at least ~4 k-blocks each so a flush is amortised
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, p.total_kblocks / 4));
+    p.kblocks_per_cta = (p.total_kblocks + grid - 1) / grid;
+    grid = (int)((p.total_kblocks + p.kblocks_per_cta - 1) / p.kblocks_per_cta);
+  }
   p.vec_red = ((reinterpret_cast<uintptr_t>(d_dw) & 15) == 0 && (d->Cin % 4) == 0) ? 1 : 0;
   const int stage_bytes = (2 + p.nchunks_b) * kChunkBytes;
   p.stages = std::max(2, std::min(kWStages, kWSmemBudget / stage_bytes));

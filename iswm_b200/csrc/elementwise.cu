@@ -141,7 +141,7 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float
     const float var = fmaxf(stats[C + c] * invM - mean * mean, 0.f);
     const float invstd = rsqrtf(var + eps);
     sc[j] = gamma[c] * invstd;
-    sh[j] = beta[c] - mean * sc[j];
+    sh[j] = fmaf(-mean, sc[j], beta[c]);          // same expression in the backward kernels (mask recomputation)
     if (blockIdx.x == 0 && ty == 0) {
       if (save_mean) save_mean[c] = mean;
       if (save_invstd) save_invstd[c] = invstd;
@@ -204,11 +204,12 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 }
 
 // BatchNorm backward pass 1: per-channel sum(dz), sum(dz * xhat)
-__global__ void __launch_bounds__(kT, 3)
+__global__ void __launch_bounds__(kT, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      const __nv_bfloat16* __restrict__ x, int x_ld,
                      const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
-                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                      float drop_p, uint64_t drop_seed, float* __restrict__ sums, int nx, int ny,
                      int rows_per_block) {
   __shared__ float s_red[kT * 16];
@@ -217,11 +218,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
   const int c0 = tx << 3;
-  float a[8], b[8], mu[8], is[8];
+  // ReLU mask: from the stored post-activation tensor when given (residual units), otherwise recomputed
+  // from x with the forward kernel's own scale/shift arithmetic (saves one tensor read)
+  const bool mask_act = relu && act != nullptr, mask_re = relu && act == nullptr;
+  float a[8], b[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) { a[j] = 0.f; b[j] = 0.f; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+  for (int j = 0; j < 8; j++) {
+    a[j] = 0.f; b[j] = 0.f; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j];
+    sc[j] = mask_re ? gamma[c0 + j] * is[j] : 0.f;
+    sh[j] = mask_re ? fmaf(-mu[j], sc[j], beta[c0 + j]) : 0.f;
+  }
   if (ty < ny) {
-    constexpr int U = 2;
+    constexpr int U = 4;
     for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
       uint4 gr[U], xr[U], orr[U];
 #pragma unroll
@@ -230,7 +238,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
         if (row < r1) {
           gr[u] = load_raw(dout + row * dout_ld + c0);
           xr[u] = load_raw(x + row * x_ld + c0);
-          if (relu) orr[u] = load_raw(act + row * act_ld + c0);
+          if (mask_act) orr[u] = load_raw(act + row * act_ld + c0);
         }
       }
 #pragma unroll
@@ -239,10 +247,13 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
         if (row >= r1) continue;
         F8 g = unpack8(gr[u]);
         const F8 xv = unpack8(xr[u]);
-        if (relu) {
+        if (mask_act) {
           const F8 o = unpack8(orr[u]);
 #pragma unroll
           for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+        } else if (mask_re) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], sc[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
         }
         if (drop_p > 0.f) {
 #pragma unroll
@@ -274,11 +285,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
 }
 
 // BatchNorm backward pass 2
-__global__ void __launch_bounds__(kT, 3)
+__global__ void __launch_bounds__(kT, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     const __nv_bfloat16* __restrict__ x, int x_ld,
                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
-                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ sums, int relu,
                     float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
                     __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta, int nx,
@@ -288,12 +299,14 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const int c0 = tx << 3;
   const float invM = 1.0f / (float)M;
   // dx = k*dz + p*x + q  with  k = gamma*invstd, p = -k*invstd*mean(dz*xhat), q = -k*mean(dz) - p*mu
-  float kk[8], pp[8], qq[8];
+  const bool mask_act = relu && act != nullptr, mask_re = relu && act == nullptr;
+  float kk[8], pp[8], qq[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int c = c0 + j;
     const float is = invstd[c], mu = mean[c];
     const float k = gamma[c] * is;
+    sh[j] = mask_re ? fmaf(-mu, k, beta[c]) : 0.f;
     const float ma = sums[c] * invM, mb = sums[C + c] * invM;
     kk[j] = k;
     pp[j] = -k * is * mb;
@@ -306,7 +319,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
-  constexpr int U = 2;
+  constexpr int U = 4;
   for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
     uint4 gr[U], xr[U], orr[U];
 #pragma unroll
@@ -315,7 +328,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       if (row < r1) {
         gr[u] = load_raw(dout + row * dout_ld + c0);
         xr[u] = load_raw(x + row * x_ld + c0);
-        if (relu) orr[u] = load_raw(act + row * act_ld + c0);
+        if (mask_act) orr[u] = load_raw(act + row * act_ld + c0);
       }
     }
 #pragma unroll
@@ -324,10 +337,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       if (row >= r1) continue;
       F8 g = unpack8(gr[u]);
       const F8 xv = unpack8(xr[u]);
-      if (relu) {
+      if (mask_act) {
         const F8 o = unpack8(orr[u]);
 #pragma unroll
         for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+      } else if (mask_re) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], kk[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
       }
       if (drop_p > 0.f) {
 #pragma unroll
@@ -884,34 +900,37 @@ extern "C" int iswm_bn_fold(const float* d_gamma, const float* d_beta, const flo
 
 extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                                   const void* d_out_act, int act_ld, int64_t M, int C,
-                                  const float* d_save_mean, const float* d_save_invstd, int relu,
+                                  const float* d_save_mean, const float* d_save_invstd,
+                                  const float* d_gamma, const float* d_beta, int relu,
                                   float drop_p, uint64_t drop_seed, float* d_sums, void* stream) {
   REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
-  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_reduce: relu needs the activation");
+  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_gamma && d_beta),
+               "bn_bwd_reduce: relu needs the activation (or gamma and beta to recompute the mask)");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny, rows_per_block, blocks;
   bn_row_grid(C, M, 16, nx, ny, rows_per_block, blocks);
   bn_bwd_reduce_kernel<<<blocks, kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
-                                                      M, C, d_save_mean, d_save_invstd, relu, drop_p,
+                                                      M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, relu, drop_p,
                                                       drop_seed, d_sums, nx, ny, rows_per_block);
   return check_launch("bn_bwd_reduce");
 }
 extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                                  const void* d_out_act, int act_ld, int64_t M, int C,
-                                 const float* d_gamma, const float* d_save_mean, const float* d_save_invstd,
-                                 const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                                 const float* d_gamma, const float* d_beta, const float* d_save_mean,
+                                 const float* d_save_invstd, const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
                                  void* d_dx, int dx_ld, void* d_dz, int dz_ld, float* d_dgamma,
                                  float* d_dbeta, void* stream) {
   REQ_C8(C, "bn_bwd_apply"); REQ_LD8(dout_ld, "bn_bwd_apply"); REQ_LD8(x_ld, "bn_bwd_apply"); REQ_LD8(dx_ld, "bn_bwd_apply");
   ISWM_REQUIRE(d_dout && d_x && d_gamma && d_save_mean && d_save_invstd && d_sums && d_dx && M > 0, "bn_bwd_apply: null/empty");
-  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0), "bn_bwd_apply: relu needs the activation");
+  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_beta),
+               "bn_bwd_apply: relu needs the activation (or beta to recompute the mask)");
   ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd_apply: dz_ld");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
   bn_row_grid(C, M, 8, nx, ny, rpb, blocks);
   bn_bwd_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
-      BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_save_mean,
+      BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean,
       d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta,
       nx, ny, rpb);
   return check_launch("bn_bwd_apply");

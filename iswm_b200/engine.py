@@ -342,9 +342,12 @@ class Engine:
                            xgrad_before=None if x.grad is None else x.grad.t.clone(),
                            resgrad_before=None if (residual is None or residual.grad is None) else residual.grad.t.clone())
             sums = self._stats_slot(2 * Cout)
-            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, out.ptr, out.ld, M, Cout,
-                                       save.data_ptr(), save[Cout:].data_ptr(), 1 if use_mask else 0, drop_p, seed,
-                                       sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+            # the ReLU mask is read from the block output only where a residual was added; otherwise the
+            # kernels recompute it from raw (one tensor read less in each pass)
+            act_ptr = out.ptr if (use_mask and residual is not None) else None
+            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
+                                       save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                       1 if use_mask else 0, drop_p, seed, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
             dy = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
             dz_ptr, dz_ld, dz_tmp = None, 0, None
             if residual is not None:
@@ -355,8 +358,8 @@ class Engine:
                     assert residual.grad.ld == residual.C
                     dz_tmp = torch.empty_like(residual.grad.t)
                     dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
-            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, out.ptr, out.ld, M, Cout,
-                                      bn.weight.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
+            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
+                                      bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
                                       1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
                                       self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                   "bn_bwd_apply " + s.name)
@@ -605,10 +608,10 @@ class Engine:
         def backward():
             dout = out.grad
             sums = self._stats_slot(128)
-            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), 64, out.ptr, 64, M, 64, save.data_ptr(), save[64:].data_ptr(),
-                                       1, 0.0, 0, sums.data_ptr(), _st()), "bn_bwd_reduce stem")
+            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, save.data_ptr(), save[64:].data_ptr(),
+                                       bn.weight.data_ptr(), bn.bias.data_ptr(), 1, 0.0, 0, sums.data_ptr(), _st()), "bn_bwd_reduce stem")
             dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
-            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), 64, out.ptr, 64, M, 64, bn.weight.data_ptr(), save.data_ptr(),
+            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
                                       save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, dy.data_ptr(), 64, None, 0,
                                       self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd_apply stem")
             out.grad = None

@@ -73,13 +73,20 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     assert nbt.item() == 1
     dd = nhwc(dout).to(DEV)
     sums = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
-    check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, save.data_ptr(), save[C:].data_ptr(),
-                                 1 if relu else 0, 0.0, 0, sums.data_ptr(), st()))
+    # units without a residual recompute the ReLU mask from x (act = NULL); residual units read the block output
+    act_ptr = out.data_ptr() if with_res else None
+    check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, save.data_ptr(), save[C:].data_ptr(),
+                                 gd.data_ptr(), bd.data_ptr(), 1 if relu else 0, 0.0, 0, sums.data_ptr(), st()))
+    if relu and not with_res:                       # both mask sources must agree bit for bit
+        sums2 = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+        check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, save.data_ptr(), save[C:].data_ptr(),
+                                     gd.data_ptr(), bd.data_ptr(), 1, 0.0, 0, sums2.data_ptr(), st()))
+        assert torch.equal(sums, sums2)
     dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     dg = torch.zeros(C, dtype=torch.float32, device=DEV)
     db = torch.zeros(C, dtype=torch.float32, device=DEV)
-    check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, gd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
+    check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
                                 sums.data_ptr(), 1 if relu else 0, 0.0, 0, dx.data_ptr(), C, dz.data_ptr(), C, dg.data_ptr(), db.data_ptr(), st()))
     scale = float(xr.grad.abs().max())
     close(nchw(dx), xr.grad, 2e-2, 2e-2 * scale)
