@@ -105,7 +105,7 @@ enum {
   ISWM_EPI_AFFINE   = 1,  /* y = acc * scale[c] + shift[c] (eval BN folded / bias) */
   ISWM_EPI_RELU     = 2,
   ISWM_EPI_RESIDUAL = 4,  /* y += residual (bf16, same geometry, own ld)      */
-  ISWM_EPI_STATS    = 8,  /* accumulate per-channel sum / sum^2 of acc (fp32) */
+  ISWM_EPI_STATS    = 8,  /* accumulate per-channel fp32 sum / sum^2 of the STORED bf16 outputs (needs bf16 out, out_ld % 8 == 0) */
   ISWM_EPI_OUT_F32  = 16  /* write fp32 instead of bf16                       */
 };
 

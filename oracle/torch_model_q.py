@@ -49,18 +49,19 @@ class _QBoth(torch.autograd.Function):
 
 
 class _BNTrainQ(torch.autograd.Function):
-    """conv output (fp32 accumulator) -> [stats in fp32] -> bf16 raw -> normalise (+res) (+ReLU) -> bf16,
-    with the engine's explicit backward (iswm_bn_bwd_reduce / iswm_bn_bwd_apply)."""
+    """conv output (fp32 accumulator) -> bf16 raw -> [fp32 stats OF THE STORED bf16 VALUES, as the conv epilogue
+    sums its staged tile] -> normalise (+res) (+ReLU) -> bf16, with the engine's explicit backward
+    (iswm_bn_bwd_reduce / iswm_bn_bwd_apply)."""
 
     @staticmethod
     def forward(ctx, y32, gamma, beta, residual, relu, running_mean, running_var):
         M = y32.numel() // y32.shape[1]
-        mean = y32.sum((0, 2, 3)) / M
-        var = ((y32 * y32).sum((0, 2, 3)) / M - mean * mean).clamp_min(0)
+        yq = q(y32)
+        mean = yq.sum((0, 2, 3)) / M
+        var = ((yq * yq).sum((0, 2, 3)) / M - mean * mean).clamp_min(0)
         invstd = torch.rsqrt(var + BN_EPS)
         scale = gamma * invstd
         shift = beta - mean * scale
-        yq = q(y32)
         z = yq * scale[None, :, None, None] + shift[None, :, None, None]
         if residual is not None:
             z = z + residual

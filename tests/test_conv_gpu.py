@@ -66,8 +66,11 @@ def test_conv_fwd_raw_and_stats(B, Cin, H, W, Cout, k, dil):
     got = out[..., :Cout].float().cpu().permute(0, 3, 1, 2)
     assert _rel_err(got, ref) < 1e-2
     s = stats.cpu()
-    np.testing.assert_allclose(s[:Cout].numpy(), ref.sum((0, 2, 3)).numpy(), rtol=2e-3, atol=2e-2)
-    np.testing.assert_allclose(s[Cout:].numpy(), (ref * ref).sum((0, 2, 3)).numpy(), rtol=2e-3, atol=2e-2)
+    # the statistics are fp32 sums of the bf16 values the kernel STORED (what BatchNorm reads back)
+    np.testing.assert_allclose(s[:Cout].numpy(), got.sum((0, 2, 3)).numpy(), rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(s[Cout:].numpy(), (got * got).sum((0, 2, 3)).numpy(), rtol=1e-4, atol=2e-3)
+    # and stay within bf16 rounding noise of the unrounded sums
+    np.testing.assert_allclose(s[:Cout].numpy(), ref.sum((0, 2, 3)).numpy(), rtol=2e-2, atol=0.5)
 
 
 def test_conv_fwd_affine_relu_residual_f32():

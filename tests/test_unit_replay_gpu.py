@@ -74,10 +74,13 @@ def test_every_unit_matches_torch_on_the_engines_own_tensors(backbone, os_, B, H
         # ---- forward
         y32 = F.conv2d(xin, wq, None, stride, pad, dil)
         chk(name, "conv", raw, y32, 4e-3)
-        mean = y32.mean((0, 2, 3))
-        var = y32.var((0, 2, 3), unbiased=False)
+        # batch statistics are those of the STORED bf16 conv output (the conv epilogue sums its staged tile)
+        mean = raw.mean((0, 2, 3))
+        var = raw.var((0, 2, 3), unbiased=False)
         chk(name, "mean", r["mean"], mean, 2e-3 if Mn > 8 else 2e-2)
         chk(name, "invstd", r["invstd"], torch.rsqrt(var + 1e-5), 2e-3 if Mn > 8 else 5e-2)
+        if Mn > 8:   # ... and within bf16 rounding noise of the unrounded accumulator's statistics
+            chk(name, "invstd(fp32 acc)", r["invstd"], torch.rsqrt(y32.var((0, 2, 3), unbiased=False) + 1e-5), 1e-2)
         mu, istd = r["mean"][None, :, None, None], r["invstd"][None, :, None, None]
         z = (raw - mu) * istd * r["gamma"][None, :, None, None] + r["beta"][None, :, None, None]
         if r["residual"] is not None:
