@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libiswm_b200.so")
+# ISWM_B200_LIB selects an alternative build of the SAME library (e.g. the -DISWM_EPI_TIMING debug build of tools/)
+LIB_PATH = os.environ.get("ISWM_B200_LIB") or os.path.join(_HERE, "libiswm_b200.so")
 
 MAX_TAPS = 16
 U8, I32, I64 = 0, 1, 2

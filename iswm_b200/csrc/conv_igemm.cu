@@ -208,6 +208,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     };
     int as = 0, it = 0, cur_n0 = -1;
     uint32_t aphase = 0;
+#ifdef ISWM_EPI_TIMING
+    long long tm[6] = {0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define TMARK(i) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
+#else
+#define TMARK(i)
+#endif
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
       const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
@@ -228,8 +235,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         cur_n0 = n0;
       }
+      TMARK(0)
       if (!tc::mbar_wait(bar_tfull + 8 * as, aphase, p.abort_flag, 4)) break;
       tc::tc_fence_after();
+      TMARK(1)
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       for (int c64 = 0; c64 < nchunk64; c64++) {
         if (((it * nchunk64 + c64) & 1) != wg) continue;
@@ -247,6 +256,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int j = 0; j < 8; j++) rr[j] = rp[j];
         }
         tc::tmem_ld_wait();
+        TMARK(2)
         float f[64];
 #pragma unroll
         for (int j = 0; j < 64; j++) f[j] = __uint_as_float(v[j]);
@@ -292,8 +302,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int j = 0; j < 32; j++) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
           // the previous store of this warpgroup has finished reading the staging tile (and so have the
           // statistics readers, who arrive at this barrier after their loop)
+          TMARK(0)
           if (issuer) tc::tma_store_wait_read<0>();
           asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
+          TMARK(3)
 #pragma unroll
           for (int j = 0; j < 8; j++)
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ob + row_off + ((((uint32_t)j) ^ sw) << 4)),
@@ -304,6 +316,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc::tma_store_4d(&tmap_out, ob, nc, w0, h0, b0);
             tc::tma_store_commit();
           }
+          TMARK(4)
           if (f_stats) {
             const int slot = c64 >> 1;
             const uint32_t base = ob + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
@@ -319,6 +332,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
             }
             st[slot][0] += s0; st[slot][1] += s1; st[slot][2] += q0; st[slot][3] += q1;
+            TMARK(5)
           }
         } else if (valid) {
           if (f_f32) {
@@ -347,6 +361,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (as == 0) aphase ^= 1;
     }
     if (f_stats && cur_n0 >= 0) flush_stats(cur_n0);
+#ifdef ISWM_EPI_TIMING
+    // debug build only: [math+other, tfull wait, tmem load, staging free wait, stage+store, stats] cycles of thread 0/32 of each warpgroup
+    if (blockIdx.x == 0 && (row == 0 || row == 32)) {
+      printf("epi timing wg%d row%d: other %lld  tfull %lld  tmem %lld  stfree %lld  stage %lld  stats %lld  (tiles %d)\n", wg, row,
+             tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], it);
+    }
+#endif
     if (tma_out && issuer) tc::tma_store_wait_all();         // staging smem must outlive the last store
   }
 
