@@ -153,13 +153,16 @@ int iswm_pack_weight_dgrad(const float* d_w, int Cout, int Cin, int RS, int cout
                            void* stream);
 /* One launch for many weight tensors (after an optimiser step): d_jobs is a DEVICE array of n_jobs
  * records; mode 0 = forward operand (as iswm_pack_weight_fwd, pad = cin_pad), mode 1 = dgrad operand
- * (as iswm_pack_weight_dgrad, pad = cout_pad, row_ld unused). */
+ * (as iswm_pack_weight_dgrad, pad = cout_pad, row_ld unused). The caller deals thread blocks to jobs in
+ * proportion to their size: job i owns blocks [blk_begin, blk_begin + blk_count), blk_begin ascending and
+ * contiguous from 0; total_blocks = sum of blk_count. */
 typedef struct {
   const float* w;      /* fp32 OIHW source (device) */
   void* dst;           /* bf16 destination (device) */
   int32_t Cout, Cin, RS, pad, row_ld, mode;
+  int32_t blk_begin, blk_count;
 } iswm_pack_job;
-int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, void* stream);
+int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int total_blocks, void* stream);
 
 /* wgrad accumulator (fp32 rows of row_ld, element t*cin_stride + c) -> fp32 OIHW grad,
  * dst = beta*dst + src. Normal: cin_stride = Cin, row_ld = R*S*Cin. */

@@ -37,7 +37,21 @@ class PackJob(C.Structure):
     """Mirror of iswm_pack_job."""
 
     _fields_ = [("w", C.c_void_p), ("dst", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32), ("RS", C.c_int32),
-                ("pad", C.c_int32), ("row_ld", C.c_int32), ("mode", C.c_int32)]
+                ("pad", C.c_int32), ("row_ld", C.c_int32), ("mode", C.c_int32), ("blk_begin", C.c_int32), ("blk_count", C.c_int32)]
+
+
+def fill_pack_jobs(jobs):
+    """jobs: list of (w_ptr, dst_ptr, Cout, Cin, RS, pad, row_ld, mode) -> (ctypes array, total_blocks); thread
+    blocks are dealt to jobs in proportion to their element count (one per 16 Ki elements, 1..256)."""
+    arr = (PackJob * len(jobs))()
+    begin = 0
+    for i, j in enumerate(jobs):
+        arr[i].w, arr[i].dst, arr[i].Cout, arr[i].Cin, arr[i].RS, arr[i].pad, arr[i].row_ld, arr[i].mode = j
+        n = j[2] * j[3] * j[4]
+        arr[i].blk_begin = begin
+        arr[i].blk_count = max(1, min(256, (n + 16383) // 16384))
+        begin += arr[i].blk_count
+    return arr, begin
 
 
 _p, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
@@ -57,7 +71,7 @@ SIGNATURES = {
     "iswm_conv_wgrad": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p]),
     "iswm_pack_weight_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weight_dgrad": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "iswm_pack_weights_batched": (_i, [_p, _i, _p]),
+    "iswm_pack_weights_batched": (_i, [_p, _i, _i, _p]),
     "iswm_unpack_wgrad": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
     "iswm_bn_train_apply": (_i, [_p, _i, _p, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _i, _p]),
     "iswm_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),

@@ -83,19 +83,72 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int 
   }
 }
 
-// all convolutions' weights packed in ONE launch: blockIdx.y = job, blockIdx.x strides the job's output
+// all convolutions' weights packed in ONE launch. Blocks are dealt to jobs in proportion to their size
+// (blk_begin / blk_count, filled in by the host); a block finds its job by binary search.
 struct PackJob {
   const float* w;
   __nv_bfloat16* dst;
   int Cout, Cin, RS, pad, row_ld, mode;   // mode 0: forward operand (pad = cin_pad), 1: dgrad operand (pad = cout_pad)
+  int blk_begin, blk_count;               // this job owns blocks [blk_begin, blk_begin + blk_count)
 };
 __global__ void __launch_bounds__(kT)
-pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
-  const PackJob j = jobs[blockIdx.y];
-  const int64_t stride = (int64_t)gridDim.x * kT;
-  if (j.mode == 0) {
+pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
+  // Both packings are transposes of small matrices, staged through shared memory so that the fp32 reads AND the
+  // bf16 writes are coalesced (the source is [Cout][Cin][RS] with RS innermost).
+  __shared__ float tile[64 * 65];
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const int lb = (int)blockIdx.x - j.blk_begin, nb = j.blk_count;
+  if (lb >= nb) return;
+  const int tid = threadIdx.x;
+  if (j.mode == 0 && j.RS == 1 && (j.Cin & 7) == 0) {
+    // 1x1 forward operand: dst[o][c] = w[o][c], zero padded to `pad` channels: 8 elements per thread
+    const int vec_per_row = j.pad >> 3;
+    const int64_t total = (int64_t)j.Cout * vec_per_row;
+    for (int64_t i = (int64_t)lb * kT + tid; i < total; i += (int64_t)nb * kT) {
+      const int o = (int)(i / vec_per_row), c = (int)(i - (int64_t)o * vec_per_row) << 3;
+      F8 f;
+      if (c < j.Cin) {
+        const float4 a = *reinterpret_cast<const float4*>(j.w + (int64_t)o * j.Cin + c);
+        const float4 b2 = *reinterpret_cast<const float4*>(j.w + (int64_t)o * j.Cin + c + 4);
+        f.v[0] = a.x; f.v[1] = a.y; f.v[2] = a.z; f.v[3] = a.w; f.v[4] = b2.x; f.v[5] = b2.y; f.v[6] = b2.z; f.v[7] = b2.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) f.v[k] = 0.f;
+      }
+      store8(j.dst + (int64_t)o * j.row_ld + c, f);
+    }
+  } else if (j.mode == 0 && j.pad >= 64 && j.RS <= 16) {
+    // k x k forward operand: dst[o][t][c] <- w[o][c][t]. unit = (o, 256-channel chunk): RS*256 contiguous floats in
+    // (every thread has RS independent loads in flight), RS rows of 256 bf16 out, 8 channels per store.
+    const int RS = j.RS;
+    const int cchunks = (j.pad + 255) >> 8;
+    const int units = j.Cout * cchunks;
+    for (int u = lb; u < units; u += nb) {
+      const int o = u / cchunks, c0 = (u - o * cchunks) << 8;
+      const int ncp = min(256, j.pad - c0);               // padded channels of this chunk (multiple of 64)
+      const int nc = max(0, min(256, j.Cin - c0));        // valid channels
+      const float* src = j.w + ((int64_t)o * j.Cin + c0) * RS;
+      __syncthreads();
+      for (int i = tid; i < nc * RS; i += kT) tile[i] = src[i];          // tile[c*RS + t]
+      __syncthreads();
+      const int vecs = ncp >> 3;
+      for (int i = tid; i < RS * vecs; i += kT) {
+        const int t = i / vecs, c = (i - t * vecs) << 3;
+        F8 f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) f.v[k] = (c + k < nc) ? tile[(c + k) * RS + t] : 0.f;
+        store8(j.dst + (int64_t)o * j.row_ld + (int64_t)t * j.pad + c0 + c, f);
+      }
+    }
+  } else if (j.mode == 0) {
+    // anything else (the stem: pad = Cin = 3, RS = 49): element-wise
     const int64_t total = (int64_t)j.Cout * j.row_ld;
-    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += stride) {
+    for (int64_t i = (int64_t)lb * kT + tid; i < total; i += (int64_t)nb * kT) {
       const int o = (int)(i / j.row_ld), k = (int)(i % j.row_ld);
       const int t = k / j.pad, c = k % j.pad;
       float v = 0.f;
@@ -103,14 +156,30 @@ pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
       j.dst[i] = __float2bfloat16_rn(v);
     }
   } else {
-    const int64_t total = (int64_t)j.Cin * j.RS * j.pad;
-    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += stride) {
-      const int o = (int)(i % j.pad);
-      const int t = (int)((i / j.pad) % j.RS);
-      const int c = (int)(i / ((int64_t)j.pad * j.RS));
-      float v = 0.f;
-      if (o < j.Cout) v = j.w[((int64_t)o * j.Cin + c) * j.RS + t];
-      j.dst[i] = __float2bfloat16_rn(v);
+    // dgrad operand: dst[f][o] (f = c*RS + t, o padded to `pad`) <- w[o][f]: a [Cout x F] -> [F x pad] transpose,
+    // 64 x 64 tiles; writes are 8 output channels (16 bytes) per thread
+    const int F = j.Cin * j.RS;
+    const int ftiles = (F + 63) >> 6, otiles = j.pad >> 6;
+    const int units = ftiles * otiles;
+    for (int u = lb; u < units; u += nb) {
+      const int ot = u / ftiles, ft = u - ot * ftiles;
+      const int o0 = ot << 6, f0 = ft << 6;
+      __syncthreads();
+#pragma unroll 4
+      for (int i = tid; i < 64 * 64; i += kT) {
+        const int o = i >> 6, f = i & 63;
+        tile[o * 65 + f] = (o0 + o < j.Cout && f0 + f < F) ? j.w[(int64_t)(o0 + o) * F + f0 + f] : 0.f;
+      }
+      __syncthreads();
+      for (int i = tid; i < 64 * 8; i += kT) {
+        const int f = i >> 3, o = (i & 7) << 3;
+        if (f0 + f < F) {
+          F8 v;
+#pragma unroll
+          for (int k = 0; k < 8; k++) v.v[k] = tile[(o + k) * 65 + f];
+          store8(j.dst + (int64_t)(f0 + f) * j.pad + o0 + o, v);
+        }
+      }
     }
   }
 }
@@ -360,32 +429,55 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
 }
 
 // ---------------------------------------------------------------------------
-// stem im2col: NCHW fp32 image -> [B*Ho*Wo][Kpad] bf16, col = (r*7+s)*Cin + c
+// stem im2col: NCHW fp32 image -> [B*Ho*Wo][Kpad] bf16, col = (r*7+s)*Cin + c.
+// One block per (image, output row, 64-pixel strip): the 7-row input patch is staged in shared memory with
+// coalesced reads along W, then every thread emits 16-byte chunks of consecutive output rows.
+constexpr int kStemStrip = 64;
+constexpr int kStemPatchW = 2 * kStemStrip + 5;           // 133 input columns feed 64 stride-2 outputs
 __global__ void __launch_bounds__(kT)
 stem_im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int Ho, int Wo,
                    int Kpad, __nv_bfloat16* __restrict__ out) {
-  const int koct = Kpad >> 3;
-  const int64_t total = (int64_t)B * Ho * Wo * koct;
+  extern __shared__ float patch[];                          // [Cin][7][kStemPatchW + 1]
+  constexpr int PW = kStemPatchW + 1;
+  const int strips = (Wo + kStemStrip - 1) / kStemStrip;
+  const int wo0 = (blockIdx.x % strips) * kStemStrip;
+  const int ho = (blockIdx.x / strips) % Ho;
+  const int b = blockIdx.x / (strips * Ho);
+  const int wi0 = 2 * wo0 - 3, hi0 = 2 * ho - 3;
+  for (int i = threadIdx.x; i < Cin * 7 * kStemPatchW; i += kT) {
+    const int col = i % kStemPatchW, rc = i / kStemPatchW;
+    const int r = rc % 7, c = rc / 7;
+    const int hi = hi0 + r, wi = wi0 + col;
+    float v = 0.f;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(img + (((int64_t)b * Cin + c) * H + hi) * W + wi);
+    patch[(c * 7 + r) * PW + col] = v;
+  }
+  // column k of the im2col row -> offset of its tap inside the patch (-1: zero padding of K up to Kpad)
+  __shared__ int koff[256];
   const int K = 49 * Cin;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int ko = (int)(i % koct);
-    const int64_t m = i / koct;
-    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+  for (int k = threadIdx.x; k < Kpad; k += kT) {
+    int off = -1;
+    if (k < K) {
+      const int t = k / Cin, c = k - t * Cin;
+      const int r = t / 7, sx = t - r * 7;
+      off = (c * 7 + r) * PW + sx;
+    }
+    koff[k] = off;
+  }
+  __syncthreads();
+  const int koct = Kpad >> 3;
+  const int npx = min(kStemStrip, Wo - wo0);
+  const int64_t m0 = ((int64_t)b * Ho + ho) * Wo + wo0;
+  for (int i = threadIdx.x; i < npx * koct; i += kT) {
+    const int px = i / koct, ko = i - px * koct;
+    const float* pp = patch + 2 * px;
     F8 f;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int k = ko * 8 + j;
-      float v = 0.f;
-      if (k < K) {
-        const int c = k % Cin, t = k / Cin;
-        const int r = t / 7, s = t % 7;
-        const int hi = 2 * ho + r - 3, wi = 2 * wo + s - 3;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-          v = __ldg(img + (((int64_t)b * Cin + c) * H + hi) * W + wi);
-      }
-      f.v[j] = v;
+    for (int jj = 0; jj < 8; jj++) {
+      const int off = koff[ko * 8 + jj];
+      f.v[jj] = off >= 0 ? pp[off] : 0.f;
     }
-    store8(out + m * Kpad + ko * 8, f);
+    store8(out + (m0 + px) * Kpad + ko * 8, f);
   }
 }
 
@@ -428,41 +520,67 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
     }
   }
 }
+// Each thread owns a 2x2 block of input pixels (8 channels): the only windows that can have selected them are
+// (ho, wo) in {i, i+1} x {j, j+1}, loaded once each (row 2i belongs to window row i as r=1, row 2i+1 to window
+// row i as r=2 and to window row i+1 as r=0; columns alike).
 __global__ void __launch_bounds__(kT)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx, int B,
                    int H, int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
   const int nvec = C >> 3;
-  const int64_t total = (int64_t)B * H * W * nvec;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int cg = (int)(i % nvec);
-    const int64_t m = i / nvec;
-    const int wi = (int)(m % W), hi = (int)((m / W) % H), b = (int)(m / ((int64_t)W * H));
-    F8 acc;
+  const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
+  const int64_t total = (int64_t)B * Hb * Wb * nvec;
+  for (int64_t it = (int64_t)blockIdx.x * kT + threadIdx.x; it < total; it += (int64_t)gridDim.x * kT) {
+    const int cg = (int)(it % nvec);
+    const int64_t m = it / nvec;
+    const int j = (int)(m % Wb), i = (int)((m / Wb) % Hb), b = (int)(m / ((int64_t)Wb * Hb));
+    float acc[2][2][8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc.v[j] = 0.f;
-    // output windows containing (hi, wi): ho in {floor((hi+1)/2) - ?}: 2*ho + r - 1 == hi, r in 0..2
-    for (int r = 0; r < 3; r++) {
-      const int hnum = hi + 1 - r;
-      if (hnum < 0 || (hnum & 1)) continue;
-      const int ho = hnum >> 1;
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[a][c][k] = 0.f;
+#pragma unroll
+    for (int dho = 0; dho < 2; dho++) {
+      const int ho = i + dho;
       if (ho >= Ho) continue;
-      for (int s = 0; s < 3; s++) {
-        const int wnum = wi + 1 - s;
-        if (wnum < 0 || (wnum & 1)) continue;
-        const int wo = wnum >> 1;
+#pragma unroll
+      for (int dwo = 0; dwo < 2; dwo++) {
+        const int wo = j + dwo;
         if (wo >= Wo) continue;
         const int64_t om = ((int64_t)b * Ho + ho) * Wo + wo;
         const uint2 pk = *reinterpret_cast<const uint2*>(idx + om * C + cg * 8);
         const F8 g = load8(dout + om * C + cg * 8);
-        const int code = r * 3 + s;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int a = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
-          if (a == code) acc.v[j] += g.v[j];
+        for (int dy = dho; dy < 2; dy++) {                 // window row i+1 reaches only block row 1 (as r = 0)
+          const int r = dho ? 0 : 1 + dy;
+#pragma unroll
+          for (int dxx = dwo; dxx < 2; dxx++) {
+            const int sx = dwo ? 0 : 1 + dxx;
+            const int code = r * 3 + sx;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xff;
+              if (a == code) acc[dy][dxx][k] += g.v[k];
+            }
+          }
         }
       }
     }
-    store8(dx + m * C + cg * 8, acc);
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+      const int hi = 2 * i + dy;
+      if (hi >= H) continue;
+#pragma unroll
+      for (int dxx = 0; dxx < 2; dxx++) {
+        const int wi = 2 * j + dxx;
+        if (wi >= W) continue;
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.v[k] = acc[dy][dxx][k];
+        store8(dx + (((int64_t)b * H + hi) * W + wi) * C + cg * 8, o);
+      }
+    }
   }
 }
 
@@ -863,11 +981,13 @@ static void bn_red_shape(int C, int& nx, int& ny) {
   nx = std::min(nvec, kT);
   ny = std::max(1, kT / nx);
 }
-// rows per block so that every thread walks >= rows_per_thread rows, capped at 8 blocks per SM
-static void bn_row_grid(int C, int64_t M, int rows_per_thread, int& nx, int& ny, int& rows_per_block, int& blocks) {
+// rows per block: every thread walks >= min_rows rows (amortises the per-channel constant setup), but small
+// tensors still get several blocks per SM (the kernels are latency-bound below ~4 resident blocks per SM);
+// capped at 6 blocks per SM
+static void bn_row_grid(int C, int64_t M, int min_rows, int& nx, int& ny, int& rows_per_block, int& blocks) {
   bn_red_shape(C, nx, ny);
-  int64_t want = (M + (int64_t)ny * rows_per_thread - 1) / ((int64_t)ny * rows_per_thread);
-  want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * 8));
+  int64_t want = (M + (int64_t)ny * min_rows - 1) / ((int64_t)ny * min_rows);
+  want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * 6));
   rows_per_block = (int)((M + want - 1) / want);
   blocks = (int)((M + rows_per_block - 1) / rows_per_block);
 }
@@ -883,7 +1003,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_sta
   ISWM_REQUIRE(!d_res || (res_ld % 8) == 0, "bn_train_apply: res_ld");
   ISWM_REQUIRE(C <= 2048, "bn_train_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
-  bn_row_grid(C, M, 16, nx, ny, rpb, blocks);
+  bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
   bn_train_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
       BF(d_x), x_ld, d_stats, M, C, d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var,
       reinterpret_cast<long long*>(d_nbt), d_save_mean, d_save_invstd, BF(d_res), res_ld, relu,
@@ -909,7 +1029,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
                "bn_bwd_reduce: relu needs the activation (or gamma and beta to recompute the mask)");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny, rows_per_block, blocks;
-  bn_row_grid(C, M, 16, nx, ny, rows_per_block, blocks);
+  bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks);
   bn_bwd_reduce_kernel<<<blocks, kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
                                                       M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, relu, drop_p,
                                                       drop_seed, d_sums, nx, ny, rows_per_block);
@@ -928,7 +1048,7 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd_apply: dz_ld");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
-  bn_row_grid(C, M, 8, nx, ny, rpb, blocks);
+  bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
   bn_bwd_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
       BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean,
       d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta,
@@ -938,8 +1058,17 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
 
 extern "C" int iswm_stem_im2col(const float* d_img, int B, int Cin, int H, int W, int Ho, int Wo,
                                 int Kpad, void* d_out, void* stream) {
-  ISWM_REQUIRE(d_img && d_out && (Kpad % 8) == 0 && Kpad >= 49 * Cin, "stem_im2col: bad args");
-  stem_im2col_kernel<<<grid_for((int64_t)B * Ho * Wo * (Kpad / 8)), kT, 0, ST(stream)>>>(d_img, B, Cin, H, W, Ho, Wo, Kpad, BFW(d_out));
+  ISWM_REQUIRE(d_img && d_out && (Kpad % 8) == 0 && Kpad >= 49 * Cin && Kpad <= 256, "stem_im2col: bad args (Kpad %% 8 == 0, 49*Cin <= Kpad <= 256)");
+  ISWM_REQUIRE(Cin >= 1 && Cin <= 5, "stem_im2col: Cin=%d (1..5 supported)", Cin);
+  const int strips = (Wo + kStemStrip - 1) / kStemStrip;
+  const int64_t blocks = (int64_t)B * Ho * strips;
+  ISWM_REQUIRE(blocks < (1ll << 31), "stem_im2col: too many blocks");
+  const size_t smem = (size_t)Cin * 7 * (kStemPatchW + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ISWM_REQUIRE(e == cudaSuccess, "stem_im2col: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  stem_im2col_kernel<<<(unsigned)blocks, kT, smem, ST(stream)>>>(d_img, B, Cin, H, W, Ho, Wo, Kpad, BFW(d_out));
   return check_launch("stem_im2col");
 }
 extern "C" int iswm_maxpool_fwd(const void* d_x, int B, int H, int W, int C, int Ho, int Wo,
@@ -953,7 +1082,7 @@ extern "C" int iswm_maxpool_bwd(const void* d_dout, const uint8_t* d_idx, int B,
                                 int Ho, int Wo, void* d_dx, void* stream) {
   REQ_C8(C, "maxpool_bwd");
   ISWM_REQUIRE(d_dout && d_idx && d_dx, "maxpool_bwd: null");
-  maxpool_bwd_kernel<<<grid_for((int64_t)B * H * W * (C / 8)), kT, 0, ST(stream)>>>(BF(d_dout), d_idx, B, H, W, C, Ho, Wo, BFW(d_dx));
+  maxpool_bwd_kernel<<<grid_for((int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), kT, 16), kT, 0, ST(stream)>>>(BF(d_dout), d_idx, B, H, W, C, Ho, Wo, BFW(d_dx));
   return check_launch("maxpool_bwd");
 }
 
@@ -1079,10 +1208,9 @@ extern "C" int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, cons
   return check_launch("scale_by_device_scalar");
 }
 
-extern "C" int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, void* stream) {
-  static_assert(sizeof(PackJob) == 40, "PackJob layout is part of the C ABI (iswm_pack_job)");
-  ISWM_REQUIRE(d_jobs && n_jobs >= 1 && n_jobs <= 65535, "pack_weights_batched: bad args");
-  dim3 grid(96, n_jobs);
-  pack_weights_batched_kernel<<<grid, kT, 0, ST(stream)>>>(static_cast<const PackJob*>(d_jobs));
+extern "C" int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int total_blocks, void* stream) {
+  static_assert(sizeof(PackJob) == 48, "PackJob layout is part of the C ABI (iswm_pack_job)");
+  ISWM_REQUIRE(d_jobs && n_jobs >= 1 && total_blocks >= 1, "pack_weights_batched: bad args");
+  pack_weights_batched_kernel<<<total_blocks, kT, 0, ST(stream)>>>(static_cast<const PackJob*>(d_jobs), n_jobs);
   return check_launch("pack_weights_batched");
 }

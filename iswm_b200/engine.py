@@ -169,14 +169,12 @@ class Engine:
                     if s.packed_dgrad is None or s.packed_dgrad.numel() != n or s.packed_dgrad.device != w.device:
                         s.packed_dgrad = torch.empty(n, dtype=torch.bfloat16, device=w.device)
                     jobs.append((w.data_ptr(), s.packed_dgrad.data_ptr(), Cout, Cin, RS, cout_pad, 0, 1))
-            arr = (_lib.PackJob * len(jobs))()
-            for i, j in enumerate(jobs):
-                arr[i].w, arr[i].dst, arr[i].Cout, arr[i].Cin, arr[i].RS, arr[i].pad, arr[i].row_ld, arr[i].mode = j
+            arr, self._pack_blocks = _lib.fill_pack_jobs(jobs)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
             self._pack_jobs = host.to(self.device)
             self._pack_njobs = len(jobs)
             self._pack_sig = sig
-        check(_lib.lib().iswm_pack_weights_batched(self._pack_jobs.data_ptr(), self._pack_njobs, _st()), "pack_weights_batched")
+        check(_lib.lib().iswm_pack_weights_batched(self._pack_jobs.data_ptr(), self._pack_njobs, self._pack_blocks, _st()), "pack_weights_batched")
         for s in self.specs:
             w = s.conv.weight
             s.version = (w._version, self.weights_epoch, w.data_ptr())

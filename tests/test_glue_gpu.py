@@ -216,6 +216,54 @@ def test_stem_im2col_and_pack():
     assert torch.count_nonzero(col[:, 147:]).item() == 0
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 200, 200), (2, 65, 301)])
+def test_stem_im2col_strips_and_edges(B, H, W):
+    """several 64-pixel strips per row, ragged last strip, odd sizes: against unfold of the padded image."""
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn((B, 3, H, W), generator=g)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    col = torch.full((B * Ho * Wo, 160), 7.0, dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_stem_im2col(img.to(DEV).data_ptr(), B, 3, H, W, Ho, Wo, 160, col.data_ptr(), st()))
+    unf = F.unfold(img, kernel_size=7, padding=3, stride=2)            # [B, 3*49, Ho*Wo], row = c*49 + t
+    ref = unf.view(B, 3, 49, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 147)   # col = t*3 + c
+    assert torch.equal(col[:, :147].cpu(), ref.to(torch.bfloat16))
+    assert torch.count_nonzero(col[:, 147:]).item() == 0
+
+
+def test_pack_weights_batched_matches_single_kernels():
+    """the smem-tiled batched packer must reproduce the element-wise packers bit for bit."""
+    import ctypes as C
+    from iswm_b200 import ops, _lib
+    g = torch.Generator().manual_seed(21)
+    shapes = [(64, 3, 7, 7, True), (64, 64, 1, 1, False), (256, 304, 3, 3, False), (48, 256, 1, 1, False),
+              (2, 256, 1, 1, False), (128, 128, 3, 3, False), (256, 1280, 1, 1, False), (72, 40, 3, 3, False)]
+    jobs, expect = [], []
+    keep = []
+    for (Cout, Cin, R, S, stem) in shapes:
+        w = (torch.randn((Cout, Cin, R, S), generator=g)).to(DEV)
+        keep.append(w)
+        RS = R * S
+        if stem:
+            cin_pad, row_ld = Cin, ((RS * Cin + 63) // 64) * 64
+        else:
+            cin_pad = ((Cin + 63) // 64) * 64
+            row_ld = RS * cin_pad
+        dst = torch.full((Cout * row_ld,), 3.0, dtype=torch.bfloat16, device=DEV)
+        jobs.append((w.data_ptr(), dst.data_ptr(), Cout, Cin, RS, cin_pad, row_ld, 0))
+        expect.append((dst, ops.pack_weight_fwd(w, stem=stem)))
+        if not stem:
+            cout_pad = ((Cout + 63) // 64) * 64
+            dst2 = torch.full((Cin * RS * cout_pad,), 3.0, dtype=torch.bfloat16, device=DEV)
+            jobs.append((w.data_ptr(), dst2.data_ptr(), Cout, Cin, RS, cout_pad, 0, 1))
+            expect.append((dst2, ops.pack_weight_dgrad(w)))
+    arr, nblk = _lib.fill_pack_jobs(jobs)
+    dj = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(DEV)
+    check(L().iswm_pack_weights_batched(dj.data_ptr(), len(jobs), nblk, st()))
+    torch.cuda.synchronize()
+    for i, (got, ref) in enumerate(expect):
+        assert torch.equal(got, ref), f"job {i} {jobs[i][2:]}"
+
+
 def test_sgd_step_matches_torch():
     g = torch.Generator().manual_seed(14)
     p0 = torch.randn(10007, generator=g)
