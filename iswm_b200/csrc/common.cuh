@@ -32,6 +32,31 @@ inline int check_launch(const char* what) {
     }                                      \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Kernels launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
+// of the stream may be scheduled (and run its prologue: barrier init, TMEM allocation, index setup) while this
+// one drains. Every such kernel calls pdl_wait() before its first access to global memory (it returns once the
+// preceding grid has completed and its writes are visible) and then pdl_launch() to let ITS successor queue up.
+// ISWM_PDL=0 in the environment turns the attribute off (plain stream order; the device calls become no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

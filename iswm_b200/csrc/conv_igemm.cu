@@ -105,65 +105,110 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM, descriptor prefetch touch no global data): wait for the producer grid, then let
+  // the next kernel of the stream start its own prologue under our main loop
+  pdl_wait();
+  pdl_launch();
 
   const int kblocks = p.ntaps * p.kchunks;
   const int BW = 1 << p.lgBW, BH = 1 << p.lgBH;
   const int BB = kTileM >> (p.lgBW + p.lgBH);
 
+  // The producer and MMA warps walk their schedules with ALL 32 lanes (warp-uniform control flow and operands, so
+  // descriptors / coordinates live in uniform registers) and elect one lane only for the issue instructions; a
+  // lane-0-only loop makes the compiler wrap every UTMALDG / UTCHMMA in a register->uniform "waterfall" loop,
+  // which costs more than a 128 x 64 x 16 MMA itself.
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h,
-                  tb = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB, n0 = nt * p.BN;
-        for (int t = 0; t < p.ntaps && ok; t++) {
-          const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
-          for (int kc = 0; kc < p.kchunks; kc++) {
-            if (!tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 1)) { ok = false; break; }
-            const uint32_t a_dst = ring + stage * stage_bytes;
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+#ifdef ISWM_EPI_TIMING
+    long long pw = 0, pt0 = clock64();
+#endif
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h,
+                tb = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB, n0 = nt * p.BN;
+      for (int t = 0; t < p.ntaps && ok; t++) {
+        const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
+        for (int kc = 0; kc < p.kchunks; kc++) {
+#ifdef ISWM_EPI_TIMING
+          const long long w0c = clock64();
+#endif
+          ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 1) ? 1 : 0, 0) != 0;
+          if (!ok) break;
+#ifdef ISWM_EPI_TIMING
+          pw += clock64() - w0c;
+#endif
+          const uint32_t a_dst = ring + stage * stage_bytes;
+          if (tc::elect_one()) {
             tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
             tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, kc * kKBlock, cw, ch, cb);
             tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage,
                             t * p.cin_pad + kc * kKBlock, n0);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
+#ifdef ISWM_EPI_TIMING
+    if (blockIdx.x == 0 && lane == 0) printf("producer: total %lld  waiting for a free stage %lld  (stages %d, kblocks/tile %d)\n", clock64() - pt0, pw, p.stages, kblocks);
+#endif
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 0, 0);
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-        if (!tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 2)) break;
+    const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 0, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    bool ok = true;
+#ifdef ISWM_EPI_TIMING
+    long long mw_acc = 0, mw_full = 0, mt0 = clock64();
+#endif
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+#ifdef ISWM_EPI_TIMING
+      long long c0 = clock64();
+#endif
+      ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 2) ? 1 : 0, 0) != 0;
+      if (!ok) break;
+      tc::tc_fence_after();
+#ifdef ISWM_EPI_TIMING
+      mw_acc += clock64() - c0;
+#endif
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * p.BN);
+      for (int kb = 0; kb < kblocks; kb++) {
+#ifdef ISWM_EPI_TIMING
+        c0 = clock64();
+#endif
+        ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 3) ? 1 : 0, 0) != 0;
+        if (!ok) break;
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-        for (int kb = 0; kb < kblocks; kb++) {
-          if (!tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 3)) { ok = false; break; }
-          tc::tc_fence_after();
-          const uint32_t a_addr = ring + stage * stage_bytes;
-          const uint64_t da = tc::make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db = tc::make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#ifdef ISWM_EPI_TIMING
+        mw_full += clock64() - c0;
+#endif
+        const uint32_t a_addr = ring + stage * stage_bytes;
+        const uint64_t da = tc::make_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t db = tc::make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+        if (tc::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kKBlock / 16; k++)
             tc::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           tc::umma_commit(bar_empty + 8 * stage);     // frees this smem stage when the MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (!ok) break;
-        tc::umma_commit(bar_tfull + 8 * as);          // accumulator complete -> epilogue
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (!ok) break;
+      if (tc::elect_one()) tc::umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
+#ifdef ISWM_EPI_TIMING
+    if (blockIdx.x == 0 && lane == 0) printf("mma: total %lld  waiting for operands %lld  waiting for a free accumulator %lld\n", clock64() - mt0, mw_full, mw_acc);
+#endif
   } else if (warp >= 4) {
     // ===================== epilogue: two warpgroups, 64-channel chunks alternate between them =====================
     const int wg = (warp - 4) >> 2;                     // warpgroup 0 / 1
@@ -478,6 +523,6 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, num_sms());
-  conv_igemm_kernel<<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, tmap_out, p);
+  launch_k(conv_igemm_kernel, dim3(grid), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), tmap_a, tmap_b, tmap_out, p);
   return check_launch("conv_igemm");
 }

@@ -83,6 +83,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM, descriptor prefetch touch no global data): wait for the producer grid, then let
+  // the next kernel of the stream start its own prologue under our main loop
+  pdl_wait();
+  pdl_launch();
 
   const int BW = 1 << p.lgBW, BH = 1 << p.lgBH;
   const int BB = kPixBlock >> (p.lgBW + p.lgBH);
@@ -108,69 +112,78 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
     range_hi = min(range_lo + p.kblocks_per_cta, p.total_kblocks);
   }
 
+  // producer / MMA warps: warp-uniform loops, one elected lane issues (see conv_igemm.cu)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (long long cur = range_lo; cur < range_hi && ok;) {
-        const int tile = (int)(cur / p.pix_blocks);
-        const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
-        const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
-        int mt, tap, nt;
-        decode(tile, mt, tap, nt);
-        const int m0 = mt * kWTileM, n0 = nt * p.BN;
-        for (int pb = pb0; pb < pb1; pb++) {
-          const int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h,
-                    tb = pb / (p.tiles_w * p.tiles_h);
-          const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB;
-          if (!tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 11)) { ok = false; break; }
-          const uint32_t dst = ring + stage * stage_bytes;
-          const uint32_t bar = bar_full + 8 * stage;
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (long long cur = range_lo; cur < range_hi && ok;) {
+      const int tile = (int)(cur / p.pix_blocks);
+      const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+      const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+      int mt, tap, nt;
+      decode(tile, mt, tap, nt);
+      const int m0 = mt * kWTileM, n0 = nt * p.BN;
+      for (int pb = pb0; pb < pb1; pb++) {
+        const int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h,
+                  tb = pb / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB;
+        ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 11) ? 1 : 0, 0) != 0;
+        if (!ok) break;
+        const uint32_t dst = ring + stage * stage_bytes;
+        const uint32_t bar = bar_full + 8 * stage;
+        const int xw = w0 + p.dw[tap], xh = h0 + p.dh[tap],
+                  xb = p.phase[tap] * p.n_img_per_phase + b0;
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(bar, stage_bytes);
           tc::tma_load_4d(dst, &tmap_dy, bar, m0, w0, h0, b0);
           tc::tma_load_4d(dst + kChunkBytes, &tmap_dy, bar, m0 + 64, w0, h0, b0);
-          const int xw = w0 + p.dw[tap], xh = h0 + p.dh[tap],
-                    xb = p.phase[tap] * p.n_img_per_phase + b0;
           for (int j = 0; j < p.nchunks_b; j++)
             tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, n0 + 64 * j, xw, xh, xb);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        cur += pb1 - pb0;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      cur += pb1 - pb0;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(kWTileM, p.BN, 1, 1);   // both operands MN-major
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      bool ok = true;
-      for (long long cur = range_lo; cur < range_hi && ok;) {
-        const int tile = (int)(cur / p.pix_blocks);
-        const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
-        const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
-        if (!tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 12)) break;
+    const uint32_t idesc = tc::make_idesc_bf16(kWTileM, p.BN, 1, 1);   // both operands MN-major
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    bool ok = true;
+    for (long long cur = range_lo; cur < range_hi && ok;) {
+      const int tile = (int)(cur / p.pix_blocks);
+      const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+      const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+      ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 12) ? 1 : 0, 0) != 0;
+      if (!ok) break;
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * p.BN);
+      for (int pb = pb0; pb < pb1; pb++) {
+        ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 13) ? 1 : 0, 0) != 0;
+        if (!ok) break;
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-        for (int pb = pb0; pb < pb1; pb++) {
-          if (!tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 13)) { ok = false; break; }
-          tc::tc_fence_after();
-          const uint32_t a_addr = ring + stage * stage_bytes;
-          // MN-major SW128: LBO = byte stride between 64-channel chunks, SBO = 8 pixel rows
-          const uint64_t da = tc::make_smem_desc_sw128(a_addr, kChunkBytes, 1024);
-          const uint64_t db = tc::make_smem_desc_sw128(a_addr + a_bytes, kChunkBytes, 1024);
+        const uint32_t a_addr = ring + stage * stage_bytes;
+        // MN-major SW128: LBO = byte stride between 64-channel chunks, SBO = 8 pixel rows
+        const uint64_t da = tc::make_smem_desc_sw128(a_addr, kChunkBytes, 1024);
+        const uint64_t db = tc::make_smem_desc_sw128(a_addr + a_bytes, kChunkBytes, 1024);
+        const uint32_t first = (pb > pb0) ? 1u : 0u;
+        if (tc::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kPixBlock / 16; k++)     // 16 pixel rows = 2048 bytes per MMA
-            tc::umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (pb > pb0) || (k > 0));
+            tc::umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, first | (uint32_t)(k > 0));
           tc::umma_commit(bar_empty + 8 * stage);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (!ok) break;
-        tc::umma_commit(bar_tfull + 8 * as);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-        cur += pb1 - pb0;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (!ok) break;
+      if (tc::elect_one()) tc::umma_commit(bar_tfull + 8 * as);
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+      cur += pb1 - pb0;
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -322,6 +335,6 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
     ISWM_REQUIRE(e == cudaSuccess, "conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_wgrad_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_dy, tmap_x, p);
+  launch_k(conv_wgrad_kernel, dim3(grid), dim3(256), smem_bytes, static_cast<cudaStream_t>(stream), tmap_dy, tmap_x, p);
   return check_launch("conv_wgrad");
 }

@@ -50,6 +50,8 @@ static inline int grid_for(int64_t work, int per_block = kT, int waves = 8) {
 // weight packing
 __global__ void pack_weight_fwd_kernel(const float* __restrict__ w, int Cout, int Cin, int RS,
                                        int cin_pad, int row_ld, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int64_t total = (int64_t)Cout * row_ld;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int o = (int)(i / row_ld), k = (int)(i % row_ld);
@@ -61,6 +63,8 @@ __global__ void pack_weight_fwd_kernel(const float* __restrict__ w, int Cout, in
 }
 __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int RS,
                                          int cout_pad, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int64_t total = (int64_t)Cin * RS * cout_pad;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int o = (int)(i % cout_pad);
@@ -73,6 +77,8 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int Cout, 
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int Cin, int RS,
                                     int cin_stride, int row_ld, float beta, float* __restrict__ g) {
+  pdl_wait();
+  pdl_launch();
   const int64_t total = (int64_t)Cout * Cin * RS;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int t = (int)(i % RS);
@@ -93,6 +99,8 @@ struct PackJob {
 };
 __global__ void __launch_bounds__(kT)
 pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
+  pdl_wait();
+  pdl_launch();
   // Both packings are transposes of small matrices, staged through shared memory so that the fp32 reads AND the
   // bf16 writes are coalesced (the source is [Cout][Cin][RS] with RS innermost).
   __shared__ float tile[64 * 65];
@@ -198,6 +206,8 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float
                       const __nv_bfloat16* __restrict__ res, int res_ld, int relu, float drop_p,
                       uint64_t drop_seed, __nv_bfloat16* __restrict__ out, int out_ld, int nx, int ny,
                       int rows_per_block) {
+  pdl_wait();
+  pdl_launch();
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
@@ -264,6 +274,8 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float
 
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean,
                                const float* var, float eps, int C, float* scale, float* shift) {
+  pdl_wait();
+  pdl_launch();
   const int c = blockIdx.x * kT + threadIdx.x;
   if (c < C) {
     const float sc = gamma[c] / sqrtf(var[c] + eps);
@@ -281,6 +293,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                      float drop_p, uint64_t drop_seed, float* __restrict__ sums, int nx, int ny,
                      int rows_per_block) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_red[kT * 16];
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
@@ -363,6 +377,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
                     __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta, int nx,
                     int ny, int rows_per_block) {
+  pdl_wait();
+  pdl_launch();
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
@@ -437,6 +453,8 @@ constexpr int kStemPatchW = 2 * kStemStrip + 5;           // 133 input columns f
 __global__ void __launch_bounds__(kT)
 stem_im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int Ho, int Wo,
                    int Kpad, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float patch[];                          // [Cin][7][kStemPatchW + 1]
   constexpr int PW = kStemPatchW + 1;
   const int strips = (Wo + kStemStrip - 1) / kStemStrip;
@@ -486,6 +504,8 @@ stem_im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, 
 __global__ void __launch_bounds__(kT)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
                    __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const int64_t total = (int64_t)B * Ho * Wo * nvec;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -526,6 +546,8 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
 __global__ void __launch_bounds__(kT)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx, int B,
                    int H, int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
   const int64_t total = (int64_t)B * Hb * Wb * nvec;
@@ -589,6 +611,8 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __rest
 __global__ void __launch_bounds__(kT)
 reduce_hw_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int64_t HW, int C, float scale,
                  __nv_bfloat16* __restrict__ out, int nx, int ny) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_red[kT * 8];
   const int b = blockIdx.y;
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
@@ -622,6 +646,8 @@ reduce_hw_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int64_t HW, int 
 __global__ void __launch_bounds__(kT)
 broadcast_hw_kernel(const __nv_bfloat16* __restrict__ x, int B, int64_t HW, int C,
                     __nv_bfloat16* __restrict__ out, int out_ld, float scale, int accumulate) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const int64_t total = (int64_t)B * HW * nvec;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -656,6 +682,8 @@ __device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int
 __global__ void __launch_bounds__(kT)
 bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int Hi, int Wi, int C,
                     int Ho, int Wo, __nv_bfloat16* __restrict__ out, int out_ld) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const int64_t total = (int64_t)B * Ho * Wo * nvec;
@@ -691,6 +719,8 @@ __device__ __forceinline__ void bil_range(int i, float rscale, int out, int& lo,
 __global__ void __launch_bounds__(kT)
 bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, int Hi, int Wi,
                     int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, int dx_ld) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
@@ -730,6 +760,8 @@ bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, 
 __global__ void __launch_bounds__(kT)
 logits_up_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, int Ho, int Wo,
                      float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const int64_t total = (int64_t)B * Ho * Wo;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -754,6 +786,8 @@ logits_up_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, 
 __global__ void __launch_bounds__(kT)
 logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int C, int Ho, int Wo,
                      __nv_bfloat16* __restrict__ dx, int dx_ld) {
+  pdl_wait();
+  pdl_launch();
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
   const int64_t total = (int64_t)B * Hi * Wi * C;
@@ -792,6 +826,8 @@ logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int 
 __global__ void __launch_bounds__(kT)
 phase_split_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int H, int W, int C,
                    int Hp, int Wp, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const int64_t total = (int64_t)4 * B * Hp * Wp * nvec;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -815,6 +851,8 @@ phase_split_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int H, 
 __global__ void __launch_bounds__(kT)
 subsample2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int H, int W, int C,
                   int Ho, int Wo, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   const int64_t total = (int64_t)B * Ho * Wo * nvec;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -829,6 +867,8 @@ subsample2_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int H, i
 __global__ void __launch_bounds__(kT)
 stuff2_kernel(const __nv_bfloat16* __restrict__ x, int B, int Ho, int Wo, int C, int H, int W,
               __nv_bfloat16* __restrict__ out, int accumulate) {
+  pdl_wait();
+  pdl_launch();
   const int nvec = C >> 3;
   if (accumulate) {
     const int64_t total = (int64_t)B * Ho * Wo * nvec;
@@ -865,6 +905,8 @@ stuff2_kernel(const __nv_bfloat16* __restrict__ x, int B, int Ho, int Wo, int C,
 __global__ void __launch_bounds__(kT)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t nvec8,
                 __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nvec8; i += (int64_t)gridDim.x * kT) {
     F8 x = load8(a + i * 8);
     const F8 y = load8(b + i * 8);
@@ -878,6 +920,8 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(kT)
 nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int64_t HW, int C,
                         float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int64_t total = (int64_t)B * C * HW;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t p = i % HW;
@@ -889,6 +933,8 @@ nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, in
 __global__ void __launch_bounds__(kT)
 nchw_f32_to_nhwc_kernel(const float* __restrict__ x, int B, int64_t HW, int C,
                         __nv_bfloat16* __restrict__ out, int out_ld) {
+  pdl_wait();
+  pdl_launch();
   const int64_t total = (int64_t)B * HW * C;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
@@ -902,6 +948,8 @@ nchw_f32_to_nhwc_kernel(const float* __restrict__ x, int B, int64_t HW, int C,
 __global__ void __launch_bounds__(kT)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, int64_t n,
                 float lr, float momentum, float wd, int nesterov, int first) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
     float grad = g[i];
     const float w = p[i];
@@ -918,6 +966,8 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
 // per-channel sum of an NCHW fp32 tensor (classifier bias gradient): out[c] += sum_{b,p} d[b,c,p]
 __global__ void __launch_bounds__(kT)
 bias_grad_nchw_kernel(const float* __restrict__ d, int B, int C, int64_t HW, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_red[kT / 32];
   const int c = blockIdx.y;
   float acc = 0.f;
@@ -941,6 +991,8 @@ bias_grad_nchw_kernel(const float* __restrict__ d, int B, int C, int64_t HW, flo
 template <typename T>
 __global__ void __launch_bounds__(kT)
 scale_by_device_scalar_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ scalar) {
+  pdl_wait();
+  pdl_launch();
   const float s = *scalar;
   if (s == 1.0f) return;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT)
@@ -960,19 +1012,19 @@ using namespace iswm;
 extern "C" int iswm_pack_weight_fwd(const float* d_w, int Cout, int Cin, int RS, int cin_pad,
                                     int row_ld, void* d_out, void* stream) {
   ISWM_REQUIRE(d_w && d_out && cin_pad >= Cin && row_ld >= RS * cin_pad, "pack_weight_fwd: bad args");
-  pack_weight_fwd_kernel<<<grid_for((int64_t)Cout * row_ld), kT, 0, ST(stream)>>>(d_w, Cout, Cin, RS, cin_pad, row_ld, BFW(d_out));
+  launch_k(pack_weight_fwd_kernel, dim3(grid_for((int64_t)Cout * row_ld)), dim3(kT), 0, ST(stream), d_w, Cout, Cin, RS, cin_pad, row_ld, BFW(d_out));
   return check_launch("pack_weight_fwd");
 }
 extern "C" int iswm_pack_weight_dgrad(const float* d_w, int Cout, int Cin, int RS, int cout_pad,
                                       void* d_out, void* stream) {
   ISWM_REQUIRE(d_w && d_out && cout_pad >= Cout, "pack_weight_dgrad: bad args");
-  pack_weight_dgrad_kernel<<<grid_for((int64_t)Cin * RS * cout_pad), kT, 0, ST(stream)>>>(d_w, Cout, Cin, RS, cout_pad, BFW(d_out));
+  launch_k(pack_weight_dgrad_kernel, dim3(grid_for((int64_t)Cin * RS * cout_pad)), dim3(kT), 0, ST(stream), d_w, Cout, Cin, RS, cout_pad, BFW(d_out));
   return check_launch("pack_weight_dgrad");
 }
 extern "C" int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stride,
                                  int row_ld, float beta, float* d_grad_oihw, void* stream) {
   ISWM_REQUIRE(d_dw && d_grad_oihw, "unpack_wgrad: null");
-  unpack_wgrad_kernel<<<grid_for((int64_t)Cout * Cin * RS), kT, 0, ST(stream)>>>(d_dw, Cout, Cin, RS, cin_stride, row_ld, beta, d_grad_oihw);
+  launch_k(unpack_wgrad_kernel, dim3(grid_for((int64_t)Cout * Cin * RS)), dim3(kT), 0, ST(stream), d_dw, Cout, Cin, RS, cin_stride, row_ld, beta, d_grad_oihw);
   return check_launch("unpack_wgrad");
 }
 
@@ -1004,7 +1056,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_sta
   ISWM_REQUIRE(C <= 2048, "bn_train_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
-  bn_train_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
+  launch_k(bn_train_apply_kernel, dim3(blocks), dim3(kT), 0, ST(stream), 
       BF(d_x), x_ld, d_stats, M, C, d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var,
       reinterpret_cast<long long*>(d_nbt), d_save_mean, d_save_invstd, BF(d_res), res_ld, relu,
       drop_p, drop_seed, BFW(d_out), out_ld, nx, ny, rpb);
@@ -1014,7 +1066,7 @@ extern "C" int iswm_bn_fold(const float* d_gamma, const float* d_beta, const flo
                             const float* d_var, float eps, int C, float* d_scale, float* d_shift,
                             void* stream) {
   ISWM_REQUIRE(d_gamma && d_beta && d_mean && d_var && d_scale && d_shift && C > 0, "bn_fold: null");
-  bn_fold_kernel<<<(C + kT - 1) / kT, kT, 0, ST(stream)>>>(d_gamma, d_beta, d_mean, d_var, eps, C, d_scale, d_shift);
+  launch_k(bn_fold_kernel, dim3((C + kT - 1) / kT), dim3(kT), 0, ST(stream), d_gamma, d_beta, d_mean, d_var, eps, C, d_scale, d_shift);
   return check_launch("bn_fold");
 }
 
@@ -1030,7 +1082,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny, rows_per_block, blocks;
   bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks);
-  bn_bwd_reduce_kernel<<<blocks, kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
+  launch_k(bn_bwd_reduce_kernel, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
                                                       M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, relu, drop_p,
                                                       drop_seed, d_sums, nx, ny, rows_per_block);
   return check_launch("bn_bwd_reduce");
@@ -1049,7 +1101,7 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
-  bn_bwd_apply_kernel<<<blocks, kT, 0, ST(stream)>>>(
+  launch_k(bn_bwd_apply_kernel, dim3(blocks), dim3(kT), 0, ST(stream), 
       BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean,
       d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta,
       nx, ny, rpb);
@@ -1068,21 +1120,21 @@ extern "C" int iswm_stem_im2col(const float* d_img, int B, int Cin, int H, int W
     cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ISWM_REQUIRE(e == cudaSuccess, "stem_im2col: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  stem_im2col_kernel<<<(unsigned)blocks, kT, smem, ST(stream)>>>(d_img, B, Cin, H, W, Ho, Wo, Kpad, BFW(d_out));
+  launch_k(stem_im2col_kernel, dim3((unsigned)blocks), dim3(kT), smem, ST(stream), d_img, B, Cin, H, W, Ho, Wo, Kpad, BFW(d_out));
   return check_launch("stem_im2col");
 }
 extern "C" int iswm_maxpool_fwd(const void* d_x, int B, int H, int W, int C, int Ho, int Wo,
                                 void* d_out, uint8_t* d_idx, void* stream) {
   REQ_C8(C, "maxpool_fwd");
   ISWM_REQUIRE(d_x && d_out, "maxpool_fwd: null");
-  maxpool_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, H, W, C, Ho, Wo, BFW(d_out), d_idx);
+  launch_k(maxpool_fwd_kernel, dim3(grid_for((int64_t)B * Ho * Wo * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), B, H, W, C, Ho, Wo, BFW(d_out), d_idx);
   return check_launch("maxpool_fwd");
 }
 extern "C" int iswm_maxpool_bwd(const void* d_dout, const uint8_t* d_idx, int B, int H, int W, int C,
                                 int Ho, int Wo, void* d_dx, void* stream) {
   REQ_C8(C, "maxpool_bwd");
   ISWM_REQUIRE(d_dout && d_idx && d_dx, "maxpool_bwd: null");
-  maxpool_bwd_kernel<<<grid_for((int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), kT, 16), kT, 0, ST(stream)>>>(BF(d_dout), d_idx, B, H, W, C, Ho, Wo, BFW(d_dx));
+  launch_k(maxpool_bwd_kernel, dim3(grid_for((int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), kT, 16)), dim3(kT), 0, ST(stream), BF(d_dout), d_idx, B, H, W, C, Ho, Wo, BFW(d_dx));
   return check_launch("maxpool_bwd");
 }
 
@@ -1091,7 +1143,7 @@ static int launch_reduce_hw(const void* d_x, int x_ld, int B, int64_t HW, int C,
   const int nx = std::min(nvec, 16);
   const int ny = kT / nx;
   dim3 grid((nvec + nx - 1) / nx, B);
-  reduce_hw_kernel<<<grid, kT, 0, ST(stream)>>>(BF(d_x), x_ld, HW, C, scale, BFW(d_out), nx, ny);
+  launch_k(reduce_hw_kernel, dim3(grid), dim3(kT), 0, ST(stream), BF(d_x), x_ld, HW, C, scale, BFW(d_out), nx, ny);
   return check_launch("reduce_hw");
 }
 extern "C" int iswm_gap_fwd(const void* d_x, int x_ld, int B, int64_t HW, int C, void* d_out, void* stream) {
@@ -1107,86 +1159,86 @@ extern "C" int iswm_sum_hw(const void* d_x, int x_ld, int B, int64_t HW, int C, 
 extern "C" int iswm_broadcast_hw(const void* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream) {
   REQ_C8(C, "broadcast_hw"); REQ_LD8(out_ld, "broadcast_hw");
   ISWM_REQUIRE(d_x && d_out, "broadcast_hw: null");
-  broadcast_hw_kernel<<<grid_for((int64_t)B * HW * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, HW, C, BFW(d_out), out_ld, 1.f, 0);
+  launch_k(broadcast_hw_kernel, dim3(grid_for((int64_t)B * HW * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), B, HW, C, BFW(d_out), out_ld, 1.f, 0);
   return check_launch("broadcast_hw");
 }
 extern "C" int iswm_gap_bwd_add(const void* d_dpool, int B, int64_t HW, int C, void* d_dx, int dx_ld, void* stream) {
   REQ_C8(C, "gap_bwd_add"); REQ_LD8(dx_ld, "gap_bwd_add");
   ISWM_REQUIRE(d_dpool && d_dx && HW > 0, "gap_bwd_add: null/empty");
-  broadcast_hw_kernel<<<grid_for((int64_t)B * HW * (C / 8)), kT, 0, ST(stream)>>>(BF(d_dpool), B, HW, C, BFW(d_dx), dx_ld, 1.0f / (float)HW, 1);
+  launch_k(broadcast_hw_kernel, dim3(grid_for((int64_t)B * HW * (C / 8))), dim3(kT), 0, ST(stream), BF(d_dpool), B, HW, C, BFW(d_dx), dx_ld, 1.0f / (float)HW, 1);
   return check_launch("gap_bwd_add");
 }
 extern "C" int iswm_bilinear_fwd(const void* d_x, int x_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                  void* d_out, int out_ld, void* stream) {
   REQ_C8(C, "bilinear_fwd"); REQ_LD8(x_ld, "bilinear_fwd"); REQ_LD8(out_ld, "bilinear_fwd");
   ISWM_REQUIRE(d_x && d_out, "bilinear_fwd: null");
-  bilinear_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_out), out_ld);
+  launch_k(bilinear_fwd_kernel, dim3(grid_for((int64_t)B * Ho * Wo * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_out), out_ld);
   return check_launch("bilinear_fwd");
 }
 extern "C" int iswm_bilinear_bwd(const void* d_dout, int dout_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                  void* d_dx, int dx_ld, void* stream) {
   REQ_C8(C, "bilinear_bwd"); REQ_LD8(dout_ld, "bilinear_bwd"); REQ_LD8(dx_ld, "bilinear_bwd");
   ISWM_REQUIRE(d_dout && d_dx, "bilinear_bwd: null");
-  bilinear_bwd_kernel<<<grid_for((int64_t)B * Hi * Wi * (C / 8)), kT, 0, ST(stream)>>>(BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  launch_k(bilinear_bwd_kernel, dim3(grid_for((int64_t)B * Hi * Wi * (C / 8))), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
   return check_launch("bilinear_bwd");
 }
 extern "C" int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C, int Ho, int Wo, float* d_out, void* stream) {
   ISWM_REQUIRE(d_x && d_out && C >= 1, "logits_up_fwd: null");
-  logits_up_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo), kT, 0, ST(stream)>>>(d_x, B, Hi, Wi, C, Ho, Wo, d_out);
+  launch_k(logits_up_fwd_kernel, dim3(grid_for((int64_t)B * Ho * Wo)), dim3(kT), 0, ST(stream), d_x, B, Hi, Wi, C, Ho, Wo, d_out);
   return check_launch("logits_up_fwd");
 }
 extern "C" int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld, void* stream) {
   ISWM_REQUIRE(d_dout && d_dx && C >= 1 && dx_ld >= C, "logits_up_bwd: bad args");
-  logits_up_bwd_kernel<<<grid_for((int64_t)B * Hi * Wi * C), kT, 0, ST(stream)>>>(d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  launch_k(logits_up_bwd_kernel, dim3(grid_for((int64_t)B * Hi * Wi * C)), dim3(kT), 0, ST(stream), d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
   return check_launch("logits_up_bwd");
 }
 extern "C" int iswm_phase_split(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream) {
   REQ_C8(C, "phase_split"); REQ_LD8(x_ld, "phase_split");
   ISWM_REQUIRE(d_x && d_out, "phase_split: null");
   const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
-  phase_split_kernel<<<grid_for((int64_t)4 * B * Hp * Wp * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, H, W, C, Hp, Wp, BFW(d_out));
+  launch_k(phase_split_kernel, dim3(grid_for((int64_t)4 * B * Hp * Wp * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, H, W, C, Hp, Wp, BFW(d_out));
   return check_launch("phase_split");
 }
 extern "C" int iswm_subsample2(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream) {
   REQ_C8(C, "subsample2"); REQ_LD8(x_ld, "subsample2");
   ISWM_REQUIRE(d_x && d_out, "subsample2: null");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  subsample2_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, H, W, C, Ho, Wo, BFW(d_out));
+  launch_k(subsample2_kernel, dim3(grid_for((int64_t)B * Ho * Wo * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, H, W, C, Ho, Wo, BFW(d_out));
   return check_launch("subsample2");
 }
 extern "C" int iswm_zero_stuff2(const void* d_x, int B, int Ho, int Wo, int C, int H, int W, void* d_out, void* stream) {
   REQ_C8(C, "zero_stuff2");
   ISWM_REQUIRE(d_x && d_out, "zero_stuff2: null");
-  stuff2_kernel<<<grid_for((int64_t)B * H * W * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, Ho, Wo, C, H, W, BFW(d_out), 0);
+  launch_k(stuff2_kernel, dim3(grid_for((int64_t)B * H * W * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), B, Ho, Wo, C, H, W, BFW(d_out), 0);
   return check_launch("zero_stuff2");
 }
 extern "C" int iswm_scatter2_add(const void* d_x, int B, int Ho, int Wo, int C, int H, int W, void* d_inout, void* stream) {
   REQ_C8(C, "scatter2_add");
   ISWM_REQUIRE(d_x && d_inout, "scatter2_add: null");
-  stuff2_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8)), kT, 0, ST(stream)>>>(BF(d_x), B, Ho, Wo, C, H, W, BFW(d_inout), 1);
+  launch_k(stuff2_kernel, dim3(grid_for((int64_t)B * Ho * Wo * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), B, Ho, Wo, C, H, W, BFW(d_inout), 1);
   return check_launch("scatter2_add");
 }
 extern "C" int iswm_add_bf16(const void* d_a, const void* d_b, int64_t n, void* d_out, void* stream) {
   ISWM_REQUIRE(d_a && d_b && d_out && (n % 8) == 0, "add_bf16: n must be a multiple of 8");
   if (n == 0) return 0;
-  add_bf16_kernel<<<grid_for(n / 8), kT, 0, ST(stream)>>>(BF(d_a), BF(d_b), n / 8, BFW(d_out));
+  launch_k(add_bf16_kernel, dim3(grid_for(n / 8)), dim3(kT), 0, ST(stream), BF(d_a), BF(d_b), n / 8, BFW(d_out));
   return check_launch("add_bf16");
 }
 extern "C" int iswm_nhwc_to_nchw_f32(const void* d_x, int x_ld, int B, int64_t HW, int C, float* d_out, void* stream) {
   ISWM_REQUIRE(d_x && d_out, "nhwc_to_nchw_f32: null");
-  nhwc_to_nchw_f32_kernel<<<grid_for((int64_t)B * HW * C), kT, 0, ST(stream)>>>(BF(d_x), x_ld, B, HW, C, d_out);
+  launch_k(nhwc_to_nchw_f32_kernel, dim3(grid_for((int64_t)B * HW * C)), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, HW, C, d_out);
   return check_launch("nhwc_to_nchw_f32");
 }
 extern "C" int iswm_nchw_f32_to_nhwc(const float* d_x, int B, int64_t HW, int C, void* d_out, int out_ld, void* stream) {
   ISWM_REQUIRE(d_x && d_out, "nchw_f32_to_nhwc: null");
-  nchw_f32_to_nhwc_kernel<<<grid_for((int64_t)B * HW * C), kT, 0, ST(stream)>>>(d_x, B, HW, C, BFW(d_out), out_ld);
+  launch_k(nchw_f32_to_nhwc_kernel, dim3(grid_for((int64_t)B * HW * C)), dim3(kT), 0, ST(stream), d_x, B, HW, C, BFW(d_out), out_ld);
   return check_launch("nchw_f32_to_nhwc");
 }
 extern "C" int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr,
                              float momentum, float weight_decay, int nesterov, int first_step, void* stream) {
   ISWM_REQUIRE(d_param && d_grad && (momentum == 0.f || d_mom), "sgd_step: null");
   if (n == 0) return 0;
-  sgd_step_kernel<<<grid_for(n), kT, 0, ST(stream)>>>(d_param, d_grad, d_mom, n, lr, momentum, weight_decay, nesterov, first_step);
+  launch_k(sgd_step_kernel, dim3(grid_for(n)), dim3(kT), 0, ST(stream), d_param, d_grad, d_mom, n, lr, momentum, weight_decay, nesterov, first_step);
   return check_launch("sgd_step");
 }
 
@@ -1194,16 +1246,16 @@ extern "C" int iswm_bias_grad_nchw(const float* d_dout, int B, int C, int64_t HW
   ISWM_REQUIRE(d_dout && d_out && C >= 1, "bias_grad_nchw: null");
   if ((int64_t)B * HW == 0) return 0;
   dim3 grid(grid_for((int64_t)B * HW, kT * 8, 2), C);
-  bias_grad_nchw_kernel<<<grid, kT, 0, ST(stream)>>>(d_dout, B, C, HW, d_out);
+  launch_k(bias_grad_nchw_kernel, dim3(grid), dim3(kT), 0, ST(stream), d_dout, B, C, HW, d_out);
   return check_launch("bias_grad_nchw");
 }
 extern "C" int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, const float* d_scalar, void* stream) {
   ISWM_REQUIRE(d_x && d_scalar, "scale_by_device_scalar: null");
   if (n == 0) return 0;
   if (dtype == ISWM_F32)
-    scale_by_device_scalar_kernel<float><<<grid_for(n), kT, 0, ST(stream)>>>(static_cast<float*>(d_x), n, d_scalar);
+    launch_k(scale_by_device_scalar_kernel<float>, dim3(grid_for(n)), dim3(kT), 0, ST(stream), static_cast<float*>(d_x), n, d_scalar);
   else if (dtype == ISWM_BF16)
-    scale_by_device_scalar_kernel<__nv_bfloat16><<<grid_for(n), kT, 0, ST(stream)>>>(BFW(d_x), n, d_scalar);
+    launch_k(scale_by_device_scalar_kernel<__nv_bfloat16>, dim3(grid_for(n)), dim3(kT), 0, ST(stream), BFW(d_x), n, d_scalar);
   else { set_error("scale_by_device_scalar: bad dtype %d", dtype); return 2; }
   return check_launch("scale_by_device_scalar");
 }
@@ -1211,6 +1263,6 @@ extern "C" int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, cons
 extern "C" int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int total_blocks, void* stream) {
   static_assert(sizeof(PackJob) == 48, "PackJob layout is part of the C ABI (iswm_pack_job)");
   ISWM_REQUIRE(d_jobs && n_jobs >= 1 && total_blocks >= 1, "pack_weights_batched: bad args");
-  pack_weights_batched_kernel<<<total_blocks, kT, 0, ST(stream)>>>(static_cast<const PackJob*>(d_jobs), n_jobs);
+  launch_k(pack_weights_batched_kernel, dim3(total_blocks), dim3(kT), 0, ST(stream), static_cast<const PackJob*>(d_jobs), n_jobs);
   return check_launch("pack_weights_batched");
 }

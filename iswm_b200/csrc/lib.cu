@@ -2,6 +2,7 @@
 // launch counter, version.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace iswm {
 static thread_local char t_err[512] = "";
@@ -12,6 +13,13 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISWM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 }  // namespace iswm
 
