@@ -13,5 +13,5 @@ if [ -z "$2" ]; then
   $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -s 1700 -c 600 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 430 -c 3 -o gpurun_out/${tag}_prof_igemm $CMD > gpurun_out/${tag}_ncu2.log 2>&1
-  tail -2 gpurun_out/${tag}_ncu.log gpurun_out/${tag}_ncu2.log
+  tail -n 2 gpurun_out/${tag}_ncu.log; tail -n 2 gpurun_out/${tag}_ncu2.log
 fi
