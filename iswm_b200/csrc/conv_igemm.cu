@@ -44,6 +44,7 @@ struct ConvKParams {
   int n_img_per_phase;
   int out_ld, res_ld;
   int use_tma_out;               // bf16 output through smem staging + TMA store
+  int res_prefetch;              // residual rows prefetched into shared memory one chunk ahead (short-K convolutions)
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   void* out;
   const float* scale;
@@ -63,11 +64,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem = smem_raw + (ring - raw_addr);
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  // [ring stages][out staging: one 16K tile per epilogue warpgroup, if TMA out][barriers][scale, shift]
+  // [ring stages][out staging: one 16K tile per epilogue warpgroup, if TMA out][residual prefetch: same][barriers][scale, shift]
   const bool tma_out = p.use_tma_out != 0;
   uint32_t off = (uint32_t)p.stages * stage_bytes;
   const uint32_t obuf = ring + off;
   if (tma_out) off += 2 * kStageBuf;
+  const uint32_t rbuf = ring + off;                        // residual prefetch tile, one per epilogue warpgroup
+  if (p.res_prefetch) off += 2 * kStageBuf;
   uint8_t* tail = smem + off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[8] empty[8] tfull[2] tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
@@ -251,6 +254,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int j = 0; j < 4; j++) st[slot][j] = 0.f;
       }
     };
+    // Residual operand (eval-mode shortcut add, gradient accumulation): this thread's 128-byte row of the NEXT chunk
+    // is prefetched with cp.async into the warpgroup's residual tile while the current chunk is processed; only the
+    // issuing thread reads it back, so no barrier is involved.
+    const uint32_t rb_row = rbuf + (uint32_t)wg * kStageBuf + row_off;
+    const bool res_pf_ok = f_res && p.res_prefetch != 0;
+    auto chunk_owner_ok = [&](int tile_, int it_, int c_) -> bool {
+      if ((((nchunk64 == 1) ? it_ : c_) & 1) != wg) return false;
+      const int n0_ = (tile_ % p.tiles_n) * p.BN;
+      return n0_ + c_ * 64 < p.Cout;
+    };
+    // advance (tile_, it_, c_) to the next chunk this warpgroup owns; false when the CTA's schedule is exhausted
+    auto next_chunk = [&](int& tile_, int& it_, int& c_) -> bool {
+      c_++;
+      while (tile_ < p.total_tiles) {
+        for (; c_ < nchunk64; c_++)
+          if (chunk_owner_ok(tile_, it_, c_)) return true;
+        tile_ += gridDim.x; it_++; c_ = 0;
+      }
+      return false;
+    };
+    // issue the prefetch of chunk (tile_, c_); returns whether the vector path applies to it for this thread
+    auto prefetch_res = [&](int tile_, int c_) -> bool {
+      const int mt_ = tile_ / p.tiles_n, nt_ = tile_ - mt_ * p.tiles_n;
+      const int tw_ = mt_ % p.tiles_w, th_ = (mt_ / p.tiles_w) % p.tiles_h, tb_ = mt_ / (p.tiles_w * p.tiles_h);
+      const int w_ = tw_ * BW + ww, h_ = th_ * BH + hh, b_ = tb_ * BB + bb;
+      const int nc_ = nt_ * p.BN + c_ * 64;
+      const bool ok_ = (b_ < p.B) && (h_ < p.Ho) && (w_ < p.Wo) && min(p.BN - c_ * 64, p.Cout - nc_) >= 64;
+      if (ok_) {
+        const __nv_bfloat16* rp = p.res + (((size_t)b_ * p.Ho + h_) * p.Wo + w_) * (size_t)p.res_ld + nc_;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rb_row + ((((uint32_t)j) ^ sw) << 4)), "l"(rp + 8 * j) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return ok_;
+    };
+    int pf_tile = blockIdx.x, pf_it = 0, pf_c = -1;
+    bool pf_more = false, pf_vec = false;
+    if (res_pf_ok) {
+      pf_more = next_chunk(pf_tile, pf_it, pf_c);
+      if (pf_more) pf_vec = prefetch_res(pf_tile, pf_c);
+    }
     int as = 0, it = 0, cur_n0 = -1;
     uint32_t aphase = 0;
 #ifdef ISWM_EPI_TIMING
@@ -286,19 +331,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       TMARK(1)
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       for (int c64 = 0; c64 < nchunk64; c64++) {
-        if (((it * nchunk64 + c64) & 1) != wg) continue;
+        if ((((nchunk64 == 1) ? it : c64) & 1) != wg) continue;   // one chunk per tile: warpgroups alternate tiles
         const int nc = n0 + c64 * 64;                   // first output channel of this chunk
         if (nc >= p.Cout) continue;
         const int ncols = min(64, min(p.BN - c64 * 64, p.Cout - nc));
         uint32_t v[64];
         tc::tmem_ld64(t_row + c64 * 64, v);
-        // residual: this thread's row of the chunk is 128 contiguous bytes; issue the loads under the TMEM read
+        // residual: this thread's row of the chunk (128 contiguous bytes) was prefetched into shared memory
         uint4 rr[8];
-        const bool res_vec = f_res && valid && ncols == 64 && (p.res_ld & 7) == 0;
-        if (res_vec) {
+        const bool res_vec = res_pf_ok ? pf_vec : (f_res && valid && ncols == 64 && (p.res_ld & 7) == 0);
+        if (f_res && !res_pf_ok && res_vec) {             // long-K convolution: direct loads, issued under the TMEM read
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * (size_t)p.res_ld + nc);
 #pragma unroll
           for (int j = 0; j < 8; j++) rr[j] = rp[j];
+        }
+        if (res_pf_ok) {                                   // (pf_tile, pf_c) == (tile, c64) by construction
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          if (res_vec) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[j].x), "=r"(rr[j].y), "=r"(rr[j].z), "=r"(rr[j].w)
+                           : "r"(rb_row + ((((uint32_t)j) ^ sw) << 4)));
+          }
+          pf_more = next_chunk(pf_tile, pf_it, pf_c);      // the row is in registers: refill the tile for the next chunk
+          if (pf_more) pf_vec = prefetch_res(pf_tile, pf_c);
         }
         tc::tmem_ld_wait();
         TMARK(2)
@@ -465,7 +521,15 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   p.tiles_w = (Wo + BW - 1) / BW;
   p.tiles_h = (Ho + BH - 1) / BH;
   p.tiles_b = (B + BB - 1) / BB;
-  int BN = std::min(256, ((d->Cout + 15) / 16) * 16);
+  // N tile: one tile of ceil16(Cout) columns up to 256; above that equal tiles rounded up to the 64-channel store
+  // chunk (304 output channels -> 2 x 192 instead of 256 + 48-in-256: a quarter less MMA work)
+  int BN;
+  if (d->Cout <= 256) {
+    BN = ((d->Cout + 15) / 16) * 16;
+  } else {
+    const int nt = (d->Cout + 255) / 256;
+    BN = std::min(256, (((d->Cout + nt - 1) / nt + 63) / 64) * 64);
+  }
   p.BN = BN;
   p.tiles_n = (d->Cout + BN - 1) / BN;
   const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
@@ -482,6 +546,10 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   ISWM_REQUIRE(!(d->flags & ISWM_EPI_STATS) || p.use_tma_out, "conv_igemm: STATS needs a bf16 output with out_ld %% 8 == 0 and a 16-byte aligned base");
   int fixed = 1024 /*align*/ + 256 /*barriers*/ + ((d->flags & ISWM_EPI_AFFINE) ? 2048 : 0);
   if (p.use_tma_out) fixed += 2 * kStageBuf;
+  // epilogue-bound (short-K) convolutions hide the residual read behind a shared-memory prefetch; long-K ones keep
+  // the ring stage instead and load the residual directly under the TMEM read
+  p.res_prefetch = ((d->flags & ISWM_EPI_RESIDUAL) && (d->res_ld % 8) == 0 && d->ntaps * p.kchunks <= 16) ? 1 : 0;
+  if (p.res_prefetch) fixed += 2 * kStageBuf;
   p.stages = std::max(2, std::min(kMaxStages, (kSmemMax - fixed) / stage_bytes));
   p.flags = d->flags;
   p.n_img_per_phase = B;
