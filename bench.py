@@ -433,7 +433,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if args.workload == "predict":
         return run_predict(args, dev, world, rank, local)
     if args.workload == "lossmetric":
@@ -513,11 +514,13 @@ def run_ours(args):
         ms, ms_e2e = float(t[0]), float(t[1])
     # ---- roofline of the dominant kernel: one extra instrumented step (CUDA events around every launch)
     roof = None
+    # EVERY rank runs the instrumented step (it contains the data-parallel collectives); only rank 0 records events
+    eng = model.engine()
     if rank == 0:
-        eng = model.engine()
         eng.profile = []
-        step(x_dev, y_dev)
-        torch.cuda.synchronize()
+    step(x_dev, y_dev)
+    barrier()
+    if rank == 0:
         agg = {}
         detail = []
         for k, fl, a, b, tag in eng.profile:

@@ -132,10 +132,11 @@ typedef struct {
 /* d_in: bf16 activations; d_wgt: packed bf16 [Cout][ntaps][Cin_pad] (Cin_pad =
  * Cin rounded up to 64, zero padded) from iswm_pack_weight*; d_out bf16/fp32;
  * d_scale/d_shift float[Cout] (AFFINE); d_res bf16 (RESIDUAL); d_stats
- * float[2*Cout] accumulated (STATS). */
+ * double[2*Cout] accumulated (STATS): per-CTA partial sums are fp32 in a fixed order, the cross-CTA
+ * accumulation is fp64 atomics, so the fp32 mean / variance derived from them do not depend on CTA order. */
 int iswm_conv_igemm(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt,
                     void* d_out, const float* d_scale, const float* d_shift,
-                    const void* d_res, float* d_stats, void* stream);
+                    const void* d_res, double* d_stats, void* stream);
 
 /* Weight gradient: dW[n, t, c] += sum_{b,ho,wo} dy[b,ho,wo,n] * in[img(t,b), ho+dh[t], wo+dw[t], c]
  * desc as for the forward conv (Cout = channels of dy). d_dw: float [Cout][ntaps][Cin],
@@ -176,7 +177,7 @@ int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stri
  * (conv epilogue STATS) compute batch mean / biased var, write
  * out = [relu]( gamma*(x-mean)*invstd + beta [+ residual] ) with optional dropout,
  * save mean/invstd for backward, update running stats (momentum, unbiased var). */
-int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_stats, int64_t M, int C,
+int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,
                         const float* d_gamma, const float* d_beta, float eps, float momentum,
                         float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                         float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld, int relu,
@@ -194,13 +195,13 @@ int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_l
                        const void* d_out_act, int act_ld, int64_t M, int C,
                        const float* d_save_mean, const float* d_save_invstd,
                        const float* d_gamma, const float* d_beta, int relu,
-                       float drop_p, uint64_t drop_seed, float* d_sums, void* stream);
+                       float drop_p, uint64_t drop_seed, double* d_sums, void* stream);
 /* pass 2: dx = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); dgamma += , dbeta += ;
  * optionally writes dz (the pre-activation gradient, used by the residual identity path). */
 int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                       const void* d_out_act, int act_ld, int64_t M, int C,
                       const float* d_gamma, const float* d_beta, const float* d_save_mean,
-                      const float* d_save_invstd, const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                      const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed,
                       void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                       float* d_dgamma, float* d_dbeta, void* stream);
 

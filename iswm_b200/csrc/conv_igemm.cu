@@ -50,7 +50,7 @@ struct ConvKParams {
   const float* scale;
   const float* shift;
   const __nv_bfloat16* res;
-  float* stats;
+  double* stats;                 // fp64 accumulators: cross-CTA summation order no longer shows up in fp32 results
   int* abort_flag;
 };
 
@@ -236,23 +236,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int i = 0; i < 2; i++)
 #pragma unroll
       for (int j = 0; j < 4; j++) st[i][j] = 0.f;
+    // flush: the four quadrant warps of a warpgroup combine their partial sums through the (idle) staging tile in a
+    // fixed order, then ONE fp64 atomic per channel and component leaves the CTA (fp64: the order in which CTAs
+    // arrive does not show up in the fp32 mean / variance, so a training step is reproducible bit for bit)
     auto flush_stats = [&](int n0f) {
+      if (issuer) tc::tma_store_wait_read<0>();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
 #pragma unroll
-      for (int slot = 0; slot < 2; slot++) {
-        const int c64 = (nchunk64 == 1) ? 0 : 2 * slot + wg;
-        if (c64 >= nchunk64) continue;
-        const int col = n0f + c64 * 64 + 2 * lane;
-        if (col < p.Cout) {
-          atomicAdd(p.stats + col, st[slot][0]);
-          atomicAdd(p.stats + p.Cout + col, st[slot][2]);
-        }
-        if (col + 1 < p.Cout) {
-          atomicAdd(p.stats + col + 1, st[slot][1]);
-          atomicAdd(p.stats + p.Cout + col + 1, st[slot][3]);
-        }
+      for (int slot = 0; slot < 2; slot++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) st[slot][j] = 0.f;
+        for (int j = 0; j < 4; j++) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ob + (uint32_t)((((q * 2 + slot) * 4 + j) * 32 + lane) * 4)), "f"(st[slot][j]) : "memory");
+          st[slot][j] = 0.f;
+        }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
+      if (q == 0) {
+#pragma unroll
+        for (int slot = 0; slot < 2; slot++) {
+          const int c64 = (nchunk64 == 1) ? 0 : 2 * slot + wg;
+          if (c64 >= nchunk64) continue;
+          float t[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            t[j] = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; qq++) {
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ob + (uint32_t)((((qq * 2 + slot) * 4 + j) * 32 + lane) * 4)));
+              t[j] += v;
+            }
+          }
+          const int col = n0f + c64 * 64 + 2 * lane;
+          if (col < p.Cout) {
+            atomicAdd(p.stats + col, (double)t[0]);
+            atomicAdd(p.stats + p.Cout + col, (double)t[2]);
+          }
+          if (col + 1 < p.Cout) {
+            atomicAdd(p.stats + col + 1, (double)t[1]);
+            atomicAdd(p.stats + p.Cout + col + 1, (double)t[3]);
+          }
+        }
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");   // the staging tile is free for the next chunk
     };
     // Residual operand (eval-mode shortcut add, gradient accumulation): this thread's 128-byte row of the NEXT chunk
     // is prefetched with cp.async into the warpgroup's residual tile while the current chunk is processed; only the
@@ -489,7 +514,7 @@ using namespace iswm;
 
 extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const void* d_wgt,
                                void* d_out, const float* d_scale, const float* d_shift,
-                               const void* d_res, float* d_stats, void* stream) {
+                               const void* d_res, double* d_stats, void* stream) {
   ISWM_REQUIRE(d && d_in && d_wgt && d_out, "conv_igemm: null argument");
   ISWM_REQUIRE(d->ntaps >= 1 && d->ntaps <= ISWM_MAX_TAPS, "conv_igemm: ntaps=%d", d->ntaps);
   ISWM_REQUIRE(d->Cin >= 1 && d->Cout >= 1 && d->B >= 1 && d->Ho >= 1 && d->Wo >= 1, "conv_igemm: bad dims");

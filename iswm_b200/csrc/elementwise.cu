@@ -199,7 +199,7 @@ pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
 
 // BatchNorm training forward: stats -> normalise (+residual, ReLU, dropout)
 __global__ void __launch_bounds__(kT, 3)
-bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float* __restrict__ stats,
+bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const double* __restrict__ stats,
                       int64_t M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float eps, float momentum, float* running_mean, float* running_var,
                       long long* nbt, float* save_mean, float* save_invstd,
@@ -211,13 +211,14 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
-  const float invM = 1.0f / (float)M;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int c = c0 + j;
-    const float mean = stats[c] * invM;
-    const float var = fmaxf(stats[C + c] * invM - mean * mean, 0.f);
+    // fp64 sums (see conv_igemm.cu): E[x^2] - mean^2 without cancellation trouble, rounded to fp32 once
+    const double mean_d = stats[c] / (double)M;
+    const float mean = (float)mean_d;
+    const float var = fmaxf((float)(stats[C + c] / (double)M - mean_d * mean_d), 0.f);
     const float invstd = rsqrtf(var + eps);
     sc[j] = gamma[c] * invstd;
     sh[j] = fmaf(-mean, sc[j], beta[c]);          // same expression in the backward kernels (mask recomputation)
@@ -291,7 +292,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                     float drop_p, uint64_t drop_seed, float* __restrict__ sums, int nx, int ny,
+                     float drop_p, uint64_t drop_seed, double* __restrict__ sums, int nx, int ny,
                      int rows_per_block) {
   pdl_wait();
   pdl_launch();
@@ -363,7 +364,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     float t = 0.f;
     for (int y = 0; y < ny; y++) t += s_red[(y * nx + gx) * 16 + j];
     const int c = (gx << 3) + (j & 7);
-    atomicAdd(sums + (j < 8 ? c : C + c), t);
+    atomicAdd(sums + (j < 8 ? c : C + c), (double)t);
   }
 }
 
@@ -373,7 +374,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     const __nv_bfloat16* __restrict__ x, int x_ld,
                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, const float* __restrict__ sums, int relu,
+                    const float* __restrict__ invstd, const double* __restrict__ sums, int relu,
                     float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
                     __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta, int nx,
                     int ny, int rows_per_block) {
@@ -392,13 +393,14 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     const float is = invstd[c], mu = mean[c];
     const float k = gamma[c] * is;
     sh[j] = mask_re ? fmaf(-mu, k, beta[c]) : 0.f;
-    const float ma = sums[c] * invM, mb = sums[C + c] * invM;
+    const float sa = (float)sums[c], sb = (float)sums[C + c];
+    const float ma = sa * invM, mb = sb * invM;
     kk[j] = k;
     pp[j] = -k * is * mb;
     qq[j] = -k * ma - pp[j] * mu;
     if (blockIdx.x == 0 && ty == 0) {
-      if (dbeta) dbeta[c] += sums[c];
-      if (dgamma) dgamma[c] += sums[C + c];
+      if (dbeta) dbeta[c] += sa;
+      if (dgamma) dgamma[c] += sb;
     }
   }
   const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
@@ -1036,15 +1038,15 @@ static void bn_red_shape(int C, int& nx, int& ny) {
 // rows per block: every thread walks >= min_rows rows (amortises the per-channel constant setup), but small
 // tensors still get several blocks per SM (the kernels are latency-bound below ~4 resident blocks per SM);
 // capped at 6 blocks per SM
-static void bn_row_grid(int C, int64_t M, int min_rows, int& nx, int& ny, int& rows_per_block, int& blocks) {
+static void bn_row_grid(int C, int64_t M, int min_rows, int& nx, int& ny, int& rows_per_block, int& blocks, int blocks_per_sm = 6) {
   bn_red_shape(C, nx, ny);
   int64_t want = (M + (int64_t)ny * min_rows - 1) / ((int64_t)ny * min_rows);
-  want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * 6));
+  want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * blocks_per_sm));
   rows_per_block = (int)((M + want - 1) / want);
   blocks = (int)((M + rows_per_block - 1) / rows_per_block);
 }
 
-extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const float* d_stats, int64_t M, int C,
+extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,
                                    const float* d_gamma, const float* d_beta, float eps, float momentum,
                                    float* d_running_mean, float* d_running_var, int64_t* d_nbt,
                                    float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld,
@@ -1074,14 +1076,14 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
                                   const void* d_out_act, int act_ld, int64_t M, int C,
                                   const float* d_save_mean, const float* d_save_invstd,
                                   const float* d_gamma, const float* d_beta, int relu,
-                                  float drop_p, uint64_t drop_seed, float* d_sums, void* stream) {
+                                  float drop_p, uint64_t drop_seed, double* d_sums, void* stream) {
   REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_gamma && d_beta),
                "bn_bwd_reduce: relu needs the activation (or gamma and beta to recompute the mask)");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny, rows_per_block, blocks;
-  bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks);
+  bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 2);   // one wave: every block ends with fp64 atomics on the same 2C addresses
   launch_k(bn_bwd_reduce_kernel, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
                                                       M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, relu, drop_p,
                                                       drop_seed, d_sums, nx, ny, rows_per_block);
@@ -1090,7 +1092,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
 extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                                  const void* d_out_act, int act_ld, int64_t M, int C,
                                  const float* d_gamma, const float* d_beta, const float* d_save_mean,
-                                 const float* d_save_invstd, const float* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                                 const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed,
                                  void* d_dx, int dx_ld, void* d_dz, int dz_ld, float* d_dgamma,
                                  float* d_dbeta, void* stream) {
   REQ_C8(C, "bn_bwd_apply"); REQ_LD8(dout_ld, "bn_bwd_apply"); REQ_LD8(x_ld, "bn_bwd_apply"); REQ_LD8(dx_ld, "bn_bwd_apply");

@@ -458,26 +458,36 @@ class Engine:
         if self.grad_ready_hook is not None:
             self.grad_ready_hook(p)
 
-    # per-step scratch (fp32), carved from one zeroed buffer
+    # per-step scratch carved from two zeroed buffers: fp64 accumulators (conv-epilogue statistics, BN-backward sums)
+    # and fp32 saved mean / invstd
     def _begin_scratch(self):
         need = 0
         for s in self.specs:
             if s.bn is not None:
-                need += 8 * s.cout        # fwd stats, bwd sums, save mean/invstd (+ slack)
+                need += 4 * s.cout + 128    # fwd stats + bwd sums (fp64); the same count covers mean/invstd (fp32)
         need += 4096
-        if getattr(self, "_scratch", None) is None or self._scratch.numel() < need or self._scratch.device != self.device:
-            self._scratch = torch.empty(need, dtype=torch.float32, device=self.device)
-        self._scratch.zero_()
-        self._scratch_off = 0
+        if getattr(self, "_scratch64", None) is None or self._scratch64.numel() < need or self._scratch64.device != self.device:
+            self._scratch64 = torch.empty(need, dtype=torch.float64, device=self.device)
+            self._scratch32 = torch.empty(need, dtype=torch.float32, device=self.device)
+        self._scratch64.zero_()
+        self._scratch64_off = 0
+        self._scratch32_off = 0
 
     def _stats_slot(self, n: int) -> torch.Tensor:
+        """zeroed fp64 accumulator slot"""
         n_al = (n + 63) // 64 * 64
-        t = self._scratch[self._scratch_off:self._scratch_off + n]
-        self._scratch_off += n_al
-        assert self._scratch_off <= self._scratch.numel(), "scratch exhausted"
+        t = self._scratch64[self._scratch64_off:self._scratch64_off + n]
+        self._scratch64_off += n_al
+        assert self._scratch64_off <= self._scratch64.numel(), "scratch exhausted"
         return t
 
-    _save_slot = _stats_slot
+    def _save_slot(self, n: int) -> torch.Tensor:
+        """fp32 slot (fully overwritten by its producer)"""
+        n_al = (n + 63) // 64 * 64
+        t = self._scratch32[self._scratch32_off:self._scratch32_off + n]
+        self._scratch32_off += n_al
+        assert self._scratch32_off <= self._scratch32.numel(), "scratch exhausted"
+        return t
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:

@@ -58,14 +58,14 @@ def test_conv_fwd_raw_and_stats(B, Cin, H, W, Cout, k, dil):
     wp = ops.pack_weight_fwd(w.to(DEV))
     out_ld = ((Cout + 7) // 8) * 8
     out = torch.zeros((B, H, W, out_ld), dtype=torch.bfloat16, device=DEV)
-    stats = torch.zeros(2 * Cout, dtype=torch.float32, device=DEV)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
     d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, out_ld, ops.conv_taps(k, dil), flags=_lib.EPI_STATS)
     ops.conv_igemm(d, xd, wp, out, stats=stats)
     _assert_healthy()
     ref = F.conv2d(x.float(), w.to(torch.bfloat16).float(), padding=dil * (k // 2), dilation=dil)
     got = out[..., :Cout].float().cpu().permute(0, 3, 1, 2)
     assert _rel_err(got, ref) < 1e-2
-    s = stats.cpu()
+    s = stats.float().cpu()
     # the statistics are fp32 sums of the bf16 values the kernel STORED (what BatchNorm reads back)
     np.testing.assert_allclose(s[:Cout].numpy(), got.sum((0, 2, 3)).numpy(), rtol=1e-4, atol=2e-3)
     np.testing.assert_allclose(s[Cout:].numpy(), (got * got).sum((0, 2, 3)).numpy(), rtol=1e-4, atol=2e-3)

@@ -57,7 +57,7 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     # ours
     M = B * H * W
     xd = nhwc(x).to(DEV)
-    stats = torch.stack([x.float().sum((0, 2, 3)), (x.float() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    stats = torch.stack([x.double().sum((0, 2, 3)), (x.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
     out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     save = torch.empty(2 * C, dtype=torch.float32, device=DEV)
     rmd, rvd = rm.to(DEV), rv.to(DEV)
@@ -72,16 +72,16 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     close(rvd, rv_ref, 1e-3, 1e-4)
     assert nbt.item() == 1
     dd = nhwc(dout).to(DEV)
-    sums = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
     # units without a residual recompute the ReLU mask from x (act = NULL); residual units read the block output
     act_ptr = out.data_ptr() if with_res else None
     check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, save.data_ptr(), save[C:].data_ptr(),
                                  gd.data_ptr(), bd.data_ptr(), 1 if relu else 0, 0.0, 0, sums.data_ptr(), st()))
     if relu and not with_res:                       # both mask sources must agree bit for bit
-        sums2 = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+        sums2 = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
         check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, save.data_ptr(), save[C:].data_ptr(),
                                      gd.data_ptr(), bd.data_ptr(), 1, 0.0, 0, sums2.data_ptr(), st()))
-        assert torch.equal(sums, sums2)
+        assert torch.equal(sums.float(), sums2.float())   # fp64 accumulators: atomics order is invisible in fp32
     dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     dg = torch.zeros(C, dtype=torch.float32, device=DEV)

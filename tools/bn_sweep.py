@@ -25,10 +25,10 @@ for M, C in shapes:
     res = torch.randn((M, C), device=dev).to(torch.bfloat16)
     out = torch.empty_like(x); dy = torch.empty_like(x); dz = torch.empty_like(x)
     dout = torch.randn((M, C), device=dev).to(torch.bfloat16)
-    stats = torch.stack([x.float().sum(0), (x.float() ** 2).sum(0)]).reshape(-1).contiguous()
+    stats = torch.stack([x.double().sum(0), (x.double() ** 2).sum(0)]).reshape(-1).contiguous()
     g = torch.rand(C, device=dev) + 0.5; b = torch.randn(C, device=dev) * 0.1
     rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev); nbt = torch.zeros((), dtype=torch.long, device=dev)
-    save = torch.empty(2 * C, device=dev); sums = torch.zeros(2 * C, device=dev); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
+    save = torch.empty(2 * C, device=dev); sums = torch.zeros(2 * C, dtype=torch.float64, device=dev); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
     for with_res in (False, True):
         rp = res.data_ptr() if with_res else None
         t1 = timeit(lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), M, C, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),

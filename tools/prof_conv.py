@@ -16,7 +16,7 @@ x = torch.randn((B, H, W, Cin), device=dev).to(torch.bfloat16)
 w = torch.randn((Cout, Cin, k, k), device=dev) * 0.05
 wp = ops.pack_weight_fwd(w)
 out = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=dev)
-stats = torch.zeros(2 * Cout, dtype=torch.float32, device=dev)
+stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
 res = torch.randn((B, H, W, Cout), device=dev).to(torch.bfloat16) if flags & _lib.EPI_RESIDUAL else None
 d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, Cout, ops.conv_taps(k, dil), flags=flags, res_ld=Cout)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
