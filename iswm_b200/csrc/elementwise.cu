@@ -681,6 +681,8 @@ __device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int
   l1 = src - (float)i0;
 }
 
+// One grid row (blockIdx.x, up to 2^31-1 of them) per output image row: the vertical source rows / weight are block constants and the
+// remaining index math is 32-bit.
 __global__ void __launch_bounds__(kT)
 bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int Hi, int Wi, int C,
                     int Ho, int Wo, __nv_bfloat16* __restrict__ out, int out_ld) {
@@ -688,25 +690,28 @@ bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int Hi
   pdl_launch();
   const int nvec = C >> 3;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const int64_t total = (int64_t)B * Ho * Wo * nvec;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int cg = (int)(i % nvec);
-    const int64_t m = i / nvec;
-    const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bil_src(ho, sh, Hi, y0, y1, ly);
+  const int ho = blockIdx.x % Ho, b = blockIdx.x / Ho;
+  int y0, y1;
+  float ly;
+  bil_src(ho, sh, Hi, y0, y1, ly);
+  const __nv_bfloat16* r0 = x + ((int64_t)b * Hi + y0) * Wi * x_ld;
+  const __nv_bfloat16* r1 = x + ((int64_t)b * Hi + y1) * Wi * x_ld;
+  __nv_bfloat16* orow = out + ((int64_t)b * Ho + ho) * Wo * out_ld;
+  const int total = Wo * nvec;
+  for (int i = blockIdx.y * kT + threadIdx.x; i < total; i += gridDim.y * kT) {
+    const int wo = i / nvec, c8 = (i - wo * nvec) << 3;
+    int x0, x1;
+    float lx;
     bil_src(wo, sw, Wi, x0, x1, lx);
-    const __nv_bfloat16* base = x + (int64_t)b * Hi * Wi * x_ld + cg * 8;
-    const F8 v00 = load8(base + ((int64_t)y0 * Wi + x0) * x_ld);
-    const F8 v01 = load8(base + ((int64_t)y0 * Wi + x1) * x_ld);
-    const F8 v10 = load8(base + ((int64_t)y1 * Wi + x0) * x_ld);
-    const F8 v11 = load8(base + ((int64_t)y1 * Wi + x1) * x_ld);
+    const F8 v00 = load8(r0 + (int64_t)x0 * x_ld + c8);
+    const F8 v01 = load8(r0 + (int64_t)x1 * x_ld + c8);
+    const F8 v10 = load8(r1 + (int64_t)x0 * x_ld + c8);
+    const F8 v11 = load8(r1 + (int64_t)x1 * x_ld + c8);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
     F8 o;
 #pragma unroll
     for (int j = 0; j < 8; j++) o.v[j] = w00 * v00.v[j] + w01 * v01.v[j] + w10 * v10.v[j] + w11 * v11.v[j];
-    store8(out + m * out_ld + cg * 8, o);
+    store8(orow + (int64_t)wo * out_ld + c8, o);
   }
 }
 
@@ -718,6 +723,7 @@ __device__ __forceinline__ void bil_range(int i, float rscale, int out, int& lo,
   hi = hi > out - 1 ? out - 1 : hi;
 }
 
+// adjoint (gather form): one grid row per INPUT image row
 __global__ void __launch_bounds__(kT)
 bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, int Hi, int Wi,
                     int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, int dx_ld) {
@@ -726,18 +732,19 @@ bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, 
   const int nvec = C >> 3;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
-  const int64_t total = (int64_t)B * Hi * Wi * nvec;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int cg = (int)(i % nvec);
-    const int64_t m = i / nvec;
-    const int xi = (int)(m % Wi), yi = (int)((m / Wi) % Hi), b = (int)(m / ((int64_t)Wi * Hi));
-    int ylo, yhi, xlo, xhi;
-    bil_range(yi, rh, Ho, ylo, yhi);
+  const int yi = blockIdx.x % Hi, b = blockIdx.x / Hi;
+  int ylo, yhi;
+  bil_range(yi, rh, Ho, ylo, yhi);
+  const __nv_bfloat16* base = dout + (int64_t)b * Ho * Wo * dout_ld;
+  __nv_bfloat16* orow = dx + ((int64_t)b * Hi + yi) * Wi * dx_ld;
+  const int total = Wi * nvec;
+  for (int i = blockIdx.y * kT + threadIdx.x; i < total; i += gridDim.y * kT) {
+    const int xi = i / nvec, c8 = (i - xi * nvec) << 3;
+    int xlo, xhi;
     bil_range(xi, rw, Wo, xlo, xhi);
     F8 acc;
 #pragma unroll
     for (int j = 0; j < 8; j++) acc.v[j] = 0.f;
-    const __nv_bfloat16* base = dout + (int64_t)b * Ho * Wo * dout_ld + cg * 8;
     for (int oy = ylo; oy <= yhi; oy++) {
       int y0, y1; float ly;
       bil_src(oy, sh, Hi, y0, y1, ly);
@@ -748,43 +755,45 @@ bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, 
         bil_src(ox, sw, Wi, x0, x1, lx);
         const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
         if (wx == 0.f) continue;
-        const F8 g = load8(base + ((int64_t)oy * Wo + ox) * dout_ld);
+        const F8 g = load8(base + ((int64_t)oy * Wo + ox) * dout_ld + c8);
         const float w = wy * wx;
 #pragma unroll
         for (int j = 0; j < 8; j++) acc.v[j] = fmaf(w, g.v[j], acc.v[j]);
       }
     }
-    store8(dx + m * dx_ld + cg * 8, acc);
+    store8(orow + (int64_t)xi * dx_ld + c8, acc);
   }
 }
 
-// final logits upsample: NHWC fp32 [B,h,w,C] -> NCHW fp32 [B,C,H,W]
+// final logits upsample: NHWC fp32 [B,h,w,C] -> NCHW fp32 [B,C,H,W]; grid row = (image, output row)
 __global__ void __launch_bounds__(kT)
 logits_up_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, int Ho, int Wo,
                      float* __restrict__ out) {
   pdl_wait();
   pdl_launch();
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const int64_t total = (int64_t)B * Ho * Wo;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int wo = (int)(i % Wo), ho = (int)((i / Wo) % Ho), b = (int)(i / ((int64_t)Wo * Ho));
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bil_src(ho, sh, Hi, y0, y1, ly);
+  const int ho = blockIdx.x % Ho, b = blockIdx.x / Ho;
+  int y0, y1;
+  float ly;
+  bil_src(ho, sh, Hi, y0, y1, ly);
+  const float* r0 = x + ((int64_t)b * Hi + y0) * Wi * C;
+  const float* r1 = x + ((int64_t)b * Hi + y1) * Wi * C;
+  for (int wo = blockIdx.y * kT + threadIdx.x; wo < Wo; wo += gridDim.y * kT) {
+    int x0, x1;
+    float lx;
     bil_src(wo, sw, Wi, x0, x1, lx);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const float* base = x + (int64_t)b * Hi * Wi * C;
-    const float* p00 = base + ((int64_t)y0 * Wi + x0) * C;
-    const float* p01 = base + ((int64_t)y0 * Wi + x1) * C;
-    const float* p10 = base + ((int64_t)y1 * Wi + x0) * C;
-    const float* p11 = base + ((int64_t)y1 * Wi + x1) * C;
+    const float* p00 = r0 + (int64_t)x0 * C;
+    const float* p01 = r0 + (int64_t)x1 * C;
+    const float* p10 = r1 + (int64_t)x0 * C;
+    const float* p11 = r1 + (int64_t)x1 * C;
     for (int c = 0; c < C; c++) {
       const float v = w00 * __ldg(p00 + c) + w01 * __ldg(p01 + c) + w10 * __ldg(p10 + c) + w11 * __ldg(p11 + c);
       out[(((int64_t)b * C + c) * Ho + ho) * Wo + wo] = v;
     }
   }
 }
-// adjoint: NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels >= C zero-filled)
+// adjoint: NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels >= C zero-filled); grid row = (image, input row)
 __global__ void __launch_bounds__(kT)
 logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int C, int Ho, int Wo,
                      __nv_bfloat16* __restrict__ dx, int dx_ld) {
@@ -792,13 +801,13 @@ logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int 
   pdl_launch();
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
-  const int64_t total = (int64_t)B * Hi * Wi * C;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int c = (int)(i % C);
-    const int64_t m = i / C;
-    const int xi = (int)(m % Wi), yi = (int)((m / Wi) % Hi), b = (int)(m / ((int64_t)Wi * Hi));
-    int ylo, yhi, xlo, xhi;
-    bil_range(yi, rh, Ho, ylo, yhi);
+  const int yi = blockIdx.x % Hi, b = blockIdx.x / Hi;
+  int ylo, yhi;
+  bil_range(yi, rh, Ho, ylo, yhi);
+  const int total = Wi * C;
+  for (int i = blockIdx.y * kT + threadIdx.x; i < total; i += gridDim.y * kT) {
+    const int xi = i / C, c = i - xi * C;
+    int xlo, xhi;
     bil_range(xi, rw, Wo, xlo, xhi);
     const float* base = dout + ((int64_t)b * C + c) * Ho * Wo;
     float acc = 0.f;
@@ -816,6 +825,7 @@ logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int 
       }
       acc = fmaf(wy, rowacc, acc);
     }
+    const int64_t m = ((int64_t)b * Hi + yi) * Wi + xi;
     dx[m * dx_ld + c] = __float2bfloat16_rn(acc);
     if (c == C - 1)
       for (int cc = C; cc < dx_ld; cc++) dx[m * dx_ld + cc] = __float2bfloat16_rn(0.f);
@@ -1174,24 +1184,24 @@ extern "C" int iswm_bilinear_fwd(const void* d_x, int x_ld, int B, int Hi, int W
                                  void* d_out, int out_ld, void* stream) {
   REQ_C8(C, "bilinear_fwd"); REQ_LD8(x_ld, "bilinear_fwd"); REQ_LD8(out_ld, "bilinear_fwd");
   ISWM_REQUIRE(d_x && d_out, "bilinear_fwd: null");
-  launch_k(bilinear_fwd_kernel, dim3(grid_for((int64_t)B * Ho * Wo * (C / 8))), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_out), out_ld);
+  launch_k(bilinear_fwd_kernel, dim3((unsigned)(B * Ho), (unsigned)std::min(8, (Wo * (C / 8) + kT - 1) / kT)), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_out), out_ld);
   return check_launch("bilinear_fwd");
 }
 extern "C" int iswm_bilinear_bwd(const void* d_dout, int dout_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                  void* d_dx, int dx_ld, void* stream) {
   REQ_C8(C, "bilinear_bwd"); REQ_LD8(dout_ld, "bilinear_bwd"); REQ_LD8(dx_ld, "bilinear_bwd");
   ISWM_REQUIRE(d_dout && d_dx, "bilinear_bwd: null");
-  launch_k(bilinear_bwd_kernel, dim3(grid_for((int64_t)B * Hi * Wi * (C / 8))), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  launch_k(bilinear_bwd_kernel, dim3((unsigned)(B * Hi), (unsigned)std::min(8, (Wi * (C / 8) + kT - 1) / kT)), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
   return check_launch("bilinear_bwd");
 }
 extern "C" int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C, int Ho, int Wo, float* d_out, void* stream) {
   ISWM_REQUIRE(d_x && d_out && C >= 1, "logits_up_fwd: null");
-  launch_k(logits_up_fwd_kernel, dim3(grid_for((int64_t)B * Ho * Wo)), dim3(kT), 0, ST(stream), d_x, B, Hi, Wi, C, Ho, Wo, d_out);
+  launch_k(logits_up_fwd_kernel, dim3((unsigned)(B * Ho), (unsigned)std::min(8, (Wo + kT - 1) / kT)), dim3(kT), 0, ST(stream), d_x, B, Hi, Wi, C, Ho, Wo, d_out);
   return check_launch("logits_up_fwd");
 }
 extern "C" int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld, void* stream) {
   ISWM_REQUIRE(d_dout && d_dx && C >= 1 && dx_ld >= C, "logits_up_bwd: bad args");
-  launch_k(logits_up_bwd_kernel, dim3(grid_for((int64_t)B * Hi * Wi * C)), dim3(kT), 0, ST(stream), d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  launch_k(logits_up_bwd_kernel, dim3((unsigned)(B * Hi), (unsigned)std::min(8, (Wi * C + kT - 1) / kT)), dim3(kT), 0, ST(stream), d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
   return check_launch("logits_up_bwd");
 }
 extern "C" int iswm_phase_split(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream) {
