@@ -197,13 +197,30 @@ pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
 // (8 channels = 16 bytes), ty = row lane. Per-channel constants live in registers; a block walks
 // its row range with several rows in flight per thread, so there is no per-element index math.
 
+// Row walk shared by the three kernels: thread (tx, ty) owns channels [8tx, 8tx+8) of rows r0+ty, r0+ty+ny, ...
+// of its block; pointers advance by a fixed stride (no per-row 64-bit multiplies) and the main loop handles U rows
+// per trip without bounds checks (U independent 16-byte loads per tensor in flight), a scalar tail the rest.
+struct RowWalk {
+  int64_t first;      // first row of this thread
+  int n;              // rows this thread owns
+};
+__device__ __forceinline__ RowWalk row_walk(int64_t M, int rows_per_block, int ty, int ny) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  RowWalk w;
+  w.first = r0 + ty;
+  w.n = (w.first < r1) ? (int)((r1 - w.first + ny - 1) / ny) : 0;
+  return w;
+}
+
 // BatchNorm training forward: stats -> normalise (+residual, ReLU, dropout)
+template <bool RES, bool RELU, bool DROP>
 __global__ void __launch_bounds__(kT, 3)
 bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const double* __restrict__ stats,
                       int64_t M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float eps, float momentum, float* running_mean, float* running_var,
                       long long* nbt, float* save_mean, float* save_invstd,
-                      const __nv_bfloat16* __restrict__ res, int res_ld, int relu, float drop_p,
+                      const __nv_bfloat16* __restrict__ res, int res_ld, float drop_p,
                       uint64_t drop_seed, __nv_bfloat16* __restrict__ out, int out_ld, int nx, int ny,
                       int rows_per_block) {
   pdl_wait();
@@ -211,14 +228,15 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
+  const double invM = 1.0 / (double)M;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int c = c0 + j;
     // fp64 sums (see conv_igemm.cu): E[x^2] - mean^2 without cancellation trouble, rounded to fp32 once
-    const double mean_d = stats[c] / (double)M;
+    const double mean_d = stats[c] * invM;
     const float mean = (float)mean_d;
-    const float var = fmaxf((float)(stats[C + c] / (double)M - mean_d * mean_d), 0.f);
+    const float var = fmaxf((float)(stats[C + c] * invM - mean_d * mean_d), 0.f);
     const float invstd = rsqrtf(var + eps);
     sc[j] = gamma[c] * invstd;
     sh[j] = fmaf(-mean, sc[j], beta[c]);          // same expression in the backward kernels (mask recomputation)
@@ -233,43 +251,54 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
-  const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
+  const RowWalk w = row_walk(M, rows_per_block, ty, ny);
+  const __nv_bfloat16* px = x + w.first * x_ld + c0;
+  const __nv_bfloat16* pr = RES ? res + w.first * res_ld + c0 : nullptr;
+  __nv_bfloat16* po = out + w.first * out_ld + c0;
+  const int64_t sx = (int64_t)ny * x_ld, sr = (int64_t)ny * res_ld, so = (int64_t)ny * out_ld;
+  uint64_t didx = (uint64_t)w.first * C + c0;                 // dropout counter of this thread's first element
+  const uint64_t sd = (uint64_t)ny * C;
+  auto one = [&](const uint4& fr, const uint4& rr, __nv_bfloat16* o, uint64_t di) {
+    F8 f = unpack8(fr);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
+    if (RES) {
+      const F8 r = unpack8(rr);
+#pragma unroll
+      for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
+    }
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) f.v[j] = fmaxf(f.v[j], 0.f);
+    }
+    if (DROP) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) f.v[j] = drop_keep(drop_seed, di + j, drop_p) ? f.v[j] * keep_scale : 0.f;
+    }
+    store8(o, f);
+  };
   constexpr int U = 4;
-  for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
+  int i = 0;
+  for (; i + U <= w.n; i += U) {
     uint4 fr[U], rr[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int64_t row = base + (int64_t)u * ny;
-      if (row < r1) {
-        fr[u] = load_raw(x + row * x_ld + c0);
-        if (res) rr[u] = load_raw(res + row * res_ld + c0);
-      }
+      fr[u] = load_raw(px + u * sx);
+      if (RES) rr[u] = load_raw(pr + u * sr);
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int64_t row = base + (int64_t)u * ny;
-      if (row >= r1) continue;
-      F8 f = unpack8(fr[u]);
-#pragma unroll
-      for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
-      if (res) {
-        const F8 r = unpack8(rr[u]);
-#pragma unroll
-        for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
-      }
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) f.v[j] = fmaxf(f.v[j], 0.f);
-      }
-      if (drop_p > 0.f) {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          f.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? f.v[j] * keep_scale : 0.f;
-      }
-      store8(out + row * out_ld + c0, f);
-    }
+    for (int u = 0; u < U; u++) one(fr[u], rr[u], po + u * so, didx + u * sd);
+    px += U * sx; po += U * so; didx += U * sd;
+    if (RES) pr += U * sr;
+  }
+  for (; i < w.n; i++) {
+    const uint4 fr = load_raw(px);
+    uint4 rr = fr;
+    if (RES) rr = load_raw(pr);
+    one(fr, rr, po, didx);
+    px += sx; po += so; didx += sd;
+    if (RES) pr += sr;
   }
 }
 
@@ -285,71 +314,87 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
   }
 }
 
-// BatchNorm backward pass 1: per-channel sum(dz), sum(dz * xhat)
-__global__ void __launch_bounds__(kT, 2)
+// BatchNorm backward pass 1: per-channel sum(dz), sum(dz * xhat). MASK: 0 none, 1 from the stored activation
+// (residual units), 2 recomputed from x with the forward kernel's own scale/shift arithmetic (one tensor read less).
+// The loop accumulates sum(dz) and sum(dz * x); sum(dz * xhat) = invstd * (sum(dz*x) - mean * sum(dz)) is formed once
+// per block in fp64.
+template <int MASK, bool DROP>
+__global__ void __launch_bounds__(kT, 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      const __nv_bfloat16* __restrict__ x, int x_ld,
                      const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
                      float drop_p, uint64_t drop_seed, double* __restrict__ sums, int nx, int ny,
                      int rows_per_block) {
   pdl_wait();
   pdl_launch();
   __shared__ float s_red[kT * 16];
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
-  const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
   const int c0 = tx << 3;
-  // ReLU mask: from the stored post-activation tensor when given (residual units), otherwise recomputed
-  // from x with the forward kernel's own scale/shift arithmetic (saves one tensor read)
-  const bool mask_act = relu && act != nullptr, mask_re = relu && act == nullptr;
-  float a[8], b[8], mu[8], is[8], sc[8], sh[8];
+  float a[8], b[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    a[j] = 0.f; b[j] = 0.f; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j];
-    sc[j] = mask_re ? gamma[c0 + j] * is[j] : 0.f;
-    sh[j] = mask_re ? fmaf(-mu[j], sc[j], beta[c0 + j]) : 0.f;
+    a[j] = 0.f; b[j] = 0.f;
+    if (MASK == 2) {
+      sc[j] = gamma[c0 + j] * invstd[c0 + j];
+      sh[j] = fmaf(-mean[c0 + j], sc[j], beta[c0 + j]);
+    } else {
+      sc[j] = 0.f; sh[j] = 0.f;
+    }
   }
   if (ty < ny) {
+    const RowWalk w = row_walk(M, rows_per_block, ty, ny);
+    const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
+    const __nv_bfloat16* px = x + w.first * x_ld + c0;
+    const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
+    const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa = (int64_t)ny * act_ld;
+    uint64_t didx = (uint64_t)w.first * C + c0;
+    const uint64_t sd = (uint64_t)ny * C;
+    auto one = [&](const uint4& gr, const uint4& xr, const uint4& orr, uint64_t di) {
+      F8 g = unpack8(gr);
+      const F8 xv = unpack8(xr);
+      if (MASK == 1) {
+        const F8 o = unpack8(orr);
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+      } else if (MASK == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], sc[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
+      }
+      if (DROP) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.v[j] = drop_keep(drop_seed, di + j, drop_p) ? g.v[j] * keep_scale : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        a[j] += g.v[j];
+        b[j] = fmaf(g.v[j], xv.v[j], b[j]);
+      }
+    };
     constexpr int U = 4;
-    for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
+    int i = 0;
+    for (; i + U <= w.n; i += U) {
       uint4 gr[U], xr[U], orr[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int64_t row = base + (int64_t)u * ny;
-        if (row < r1) {
-          gr[u] = load_raw(dout + row * dout_ld + c0);
-          xr[u] = load_raw(x + row * x_ld + c0);
-          if (mask_act) orr[u] = load_raw(act + row * act_ld + c0);
-        }
+        gr[u] = load_raw(pg + u * sg);
+        xr[u] = load_raw(px + u * sx);
+        if (MASK == 1) orr[u] = load_raw(pa + u * sa); else orr[u] = gr[u];
       }
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int64_t row = base + (int64_t)u * ny;
-        if (row >= r1) continue;
-        F8 g = unpack8(gr[u]);
-        const F8 xv = unpack8(xr[u]);
-        if (mask_act) {
-          const F8 o = unpack8(orr[u]);
-#pragma unroll
-          for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
-        } else if (mask_re) {
-#pragma unroll
-          for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], sc[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
-        }
-        if (drop_p > 0.f) {
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            g.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? g.v[j] * keep_scale : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          a[j] += g.v[j];
-          b[j] = fmaf(g.v[j], (xv.v[j] - mu[j]) * is[j], b[j]);
-        }
-      }
+      for (int u = 0; u < U; u++) one(gr[u], xr[u], orr[u], didx + u * sd);
+      pg += U * sg; px += U * sx; didx += U * sd;
+      if (MASK == 1) pa += U * sa;
+    }
+    for (; i < w.n; i++) {
+      const uint4 gr = load_raw(pg), xr = load_raw(px);
+      uint4 orr = gr;
+      if (MASK == 1) orr = load_raw(pa);
+      one(gr, xr, orr, didx);
+      pg += sg; px += sx; didx += sd;
+      if (MASK == 1) pa += sa;
     }
   }
 #pragma unroll
@@ -358,23 +403,28 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     s_red[threadIdx.x * 16 + 8 + j] = b[j];
   }
   __syncthreads();
-  // one thread per (channel group, component): 16 * nx outputs per block
-  for (int o = threadIdx.x; o < nx * 16; o += kT) {
-    const int gx = o >> 4, j = o & 15;
-    float t = 0.f;
-    for (int y = 0; y < ny; y++) t += s_red[(y * nx + gx) * 16 + j];
-    const int c = (gx << 3) + (j & 7);
-    atomicAdd(sums + (j < 8 ? c : C + c), (double)t);
+  // one thread per channel of the block's channel range: fixed-order sum over ty, xhat fix-up in fp64, two atomics
+  for (int o = threadIdx.x; o < nx * 8; o += kT) {
+    const int gx = o >> 3, j = o & 7;
+    float ta = 0.f, tb = 0.f;
+    for (int y = 0; y < ny; y++) {
+      ta += s_red[(y * nx + gx) * 16 + j];
+      tb += s_red[(y * nx + gx) * 16 + 8 + j];
+    }
+    const int c = (gx << 3) + j;
+    atomicAdd(sums + c, (double)ta);
+    atomicAdd(sums + C + c, (double)invstd[c] * ((double)tb - (double)mean[c] * (double)ta));
   }
 }
 
 // BatchNorm backward pass 2
-__global__ void __launch_bounds__(kT, 2)
+template <int MASK, bool DROP, bool DZ>
+__global__ void __launch_bounds__(kT, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     const __nv_bfloat16* __restrict__ x, int x_ld,
                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, const double* __restrict__ sums, int relu,
+                    const float* __restrict__ invstd, const double* __restrict__ sums,
                     float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
                     __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta, int nx,
                     int ny, int rows_per_block) {
@@ -385,14 +435,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const int c0 = tx << 3;
   const float invM = 1.0f / (float)M;
   // dx = k*dz + p*x + q  with  k = gamma*invstd, p = -k*invstd*mean(dz*xhat), q = -k*mean(dz) - p*mu
-  const bool mask_act = relu && act != nullptr, mask_re = relu && act == nullptr;
   float kk[8], pp[8], qq[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int c = c0 + j;
     const float is = invstd[c], mu = mean[c];
     const float k = gamma[c] * is;
-    sh[j] = mask_re ? fmaf(-mu, k, beta[c]) : 0.f;
+    sh[j] = (MASK == 2) ? fmaf(-mu, k, beta[c]) : 0.f;
     const float sa = (float)sums[c], sb = (float)sums[C + c];
     const float ma = sa * invM, mb = sb * invM;
     kk[j] = k;
@@ -403,46 +452,62 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       if (dgamma) dgamma[c] += sb;
     }
   }
-  const float keep_scale = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
+  const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
+  const RowWalk w = row_walk(M, rows_per_block, ty, ny);
+  const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
+  const __nv_bfloat16* px = x + w.first * x_ld + c0;
+  const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
+  __nv_bfloat16* pdx = dx + w.first * dx_ld + c0;
+  __nv_bfloat16* pdz = DZ ? dz + w.first * dz_ld + c0 : nullptr;
+  const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa_ = (int64_t)ny * act_ld,
+                sdx = (int64_t)ny * dx_ld, sdz = (int64_t)ny * dz_ld;
+  uint64_t didx = (uint64_t)w.first * C + c0;
+  const uint64_t sd = (uint64_t)ny * C;
+  auto one = [&](const uint4& gr, const uint4& xr, const uint4& orr, __nv_bfloat16* odx, __nv_bfloat16* odz, uint64_t di) {
+    F8 g = unpack8(gr);
+    const F8 xv = unpack8(xr);
+    if (MASK == 1) {
+      const F8 o = unpack8(orr);
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+    } else if (MASK == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], kk[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
+    }
+    if (DROP) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = drop_keep(drop_seed, di + j, drop_p) ? g.v[j] * keep_scale : 0.f;
+    }
+    if (DZ) store8(odz, g);
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r.v[j] = fmaf(kk[j], g.v[j], fmaf(pp[j], xv.v[j], qq[j]));
+    store8(odx, r);
+  };
   constexpr int U = 4;
-  for (int64_t base = r0 + ty; base < r1; base += (int64_t)ny * U) {
+  int i = 0;
+  for (; i + U <= w.n; i += U) {
     uint4 gr[U], xr[U], orr[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int64_t row = base + (int64_t)u * ny;
-      if (row < r1) {
-        gr[u] = load_raw(dout + row * dout_ld + c0);
-        xr[u] = load_raw(x + row * x_ld + c0);
-        if (mask_act) orr[u] = load_raw(act + row * act_ld + c0);
-      }
+      gr[u] = load_raw(pg + u * sg);
+      xr[u] = load_raw(px + u * sx);
+      if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else orr[u] = gr[u];
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int64_t row = base + (int64_t)u * ny;
-      if (row >= r1) continue;
-      F8 g = unpack8(gr[u]);
-      const F8 xv = unpack8(xr[u]);
-      if (mask_act) {
-        const F8 o = unpack8(orr[u]);
-#pragma unroll
-        for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
-      } else if (mask_re) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], kk[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
-      }
-      if (drop_p > 0.f) {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          g.v[j] = drop_keep(drop_seed, (uint64_t)row * C + c0 + j, drop_p) ? g.v[j] * keep_scale : 0.f;
-      }
-      if (dz) store8(dz + row * dz_ld + c0, g);
-      F8 r;
-#pragma unroll
-      for (int j = 0; j < 8; j++) r.v[j] = fmaf(kk[j], g.v[j], fmaf(pp[j], xv.v[j], qq[j]));
-      store8(dx + row * dx_ld + c0, r);
-    }
+    for (int u = 0; u < U; u++) one(gr[u], xr[u], orr[u], pdx + u * sdx, DZ ? pdz + u * sdz : nullptr, didx + u * sd);
+    pg += U * sg; px += U * sx; pdx += U * sdx; didx += U * sd;
+    if (MASK == 1) pa += U * sa_;
+    if (DZ) pdz += U * sdz;
+  }
+  for (; i < w.n; i++) {
+    const uint4 gr = load_raw(pg), xr = load_raw(px);
+    uint4 orr = gr;
+    if (MASK == 1) orr = load_raw(pa);
+    one(gr, xr, orr, pdx, pdz, didx);
+    pg += sg; px += sx; pdx += sdx; didx += sd;
+    if (MASK == 1) pa += sa_;
+    if (DZ) pdz += sdz;
   }
 }
 
@@ -1068,10 +1133,19 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
   ISWM_REQUIRE(C <= 2048, "bn_train_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
-  launch_k(bn_train_apply_kernel, dim3(blocks), dim3(kT), 0, ST(stream), 
-      BF(d_x), x_ld, d_stats, M, C, d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var,
-      reinterpret_cast<long long*>(d_nbt), d_save_mean, d_save_invstd, BF(d_res), res_ld, relu,
-      drop_p, drop_seed, BFW(d_out), out_ld, nx, ny, rpb);
+  const bool has_res = d_res != nullptr, has_drop = drop_p > 0.f;
+#define ISWM_BN_APPLY(R, L, D)                                                                                     \
+  launch_k(bn_train_apply_kernel<R, L, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, d_stats, M, C,    \
+           d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var, reinterpret_cast<long long*>(d_nbt),      \
+           d_save_mean, d_save_invstd, BF(d_res), res_ld, drop_p, drop_seed, BFW(d_out), out_ld, nx, ny, rpb)
+  if (has_drop) {
+    if (has_res) { if (relu) ISWM_BN_APPLY(true, true, true); else ISWM_BN_APPLY(true, false, true); }
+    else         { if (relu) ISWM_BN_APPLY(false, true, true); else ISWM_BN_APPLY(false, false, true); }
+  } else {
+    if (has_res) { if (relu) ISWM_BN_APPLY(true, true, false); else ISWM_BN_APPLY(true, false, false); }
+    else         { if (relu) ISWM_BN_APPLY(false, true, false); else ISWM_BN_APPLY(false, false, false); }
+  }
+#undef ISWM_BN_APPLY
   return check_launch("bn_train_apply");
 }
 extern "C" int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean,
@@ -1093,10 +1167,16 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
                "bn_bwd_reduce: relu needs the activation (or gamma and beta to recompute the mask)");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny, rows_per_block, blocks;
-  bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 2);   // one wave: every block ends with fp64 atomics on the same 2C addresses
-  launch_k(bn_bwd_reduce_kernel, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld,
-                                                      M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, relu, drop_p,
-                                                      drop_seed, d_sums, nx, ny, rows_per_block);
+  bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 3);   // one wave: every block ends with fp64 atomics on the same 2C addresses
+  const int mask = !relu ? 0 : (d_out_act ? 1 : 2);
+  const bool has_drop = drop_p > 0.f;
+#define ISWM_BN_RED(MK, D)                                                                                          \
+  launch_k(bn_bwd_reduce_kernel<MK, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,   \
+           BF(d_out_act), act_ld, M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, drop_p, drop_seed, d_sums, nx, \
+           ny, rows_per_block)
+  if (has_drop) { if (mask == 0) ISWM_BN_RED(0, true); else if (mask == 1) ISWM_BN_RED(1, true); else ISWM_BN_RED(2, true); }
+  else          { if (mask == 0) ISWM_BN_RED(0, false); else if (mask == 1) ISWM_BN_RED(1, false); else ISWM_BN_RED(2, false); }
+#undef ISWM_BN_RED
   return check_launch("bn_bwd_reduce");
 }
 extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
@@ -1113,10 +1193,18 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
-  launch_k(bn_bwd_apply_kernel, dim3(blocks), dim3(kT), 0, ST(stream), 
-      BF(d_dout), dout_ld, BF(d_x), x_ld, BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean,
-      d_save_invstd, d_sums, relu, drop_p, drop_seed, BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta,
-      nx, ny, rpb);
+  const int mask = !relu ? 0 : (d_out_act ? 1 : 2);
+  const bool has_drop = drop_p > 0.f, has_dz = d_dz != nullptr;
+#define ISWM_BN_BAP(MK, D, Z)                                                                                          \
+  launch_k(bn_bwd_apply_kernel<MK, D, Z>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,    \
+           BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean, d_save_invstd, d_sums, drop_p, drop_seed,        \
+           BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta, nx, ny, rpb)
+#define ISWM_BN_BAP_M(D, Z) \
+  do { if (mask == 0) ISWM_BN_BAP(0, D, Z); else if (mask == 1) ISWM_BN_BAP(1, D, Z); else ISWM_BN_BAP(2, D, Z); } while (0)
+  if (has_drop) { if (has_dz) ISWM_BN_BAP_M(true, true); else ISWM_BN_BAP_M(true, false); }
+  else          { if (has_dz) ISWM_BN_BAP_M(false, true); else ISWM_BN_BAP_M(false, false); }
+#undef ISWM_BN_BAP_M
+#undef ISWM_BN_BAP
   return check_launch("bn_bwd_apply");
 }
 
