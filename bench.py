@@ -520,6 +520,44 @@ def run_ours(args):
         eng.profile = []
     step(x_dev, y_dev)
     barrier()
+    if rank == 0 and args.profile_detail:
+        # second instrumented step: CUDA events around EVERY library launch, grouped by C-ABI entry point
+        real = _lib._lib
+        rec = []
+
+        class _Prof:
+            def __getattr__(self, name):
+                fn = getattr(real, name)
+                if not name.startswith("iswm_") or name in ("iswm_last_error", "iswm_launch_count"):
+                    return fn
+
+                def wrapped(*a):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = fn(*a)
+                    e1.record()
+                    rec.append((name, e0, e1))
+                    return r
+                return wrapped
+        _lib._lib = _Prof()
+        eng.profile = None
+        try:
+            step(x_dev, y_dev)
+            torch.cuda.synchronize()
+        finally:
+            _lib._lib = real
+        by = {}
+        for name, e0, e1 in rec:
+            t, n = by.get(name, (0.0, 0))
+            by[name] = (t + e0.elapsed_time(e1), n + 1)
+        with open(args.profile_detail + ".by_entry", "w") as f:
+            tot = sum(t for t, n in by.values())
+            for name, (t, n) in sorted(by.items(), key=lambda kv: -kv[1][0]):
+                f.write(f"{name:34s} {n:4d} launches {t * 1e3:9.1f} us {100 * t / tot:5.1f}%\n")
+            f.write(f"{'total':34s} {len(rec):4d} launches {tot * 1e3:9.1f} us\n")
+        eng.profile = []
+        step(x_dev, y_dev)
+        torch.cuda.synchronize()
     if rank == 0:
         agg = {}
         detail = []

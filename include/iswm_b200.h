@@ -205,6 +205,17 @@ int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld
                       void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                       float* d_dgamma, float* d_dbeta, void* stream);
 
+/* Both passes in ONE launch (what the engine uses): pass 1, a grid-wide barrier, pass 2 over the same rows (served
+ * from L2 for all but the largest tensors). d_sums: double[2*C + 1], zeroed by the caller; the extra cell is the
+ * barrier's arrival counter. The grid is sized to be co-resident; the barrier wait is bounded
+ * (iswm_debug_abort_code() reports 21 if it ever timed out). */
+int iswm_bn_bwd(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
+                const void* d_out_act, int act_ld, int64_t M, int C,
+                const float* d_gamma, const float* d_beta, const float* d_save_mean,
+                const float* d_save_invstd, double* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                void* d_dx, int dx_ld, void* d_dz, int dz_ld,
+                float* d_dgamma, float* d_dbeta, void* stream);
+
 /* NCHW fp32 image -> stem im2col matrix bf16 [B*Ho*Wo][Kpad] for the 7x7/s2/p3 conv
  * (network/backbone/resnet.py:144); column = (r*7+s)*Cin + c, zero padded to Kpad. */
 int iswm_stem_im2col(const float* d_img, int B, int Cin, int H, int W, int Ho, int Wo,

@@ -425,7 +425,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (tma_out) {
           uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+          for (int j = 0; j < 32; j++) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          if (!valid) {                                    // rows outside the image: clipped by the store, zero for the statistics
+#pragma unroll
+            for (int j = 0; j < 32; j++) pk[j] = 0u;
+          }
           // the previous store of this warpgroup has finished reading the staging tile (and so have the
           // statistics readers, who arrive at this barrier after their loop)
           TMARK(0)
@@ -445,17 +449,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           TMARK(4)
           if (f_stats) {
             const int slot = c64 >> 1;
-            const uint32_t base = ob + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
+            // plain shared-memory loads (ordered after the barrier above by its memory clobber): 8 rows in flight,
+            // then their sums, so the loads are not serialised behind the dependent adds
+            const uint8_t* sbase = smem + (ob - ring) + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
             const uint32_t ch = (uint32_t)(lane >> 2);
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; r++) {
-              uint32_t wv;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(base + (uint32_t)r * 128u + ((ch ^ (uint32_t)(r & 7)) << 4)));
-              float lo, hi;
-              unpack_bf16x2(wv, lo, hi);
-              s0 += lo; s1 += hi;
-              q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              uint32_t wv[8];
+#pragma unroll
+              for (int r = 0; r < 8; r++)
+                wv[r] = *reinterpret_cast<const uint32_t*>(sbase + (uint32_t)(r0 + r) * 128u + ((ch ^ (uint32_t)r) << 4));
+#pragma unroll
+              for (int r = 0; r < 8; r++) {
+                float lo, hi;
+                unpack_bf16x2(wv[r], lo, hi);
+                s0 += lo; s1 += hi;
+                q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+              }
             }
             st[slot][0] += s0; st[slot][1] += s1; st[slot][2] += q0; st[slot][3] += q1;
             TMARK(5)

@@ -93,6 +93,10 @@ class Engine:
         self.weights_epoch = 0        # bumped by optimisers that update parameters behind autograd's back
         self.flat_w = None            # fp32 flat master weights (parameters become views of it)
         self.batched_pack = True      # repack all weights in one launch when any changed
+        # BatchNorm backward as ONE launch (iswm_bn_bwd: pass 1, grid barrier, pass 2) for tensors up to this many
+        # elements. Measured on B200 (cfg2): 15.58 ms/step with 0 (two launches everywhere), 15.74 / 15.92 / 16.03 with
+        # 4 Mi / 16 Mi / all -> the barrier and the 3-blocks-per-SM cap cost more than the saved launch; off by default.
+        self.bn_fused_max_elems = int(__import__("os").environ.get("ISWM_BN_FUSED_MAX", "0"))
         self.profile = None           # list of (kernel, algorithmic_flops, start_event, end_event) when profiling
         self.debug_taps = None        # dict name -> NCHW fp32 copy of each unit's output (tools/layer_diff.py)
         self.debug_units = None       # list of per-unit records of the engine's own tensors (tests/test_unit_replay_gpu.py)
@@ -339,13 +343,10 @@ class Engine:
                            residual=None if residual is None else residual.t.clone(),
                            xgrad_before=None if x.grad is None else x.grad.t.clone(),
                            resgrad_before=None if (residual is None or residual.grad is None) else residual.grad.t.clone())
-            sums = self._stats_slot(2 * Cout)
+            sums = self._stats_slot(2 * Cout + 2)        # + the grid barrier's arrival counter
             # the ReLU mask is read from the block output only where a residual was added; otherwise the
-            # kernels recompute it from raw (one tensor read less in each pass)
+            # kernel recomputes it from raw (one tensor read less in each pass)
             act_ptr = out.ptr if (use_mask and residual is not None) else None
-            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
-                                       save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                       1 if use_mask else 0, drop_p, seed, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
             dy = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
             dz_ptr, dz_ld, dz_tmp = None, 0, None
             if residual is not None:
@@ -356,11 +357,22 @@ class Engine:
                     assert residual.grad.ld == residual.C
                     dz_tmp = torch.empty_like(residual.grad.t)
                     dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
-            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
-                                      bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
-                                      1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
-                                      self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
-                  "bn_bwd_apply " + s.name)
+            if M * Cout <= self.bn_fused_max_elems:
+                # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
+                check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
+                                    bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
+                                    1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                    self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
+                      "bn_bwd " + s.name)
+            else:
+                check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
+                                           save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                           1 if use_mask else 0, drop_p, seed, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+                check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
+                                          bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
+                                          1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                          self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
+                      "bn_bwd_apply " + s.name)
             if dz_tmp is not None:
                 check(L.iswm_add_bf16(residual.grad.ptr, dz_tmp.data_ptr(), dz_tmp.numel(), residual.grad.ptr, _st()), "add_bf16")
             out.grad = None
@@ -464,7 +476,7 @@ class Engine:
         need = 0
         for s in self.specs:
             if s.bn is not None:
-                need += 4 * s.cout + 128    # fwd stats + bwd sums (fp64); the same count covers mean/invstd (fp32)
+                need += 4 * s.cout + 192    # fwd stats + bwd sums and barrier counter (fp64); the same count covers mean/invstd (fp32)
         need += 4096
         if getattr(self, "_scratch64", None) is None or self._scratch64.numel() < need or self._scratch64.device != self.device:
             self._scratch64 = torch.empty(need, dtype=torch.float64, device=self.device)
@@ -615,13 +627,11 @@ class Engine:
 
         def backward():
             dout = out.grad
-            sums = self._stats_slot(128)
-            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, save.data_ptr(), save[64:].data_ptr(),
-                                       bn.weight.data_ptr(), bn.bias.data_ptr(), 1, 0.0, 0, sums.data_ptr(), _st()), "bn_bwd_reduce stem")
+            sums = self._stats_slot(130)
             dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
-            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
-                                      save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, dy.data_ptr(), 64, None, 0,
-                                      self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd_apply stem")
+            check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
+                                save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, dy.data_ptr(), 64, None, 0,
+                                self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd stem")
             out.grad = None
             off, n = self.wacc_off[s.name]
             acc = self.wacc[off:off + n]

@@ -34,7 +34,8 @@ def rnd(shape, seed=0, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("B,C,H,W,relu,with_res", [(2, 64, 9, 7, True, False), (3, 48, 8, 8, True, True), (2, 256, 5, 5, False, False), (2, 2048, 4, 4, True, True)])
+@pytest.mark.parametrize("B,C,H,W,relu,with_res", [(2, 64, 9, 7, True, False), (3, 48, 8, 8, True, True), (2, 256, 5, 5, False, False), (2, 2048, 4, 4, True, True),
+                                                    (4, 64, 96, 96, True, False), (4, 256, 48, 48, True, True)])
 def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     x = rnd((B, C, H, W), 1, 2.0)
     res = rnd((B, C, H, W), 2) if with_res else None
@@ -94,6 +95,22 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     close(db, br.grad, 2e-2, 5e-2)
     if with_res:
         close(nchw(dz), resr.grad, 1e-2, 1e-2)
+    # the single-launch version (pass 1, grid barrier, pass 2) must reproduce the two-kernel result bit for bit
+    sums_f = torch.zeros(2 * C + 2, dtype=torch.float64, device=DEV)
+    dx_f = torch.empty_like(dx); dz_f = torch.empty_like(dz)
+    dg_f = torch.zeros(C, dtype=torch.float32, device=DEV); db_f = torch.zeros(C, dtype=torch.float32, device=DEV)
+    check(L().iswm_bn_bwd(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
+                          sums_f.data_ptr(), 1 if relu else 0, 0.0, 0, dx_f.data_ptr(), C, dz_f.data_ptr() if with_res else None, C,
+                          dg_f.data_ptr(), db_f.data_ptr(), st()))
+    torch.cuda.synchronize()
+    from iswm_b200 import ops
+    assert ops.abort_code() == 0
+    # same arithmetic, possibly a different row partition (fp32 partial-sum order): equal to ~1 bf16 ulp / 1e-5
+    close(dx_f.float(), dx.float(), 8e-3, 1e-3 * scale)
+    close(dg_f, dg, 1e-4, 1e-4)
+    close(db_f, db, 1e-4, 1e-4)
+    if with_res:
+        assert torch.equal(dz_f, dz)
 
 
 def test_maxpool_fwd_bwd():
