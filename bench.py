@@ -202,6 +202,45 @@ def traffic_from_profiles(kernel: str):
         return None
 
 
+def profile_by_entry(fn, path):
+    """One instrumented call of `fn`: CUDA events around EVERY library launch, grouped by C-ABI entry point
+    (in-situ times: warm L2, pipelined launches - unlike ncu's serialised cold-cache list)."""
+    from iswm_b200 import _lib
+    _lib.lib()
+    real = _lib._lib
+    rec = []
+
+    class _Prof:
+        def __getattr__(self, name):
+            f = getattr(real, name)
+            if not name.startswith("iswm_") or name in ("iswm_last_error", "iswm_launch_count"):
+                return f
+
+            def wrapped(*a):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = f(*a)
+                e1.record()
+                rec.append((name, e0, e1))
+                return r
+            return wrapped
+    _lib._lib = _Prof()
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        _lib._lib = real
+    by = {}
+    for name, e0, e1 in rec:
+        t, n = by.get(name, (0.0, 0))
+        by[name] = (t + e0.elapsed_time(e1), n + 1)
+    with open(path, "w") as f:
+        tot = sum(t for t, n in by.values())
+        for name, (t, n) in sorted(by.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{name:34s} {n:4d} launches {t * 1e3:9.1f} us {100 * t / tot:5.1f}%\n")
+        f.write(f"{'total':34s} {len(rec):4d} launches {tot * 1e3:9.1f} us\n")
+
+
 def _time_region(fn, steps, barrier):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -308,7 +347,14 @@ def run_predict(args, dev, world, rank, local):
         t_ms = sum(a.elapsed_time(b) for k, fl, a, b, tag in eng.profile if k == "conv_igemm")
         fl = sum(fl for k, fl, a, b, tag in eng.profile if k == "conv_igemm")
         n = sum(1 for k, *_ in eng.profile if k == "conv_igemm")
+        if args.profile_detail:
+            with open(args.profile_detail, "w") as f:
+                for k, fl_, a, b, tag in eng.profile:
+                    dt = a.elapsed_time(b)
+                    f.write(f"{tag:55s} {fl_ / 1e9:10.2f} GF {dt * 1e3:9.1f} us {fl_ / (dt * 1e-3) / 1e12:8.1f} TF/s\n")
         eng.profile = None
+        if args.profile_detail:
+            profile_by_entry(lambda: step(x_dev, y_dev), args.profile_detail + ".by_entry")
         pk = peaks()
         peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         ach = fl / (t_ms * 1e-3) / 1e12
@@ -521,40 +567,8 @@ def run_ours(args):
     step(x_dev, y_dev)
     barrier()
     if rank == 0 and args.profile_detail:
-        # second instrumented step: CUDA events around EVERY library launch, grouped by C-ABI entry point
-        real = _lib._lib
-        rec = []
-
-        class _Prof:
-            def __getattr__(self, name):
-                fn = getattr(real, name)
-                if not name.startswith("iswm_") or name in ("iswm_last_error", "iswm_launch_count"):
-                    return fn
-
-                def wrapped(*a):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    r = fn(*a)
-                    e1.record()
-                    rec.append((name, e0, e1))
-                    return r
-                return wrapped
-        _lib._lib = _Prof()
         eng.profile = None
-        try:
-            step(x_dev, y_dev)
-            torch.cuda.synchronize()
-        finally:
-            _lib._lib = real
-        by = {}
-        for name, e0, e1 in rec:
-            t, n = by.get(name, (0.0, 0))
-            by[name] = (t + e0.elapsed_time(e1), n + 1)
-        with open(args.profile_detail + ".by_entry", "w") as f:
-            tot = sum(t for t, n in by.values())
-            for name, (t, n) in sorted(by.items(), key=lambda kv: -kv[1][0]):
-                f.write(f"{name:34s} {n:4d} launches {t * 1e3:9.1f} us {100 * t / tot:5.1f}%\n")
-            f.write(f"{'total':34s} {len(rec):4d} launches {tot * 1e3:9.1f} us\n")
+        profile_by_entry(lambda: step(x_dev, y_dev), args.profile_detail + ".by_entry")
         eng.profile = []
         step(x_dev, y_dev)
         torch.cuda.synchronize()

@@ -25,6 +25,7 @@
 // same kernel with transposed packed weights and negated tap offsets.
 #include "tc_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace iswm {
 
@@ -54,7 +55,10 @@ struct ConvKParams {
   int* abort_flag;
 };
 
-__global__ void __launch_bounds__(384, 1)
+// NWG = number of epilogue warpgroups: 2 (384 threads, up to 168 registers each) for long-K convolutions whose epilogue
+// hides under the MMA main loop, 3 (512 threads, 128 registers) for short-K ones that are bound by the epilogue.
+template <int NWG>
+__global__ void __launch_bounds__(128 * (NWG + 1), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const ConvKParams p) {
@@ -68,9 +72,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const bool tma_out = p.use_tma_out != 0;
   uint32_t off = (uint32_t)p.stages * stage_bytes;
   const uint32_t obuf = ring + off;
-  if (tma_out) off += 2 * kStageBuf;
+  if (tma_out) off += NWG * kStageBuf;
   const uint32_t rbuf = ring + off;                        // residual prefetch tile, one per epilogue warpgroup
-  if (p.res_prefetch) off += 2 * kStageBuf;
+  if (p.res_prefetch) off += NWG * kStageBuf;
   uint8_t* tail = smem + off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[8] empty[8] tfull[2] tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
@@ -96,7 +100,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; s++) {
       tc::mbar_init(bar_tfull + 8 * s, 1);
-      tc::mbar_init(bar_tempty + 8 * s, 8);   // one arrival per epilogue warp
+      tc::mbar_init(bar_tempty + 8 * s, 4 * NWG);   // one arrival per epilogue warp
     }
     tc::fence_barrier_init();
   }
@@ -214,7 +218,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #endif
   } else if (warp >= 4) {
     // ===================== epilogue: two warpgroups, 64-channel chunks alternate between them =====================
-    const int wg = (warp - 4) >> 2;                     // warpgroup 0 / 1
+    const int nchunk64 = (p.BN + 63) >> 6;
+    const int wg = (warp - 4) >> 2;                     // warpgroup 0 .. NWG-1
+    constexpr int NSLOT = (NWG == 2) ? 2 : 4;           // statistics slots per thread (chunk positions it can own)
+    // which warpgroup owns 64-channel chunk c of this CTA's it-th tile: two warpgroups take alternate chunks
+    // (alternate tiles when a tile is a single chunk), three rotate over the running chunk count
+    auto owner_of = [&](int it_, int c_) -> int {
+      if (NWG == 2) return ((nchunk64 == 1) ? it_ : c_) & 1;
+      return (it_ * nchunk64 + c_) % 3;
+    };
     const int q = warp & 3;                             // TMEM lane quadrant of this warp (warp % 4)
     const int row = q * 32 + lane;                      // accumulator row = thread index inside the warpgroup
     const int bb = row >> (p.lgBW + p.lgBH);
@@ -224,16 +236,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                f_res = p.flags & ISWM_EPI_RESIDUAL, f_stats = p.flags & ISWM_EPI_STATS,
                f_f32 = p.flags & ISWM_EPI_OUT_F32;
     const bool issuer = (row == 0);                     // issues this warpgroup's TMA stores
-    const int nchunk64 = (p.BN + 63) >> 6;
     const uint32_t ob = obuf + (uint32_t)wg * kStageBuf; // this warpgroup's 128 x 64 bf16 staging tile
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);            // 128B swizzle: 16-byte chunk index ^= row % 8
-    const int bar_wg = 1 + wg;                          // named barrier of this warpgroup
+    const int bar_wg = 4 + wg;                          // named barrier of this warpgroup (3 = all epilogue warps)
     // BatchNorm statistics: thread (q, lane) owns channel pair `lane` of rows [32q, 32q+32) of each staged
     // chunk; partial sums stay in registers across this CTA's tiles while the channel tile is unchanged.
-    float st[2][4];
+    float st[NSLOT][4];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < NSLOT; i++)
 #pragma unroll
       for (int j = 0; j < 4; j++) st[i][j] = 0.f;
     // flush: the four quadrant warps of a warpgroup combine their partial sums through the (idle) staging tile in a
@@ -243,17 +254,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (issuer) tc::tma_store_wait_read<0>();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
 #pragma unroll
-      for (int slot = 0; slot < 2; slot++)
+      for (int slot = 0; slot < NSLOT; slot++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ob + (uint32_t)((((q * 2 + slot) * 4 + j) * 32 + lane) * 4)), "f"(st[slot][j]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ob + (uint32_t)((((q * NSLOT + slot) * 4 + j) * 32 + lane) * 4)), "f"(st[slot][j]) : "memory");
           st[slot][j] = 0.f;
         }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
       if (q == 0) {
 #pragma unroll
-        for (int slot = 0; slot < 2; slot++) {
-          const int c64 = (nchunk64 == 1) ? 0 : 2 * slot + wg;
+        for (int slot = 0; slot < NSLOT; slot++) {
+          const int c64 = (NWG == 2) ? ((nchunk64 == 1) ? 0 : 2 * slot + wg) : slot;
           if (c64 >= nchunk64) continue;
           float t[4];
 #pragma unroll
@@ -262,7 +273,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int qq = 0; qq < 4; qq++) {
               float v;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ob + (uint32_t)((((qq * 2 + slot) * 4 + j) * 32 + lane) * 4)));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ob + (uint32_t)((((qq * NSLOT + slot) * 4 + j) * 32 + lane) * 4)));
               t[j] += v;
             }
           }
@@ -285,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t rb_row = rbuf + (uint32_t)wg * kStageBuf + row_off;
     const bool res_pf_ok = f_res && p.res_prefetch != 0;
     auto chunk_owner_ok = [&](int tile_, int it_, int c_) -> bool {
-      if ((((nchunk64 == 1) ? it_ : c_) & 1) != wg) return false;
+      if (owner_of(it_, c_) != wg) return false;
       const int n0_ = (tile_ % p.tiles_n) * p.BN;
       return n0_ + c_ * 64 < p.Cout;
     };
@@ -340,13 +351,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (n0 != cur_n0) {
         if (f_stats && cur_n0 >= 0) flush_stats(cur_n0);
         if (f_aff) {
-          asm volatile("bar.sync 3, 256;" ::: "memory");   // every reader of the previous channel tile is done
-          for (int i = threadIdx.x - 128; i < p.BN; i += 256) {
+          asm volatile("bar.sync 3, %0;" ::"n"(128 * NWG) : "memory");   // every reader of the previous channel tile is done
+          for (int i = threadIdx.x - 128; i < p.BN; i += 128 * NWG) {
             const int n = n0 + i;
             s_scale[i] = (n < p.Cout) ? p.scale[n] : 0.f;
             s_shift[i] = (n < p.Cout) ? p.shift[n] : 0.f;
           }
-          asm volatile("bar.sync 3, 256;" ::: "memory");
+          asm volatile("bar.sync 3, %0;" ::"n"(128 * NWG) : "memory");
         }
         cur_n0 = n0;
       }
@@ -356,7 +367,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       TMARK(1)
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       for (int c64 = 0; c64 < nchunk64; c64++) {
-        if ((((nchunk64 == 1) ? it : c64) & 1) != wg) continue;   // one chunk per tile: warpgroups alternate tiles
+        if (owner_of(it, c64) != wg) continue;
         const int nc = n0 + c64 * 64;                   // first output channel of this chunk
         if (nc >= p.Cout) continue;
         const int ncols = min(64, min(p.BN - c64 * 64, p.Cout - nc));
@@ -448,7 +459,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           TMARK(4)
           if (f_stats) {
-            const int slot = c64 >> 1;
+            const int slot = (NWG == 2) ? (c64 >> 1) : c64;
             // plain shared-memory loads (ordered after the barrier above by its memory clobber): 8 rows in flight,
             // then their sums, so the loads are not serialised behind the dependent adds
             const uint8_t* sbase = smem + (ob - ring) + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
@@ -581,11 +592,21 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
                "conv_igemm: a residual with res_ld %% 8 == 0 must be 16-byte aligned");
   ISWM_REQUIRE(!(d->flags & ISWM_EPI_STATS) || p.use_tma_out, "conv_igemm: STATS needs a bf16 output with out_ld %% 8 == 0 and a 16-byte aligned base");
   int fixed = 1024 /*align*/ + 256 /*barriers*/ + ((d->flags & ISWM_EPI_AFFINE) ? 2048 : 0);
-  if (p.use_tma_out) fixed += 2 * kStageBuf;
+  // Epilogue warpgroups: two. A third one for short-K (epilogue-bound) convolutions was measured and LOST (cfg2
+  // 16.05 vs 15.64 ms/step, cfg4 27.1 vs 26.5): it costs a ring stage and 40 registers per thread, and the epilogue is
+  // paced by TMEM-read and barrier latency rather than by warp count. ISWM_CONV_NWG=3 / ISWM_CONV_NWG3_MAXK=<k-blocks>
+  // re-enable it for experiments.
+  static const int env_nwg = [] { const char* e = getenv("ISWM_CONV_NWG"); return e ? atoi(e) : 2; }();
+  static const int env_rpf = [] { const char* e = getenv("ISWM_RES_PREFETCH"); return e ? atoi(e) : -1; }();
+  static const int env_k3 = [] { const char* e = getenv("ISWM_CONV_NWG3_MAXK"); return e ? atoi(e) : 16; }();
+  int nwg = (env_nwg == 3 || (env_nwg == 0 && d->ntaps * p.kchunks <= env_k3)) ? 3 : 2;
+  if (p.use_tma_out) fixed += nwg * kStageBuf;
   // epilogue-bound (short-K) convolutions hide the residual read behind a shared-memory prefetch; long-K ones keep
   // the ring stage instead and load the residual directly under the TMEM read
   p.res_prefetch = ((d->flags & ISWM_EPI_RESIDUAL) && (d->res_ld % 8) == 0 && d->ntaps * p.kchunks <= 16) ? 1 : 0;
-  if (p.res_prefetch) fixed += 2 * kStageBuf;
+  if (env_rpf == 0) p.res_prefetch = 0;
+  if (env_rpf == 2 && nwg == 3) p.res_prefetch = 0;      // 2: prefetch only with two warpgroups
+  if (p.res_prefetch) fixed += nwg * kStageBuf;
   p.stages = std::max(2, std::min(kMaxStages, (kSmemMax - fixed) / stage_bytes));
   p.flags = d->flags;
   p.n_img_per_phase = B;
@@ -621,12 +642,16 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   const int smem_bytes = p.stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     ISWM_REQUIRE(e == cudaSuccess, "conv_igemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     static_assert(kSmemMax == 232448, "opt-in shared memory limit of sm_100");
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, num_sms());
-  launch_k(conv_igemm_kernel, dim3(grid), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), tmap_a, tmap_b, tmap_out, p);
+  if (nwg == 3)
+    launch_k(conv_igemm_kernel<3>, dim3(grid), dim3(512), smem_bytes, static_cast<cudaStream_t>(stream), tmap_a, tmap_b, tmap_out, p);
+  else
+    launch_k(conv_igemm_kernel<2>, dim3(grid), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), tmap_a, tmap_b, tmap_out, p);
   return check_launch("conv_igemm");
 }
