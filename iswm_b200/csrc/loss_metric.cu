@@ -101,6 +101,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 class_hist_small_kernel(const T* __restrict__ labels, int64_t n, int n_classes,
                         unsigned long long* __restrict__ hist) {
+  pdl_wait();
+  pdl_launch();
   constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte load
   constexpr int UNROLL = 4;
   unsigned cnt[4] = {0, 0, 0, 0};
@@ -145,6 +147,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 class_hist_generic_kernel(const T* __restrict__ labels, int64_t n, int n_classes,
                           unsigned long long* __restrict__ hist) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ unsigned s_hist[];
   for (int i = threadIdx.x; i < n_classes; i += kThreads) s_hist[i] = 0;
   __syncthreads();
@@ -175,11 +179,11 @@ static int launch_class_hist(const void* labels, int64_t n, int n_classes, int64
     constexpr int VEC = 16 / sizeof(T);
     int64_t want = (n / VEC + kThreads * 4 - 1) / (kThreads * 4);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
-    class_hist_small_kernel<T><<<grid, kThreads, 0, st>>>(p, n, n_classes, h);
+    launch_k(class_hist_small_kernel<T>, dim3(grid), dim3(kThreads), 0, st, p, n, n_classes, h);
   } else {
     int64_t want = (n + kThreads * 8 - 1) / (kThreads * 8);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
-    class_hist_generic_kernel<T><<<grid, kThreads, n_classes * sizeof(unsigned), st>>>(p, n, n_classes, h);
+    launch_k(class_hist_generic_kernel<T>, dim3(grid), dim3(kThreads), n_classes * sizeof(unsigned), st, p, n, n_classes, h);
   }
   return check_launch("class_hist");
 }
@@ -224,6 +228,8 @@ __global__ void __launch_bounds__(kThreads)
 wce2_kernel(const LT* __restrict__ logits, const YT* __restrict__ labels,
             const float* __restrict__ weight, const int64_t* __restrict__ hist, WceParams p,
             LT* __restrict__ grad, double* __restrict__ loss_num) {
+  pdl_wait();
+  pdl_launch();
   constexpr int VEC = 16 / sizeof(LT);
   __shared__ float s_gs;
   if (threadIdx.x == 0) {
@@ -281,6 +287,8 @@ __global__ void __launch_bounds__(kThreads)
 wce_generic_kernel(const LT* __restrict__ logits, const YT* __restrict__ labels,
                    const float* __restrict__ weight, const int64_t* __restrict__ hist,
                    WceParams p, LT* __restrict__ grad, double* __restrict__ loss_num) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float s_gs;
   if (threadIdx.x == 0) {
     const double D = wce_denominator(weight, hist, p.C, p.ignore_index);
@@ -323,6 +331,8 @@ wce_generic_kernel(const LT* __restrict__ logits, const YT* __restrict__ labels,
 
 __global__ void wce_finalize_kernel(const double* loss_num, const float* weight,
                                     const int64_t* hist, int C, int ignore_index, float* loss) {
+  pdl_wait();
+  pdl_launch();
   const double D = wce_denominator(weight, hist, C, ignore_index);
   *loss = (float)(*loss_num / D);  // 0/0 -> nan, as PyTorch for an all-ignored batch
 }
@@ -343,14 +353,14 @@ static int launch_wce(const void* logits, const void* labels, const float* weigh
     const int64_t nvec = p.B * (p.HW / VEC);
     int grid = (int)std::min<int64_t>(std::max<int64_t>((nvec + kThreads - 1) / kThreads, 1),
                                       (int64_t)num_sms() * 8);
-    if (g) wce2_kernel<LT, YT, true><<<grid, kThreads, 0, st>>>(x, y, weight, hist, p, g, loss_num);
-    else   wce2_kernel<LT, YT, false><<<grid, kThreads, 0, st>>>(x, y, weight, hist, p, g, loss_num);
+    if (g) launch_k(wce2_kernel<LT, YT, true>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
+    else   launch_k(wce2_kernel<LT, YT, false>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
   } else {
     const int64_t n = p.B * p.HW;
     int grid = (int)std::min<int64_t>(std::max<int64_t>((n + kThreads - 1) / kThreads, 1),
                                       (int64_t)num_sms() * 8);
-    if (g) wce_generic_kernel<LT, YT, true><<<grid, kThreads, 0, st>>>(x, y, weight, hist, p, g, loss_num);
-    else   wce_generic_kernel<LT, YT, false><<<grid, kThreads, 0, st>>>(x, y, weight, hist, p, g, loss_num);
+    if (g) launch_k(wce_generic_kernel<LT, YT, true>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
+    else   launch_k(wce_generic_kernel<LT, YT, false>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
   }
   return check_launch("wce_fwd_bwd");
 }
@@ -362,6 +372,8 @@ template <typename TT, typename PT>
 __global__ void __launch_bounds__(kThreads)
 confusion2_kernel(const TT* __restrict__ tru, const PT* __restrict__ prd, int64_t n,
                   unsigned long long* __restrict__ cm) {
+  pdl_wait();
+  pdl_launch();
   // n_classes == 2: 4 cells + 1 "pred out of range" slot kept in registers
   constexpr int VEC = (sizeof(TT) >= sizeof(PT)) ? 16 / sizeof(TT) : 16 / sizeof(PT);
   unsigned cnt[5] = {0, 0, 0, 0, 0};
@@ -406,6 +418,8 @@ template <typename TT, typename PT>
 __global__ void __launch_bounds__(kThreads)
 confusion_generic_kernel(const TT* __restrict__ tru, const PT* __restrict__ prd, int64_t n,
                          int nc, unsigned long long* __restrict__ cm) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ unsigned s_cm[];
   const int cells = nc * nc + 1;
   for (int i = threadIdx.x; i < cells; i += kThreads) s_cm[i] = 0;
@@ -438,11 +452,11 @@ static int launch_confusion(const void* tru, const void* prd, int64_t n, int nc,
   if (nc == 2 && aligned) {
     int64_t want = (n / VEC + kThreads * 2 - 1) / (kThreads * 2);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
-    confusion2_kernel<TT, PT><<<grid, kThreads, 0, st>>>(t, q, n, c);
+    launch_k(confusion2_kernel<TT, PT>, dim3(grid), dim3(kThreads), 0, st, t, q, n, c);
   } else {
     int64_t want = (n + kThreads * 8 - 1) / (kThreads * 8);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
-    confusion_generic_kernel<TT, PT><<<grid, kThreads, (nc * nc + 1) * sizeof(unsigned), st>>>(t, q, n, nc, c);
+    launch_k(confusion_generic_kernel<TT, PT>, dim3(grid), dim3(kThreads), (nc * nc + 1) * sizeof(unsigned), st, t, q, n, nc, c);
   }
   return check_launch("confusion");
 }
@@ -456,6 +470,8 @@ argmax_confusion_kernel(const LT* __restrict__ logits, const TT* __restrict__ tr
                         int C, int64_t HW, int mode, float threshold,
                         uint8_t* __restrict__ pred_out, uint8_t* __restrict__ conf_out,
                         unsigned long long* __restrict__ cm) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ unsigned s_cm[];
   const int cells = C * C + 1;
   if (cm) {
@@ -509,6 +525,8 @@ __global__ void __launch_bounds__(kThreads)
 argmax_confusion2_kernel(const LT* __restrict__ logits, const TT* __restrict__ tru, int64_t B,
                          int64_t HW, int mode, float threshold, uint8_t* __restrict__ pred_out,
                          uint8_t* __restrict__ conf_out, unsigned long long* __restrict__ cm) {
+  pdl_wait();
+  pdl_launch();
   constexpr int VEC = 16 / sizeof(LT);
   unsigned cnt[4] = {0, 0, 0, 0};
   const int64_t vec_per_img = HW / VEC;
@@ -571,14 +589,14 @@ static int launch_argmax_confusion(const void* logits, const void* tru, int64_t 
     int grid = (int)std::min<int64_t>(std::max<int64_t>((nvec + kThreads - 1) / kThreads, 1),
                                       (int64_t)num_sms() * 8);
     if (has_cm)
-      argmax_confusion2_kernel<LT, TT, true><<<grid, kThreads, 0, st>>>(x, t, B, HW, mode, threshold, pred_out, conf_out, c);
+      launch_k(argmax_confusion2_kernel<LT, TT, true>, dim3(grid), dim3(kThreads), 0, st, x, t, B, HW, mode, threshold, pred_out, conf_out, c);
     else
-      argmax_confusion2_kernel<LT, TT, false><<<grid, kThreads, 0, st>>>(x, t, B, HW, mode, threshold, pred_out, conf_out, c);
+      launch_k(argmax_confusion2_kernel<LT, TT, false>, dim3(grid), dim3(kThreads), 0, st, x, t, B, HW, mode, threshold, pred_out, conf_out, c);
   } else {
     const int64_t n = B * HW;
     int grid = (int)std::min<int64_t>(std::max<int64_t>((n + kThreads - 1) / kThreads, 1),
                                       (int64_t)num_sms() * 8);
-    argmax_confusion_kernel<LT, TT><<<grid, kThreads, (C * C + 1) * sizeof(unsigned), st>>>(
+    launch_k(argmax_confusion_kernel<LT, TT>, dim3(grid), dim3(kThreads), (C * C + 1) * sizeof(unsigned), st, 
         x, t, B, C, HW, mode, threshold, pred_out, conf_out, has_cm ? c : nullptr);
   }
   return check_launch("argmax_confusion");
@@ -639,7 +657,7 @@ extern "C" int iswm_wce_fwd_bwd(const void* d_logits, int logit_dtype, const voi
     if (rc) return rc;
   }
   if (d_loss) {
-    wce_finalize_kernel<<<1, 1, 0, st>>>(d_loss_num, d_weight, d_hist, C, ignore_index, d_loss);
+    launch_k(wce_finalize_kernel, dim3(1), dim3(1), 0, st, d_loss_num, d_weight, d_hist, C, ignore_index, d_loss);
     return check_launch("wce_finalize");
   }
   return 0;

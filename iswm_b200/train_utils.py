@@ -38,3 +38,37 @@ def setup_criterion(opts, class_weights):
     elif opts.loss_type == "IWce_loss":
         return CrossEntropyLoss(weight=class_weights, ignore_index=255, reduction="mean")
     return None
+
+
+class DeferredLoss:
+    """Per-step loss logging without stalling the launch pipeline.
+
+    The reference reads the loss synchronously right after every step (`np_loss = loss.detach().cpu().numpy()`,
+    train.py:1051), which idles the GPU while the host enqueues the next step. `push(loss)` starts an asynchronous
+    device->host copy of THIS step's loss into pinned memory and returns the PREVIOUS step's value as a Python float
+    (None on the first call): every step's loss still reaches the host, one step later; `flush()` returns the last one.
+    """
+
+    def __init__(self):
+        self._host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._ev = [None, None]
+        self._n = 0
+
+    def push(self, loss: torch.Tensor):
+        slot = self._n & 1
+        prev = self.flush() if self._n > 0 else None
+        self._host[slot].copy_(loss.detach(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ev[slot] = ev
+        self._n += 1
+        self._pending = slot
+        return prev
+
+    def flush(self):
+        slot = getattr(self, "_pending", None)
+        if slot is None:
+            return None
+        self._ev[slot].synchronize()
+        self._pending = None
+        return float(self._host[slot])

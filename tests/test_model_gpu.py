@@ -235,3 +235,24 @@ def test_train_two_steps_with_torch_optimizer_changes_output():
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_predict_mask_matches_reference_semantics(golden_dir):
+    """predict.py:262-278 on our logits: class map and uint8 confidence bit-exact vs the numpy oracle applied to the SAME
+    logits, confusion counts equal to StreamMetrics._fast_hist of that class map."""
+    from iswm_b200.metrics import StreamMetrics
+    from iswm_b200.predict import predict_mask
+    from oracle import oracle_np as O
+    g = np.load(os.path.join(golden_dir, "model_r50_os16.npz"))
+    m, _ = build("resnet50", 16)
+    m.to(DEV).eval()
+    x, y = torch.tensor(g["x"]).to(DEV), torch.tensor(g["y"]).to(DEV)
+    sm = StreamMetrics(2, device=DEV)
+    pred, conf = predict_mask(m, x, threshold=0.5, labels=y, metrics=sm)
+    logits = m(x).cpu().numpy()
+    ref_pred, ref_conf = O.threshold_pred(logits, 0.5)
+    assert pred.dtype == torch.uint8 and conf.dtype == torch.uint8
+    assert np.array_equal(pred.cpu().numpy(), ref_pred.astype(np.uint8))
+    assert np.abs(conf.cpu().numpy().astype(np.int32) - ref_conf.astype(np.int32)).max() <= 1     # uint8(p*255) at a rounding edge
+    ref_cm = O.fast_hist(g["y"].reshape(-1), ref_pred.reshape(-1), 2)
+    assert sm.confusion_matrix.astype(np.int64).tolist() == ref_cm.tolist()
