@@ -97,6 +97,12 @@ class Engine:
         # elements. Measured on B200 (cfg2): 15.58 ms/step with 0 (two launches everywhere), 15.74 / 15.92 / 16.03 with
         # 4 Mi / 16 Mi / all -> the barrier and the 3-blocks-per-SM cap cost more than the saved launch; off by default.
         self.bn_fused_max_elems = int(__import__("os").environ.get("ISWM_BN_FUSED_MAX", "0"))
+        # weight gradients feed nothing inside the backward sweep: they run on a second stream so that their
+        # (tensor-core) kernels overlap the HBM-bound BatchNorm kernels and the launch / fill / drain gaps of the
+        # data-gradient chain; ISWM_ASYNC_WGRAD=0 puts them back in line
+        self.async_wgrad = __import__("os").environ.get("ISWM_ASYNC_WGRAD", "1") != "0"
+        self._wstream = None
+        self._wgrad_keep = []
         self.profile = None           # list of (kernel, algorithmic_flops, start_event, end_event) when profiling
         self.debug_taps = None        # dict name -> NCHW fp32 copy of each unit's output (tools/layer_diff.py)
         self.debug_units = None       # list of per-unit records of the engine's own tensors (tests/test_unit_replay_gpu.py)
@@ -382,8 +388,6 @@ class Engine:
                            dbeta=self.grad_views[id(bn.bias)].clone(), xgrad_after=None if x.grad is None else x.grad.t.clone(),
                            resgrad_after=None if residual is None else residual.grad.t.clone())
                 self.debug_units.append(rec)
-            self._notify(bn.weight)
-            self._notify(bn.bias)
 
         self.tape.append(backward)
         return out
@@ -395,17 +399,23 @@ class Engine:
         dy_ld = dy.shape[-1]
         gview = self.grad_views[id(s.conv.weight)]
         d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps)
-        ev = self._prof_begin()
-        if s.k == 1:
-            check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), gview.data_ptr(), _st()), "conv_wgrad " + s.name)
-            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin, "wgrad " + s.name)
-        else:
-            off, n = self.wacc_off[s.name]
-            acc = self.wacc[off:off + n]
-            check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
-            self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k, "wgrad " + s.name)
-            check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
-        self._notify(s.conv.weight)
+        with self._wgrad_ctx(dy, xin.t):
+            ev = self._prof_begin()
+            if s.k == 1:
+                check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), gview.data_ptr(), _st()), "conv_wgrad " + s.name)
+                self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin, "wgrad " + s.name)
+            else:
+                off, n = self.wacc_off[s.name]
+                acc = self.wacc[off:off + n]
+                check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
+                self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k, "wgrad " + s.name)
+                check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
+            # notifications are issued in the same context: a bucket all-reduce launched from here orders itself after
+            # this stream, which has seen everything the main stream produced up to this unit (BatchNorm gradients too)
+            self._notify(s.conv.weight)
+            if s.bn is not None:
+                self._notify(s.bn.weight)
+                self._notify(s.bn.bias)
         if not need_dx:
             return
         Cin = s.cin
@@ -447,6 +457,32 @@ class Engine:
         # for the zero-stuffed positions of the stride-2 case)
         fwd_pix = B * (Ho // s.stride if s.stride > 1 else Ho) * (Wo // s.stride if s.stride > 1 else Wo)
         self._prof_end(ev, "conv_igemm", 2.0 * fwd_pix * Cout * Cin * len(dtaps), "dgrad " + s.name)
+
+    # ------------------------------------------------------------------ weight-gradient stream
+    class _NullCtx:
+        def __enter__(self): return None
+        def __exit__(self, *a): return False
+
+    def _wgrad_ctx(self, *keep_alive: torch.Tensor):
+        """Context in which weight-gradient kernels (and the gradient-ready notifications that depend on them) are
+        issued: the side stream, after everything enqueued so far on the main stream. `keep_alive` tensors are read
+        there, so the caching allocator must not recycle them before the side stream is done with them."""
+        if not self.async_wgrad or self.debug_units is not None:      # the unit-replay recorder reads dW right away
+            return Engine._NullCtx()
+        if self._wstream is None or self._wstream.device != self.device:
+            self._wstream = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._wstream.wait_event(main.record_event())
+        # held until the join below: their memory returns to the (main-stream) allocator pool only after the main
+        # stream has waited for the side stream, so no record_stream() bookkeeping (which makes the allocator grow
+        # and stall when the host runs far ahead) is needed
+        self._wgrad_keep.extend(keep_alive)
+        return torch.cuda.stream(self._wstream)
+
+    def _wgrad_join(self):
+        if self.async_wgrad and self._wstream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._wstream)
+        self._wgrad_keep = []
 
     def _prof_begin(self):
         if self.profile is None:
@@ -636,9 +672,13 @@ class Engine:
             off, n = self.wacc_off[s.name]
             acc = self.wacc[off:off + n]
             d = ops.make_conv_desc(1, 1, M, colA.C, colA.ld, 1, 1, M, 64, 64, taps)
-            check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
             gview = self.grad_views[id(s.conv.weight)]
-            check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
+            with self._wgrad_ctx(dy, colA.t):
+                check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
+                check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
+                self._notify(s.conv.weight)
+                self._notify(bn.weight)
+                self._notify(bn.bias)
             if self.debug_units is not None:
                 self.debug_units.append(dict(name=s.name, k=7, stride=2, dilation=1, relu=True, x=None, image=self._image, raw=raw.view(B, H1, W1, 64).clone(),
                                              out=out.t.clone(), dout=dout.t.clone(), mean=save[:64].clone(), invstd=save[64:128].clone(),
@@ -646,9 +686,6 @@ class Engine:
                                              residual=None, xgrad_before=None, resgrad_before=None, dy=dy.view(B, H1, W1, 64).clone(),
                                              dW=gview.clone(), dgamma=self.grad_views[id(bn.weight)].clone(), dbeta=self.grad_views[id(bn.bias)].clone(),
                                              xgrad_after=None, resgrad_after=None))
-            self._notify(s.conv.weight)
-            self._notify(bn.weight)
-            self._notify(bn.bias)
 
         self.tape.append(backward)
         return out
@@ -715,13 +752,14 @@ class Engine:
         # classifier: bias grad, low-res logits gradient, weight grad, data grad
         cls = self.cls
         check(L.iswm_bias_grad_nchw(dlogits.data_ptr(), B, ncls, H * W, self.grad_views[id(cls.conv.bias)].data_ptr(), _st()), "bias_grad")
-        self._notify(cls.conv.bias)
         ldp = 8 * ((ncls + 7) // 8)
         dlo = torch.empty((B, h4, w4, ldp), dtype=torch.bfloat16, device=dev)
         check(L.iswm_logits_up_bwd(dlogits.data_ptr(), B, h4, w4, ncls, H, W, dlo.data_ptr(), ldp, _st()), "logits_up_bwd")
         d = ops.make_conv_desc(B, h4, w4, y.C, y.ld, B, h4, w4, ncls, ldp, [(0, 0, 0)])
-        check(L.iswm_conv_wgrad(C.byref(d), y.ptr, dlo.data_ptr(), self.grad_views[id(cls.conv.weight)].data_ptr(), _st()), "conv_wgrad cls")
-        self._notify(cls.conv.weight)
+        with self._wgrad_ctx(dlo, y.t):
+            check(L.iswm_conv_wgrad(C.byref(d), y.ptr, dlo.data_ptr(), self.grad_views[id(cls.conv.weight)].data_ptr(), _st()), "conv_wgrad cls")
+            self._notify(cls.conv.bias)
+            self._notify(cls.conv.weight)
         self._dgrad_into(cls, y, dlo, ldp, h4, w4, [(0, 0, 0)], h4, w4)
         if self.debug_units is not None:
             self.debug_units.append(dict(name=cls.name, kind="cls", x=y.t.clone(), dlogits=dlogits.clone(), dlo=dlo.clone(),
@@ -730,5 +768,6 @@ class Engine:
         # reverse sweep
         for fn in reversed(self.tape):
             fn()
+        self._wgrad_join()                       # the optimiser / all-reduce tail sees every weight gradient
         self.tape = []
         self._saved = None
