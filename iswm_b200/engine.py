@@ -25,8 +25,29 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+class _StreamCache:
+    """Raw handle of the CUDA stream the engine is launching on. torch.cuda.current_stream() costs a few microseconds
+    per call and the engine makes ~550 launches per step, so forward() / backward() look it up once and the
+    weight-gradient context swaps it explicitly."""
+    handle = None
+
+
 def _st() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    h = _StreamCache.handle
+    return torch.cuda.current_stream().cuda_stream if h is None else h
+
+
+class _StreamScope:
+    """with _StreamScope(): ... pins _st() to the stream that is current on entry."""
+
+    def __enter__(self):
+        self.prev = _StreamCache.handle
+        _StreamCache.handle = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *a):
+        _StreamCache.handle = self.prev
+        return False
 
 
 class Act:
@@ -145,10 +166,17 @@ class Engine:
         return s
 
     # ------------------------------------------------------------------ parameters / packing
+    def _param_list(self):
+        """model.parameters() walks the whole module tree (~25k Python calls); the tree is static, so walk it once."""
+        pl = getattr(self, "_params_cache", None)
+        if pl is None:
+            pl = self._params_cache = list(self.model.parameters())
+        return pl
+
     def _check_device(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("iswm_b200 runs on CUDA only: move the model and the input to a B200 (no CPU fallback)")
-        for p in self.model.parameters():
+        for p in self._param_list():
             if p.device != x.device:
                 raise RuntimeError(f"parameter on {p.device} but input on {x.device}: call model.to(device) first")
             break
@@ -209,7 +237,7 @@ class Engine:
         """Re-point every parameter at a view of ONE flat fp32 buffer (same registration order as the flat
         gradient buffer) so the optimiser step and the gradient all-reduce are single passes over
         contiguous memory. Parameter objects keep their identity; state_dict / checkpoints are unchanged."""
-        params = [p for p in self.model.parameters()]
+        params = self._param_list()
         total = sum(p.numel() for p in params)
         dev = params[0].device
         if self.flat_w is not None and self.flat_w.device == dev and self.flat_w.numel() == total:
@@ -238,7 +266,7 @@ class Engine:
         self.weights_epoch += 1
 
     def _ensure_grad_buffers(self):
-        params = [p for p in self.model.parameters()]
+        params = self._param_list()
         total = sum(p.numel() for p in params)
         if self.flat_g is None or self.flat_g.numel() != total or self.flat_g.device != self.device:
             self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -463,6 +491,21 @@ class Engine:
         def __enter__(self): return None
         def __exit__(self, *a): return False
 
+    class _SideCtx:
+        def __init__(self, stream):
+            self.ctx = torch.cuda.stream(stream)
+            self.handle = stream.cuda_stream
+
+        def __enter__(self):
+            self.ctx.__enter__()
+            self.prev = _StreamCache.handle
+            _StreamCache.handle = self.handle
+            return self
+
+        def __exit__(self, *a):
+            _StreamCache.handle = self.prev
+            return self.ctx.__exit__(*a)
+
     def _wgrad_ctx(self, *keep_alive: torch.Tensor):
         """Context in which weight-gradient kernels (and the gradient-ready notifications that depend on them) are
         issued: the side stream, after everything enqueued so far on the main stream. `keep_alive` tensors are read
@@ -477,7 +520,7 @@ class Engine:
         # stream has waited for the side stream, so no record_stream() bookkeeping (which makes the allocator grow
         # and stall when the host runs far ahead) is needed
         self._wgrad_keep.extend(keep_alive)
-        return torch.cuda.stream(self._wstream)
+        return Engine._SideCtx(self._wstream)
 
     def _wgrad_join(self):
         if self.async_wgrad and self._wstream is not None:
@@ -540,6 +583,10 @@ class Engine:
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
         """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]."""
+        with _StreamScope():
+            return self._forward(x, train)
+
+    def _forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
         self._check_device(x)
         if x.dim() != 4 or x.shape[1] != self.stem.cin:
             raise ValueError(f"expected [B,{self.stem.cin},H,W] input, got {tuple(x.shape)}")
@@ -731,11 +778,15 @@ class Engine:
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits: torch.Tensor):
         """dlogits: fp32 NCHW gradient of the loss w.r.t. the logits returned by forward(train=True)."""
+        with _StreamScope():
+            self._backward(dlogits)
+
+    def _backward(self, dlogits: torch.Tensor):
         L = _lib.lib()
         y, B, h4, w4, H, W, ncls = self._saved
         dev = self.device
         dlogits = dlogits.contiguous().float()
-        params = list(self.model.parameters())
+        params = self._param_list()
         fresh = all(p.grad is None for p in params)
         if fresh:
             self.flat_g.zero_()

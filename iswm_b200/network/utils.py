@@ -42,11 +42,11 @@ class _SimpleSegmentationModel(nn.Module):
 
     def forward(self, x):
         eng = self.engine()
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        params = eng._param_list()                      # cached walk of the (static) module tree
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if self.training:
             if needs_grad:
-                anchor = next(self.parameters())
-                return _EngineFn.apply(x, eng, anchor, *self.parameters())
+                return _EngineFn.apply(x, eng, params[0], *params)
             return eng.forward(x, train=True)          # BN batch statistics, no tape kept for backward
         with torch.no_grad():                          # eval: BatchNorm folded into the conv epilogues
             return eng.forward(x, train=False)

@@ -23,7 +23,7 @@ class FusedSGD:
         self._steps = 0
 
     def zero_grad(self, set_to_none: bool = True):
-        for p in self.model.parameters():
+        for p in self.engine._param_list():
             if set_to_none:
                 p.grad = None
             elif p.grad is not None:
