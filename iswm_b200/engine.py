@@ -118,6 +118,7 @@ class Engine:
         # elements. Measured on B200 (cfg2): 15.58 ms/step with 0 (two launches everywhere), 15.74 / 15.92 / 16.03 with
         # 4 Mi / 16 Mi / all -> the barrier and the 3-blocks-per-SM cap cost more than the saved launch; off by default.
         self.bn_fused_max_elems = int(__import__("os").environ.get("ISWM_BN_FUSED_MAX", "0"))
+        self.bn_fused_min_elems = int(__import__("os").environ.get("ISWM_BN_FUSED_MIN", str(1 << 62)))
         # weight gradients feed nothing inside the backward sweep: they run on a second stream so that their
         # (tensor-core) kernels overlap the HBM-bound BatchNorm kernels and the launch / fill / drain gaps of the
         # data-gradient chain; ISWM_ASYNC_WGRAD=0 puts them back in line
@@ -391,7 +392,7 @@ class Engine:
                     assert residual.grad.ld == residual.C
                     dz_tmp = torch.empty_like(residual.grad.t)
                     dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
-            if M * Cout <= self.bn_fused_max_elems:
+            if M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems:
                 # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
                 check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                     bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
