@@ -228,6 +228,22 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
+  // the first U rows are requested BEFORE the per-channel constants (a chain of dependent global loads and fp64
+  // math): the two latencies overlap, which is most of a thread's life on small tensors
+  constexpr int U = 4;
+  const RowWalk w = row_walk(M, rows_per_block, ty, ny);
+  const __nv_bfloat16* px = x + w.first * x_ld + c0;
+  const __nv_bfloat16* pr = RES ? res + w.first * res_ld + c0 : nullptr;
+  const int64_t sx = (int64_t)ny * x_ld, sr = (int64_t)ny * res_ld;
+  uint4 fr[U], rr[U];
+  const bool pre = w.n >= U;
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      fr[u] = load_raw(px + u * sx);
+      if (RES) rr[u] = load_raw(pr + u * sr);
+    }
+  }
   const double invM = 1.0 / (double)M;
   float sc[8], sh[8];
 #pragma unroll
@@ -252,19 +268,16 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
   const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
-  const RowWalk w = row_walk(M, rows_per_block, ty, ny);
-  const __nv_bfloat16* px = x + w.first * x_ld + c0;
-  const __nv_bfloat16* pr = RES ? res + w.first * res_ld + c0 : nullptr;
   __nv_bfloat16* po = out + w.first * out_ld + c0;
-  const int64_t sx = (int64_t)ny * x_ld, sr = (int64_t)ny * res_ld, so = (int64_t)ny * out_ld;
+  const int64_t so = (int64_t)ny * out_ld;
   uint64_t didx = (uint64_t)w.first * C + c0;                 // dropout counter of this thread's first element
   const uint64_t sd = (uint64_t)ny * C;
-  auto one = [&](const uint4& fr, const uint4& rr, __nv_bfloat16* o, uint64_t di) {
-    F8 f = unpack8(fr);
+  auto one = [&](const uint4& f4, const uint4& r4, __nv_bfloat16* o, uint64_t di) {
+    F8 f = unpack8(f4);
 #pragma unroll
     for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
     if (RES) {
-      const F8 r = unpack8(rr);
+      const F8 r = unpack8(r4);
 #pragma unroll
       for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
     }
@@ -278,14 +291,14 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
     }
     store8(o, f);
   };
-  constexpr int U = 4;
   int i = 0;
   for (; i + U <= w.n; i += U) {
-    uint4 fr[U], rr[U];
+    if (i > 0) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      fr[u] = load_raw(px + u * sx);
-      if (RES) rr[u] = load_raw(pr + u * sr);
+      for (int u = 0; u < U; u++) {
+        fr[u] = load_raw(px + u * sx);
+        if (RES) rr[u] = load_raw(pr + u * sr);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) one(fr[u], rr[u], po + u * so, didx + u * sd);
@@ -293,10 +306,10 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
     if (RES) pr += U * sr;
   }
   for (; i < w.n; i++) {
-    const uint4 fr = load_raw(px);
-    uint4 rr = fr;
-    if (RES) rr = load_raw(pr);
-    one(fr, rr, po, didx);
+    const uint4 f4 = load_raw(px);
+    uint4 r4 = f4;
+    if (RES) r4 = load_raw(pr);
+    one(f4, r4, po, didx);
     px += sx; po += so; didx += sd;
     if (RES) pr += sr;
   }
@@ -333,6 +346,22 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
   const int c0 = tx << 3;
+  constexpr int U = 4;
+  // first batch of rows requested before the per-channel constants are loaded (overlapping latencies)
+  const RowWalk w = (ty < ny) ? row_walk(M, rows_per_block, ty, ny) : RowWalk{0, 0};
+  const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
+  const __nv_bfloat16* px = x + w.first * x_ld + c0;
+  const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
+  const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa = (int64_t)ny * act_ld;
+  uint4 gr[U], xr[U], orr[U];
+  if (w.n >= U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      gr[u] = load_raw(pg + u * sg);
+      xr[u] = load_raw(px + u * sx);
+      if (MASK == 1) orr[u] = load_raw(pa + u * sa); else orr[u] = gr[u];
+    }
+  }
   float a[8], b[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
@@ -345,11 +374,6 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     }
   }
   if (ty < ny) {
-    const RowWalk w = row_walk(M, rows_per_block, ty, ny);
-    const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
-    const __nv_bfloat16* px = x + w.first * x_ld + c0;
-    const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
-    const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa = (int64_t)ny * act_ld;
     uint64_t didx = (uint64_t)w.first * C + c0;
     const uint64_t sd = (uint64_t)ny * C;
     auto one = [&](const uint4& gr, const uint4& xr, const uint4& orr, uint64_t di) {
@@ -373,15 +397,15 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
         b[j] = fmaf(g.v[j], xv.v[j], b[j]);
       }
     };
-    constexpr int U = 4;
     int i = 0;
     for (; i + U <= w.n; i += U) {
-      uint4 gr[U], xr[U], orr[U];
+      if (i > 0) {
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        gr[u] = load_raw(pg + u * sg);
-        xr[u] = load_raw(px + u * sx);
-        if (MASK == 1) orr[u] = load_raw(pa + u * sa); else orr[u] = gr[u];
+        for (int u = 0; u < U; u++) {
+          gr[u] = load_raw(pg + u * sg);
+          xr[u] = load_raw(px + u * sx);
+          if (MASK == 1) orr[u] = load_raw(pa + u * sa); else orr[u] = gr[u];
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; u++) one(gr[u], xr[u], orr[u], didx + u * sd);
@@ -389,10 +413,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       if (MASK == 1) pa += U * sa;
     }
     for (; i < w.n; i++) {
-      const uint4 gr = load_raw(pg), xr = load_raw(px);
-      uint4 orr = gr;
-      if (MASK == 1) orr = load_raw(pa);
-      one(gr, xr, orr, didx);
+      const uint4 g1 = load_raw(pg), x1 = load_raw(px);
+      uint4 o1 = g1;
+      if (MASK == 1) o1 = load_raw(pa);
+      one(g1, x1, o1, didx);
       pg += sg; px += sx; didx += sd;
       if (MASK == 1) pa += sa;
     }
@@ -433,6 +457,22 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
+  constexpr int U = 4;
+  // first batch of rows requested before the per-channel constants are loaded (overlapping latencies)
+  const RowWalk w = row_walk(M, rows_per_block, ty, ny);
+  const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
+  const __nv_bfloat16* px = x + w.first * x_ld + c0;
+  const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
+  const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa_ = (int64_t)ny * act_ld;
+  uint4 gr[U], xr[U], orr[U];
+  if (w.n >= U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      gr[u] = load_raw(pg + u * sg);
+      xr[u] = load_raw(px + u * sx);
+      if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else orr[u] = gr[u];
+    }
+  }
   const float invM = 1.0f / (float)M;
   // dx = k*dz + p*x + q  with  k = gamma*invstd, p = -k*invstd*mean(dz*xhat), q = -k*mean(dz) - p*mu
   float kk[8], pp[8], qq[8], sh[8];
@@ -453,14 +493,9 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     }
   }
   const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
-  const RowWalk w = row_walk(M, rows_per_block, ty, ny);
-  const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
-  const __nv_bfloat16* px = x + w.first * x_ld + c0;
-  const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
   __nv_bfloat16* pdx = dx + w.first * dx_ld + c0;
   __nv_bfloat16* pdz = DZ ? dz + w.first * dz_ld + c0 : nullptr;
-  const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa_ = (int64_t)ny * act_ld,
-                sdx = (int64_t)ny * dx_ld, sdz = (int64_t)ny * dz_ld;
+  const int64_t sdx = (int64_t)ny * dx_ld, sdz = (int64_t)ny * dz_ld;
   uint64_t didx = (uint64_t)w.first * C + c0;
   const uint64_t sd = (uint64_t)ny * C;
   auto one = [&](const uint4& gr, const uint4& xr, const uint4& orr, __nv_bfloat16* odx, __nv_bfloat16* odz, uint64_t di) {
@@ -484,15 +519,15 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     for (int j = 0; j < 8; j++) r.v[j] = fmaf(kk[j], g.v[j], fmaf(pp[j], xv.v[j], qq[j]));
     store8(odx, r);
   };
-  constexpr int U = 4;
   int i = 0;
   for (; i + U <= w.n; i += U) {
-    uint4 gr[U], xr[U], orr[U];
+    if (i > 0) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      gr[u] = load_raw(pg + u * sg);
-      xr[u] = load_raw(px + u * sx);
-      if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else orr[u] = gr[u];
+      for (int u = 0; u < U; u++) {
+        gr[u] = load_raw(pg + u * sg);
+        xr[u] = load_raw(px + u * sx);
+        if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else orr[u] = gr[u];
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) one(gr[u], xr[u], orr[u], pdx + u * sdx, DZ ? pdz + u * sdz : nullptr, didx + u * sd);
@@ -501,10 +536,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     if (DZ) pdz += U * sdz;
   }
   for (; i < w.n; i++) {
-    const uint4 gr = load_raw(pg), xr = load_raw(px);
-    uint4 orr = gr;
-    if (MASK == 1) orr = load_raw(pa);
-    one(gr, xr, orr, pdx, pdz, didx);
+    const uint4 g1 = load_raw(pg), x1 = load_raw(px);
+    uint4 o1 = g1;
+    if (MASK == 1) o1 = load_raw(pa);
+    one(g1, x1, o1, pdx, pdz, didx);
     pg += sg; px += sx; pdx += sdx; didx += sd;
     if (MASK == 1) pa += sa_;
     if (DZ) pdz += sdz;
