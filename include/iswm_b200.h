@@ -96,6 +96,29 @@ int iswm_argmax_confusion(const void* d_logits, int logit_dtype, const void* d_t
                           float threshold, uint8_t* d_pred_out, uint8_t* d_conf_out,
                           int64_t* d_cm, void* stream);
 
+/* ---- the step after the hot path: fused predict epilogue ---------------- */
+/* Final bilinear upsample (network/utils.py:22, align_corners=False) of the LOW-resolution two-class logits fused with
+ * softmax + threshold + confidence map (predict.py:262-290) and, optionally, the confusion matrix
+ * (evaluate_quantization.py:265-270): writes uint8 maps only, the full-resolution fp32 logits never exist.
+ *   d_lo        float32 NHWC [B,Hi,Wi,2] (what the classifier 1x1 conv writes)
+ *   mode        0: pred = argmax (ties -> 0); 1: pred = softmax[:,1] > threshold
+ *   d_true      labels [B,Ho,Wo] or NULL; d_cm int64[5] accumulated into (layout of iswm_confusion) or NULL
+ *   d_pred_out  uint8 [B,Ho,Wo] or NULL; d_conf_out uint8 [B,Ho,Wo] = uint8(prob1*255) (mode 1) or NULL
+ * Bit-identical to iswm_logits_up_fwd followed by iswm_argmax_confusion. Requires C == 2 and Wo % 4 == 0. */
+int iswm_predict_epilogue(const float* d_lo, int B, int Hi, int Wi, int C, int Ho, int Wo, int mode,
+                          float threshold, const void* d_true, int true_dtype, uint8_t* d_pred_out,
+                          uint8_t* d_conf_out, int64_t* d_cm, void* stream);
+
+/* Focal loss forward + backward in one pass (utils/loss.py:14-35 FocalLoss, exported through create_loss :37-39):
+ *   ce_i = w[y_i] * nll_i (0 where y_i == ignore_index or outside [0,C)); pt = exp(-ce_i)
+ *   loss = sum_i alpha * (1 - pt)^gamma * ce_i, divided by the number of ALL pixels when size_average
+ *   d_grad (same shape / dtype as logits, or NULL) = dloss/dlogits; d_loss_num double[1] ACCUMULATES the sum;
+ *   d_loss float[1] or NULL receives the final scalar. */
+int iswm_focal_fwd_bwd(const void* d_logits, int logit_dtype, const void* d_labels, int label_dtype,
+                       const float* d_weight, int64_t B, int C, int64_t HW, int ignore_index,
+                       float alpha, float gamma, int size_average, void* d_grad, double* d_loss_num,
+                       float* d_loss, void* stream);
+
 /* ---- convolution as implicit GEMM on tcgen05 / TMEM / TMA -------------- */
 
 #define ISWM_MAX_TAPS 16
@@ -261,6 +284,28 @@ int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, const float* d_
 /* fused multi-tensor SGD(momentum, nesterov, weight decay) step (train.py:421-431, :1049) on a flat fp32 buffer */
 int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr, float momentum,
                   float weight_decay, int nesterov, int first_step, void* stream);
+
+/* fused Adam / AdamW step on a flat fp32 buffer: torch.optim.Adam(weight_decay) and torch.optim.AdamW(weight_decay)
+ * as train.py:432-441 builds them (torch defaults lr 1e-3, betas (0.9, 0.999), eps 1e-8), stepped at train.py:1049.
+ * adamw = 0: L2 decay added to the gradient; 1: decoupled decay. step = 1 on the first update (bias correction). */
+int iswm_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int adamw,
+                   int64_t step, void* stream);
+
+/* ---- the step before the hot path: device input pipeline ---------------- */
+/* ExtRandomCrop (window origin per image, no padding) + ExtRandomHorizontalFlip + ExtToTensor + ExtNormalize
+ * (utils/ext_transforms.py:327-393, :94-111, :273-293, :298-324; composed at train.py:355-368) on uint8 HWC tiles:
+ *   d_src        uint8 [B,Hs,Ws,C] (C = 1..4), device
+ *   d_origin_xy  int32 [B,2] = (x0, y0) of each image's H x W window, device, or NULL (0,0)
+ *   d_flip       uint8 [B], non-zero = mirror the window horizontally, device, or NULL
+ *   mean, stdv   HOST float[C]
+ *   d_out        float32 NCHW [B,C,H,W] = ((src/255) - mean) / std, IEEE arithmetic (bit-identical to torchvision)
+ * iswm_crop_flip_u8 applies the same window / flip to the uint8 label tile [B,Hs,Ws] -> [B,H,W]. */
+int iswm_u8_to_f32_norm(const uint8_t* d_src, int B, int Hs, int Ws, int C, const int32_t* d_origin_xy,
+                        const uint8_t* d_flip, const float* mean, const float* stdv, int H, int W,
+                        float* d_out, void* stream);
+int iswm_crop_flip_u8(const uint8_t* d_src, int B, int Hs, int Ws, const int32_t* d_origin_xy,
+                      const uint8_t* d_flip, int H, int W, uint8_t* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,8 @@ SIGNATURES = {
     "iswm_wce_fwd_bwd": (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _i64, _i, _f, _p, _p, _p, _p]),
     "iswm_confusion": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p]),
     "iswm_argmax_confusion": (_i, [_p, _i, _p, _i, _i64, _i, _i64, _i, _f, _p, _p, _p, _p]),
+    "iswm_predict_epilogue": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p, _p, _p, _p]),
+    "iswm_focal_fwd_bwd": (_i, [_p, _i, _p, _i, _p, _i64, _i, _i64, _i, _f, _f, _i, _p, _p, _p, _p]),
     "iswm_conv_igemm": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p]),
     "iswm_conv_wgrad": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p]),
     "iswm_pack_weight_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
@@ -99,6 +101,9 @@ SIGNATURES = {
     "iswm_bias_grad_nchw": (_i, [_p, _i, _i, _i64, _p, _p]),
     "iswm_scale_by_device_scalar": (_i, [_p, _i, _i64, _p, _p]),
     "iswm_sgd_step": (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _p]),
+    "iswm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _i64, _p]),
+    "iswm_u8_to_f32_norm": (_i, [_p, _i, _i, _i, _i, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _p, _p]),
+    "iswm_crop_flip_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
 }
 
 _lib = None

@@ -68,6 +68,26 @@ inline int num_sms() {
   return n;
 }
 
+// Largest grid of a grid-stride kernel that is resident all at once: SMs x the occupancy the compiled kernel really
+// gets (register count decides it, e.g. 44 registers x 256 threads = 5 blocks per SM, not the 8 a 32-register kernel
+// would have). A grid above this runs as 1.x waves and the partial last wave is a pure tail. Cached per kernel.
+template <typename K>
+inline int resident_grid(K kernel, int block, size_t smem = 0) {
+  struct Slot { const void* fn; int blocks; };
+  static thread_local Slot cache[64];
+  static thread_local int n_cached = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n_cached; i++)
+    if (cache[i].fn == key) return cache[i].blocks * num_sms();
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ <= 0) {
+    cudaGetLastError();
+    occ = 4;
+  }
+  if (n_cached < 64) cache[n_cached++] = Slot{key, occ};
+  return occ * num_sms();
+}
+
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) {
   return __uint_as_float(bits16 << 16);
 }
@@ -92,6 +112,21 @@ __device__ __forceinline__ void st_stream16(void* p, const int4& v) {
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+
+// bilinear source coordinates of output index o (align_corners=False, as F.interpolate at network/utils.py:22)
+__device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int& i1, float& l1) {
+  float src = ((float)o + 0.5f) * scale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+}
+// the four-tap mix with a FIXED contraction (explicit fma chain): every kernel that interpolates logits produces the
+// same bits, so the fused predict epilogue equals upsample-then-threshold exactly
+__device__ __forceinline__ float bil_mix(float w00, float v00, float w01, float v01, float w10, float v10, float w11, float v11) {
+  return fmaf(w11, v11, fmaf(w10, v10, fmaf(w01, v01, w00 * v00)));
 }
 
 // counter-based dropout keep decision shared by forward and backward

@@ -951,15 +951,6 @@ broadcast_hw_kernel(const __nv_bfloat16* __restrict__ x, int B, int64_t HW, int 
 
 // ---------------------------------------------------------------------------
 // bilinear, align_corners=False (ATen upsample_bilinear2d index rule)
-__device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int& i1, float& l1) {
-  float src = ((float)o + 0.5f) * scale - 0.5f;
-  src = src < 0.f ? 0.f : src;
-  i0 = (int)src;
-  if (i0 > in - 1) i0 = in - 1;
-  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
-  l1 = src - (float)i0;
-}
-
 // One grid row (blockIdx.x, up to 2^31-1 of them) per output image row: the vertical source rows / weight are block constants and the
 // remaining index math is 32-bit.
 __global__ void __launch_bounds__(kT)
@@ -1067,7 +1058,7 @@ logits_up_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, 
     const float* p10 = r1 + (int64_t)x0 * C;
     const float* p11 = r1 + (int64_t)x1 * C;
     for (int c = 0; c < C; c++) {
-      const float v = w00 * __ldg(p00 + c) + w01 * __ldg(p01 + c) + w10 * __ldg(p10 + c) + w11 * __ldg(p11 + c);
+      const float v = bil_mix(w00, __ldg(p00 + c), w01, __ldg(p01 + c), w10, __ldg(p10 + c), w11, __ldg(p11 + c));
       out[(((int64_t)b * C + c) * Ho + ho) * Wo + wo] = v;
     }
   }
@@ -1252,6 +1243,98 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     }
     p[i] = fmaf(-lr, grad, w);
   }
+}
+
+
+// fused Adam / AdamW over a flat fp32 buffer (torch.optim.Adam / AdamW single-tensor rule, train.py:432-441):
+//   Adam : g += wd * p            AdamW: p *= 1 - lr * wd
+//   m = m + (g - m) * (1 - b1);   v = b2 * v + (1 - b2) * g * g
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void __launch_bounds__(kT)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n, float lr, float b1, float b2, float eps, float wd, int adamw, float step_size,
+                 float inv_sqrt_bc2) {
+  pdl_wait();
+  pdl_launch();
+  auto one = [&](float& w, float grad, float& mm, float& vv) {
+    if (adamw) w = w * (1.f - lr * wd);
+    else if (wd != 0.f) grad = fmaf(wd, w, grad);
+    mm = fmaf(grad - mm, 1.f - b1, mm);
+    vv = fmaf(vv, b2, (1.f - b2) * grad * grad);
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    w = fmaf(-step_size, mm / denom, w);
+  };
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n4; i += stride) {
+    float4 w4 = reinterpret_cast<float4*>(p)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    one(w4.x, g4.x, m4.x, v4.x); one(w4.y, g4.y, m4.y, v4.y); one(w4.z, g4.z, m4.z, v4.z); one(w4.w, g4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = w4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) one(p[i], g[i], m[i], v[i]);
+}
+
+// ---------------------------------------------------------------------------
+// device input pipeline: ExtRandomCrop (window origin per image) + ExtRandomHorizontalFlip +
+// ExtToTensor + ExtNormalize (utils/ext_transforms.py:94-111, :273-324, :327-393) on uint8 HWC tiles, one pass:
+//   out[b,c,y,x] = ((float(src[b, y0+y, x0 + (flip ? W-1-x : x), c]) / 255) - mean[c]) / std[c]
+// (IEEE divisions: bit-identical to F.to_tensor + F.normalize). A thread makes 4 consecutive output pixels.
+__global__ void __launch_bounds__(kT)
+u8_to_f32_norm_kernel(const uint8_t* __restrict__ src, int Hs, int Ws, int C, const int* __restrict__ org_xy,
+                      const uint8_t* __restrict__ flip, float3 mean, float3 stdv, float mean3, float std3,
+                      int H, int W, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  const int y = blockIdx.x % H, b = blockIdx.x / H;
+  const int x0 = org_xy ? org_xy[2 * b] : 0, y0 = org_xy ? org_xy[2 * b + 1] : 0;
+  const bool fl = flip ? flip[b] != 0 : false;
+  const uint8_t* row = src + (((int64_t)b * Hs + (y0 + y)) * Ws + x0) * C;
+  const float mu[4] = {mean.x, mean.y, mean.z, mean3}, sd[4] = {stdv.x, stdv.y, stdv.z, std3};
+  const int64_t plane = (int64_t)H * W;
+  float* obase = out + (int64_t)b * C * plane + (int64_t)y * W;
+  const int nquad = (W + 3) >> 2;
+  for (int qd = blockIdx.y * kT + threadIdx.x; qd < nquad; qd += gridDim.y * kT) {
+    const int xo = qd << 2;
+    const int nval = min(4, W - xo);
+    float v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < nval) {
+        const int xs = fl ? (W - 1 - (xo + k)) : (xo + k);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (c < C) v[c][k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)row[(int64_t)xs * C + c], 255.f), mu[c]), sd[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      if (c >= C) break;
+      float* o = obase + (int64_t)c * plane + xo;
+      if (nval == 4 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+      } else {
+        for (int k = 0; k < nval; k++) o[k] = v[c][k];
+      }
+    }
+  }
+}
+
+// the label tile of the same crop / flip: uint8 [B,Hs,Ws] -> uint8 [B,H,W]
+__global__ void __launch_bounds__(kT)
+crop_flip_u8_kernel(const uint8_t* __restrict__ src, int Hs, int Ws, const int* __restrict__ org_xy,
+                    const uint8_t* __restrict__ flip, int H, int W, uint8_t* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  const int y = blockIdx.x % H, b = blockIdx.x / H;
+  const int x0 = org_xy ? org_xy[2 * b] : 0, y0 = org_xy ? org_xy[2 * b + 1] : 0;
+  const bool fl = flip ? flip[b] != 0 : false;
+  const uint8_t* row = src + ((int64_t)b * Hs + (y0 + y)) * Ws + x0;
+  uint8_t* orow = out + ((int64_t)b * H + y) * W;
+  for (int x = blockIdx.y * kT + threadIdx.x; x < W; x += gridDim.y * kT) orow[x] = row[fl ? (W - 1 - x) : x];
 }
 
 // per-channel sum of an NCHW fp32 tensor (classifier bias gradient): out[c] += sum_{b,p} d[b,c,p]
@@ -1612,4 +1695,48 @@ extern "C" int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int tot
   ISWM_REQUIRE(d_jobs && n_jobs >= 1 && total_blocks >= 1, "pack_weights_batched: bad args");
   launch_k(pack_weights_batched_kernel, dim3(total_blocks), dim3(kT), 0, ST(stream), static_cast<const PackJob*>(d_jobs), n_jobs);
   return check_launch("pack_weights_batched");
+}
+
+extern "C" int iswm_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int adamw,
+                              int64_t step, void* stream) {
+  ISWM_REQUIRE(d_param && d_grad && d_exp_avg && d_exp_avg_sq, "adam_step: null");
+  ISWM_REQUIRE(step >= 1, "adam_step: step=%lld must be >= 1 (1 on the first update)", (long long)step);
+  ISWM_REQUIRE(((reinterpret_cast<uintptr_t>(d_param) | reinterpret_cast<uintptr_t>(d_grad) | reinterpret_cast<uintptr_t>(d_exp_avg) |
+                 reinterpret_cast<uintptr_t>(d_exp_avg_sq)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  // bias corrections on the host in double, as torch computes them from a Python float step
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  launch_k(adam_step_kernel, dim3(grid_for(n, kT * 4)), dim3(kT), 0, ST(stream), d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1, beta2,
+           eps, weight_decay, adamw, step_size, inv_sqrt_bc2);
+  return check_launch("adam_step");
+}
+
+extern "C" int iswm_u8_to_f32_norm(const uint8_t* d_src, int B, int Hs, int Ws, int C, const int32_t* d_origin_xy,
+                                   const uint8_t* d_flip, const float* mean, const float* stdv, int H, int W,
+                                   float* d_out, void* stream) {
+  ISWM_REQUIRE(d_src && d_out && mean && stdv, "u8_to_f32_norm: null");
+  ISWM_REQUIRE(C >= 1 && C <= 4, "u8_to_f32_norm: C=%d (1..4 channels)", C);
+  ISWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && H <= Hs && W <= Ws, "u8_to_f32_norm: window %dx%d does not fit the %dx%d source", H, W, Hs, Ws);
+  ISWM_REQUIRE((int64_t)B * H < (1ll << 31), "u8_to_f32_norm: too many rows");
+  if (B == 0) return 0;
+  float mu[4] = {0, 0, 0, 0}, sd[4] = {1, 1, 1, 1};
+  for (int c = 0; c < C; c++) { mu[c] = mean[c]; sd[c] = stdv[c]; }       // host arrays (3 floats), passed by value
+  dim3 grid((unsigned)(B * H), (unsigned)std::max(1, std::min(8, ((W + 3) / 4 + kT - 1) / kT)));
+  launch_k(u8_to_f32_norm_kernel, grid, dim3(kT), 0, ST(stream), d_src, Hs, Ws, C, d_origin_xy, d_flip, make_float3(mu[0], mu[1], mu[2]),
+           make_float3(sd[0], sd[1], sd[2]), mu[3], sd[3], H, W, d_out);
+  return check_launch("u8_to_f32_norm");
+}
+
+extern "C" int iswm_crop_flip_u8(const uint8_t* d_src, int B, int Hs, int Ws, const int32_t* d_origin_xy,
+                                 const uint8_t* d_flip, int H, int W, uint8_t* d_out, void* stream) {
+  ISWM_REQUIRE(d_src && d_out, "crop_flip_u8: null");
+  ISWM_REQUIRE(B >= 0 && H >= 1 && W >= 1 && H <= Hs && W <= Ws, "crop_flip_u8: window %dx%d does not fit the %dx%d source", H, W, Hs, Ws);
+  ISWM_REQUIRE((int64_t)B * H < (1ll << 31), "crop_flip_u8: too many rows");
+  if (B == 0) return 0;
+  dim3 grid((unsigned)(B * H), (unsigned)std::max(1, std::min(8, (W + kT - 1) / kT)));
+  launch_k(crop_flip_u8_kernel, grid, dim3(kT), 0, ST(stream), d_src, Hs, Ws, d_origin_xy, d_flip, H, W, d_out);
+  return check_launch("crop_flip_u8");
 }

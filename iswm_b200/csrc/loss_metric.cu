@@ -178,11 +178,11 @@ static int launch_class_hist(const void* labels, int64_t n, int n_classes, int64
   if (n_classes <= 4 && aligned) {
     constexpr int VEC = 16 / sizeof(T);
     int64_t want = (n / VEC + kThreads * 4 - 1) / (kThreads * 4);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)resident_grid(class_hist_small_kernel<T>, kThreads));
     launch_k(class_hist_small_kernel<T>, dim3(grid), dim3(kThreads), 0, st, p, n, n_classes, h);
   } else {
     int64_t want = (n + kThreads * 8 - 1) / (kThreads * 8);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)resident_grid(class_hist_generic_kernel<T>, kThreads, n_classes * sizeof(unsigned)));
     launch_k(class_hist_generic_kernel<T>, dim3(grid), dim3(kThreads), n_classes * sizeof(unsigned), st, p, n, n_classes, h);
   }
   return check_launch("class_hist");
@@ -351,14 +351,14 @@ static int launch_wce(const void* logits, const void* labels, const float* weigh
                       (g == nullptr || (reinterpret_cast<uintptr_t>(g) & 15) == 0);
   if (vec_ok) {
     const int64_t nvec = p.B * (p.HW / VEC);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>((nvec + kThreads - 1) / kThreads, 1),
-                                      (int64_t)num_sms() * 8);
+    const int cap = g ? resident_grid(wce2_kernel<LT, YT, true>, kThreads) : resident_grid(wce2_kernel<LT, YT, false>, kThreads);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>((nvec + kThreads - 1) / kThreads, 1), (int64_t)cap);
     if (g) launch_k(wce2_kernel<LT, YT, true>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
     else   launch_k(wce2_kernel<LT, YT, false>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
   } else {
     const int64_t n = p.B * p.HW;
-    int grid = (int)std::min<int64_t>(std::max<int64_t>((n + kThreads - 1) / kThreads, 1),
-                                      (int64_t)num_sms() * 8);
+    const int cap = g ? resident_grid(wce_generic_kernel<LT, YT, true>, kThreads) : resident_grid(wce_generic_kernel<LT, YT, false>, kThreads);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>((n + kThreads - 1) / kThreads, 1), (int64_t)cap);
     if (g) launch_k(wce_generic_kernel<LT, YT, true>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
     else   launch_k(wce_generic_kernel<LT, YT, false>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, hist, p, g, loss_num);
   }
@@ -451,11 +451,11 @@ static int launch_confusion(const void* tru, const void* prd, int64_t n, int nc,
                        (reinterpret_cast<uintptr_t>(q) % (sizeof(PT) * VEC) == 0);
   if (nc == 2 && aligned) {
     int64_t want = (n / VEC + kThreads * 2 - 1) / (kThreads * 2);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)resident_grid(confusion2_kernel<TT, PT>, kThreads));
     launch_k(confusion2_kernel<TT, PT>, dim3(grid), dim3(kThreads), 0, st, t, q, n, c);
   } else {
     int64_t want = (n + kThreads * 8 - 1) / (kThreads * 8);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 8);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)resident_grid(confusion_generic_kernel<TT, PT>, kThreads, (nc * nc + 1) * sizeof(unsigned)));
     launch_k(confusion_generic_kernel<TT, PT>, dim3(grid), dim3(kThreads), (nc * nc + 1) * sizeof(unsigned), st, t, q, n, nc, c);
   }
   return check_launch("confusion");
@@ -586,8 +586,8 @@ static int launch_argmax_confusion(const void* logits, const void* tru, int64_t 
                       (conf_out == nullptr || (reinterpret_cast<uintptr_t>(conf_out) % VEC) == 0);
   if (vec_ok) {
     const int64_t nvec = B * (HW / VEC);
-    int grid = (int)std::min<int64_t>(std::max<int64_t>((nvec + kThreads - 1) / kThreads, 1),
-                                      (int64_t)num_sms() * 8);
+    const int cap = has_cm ? resident_grid(argmax_confusion2_kernel<LT, TT, true>, kThreads) : resident_grid(argmax_confusion2_kernel<LT, TT, false>, kThreads);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>((nvec + kThreads - 1) / kThreads, 1), (int64_t)cap);
     if (has_cm)
       launch_k(argmax_confusion2_kernel<LT, TT, true>, dim3(grid), dim3(kThreads), 0, st, x, t, B, HW, mode, threshold, pred_out, conf_out, c);
     else
@@ -595,11 +595,161 @@ static int launch_argmax_confusion(const void* logits, const void* tru, int64_t 
   } else {
     const int64_t n = B * HW;
     int grid = (int)std::min<int64_t>(std::max<int64_t>((n + kThreads - 1) / kThreads, 1),
-                                      (int64_t)num_sms() * 8);
+                                      (int64_t)resident_grid(argmax_confusion_kernel<LT, TT>, kThreads, (C * C + 1) * sizeof(unsigned)));
     launch_k(argmax_confusion_kernel<LT, TT>, dim3(grid), dim3(kThreads), (C * C + 1) * sizeof(unsigned), st, 
         x, t, B, C, HW, mode, threshold, pred_out, conf_out, has_cm ? c : nullptr);
   }
   return check_launch("argmax_confusion");
+}
+
+
+// ---------------------------------------------------------------------------
+// predict epilogue: final bilinear x4 upsample of the low-resolution logits (network/utils.py:22)
+// + 2-class softmax + threshold + uint8 confidence map (predict.py:262-290) + optional confusion matrix
+// (evaluate_quantization.py:265-270) in ONE pass that writes uint8 maps only: the full-resolution fp32 logits
+// (268 MB at 8 x 2 x 2048^2) are never materialised. Same arithmetic as logits_up_fwd followed by
+// argmax_confusion2 (bil_mix / expf / divide in the same order), so the maps and counts are bit-identical.
+// One grid row per output image row; a thread produces 4 consecutive pixels (one 32-bit store per map).
+template <typename TT, bool HAS_CM>
+__global__ void __launch_bounds__(kThreads)
+predict_epilogue2_kernel(const float* __restrict__ lo, int Hi, int Wi, int Ho, int Wo, int mode, float threshold,
+                         const TT* __restrict__ tru, uint8_t* __restrict__ pred_out,
+                         uint8_t* __restrict__ conf_out, unsigned long long* __restrict__ cm) {
+  pdl_wait();
+  pdl_launch();
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const int ho = blockIdx.x % Ho, b = blockIdx.x / Ho;
+  int y0, y1;
+  float ly;
+  bil_src(ho, sh, Hi, y0, y1, ly);
+  const float2* r0 = reinterpret_cast<const float2*>(lo) + ((int64_t)b * Hi + y0) * Wi;   // NHWC, C == 2
+  const float2* r1 = reinterpret_cast<const float2*>(lo) + ((int64_t)b * Hi + y1) * Wi;
+  const int64_t row_off = ((int64_t)b * Ho + ho) * Wo;
+  unsigned cnt[4] = {0, 0, 0, 0};
+  const int nquad = Wo >> 2;                      // Wo % 4 == 0 (checked by the launcher)
+  for (int qd = blockIdx.y * kThreads + threadIdx.x; qd < nquad; qd += gridDim.y * kThreads) {
+    const int wo0 = qd << 2;
+    Vec<TT, 4> t;
+    if constexpr (HAS_CM) vload(t, tru + row_off + wo0);
+    Vec<uint8_t, 4> po, co;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int x0, x1;
+      float lx;
+      bil_src(wo0 + k, sw, Wi, x0, x1, lx);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      const float2 v00 = __ldg(r0 + x0), v01 = __ldg(r0 + x1), v10 = __ldg(r1 + x0), v11 = __ldg(r1 + x1);
+      const float a0 = bil_mix(w00, v00.x, w01, v01.x, w10, v10.x, w11, v11.x);
+      const float a1 = bil_mix(w00, v00.y, w01, v01.y, w10, v10.y, w11, v11.y);
+      int pred;
+      float p1 = 0.0f;
+      if (mode == 0) {
+        pred = (a1 > a0) ? 1 : 0;
+      } else {
+        const float m = fmaxf(a0, a1);
+        const float e0 = expf(a0 - m), e1 = expf(a1 - m);
+        p1 = e1 / (e0 + e1);
+        pred = (p1 > threshold) ? 1 : 0;
+      }
+      po.e[k] = (uint8_t)pred;
+      co.e[k] = (uint8_t)(p1 * 255.0f);
+      if constexpr (HAS_CM) {
+        const long long tt = (long long)t.e[k];
+        const bool tv = (tt == 0 || tt == 1);
+        const int cell = (int)(tt * 2 + pred);
+#pragma unroll
+        for (int c = 0; c < 4; c++) cnt[c] += (tv && cell == c);
+      }
+    }
+    if (pred_out) vstore(pred_out + row_off + wo0, po);
+    if (conf_out) vstore(conf_out + row_off + wo0, co);
+  }
+  if constexpr (HAS_CM) flush_counters<4>(cnt, 4, cm);
+}
+
+template <typename TT>
+static int launch_predict_epilogue(const float* lo, const void* tru, int B, int Hi, int Wi, int Ho, int Wo, int mode,
+                                   float threshold, uint8_t* pred_out, uint8_t* conf_out, int64_t* cm, cudaStream_t st) {
+  const TT* t = static_cast<const TT*>(tru);
+  auto* c = reinterpret_cast<unsigned long long*>(cm);
+  const bool has_cm = (cm != nullptr && tru != nullptr);
+  dim3 grid((unsigned)(B * Ho), (unsigned)std::max(1, std::min(8, (Wo / 4 + kThreads - 1) / kThreads)));
+  if (has_cm)
+    launch_k(predict_epilogue2_kernel<TT, true>, grid, dim3(kThreads), 0, st, lo, Hi, Wi, Ho, Wo, mode, threshold, t, pred_out, conf_out, c);
+  else
+    launch_k(predict_epilogue2_kernel<TT, false>, grid, dim3(kThreads), 0, st, lo, Hi, Wi, Ho, Wo, mode, threshold, t, pred_out, conf_out, c);
+  return check_launch("predict_epilogue");
+}
+
+// ---------------------------------------------------------------------------
+// focal loss (utils/loss.py:14-35), forward + backward in one pass, any C:
+//   ce_i = w[y_i] * nll_i (0 where ignored);  pt = exp(-ce_i);  focal_i = alpha * (1 - pt)^gamma * ce_i
+//   loss = sum_i focal_i * (size_average ? 1/N : 1) with N = ALL pixels (ignored ones included, as `.mean()` does)
+//   d focal / d ce = alpha * ((1 - pt)^gamma + gamma * ce * (1 - pt)^(gamma - 1) * pt)
+template <typename LT, typename YT, bool HAS_GRAD>
+__global__ void __launch_bounds__(kThreads)
+focal_kernel(const LT* __restrict__ logits, const YT* __restrict__ labels, const float* __restrict__ weight,
+             WceParams p, float alpha, float gamma, float out_scale, LT* __restrict__ grad,
+             double* __restrict__ loss_num) {
+  pdl_wait();
+  pdl_launch();
+  const int64_t n = p.B * p.HW;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  float acc = 0.0f;
+  for (int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x; idx < n; idx += stride) {
+    const int64_t b = idx / p.HW, i = idx - b * p.HW;
+    const LT* xp = logits + b * p.C * p.HW + i;
+    const long long yy = (long long)labels[idx];
+    const bool valid = (yy >= 0 && yy < p.C && yy != p.ignore_index);
+    float m = -INFINITY;
+    for (int c = 0; c < p.C; c++) m = fmaxf(m, to_f32(xp[(int64_t)c * p.HW]));
+    float s = 0.0f;
+    for (int c = 0; c < p.C; c++) s += expf(to_f32(xp[(int64_t)c * p.HW]) - m);
+    const float lse = m + logf(s);
+    float w = 0.0f, dfdce = 0.0f;
+    if (valid) {
+      w = weight ? weight[yy] : 1.0f;
+      const float ce = w * (lse - to_f32(xp[yy * p.HW]));
+      const float pt = expf(-ce);
+      const float om = 1.0f - pt;
+      const float mod = (gamma == 0.0f) ? 1.0f : powf(om, gamma);
+      acc += alpha * mod * ce;
+      // gamma * ce * om^(gamma-1) * pt, written as gamma * ce * pt * mod / om (om > 0 whenever ce > 0)
+      dfdce = alpha * (mod + ((gamma == 0.0f || om <= 0.0f) ? 0.0f : gamma * ce * pt * mod / om));
+    }
+    if constexpr (HAS_GRAD) {
+      LT* gp = grad + b * p.C * p.HW + i;
+      for (int c = 0; c < p.C; c++) {
+        float g = 0.0f;
+        if (valid) {
+          const float pc = expf(to_f32(xp[(int64_t)c * p.HW]) - lse);
+          g = dfdce * w * (pc - (c == yy ? 1.0f : 0.0f)) * out_scale;
+        }
+        gp[(int64_t)c * p.HW] = from_f32<LT>(g);
+      }
+    }
+  }
+  block_add_double(acc, loss_num);
+}
+
+__global__ void focal_finalize_kernel(const double* loss_num, float out_scale, float* loss) {
+  pdl_wait();
+  pdl_launch();
+  *loss = (float)(*loss_num * (double)out_scale);
+}
+
+template <typename LT, typename YT>
+static int launch_focal(const void* logits, const void* labels, const float* weight, const WceParams& p, float alpha,
+                        float gamma, float out_scale, void* grad, double* loss_num, cudaStream_t st) {
+  const LT* x = static_cast<const LT*>(logits);
+  const YT* y = static_cast<const YT*>(labels);
+  LT* g = static_cast<LT*>(grad);
+  const int64_t n = p.B * p.HW;
+  const int cap = g ? resident_grid(focal_kernel<LT, YT, true>, kThreads) : resident_grid(focal_kernel<LT, YT, false>, kThreads);
+  int grid = (int)std::min<int64_t>(std::max<int64_t>((n + kThreads - 1) / kThreads, 1), (int64_t)cap);
+  if (g) launch_k(focal_kernel<LT, YT, true>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, p, alpha, gamma, out_scale, g, loss_num);
+  else   launch_k(focal_kernel<LT, YT, false>, dim3(grid), dim3(kThreads), 0, st, x, y, weight, p, alpha, gamma, out_scale, g, loss_num);
+  return check_launch("focal_fwd_bwd");
 }
 
 }  // namespace iswm
@@ -717,4 +867,70 @@ extern "C" int iswm_argmax_confusion(const void* d_logits, int logit_dtype, cons
     return amc_dispatch<__nv_bfloat16>(true_dtype, d_logits, d_true, B, C, HW, mode, threshold, d_pred_out, d_conf_out, d_cm, st);
   set_error("bad logit dtype %d", logit_dtype);
   return 2;
+}
+
+extern "C" int iswm_predict_epilogue(const float* d_lo, int B, int Hi, int Wi, int C, int Ho, int Wo, int mode,
+                                     float threshold, const void* d_true, int true_dtype, uint8_t* d_pred_out,
+                                     uint8_t* d_conf_out, int64_t* d_cm, void* stream) {
+  ISWM_REQUIRE(d_lo && B >= 0 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "predict_epilogue: bad sizes");
+  ISWM_REQUIRE(C == 2, "predict_epilogue: the fused path is the reference's two-class case (C=%d); use logits_up_fwd + argmax_confusion", C);
+  ISWM_REQUIRE(mode == 0 || mode == 1, "predict_epilogue: bad mode %d", mode);
+  ISWM_REQUIRE((Wo & 3) == 0, "predict_epilogue: output width %d must be a multiple of 4", Wo);
+  ISWM_REQUIRE((reinterpret_cast<uintptr_t>(d_lo) & 7) == 0, "predict_epilogue: logits must be 8-byte aligned");
+  ISWM_REQUIRE(!d_pred_out || (reinterpret_cast<uintptr_t>(d_pred_out) & 3) == 0, "predict_epilogue: pred map must be 4-byte aligned");
+  ISWM_REQUIRE(!d_conf_out || (reinterpret_cast<uintptr_t>(d_conf_out) & 3) == 0, "predict_epilogue: confidence map must be 4-byte aligned");
+  ISWM_REQUIRE((int64_t)B * Ho < (1ll << 31), "predict_epilogue: too many rows");
+  if (B == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d_true && d_cm) {
+    const size_t esz = true_dtype == ISWM_U8 ? 1 : (true_dtype == ISWM_I32 ? 4 : 8);
+    ISWM_REQUIRE((reinterpret_cast<uintptr_t>(d_true) % (esz * 4 >= 16 ? 16 : esz * 4)) == 0, "predict_epilogue: labels must be aligned to 4 elements");
+  }
+  switch (true_dtype) {
+    case ISWM_U8:  return launch_predict_epilogue<uint8_t>(d_lo, d_true, B, Hi, Wi, Ho, Wo, mode, threshold, d_pred_out, d_conf_out, d_cm, st);
+    case ISWM_I32: return launch_predict_epilogue<int32_t>(d_lo, d_true, B, Hi, Wi, Ho, Wo, mode, threshold, d_pred_out, d_conf_out, d_cm, st);
+    case ISWM_I64: return launch_predict_epilogue<int64_t>(d_lo, d_true, B, Hi, Wi, Ho, Wo, mode, threshold, d_pred_out, d_conf_out, d_cm, st);
+    default: set_error("bad true dtype %d", true_dtype); return 2;
+  }
+}
+
+template <typename LT>
+static int focal_dispatch_label(int label_dtype, const void* logits, const void* labels, const float* weight,
+                                const WceParams& p, float alpha, float gamma, float out_scale, void* grad,
+                                double* loss_num, cudaStream_t st) {
+  switch (label_dtype) {
+    case ISWM_U8:  return launch_focal<LT, uint8_t>(logits, labels, weight, p, alpha, gamma, out_scale, grad, loss_num, st);
+    case ISWM_I32: return launch_focal<LT, int32_t>(logits, labels, weight, p, alpha, gamma, out_scale, grad, loss_num, st);
+    case ISWM_I64: return launch_focal<LT, int64_t>(logits, labels, weight, p, alpha, gamma, out_scale, grad, loss_num, st);
+    default: set_error("bad label dtype %d", label_dtype); return 2;
+  }
+}
+
+extern "C" int iswm_focal_fwd_bwd(const void* d_logits, int logit_dtype, const void* d_labels, int label_dtype,
+                                  const float* d_weight, int64_t B, int C, int64_t HW, int ignore_index,
+                                  float alpha, float gamma, int size_average, void* d_grad, double* d_loss_num,
+                                  float* d_loss, void* stream) {
+  ISWM_REQUIRE(B >= 0 && HW >= 0 && C >= 1 && C <= 8192, "focal: bad sizes");
+  ISWM_REQUIRE(d_loss_num, "focal: null loss_num");
+  ISWM_REQUIRE(gamma >= 0.f, "focal: gamma=%f must be >= 0", (double)gamma);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WceParams p{B, HW, C, ignore_index, 1.0f};
+  const int64_t n = B * HW;
+  // mean over ALL pixels: an empty input is 0/0 = nan, as torch's .mean() of an empty tensor
+  const float out_scale = size_average ? (float)(1.0 / (double)n) : 1.0f;
+  if (n > 0) {
+    ISWM_REQUIRE(d_logits && d_labels, "focal: null logits / labels");
+    int rc;
+    if (logit_dtype == ISWM_F32)
+      rc = focal_dispatch_label<float>(label_dtype, d_logits, d_labels, d_weight, p, alpha, gamma, out_scale, d_grad, d_loss_num, st);
+    else if (logit_dtype == ISWM_BF16)
+      rc = focal_dispatch_label<__nv_bfloat16>(label_dtype, d_logits, d_labels, d_weight, p, alpha, gamma, out_scale, d_grad, d_loss_num, st);
+    else { set_error("bad logit dtype %d", logit_dtype); return 2; }
+    if (rc) return rc;
+  }
+  if (d_loss) {
+    launch_k(focal_finalize_kernel, dim3(1), dim3(1), 0, st, d_loss_num, n > 0 ? out_scale : NAN, d_loss);
+    return check_launch("focal_finalize");
+  }
+  return 0;
 }

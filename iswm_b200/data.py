@@ -73,3 +73,56 @@ class HostBatchPrefetcher:
                 nxt = None
             i += 1
             yield cur
+
+
+class DeviceTransform:
+    """The tensor half of the reference's transform pipelines on the GPU, over uint8 tiles.
+
+    val   (train.py:364-368): ExtToTensor + ExtNormalize                      -> DeviceTransform(mean, std)
+    train (train.py:355-362): ... + ExtRandomCrop + ExtRandomHorizontalFlip   -> DeviceTransform(mean, std, crop_size=S, hflip=True)
+
+    `__call__(images_u8 [B,Hs,Ws,3], labels_u8 [B,Hs,Ws]) -> (float32 [B,3,H,W], uint8 [B,H,W])` in two kernel
+    launches; the host ships uint8 tiles (1/4 of the fp32 bytes, 1/8 of the int64 label bytes over PCIe) and the
+    labels stay uint8 (the criterion and the metric read them as they are). Crop origins and flip decisions are drawn
+    on the host from `generator` (one origin / one coin per image, as ExtRandomCrop.get_params and
+    ExtRandomHorizontalFlip do per sample, utils/ext_transforms.py:350-365, :94-111). Normalisation is bit-identical
+    to torchvision's to_tensor + normalize. ExtRandomScale (PIL bilinear / nearest resampling) and the pad_if_needed
+    branch stay on the host: tiles must be at least crop_size."""
+
+    def __init__(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), crop_size=None, hflip: bool = False,
+                 p_flip: float = 0.5, generator: torch.Generator = None):
+        self.mean, self.std = tuple(mean), tuple(std)
+        self.crop_size = (crop_size, crop_size) if isinstance(crop_size, int) else crop_size
+        self.hflip, self.p_flip = hflip, p_flip
+        self.generator = generator
+
+    def draw(self, B: int, Hs: int, Ws: int):
+        """Host-side random parameters of one batch: (origin_xy int32 [B,2] or None, flip uint8 [B] or None)."""
+        org = flip = None
+        if self.crop_size is not None:
+            H, W = self.crop_size
+            if H > Hs or W > Ws:
+                raise ValueError(f"crop {H}x{W} larger than the {Hs}x{Ws} tile (pad on the host first)")
+            ys = torch.randint(0, Hs - H + 1, (B,), generator=self.generator)
+            xs = torch.randint(0, Ws - W + 1, (B,), generator=self.generator)
+            org = torch.stack([xs, ys], 1).to(torch.int32)
+        if self.hflip:
+            flip = (torch.rand(B, generator=self.generator) < self.p_flip).to(torch.uint8)
+        return org, flip
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor = None, params=None):
+        from . import ops
+        if not images.is_cuda:
+            raise RuntimeError("DeviceTransform runs on CUDA tensors (iswm_b200 has no CPU path)")
+        B, Hs, Ws, _ = images.shape
+        org, flip = params if params is not None else self.draw(B, Hs, Ws)
+        dev = images.device
+        org_d = None if org is None else org.to(dev, non_blocking=True)
+        flip_d = None if flip is None else flip.to(dev, non_blocking=True)
+        size = self.crop_size if self.crop_size is not None else (Hs, Ws)
+        x = ops.u8_to_f32_norm(images, self.mean, self.std, size, org_d, flip_d)
+        if labels is None:
+            return x
+        if org_d is None and flip_d is None:
+            return x, labels
+        return x, ops.crop_flip_u8(labels, size, org_d, flip_d)

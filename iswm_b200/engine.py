@@ -357,11 +357,14 @@ class Engine:
         save = self._save_slot(2 * Cout)
         bn = s.bn
         seed = (self.seed + self.step * 1000003 + len(self.tape)) & 0xFFFFFFFFFFFF
+        ev = self._prof_begin()
         check(L.iswm_bn_train_apply(raw.data_ptr(), Cout, stats.data_ptr(), M, Cout, bn.weight.data_ptr(), bn.bias.data_ptr(),
                                     BN_EPS, BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                     bn.num_batches_tracked.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(),
                                     None if residual is None else residual.ptr, 0 if residual is None else residual.ld,
                                     1 if relu else 0, drop_p, seed, out.ptr, out.ld, _st()), "bn_train_apply " + s.name)
+        # HBM-bound kernels are recorded with their algorithmic BYTES in the flops slot (kernel name prefixed "hbm:")
+        self._prof_end(ev, "hbm:bn_train_apply", 2.0 * M * Cout * (3 if residual is not None else 2), "bn_apply " + s.name)
         self._tap(s.name, out)
         if self.debug_taps is not None:
             self.debug_taps[s.name + ":raw"] = raw.float().permute(0, 3, 1, 2).cpu()
@@ -400,14 +403,19 @@ class Engine:
                                     self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd " + s.name)
             else:
+                nmask = 1 if act_ptr is not None else 0
+                ev = self._prof_begin()
                 check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                            save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
                                            1 if use_mask else 0, drop_p, seed, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+                self._prof_end(ev, "hbm:bn_bwd_reduce", 2.0 * M * Cout * (2 + nmask), "bn_bwd_reduce " + s.name)
+                ev = self._prof_begin()
                 check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                           bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
                                           1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
                                           self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd_apply " + s.name)
+                self._prof_end(ev, "hbm:bn_bwd_apply", 2.0 * M * Cout * (3 + nmask + (1 if dz_ptr is not None else 0)), "bn_bwd_apply " + s.name)
             if dz_tmp is not None:
                 check(L.iswm_add_bf16(residual.grad.ptr, dz_tmp.data_ptr(), dz_tmp.numel(), residual.grad.ptr, _st()), "add_bf16")
             out.grad = None
@@ -582,12 +590,14 @@ class Engine:
         return t
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
-        """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]."""
+    def forward(self, x: torch.Tensor, train: bool, lowres: bool = False) -> torch.Tensor:
+        """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]; with `lowres` (eval only) the
+        classifier's fp32 NHWC [B,H/4,W/4,num_classes] output, for consumers that fuse the final upsample
+        (ops.predict_epilogue)."""
         with _StreamScope():
-            return self._forward(x, train)
+            return self._forward(x, train, lowres)
 
-    def _forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
+    def _forward(self, x: torch.Tensor, train: bool, lowres: bool = False) -> torch.Tensor:
         self._check_device(x)
         if x.dim() != 4 or x.shape[1] != self.stem.cin:
             raise ValueError(f"expected [B,{self.stem.cin},H,W] input, got {tuple(x.shape)}")
@@ -672,6 +682,10 @@ class Engine:
         ones = self._ones(ncls)
         lo = torch.empty((B, h4, w4, ncls), dtype=torch.float32, device=dev)
         self._conv(self.cls, y, lo, ncls, h4, w4, ops.conv_taps(1, 1), B, _lib.EPI_AFFINE | _lib.EPI_OUT_F32, ones, bias.detach())
+        if lowres:
+            if train:
+                raise RuntimeError("low-resolution logits are an inference-only output")
+            return lo
         logits = torch.empty((B, ncls, H, W), dtype=torch.float32, device=dev)
         check(L.iswm_logits_up_fwd(lo.data_ptr(), B, h4, w4, ncls, H, W, logits.data_ptr(), _st()), "logits_up_fwd")
         if train:

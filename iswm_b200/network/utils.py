@@ -50,3 +50,10 @@ class _SimpleSegmentationModel(nn.Module):
             return eng.forward(x, train=True)          # BN batch statistics, no tape kept for backward
         with torch.no_grad():                          # eval: BatchNorm folded into the conv epilogues
             return eng.forward(x, train=False)
+
+    @torch.no_grad()
+    def forward_lowres(self, x):
+        """Inference only: the classifier's fp32 NHWC [B,H/4,W/4,num_classes] logits BEFORE the final bilinear
+        upsample of network/utils.py:22 (eval-mode BatchNorm / Dropout regardless of .training). Consumers that fuse
+        the upsample with what follows (iswm_b200.predict.predict_mask) read 1/16 of the pixels."""
+        return self.engine().forward(x, train=False, lowres=True)

@@ -106,6 +106,85 @@ def argmax_confusion(logits: torch.Tensor, true: Optional[torch.Tensor], mode: i
     return out, pred, conf
 
 
+def predict_epilogue(lo: torch.Tensor, H: int, W: int, true: Optional[torch.Tensor] = None, mode: int = 1,
+                     threshold: float = 0.5, want_pred: bool = True, want_conf: bool = True,
+                     out: Optional[torch.Tensor] = None):
+    """Fused final upsample + softmax/threshold + uint8 maps (+ confusion counts) from the LOW-resolution fp32 NHWC
+    logits [B,h,w,2] (network/utils.py:22 + predict.py:262-290). Returns (cm or None, pred, conf)."""
+    if lo.dtype != torch.float32 or lo.dim() != 4:
+        raise TypeError("predict_epilogue wants fp32 NHWC [B,h,w,C] low-resolution logits")
+    lo = lo.contiguous()
+    B, Hi, Wi, Cc = lo.shape
+    dev = lo.device
+    pred = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_pred else None
+    conf = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_conf else None
+    if true is not None:
+        true = true.contiguous()
+        if true.numel() != B * H * W:
+            raise ValueError(f"labels {tuple(true.shape)} do not match the {B}x{H}x{W} output")
+        if out is None:
+            out = torch.zeros(Cc * Cc + 1, dtype=torch.int64, device=dev)
+    check(_lib.lib().iswm_predict_epilogue(_ptr(lo), B, Hi, Wi, Cc, H, W, mode, threshold, _ptr(true),
+                                           _label_code(true) if true is not None else _lib.I64, _ptr(pred), _ptr(conf),
+                                           _ptr(out) if true is not None else None, _stream()), "predict_epilogue")
+    return (out if true is not None else None), pred, conf
+
+
+def focal_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, weight: Optional[torch.Tensor], alpha: float = 1.0,
+                  gamma: float = 0.0, size_average: bool = True, ignore_index: int = 255,
+                  want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Fused focal loss forward(+backward) (utils/loss.py:14-35). Returns (loss[0-dim fp32], dlogits or None)."""
+    logits = logits.contiguous()
+    labels = labels.contiguous()
+    B, Cc = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // max(1, B * Cc)
+    if labels.numel() != B * HW:
+        raise ValueError(f"labels {tuple(labels.shape)} do not match logits {tuple(logits.shape)}")
+    grad = torch.empty_like(logits) if want_grad else None
+    num = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    w = None if weight is None else weight.to(device=logits.device, dtype=torch.float32).contiguous()
+    check(_lib.lib().iswm_focal_fwd_bwd(_ptr(logits), _FLOAT_CODE[logits.dtype], _ptr(labels), _label_code(labels), _ptr(w),
+                                        B, Cc, HW, ignore_index, float(alpha), float(gamma), 1 if size_average else 0,
+                                        _ptr(grad), _ptr(num), _ptr(loss), _stream()), "focal_fwd_bwd")
+    return loss, grad
+
+
+def u8_to_f32_norm(src: torch.Tensor, mean: Sequence[float], std: Sequence[float], size: Optional[Tuple[int, int]] = None,
+                   origin_xy: Optional[torch.Tensor] = None, flip: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 [B,Hs,Ws,C] tiles -> float32 NCHW [B,C,H,W] = ((src/255) - mean) / std over an optional per-image
+    window (origin_xy int32 [B,2]) and horizontal flip (uint8 [B]) (utils/ext_transforms.py:94-111, :273-393)."""
+    if src.dtype != torch.uint8 or src.dim() != 4:
+        raise TypeError("u8_to_f32_norm wants uint8 [B,H,W,C] tiles")
+    src = src.contiguous()
+    B, Hs, Ws, Cc = src.shape
+    H, W = size if size is not None else (Hs, Ws)
+    if len(mean) != Cc or len(std) != Cc:
+        raise ValueError("mean / std need one value per channel")
+    if out is None:
+        out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=src.device)
+    mu = (C.c_float * Cc)(*[float(v) for v in mean])
+    sd = (C.c_float * Cc)(*[float(v) for v in std])
+    check(_lib.lib().iswm_u8_to_f32_norm(_ptr(src), B, Hs, Ws, Cc, _ptr(origin_xy), _ptr(flip), mu, sd, H, W, _ptr(out),
+                                         _stream()), "u8_to_f32_norm")
+    return out
+
+
+def crop_flip_u8(src: torch.Tensor, size: Optional[Tuple[int, int]] = None, origin_xy: Optional[torch.Tensor] = None,
+                 flip: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 label tiles [B,Hs,Ws] -> [B,H,W] under the same window / flip as u8_to_f32_norm."""
+    if src.dtype != torch.uint8 or src.dim() != 3:
+        raise TypeError("crop_flip_u8 wants uint8 [B,H,W] label tiles")
+    src = src.contiguous()
+    B, Hs, Ws = src.shape
+    H, W = size if size is not None else (Hs, Ws)
+    if out is None:
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=src.device)
+    check(_lib.lib().iswm_crop_flip_u8(_ptr(src), B, Hs, Ws, _ptr(origin_xy), _ptr(flip), H, W, _ptr(out), _stream()), "crop_flip_u8")
+    return out
+
+
 # ----------------------------------------------------------------------------- convolution
 
 def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,

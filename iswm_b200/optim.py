@@ -1,9 +1,9 @@
-"""Fused optimiser step for the hot path's tail (reference: train.py:421-431 builds
-torch.optim.SGD(momentum=0.9, nesterov=True, weight_decay) at torch's default lr 1e-3 — `--lr` never
-reaches it — and train.py:1049 steps it every iteration).
+"""Fused optimiser step for the hot path's tail (reference: train.py:421-444 builds
+torch.optim.SGD(momentum=0.9, nesterov=True, weight_decay), Adam or AdamW at torch's default lr 1e-3 — `--lr`
+never reaches them — and train.py:1049 steps it every iteration).
 
-`FusedSGD` has torch.optim.SGD's update rule but runs as ONE kernel over the engine's flat fp32
-master-weight / gradient / momentum buffers instead of a multi-tensor foreach sweep."""
+`FusedSGD` / `FusedAdam` / `FusedAdamW` have the torch.optim update rules but run as ONE kernel over the engine's
+flat fp32 master-weight / gradient / state buffers instead of a multi-tensor foreach sweep."""
 from __future__ import annotations
 
 import torch
@@ -53,11 +53,77 @@ class FusedSGD:
         self.param_groups = sd["param_groups"]
 
 
+class FusedAdam:
+    """torch.optim.Adam(params, weight_decay=wd) as train.py:432-436 builds it (torch defaults lr 1e-3,
+    betas (0.9, 0.999), eps 1e-8; L2 decay added to the gradient) as ONE kernel over the engine's flat buffers."""
+
+    decoupled = False
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        self.model = getattr(model, "module", model)
+        self.engine = self.model.engine()
+        self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay}]
+        self._m = self._v = None
+        self._steps = 0
+
+    zero_grad = FusedSGD.zero_grad
+
+    def step(self):
+        eng = self.engine
+        flat_w = eng.flatten_parameters()
+        flat_g = eng.flat_g
+        if flat_g is None:
+            raise RuntimeError(f"{type(self).__name__}.step() before any backward pass")
+        if self._m is None or self._m.numel() != flat_w.numel() or self._m.device != flat_w.device:
+            self._m, self._v = torch.zeros_like(flat_w), torch.zeros_like(flat_w)
+            self._steps = 0
+        self._steps += 1
+        g = self.param_groups[0]
+        _lib.check(_lib.lib().iswm_adam_step(flat_w.data_ptr(), flat_g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                                             flat_w.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
+                                             1 if self.decoupled else 0, self._steps, torch.cuda.current_stream().cuda_stream),
+                   "adam_step")
+        eng.invalidate_packed()
+
+    def state_dict(self):
+        return {"exp_avg": self._m, "exp_avg_sq": self._v, "steps": self._steps, "param_groups": self.param_groups}
+
+    def load_state_dict(self, sd):
+        self._m, self._v, self._steps = sd["exp_avg"], sd["exp_avg_sq"], sd["steps"]
+        self.param_groups = sd["param_groups"]
+
+
+class FusedAdamW(FusedAdam):
+    """torch.optim.AdamW(params, weight_decay=wd) (train.py:437-441): decoupled decay p *= 1 - lr * wd."""
+
+    decoupled = True
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        super().__init__(model, lr, betas, eps, weight_decay)
+
+
+def setup_optimizer(model, opts):
+    """train.py:421-444: opts.optimizer in {'sgd', 'adam', 'adamw'}, opts.weight_decay; the learning rate is torch's
+    default 1e-3 for all three (`--lr` only reaches the scheduler's eta_min, train.py:446-452)."""
+    if opts.optimizer == "sgd":
+        return FusedSGD(model, momentum=0.9, weight_decay=opts.weight_decay, nesterov=True)
+    elif opts.optimizer == "adam":
+        return FusedAdam(model, weight_decay=opts.weight_decay)
+    elif opts.optimizer == "adamw":
+        return FusedAdamW(model, weight_decay=opts.weight_decay)
+    raise ValueError(f"Unsupported optimizer: {opts.optimizer}")
+
+
+def setup_scheduler(optimizer, opts):
+    """train.py:446-452."""
+    return CosineAnnealingLR(optimizer, T_max=opts.total_itrs, eta_min=opts.lr * 0.01)
+
+
 class CosineAnnealingLR:
     """torch.optim.lr_scheduler.CosineAnnealingLR(T_max=total_itrs, eta_min=lr*0.01) as set up at
     train.py:446-452 and stepped every iteration (train.py:1103); closed form."""
 
-    def __init__(self, optimizer: FusedSGD, T_max: int, eta_min: float = 0.0):
+    def __init__(self, optimizer, T_max: int, eta_min: float = 0.0):
         import math
         self._math = math
         self.opt, self.T_max, self.eta_min = optimizer, T_max, eta_min

@@ -68,9 +68,29 @@ class CrossEntropyLoss(nn.Module):
         return _WeightedCEFn.apply(logits, labels, w, self.ignore_index, self.hist_hook, None)
 
 
+class _FocalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, weight, alpha, gamma, size_average, ignore_index):
+        loss, grad = ops.focal_fwd_bwd(logits, labels, weight, alpha, gamma, size_average, ignore_index, logits.requires_grad)
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grad = ctx.grad
+        if grad is None:
+            return (None,) * 7
+        ctx.grad = None
+        g = g.to(device=grad.device, dtype=torch.float32).contiguous()
+        _lib.check(_lib.lib().iswm_scale_by_device_scalar(grad.data_ptr(), ops._FLOAT_CODE[grad.dtype], grad.numel(),
+                                                          g.data_ptr(), ops._stream()), "scale_by_device_scalar")
+        return grad, None, None, None, None, None, None
+
+
 class FocalLoss(nn.Module):
-    """utils/loss.py:14-35. Only the reference's defaults-shaped case gamma == 0 is accelerated
-    (then focal == alpha * CE and `.mean()` runs over ALL pixels, ignored ones contributing 0)."""
+    """utils/loss.py:14-35, same constructor and call signature; forward and gradient run as ONE fused CUDA pass
+    (`iswm_focal_fwd_bwd`): focal_i = alpha * (1 - exp(-ce_i))^gamma * ce_i with ce_i the per-pixel weighted CE
+    (0 where ignored), `.mean()` over ALL pixels when size_average else `.sum()`."""
 
     def __init__(self, alpha=1, gamma=0, size_average=True, ignore_index=255, weight=None):
         super().__init__()
@@ -78,22 +98,12 @@ class FocalLoss(nn.Module):
         self.register_buffer("weight", None if weight is None else weight.detach().float().clone())
 
     def forward(self, inputs, targets):
-        if self.gamma != 0:
-            raise NotImplementedError("FocalLoss with gamma != 0 is outside the accelerated hot path (SURVEY.md §8f rank 4)")
-        # focal = alpha * w[y]*nll per pixel (0 where ignored); .mean() divides by ALL pixels, so
-        # focal.mean() = CE_weighted_mean * D / N with D = sum_c w_c n_c (tiny device-side scalars).
-        C = inputs.shape[1]
-        w = self.weight if self.weight is not None else torch.ones(C, device=inputs.device)
-        w = w.to(inputs.device)
-        box = []
-        ce = _WeightedCEFn.apply(inputs, targets, self.weight, self.ignore_index, None, box)
-        counts = box[0].to(torch.float32)
-        if 0 <= self.ignore_index < C:
-            counts = counts.clone()
-            counts[self.ignore_index] = 0
-        D = (counts * w).sum()
-        total = torch.where(D > 0, ce * D, torch.zeros_like(ce))
-        return self.alpha * (total / targets.numel() if self.size_average else total)
+        if not inputs.is_cuda:
+            raise RuntimeError("iswm_b200 FocalLoss runs on CUDA only (no CPU fallback)")
+        if self.gamma < 0:
+            raise ValueError("FocalLoss: gamma must be >= 0")
+        return _FocalFn.apply(inputs, targets, self.weight, float(self.alpha), float(self.gamma), bool(self.size_average),
+                              int(self.ignore_index))
 
 
 def create_loss(loss_type="focal", temporal_loss="none", temporal_weight=0.5, **kwargs):
