@@ -37,6 +37,11 @@ void iswm_reset_launch_count(void);
 /* synchronising health check (tests / debug): code recorded by a tensor-core kernel whose
  * bounded mbarrier wait timed out (0 = healthy); clears it. */
 int iswm_debug_abort_code(void);
+/* Measurement aid: entry points of the masked kernel families return 0 WITHOUT launching (outputs stay unwritten).
+ * bench.py times whole steps with and without a family to get its marginal cost inside the real launch pipeline
+ * (per-launch CUDA events add ~7 us of drain per kernel and break the programmatic-dependent-launch overlap). */
+enum { ISWM_SKIP_CONV_IGEMM = 1, ISWM_SKIP_CONV_WGRAD = 2, ISWM_SKIP_BN = 4 };
+void iswm_debug_set_skip(int mask);
 
 /* element type codes for label / prediction buffers */
 enum { ISWM_U8 = 0, ISWM_I32 = 1, ISWM_I64 = 2 };

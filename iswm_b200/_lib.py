@@ -63,6 +63,7 @@ SIGNATURES = {
     "iswm_launch_count": (_i64, []),
     "iswm_reset_launch_count": (None, []),
     "iswm_debug_abort_code": (_i, []),
+    "iswm_debug_set_skip": (None, [_i]),
     "iswm_class_hist": (_i, [_p, _i, _i64, _i, _p, _p]),
     "iswm_wce_fwd_bwd": (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _i64, _i, _f, _p, _p, _p, _p]),
     "iswm_confusion": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p]),

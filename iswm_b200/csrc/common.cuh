@@ -13,6 +13,10 @@ namespace iswm {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+// measurement aid (iswm_debug_set_skip): entry points of a masked kernel family return 0 without launching, so that a
+// whole step can be timed with and without that family (its marginal cost inside the real launch pipeline)
+extern std::atomic<int> g_skip_mask;
+inline bool debug_skip(int family_bit) { return (g_skip_mask.load(std::memory_order_relaxed) & family_bit) != 0; }
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -537,6 +537,7 @@ using namespace iswm;
 extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const void* d_wgt,
                                void* d_out, const float* d_scale, const float* d_shift,
                                const void* d_res, double* d_stats, void* stream) {
+  if (debug_skip(ISWM_SKIP_CONV_IGEMM)) return 0;
   ISWM_REQUIRE(d && d_in && d_wgt && d_out, "conv_igemm: null argument");
   ISWM_REQUIRE(d->ntaps >= 1 && d->ntaps <= ISWM_MAX_TAPS, "conv_igemm: ntaps=%d", d->ntaps);
   ISWM_REQUIRE(d->Cin >= 1 && d->Cout >= 1 && d->B >= 1 && d->Ho >= 1 && d->Wo >= 1, "conv_igemm: bad dims");

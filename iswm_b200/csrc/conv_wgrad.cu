@@ -247,6 +247,7 @@ using namespace iswm;
 
 extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const void* d_dy,
                                float* d_dw, void* stream) {
+  if (debug_skip(ISWM_SKIP_CONV_WGRAD)) return 0;
   ISWM_REQUIRE(d && d_in && d_dy && d_dw, "conv_wgrad: null argument");
   ISWM_REQUIRE(d->ntaps >= 1 && d->ntaps <= ISWM_MAX_TAPS, "conv_wgrad: ntaps=%d", d->ntaps);
   ISWM_REQUIRE((d->in_ld % 8) == 0 && (d->out_ld % 8) == 0, "conv_wgrad: row pitches must be multiples of 8 (in_ld=%d out_ld=%d)", d->in_ld, d->out_ld);

@@ -6,6 +6,7 @@
 // torch.cat (network/_deeplab.py:59, :171) never materialises.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace iswm {
 
@@ -1424,12 +1425,17 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
                                    float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld,
                                    int relu, float drop_p, uint64_t drop_seed, void* d_out, int out_ld,
                                    void* stream) {
+  if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_train_apply"); REQ_LD8(x_ld, "bn_train_apply"); REQ_LD8(out_ld, "bn_train_apply");
   ISWM_REQUIRE(d_x && d_stats && d_gamma && d_beta && d_out && M > 0, "bn_train_apply: null/empty");
   ISWM_REQUIRE(!d_res || (res_ld % 8) == 0, "bn_train_apply: res_ld");
   ISWM_REQUIRE(C <= 2048, "bn_train_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
-  bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
+  // blocks per SM the row range is cut for: 3 = exactly the resident blocks (80 registers x 256 threads), ONE wave.
+  // Measured on B200 against 6 (two waves): 33.6 MB tensor 17.1 -> 12.3 us, 67 MB 30.0 -> 24.9 us, cfg2 1074 -> 1088
+  // img/s: a second wave is mostly a tail (each thread's life is one or two batches of loads). ISWM_BN_WAVES overrides.
+  static const int env_waves = [] { const char* e = getenv("ISWM_BN_WAVES"); return e ? atoi(e) : 3; }();
+  bn_row_grid(C, M, 4, nx, ny, rpb, blocks, env_waves);
   const bool has_res = d_res != nullptr, has_drop = drop_p > 0.f;
 #define ISWM_BN_APPLY(R, L, D)                                                                                     \
   launch_k(bn_train_apply_kernel<R, L, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, d_stats, M, C,    \
@@ -1458,6 +1464,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
                                   const float* d_save_mean, const float* d_save_invstd,
                                   const float* d_gamma, const float* d_beta, int relu,
                                   float drop_p, uint64_t drop_seed, double* d_sums, void* stream) {
+  if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_gamma && d_beta),
@@ -1482,6 +1489,7 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
                                  const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed,
                                  void* d_dx, int dx_ld, void* d_dz, int dz_ld, float* d_dgamma,
                                  float* d_dbeta, void* stream) {
+  if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_bwd_apply"); REQ_LD8(dout_ld, "bn_bwd_apply"); REQ_LD8(x_ld, "bn_bwd_apply"); REQ_LD8(dx_ld, "bn_bwd_apply");
   ISWM_REQUIRE(d_dout && d_x && d_gamma && d_save_mean && d_save_invstd && d_sums && d_dx && M > 0, "bn_bwd_apply: null/empty");
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_beta),
@@ -1489,7 +1497,8 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd_apply: dz_ld");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
-  bn_row_grid(C, M, 4, nx, ny, rpb, blocks);
+  static const int env_waves = [] { const char* e = getenv("ISWM_BN_WAVES"); return e ? atoi(e) : 3; }();   // see iswm_bn_train_apply
+  bn_row_grid(C, M, 4, nx, ny, rpb, blocks, env_waves);
   const int mask = !relu ? 0 : (d_out_act ? 1 : 2);
   const bool has_drop = drop_p > 0.f, has_dz = d_dz != nullptr;
 #define ISWM_BN_BAP(MK, D, Z)                                                                                          \

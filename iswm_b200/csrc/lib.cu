@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
   va_end(ap);
 }
+std::atomic<int> g_skip_mask{0};
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("ISWM_PDL");
@@ -27,3 +28,4 @@ extern "C" const char* iswm_last_error(void) { return iswm::t_err; }
 extern "C" int iswm_version(void) { return 100; }
 extern "C" int64_t iswm_launch_count(void) { return iswm::g_launches.load(); }
 extern "C" void iswm_reset_launch_count(void) { iswm::g_launches.store(0); }
+extern "C" void iswm_debug_set_skip(int mask) { iswm::g_skip_mask.store(mask); }

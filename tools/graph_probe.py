@@ -56,4 +56,22 @@ torch.cuda.synchronize()
 for _ in range(3):
     g.replay()
 ms, host = timed(g.replay)
-print(f"graph: {ms:.2f} ms/step on the device, {host:.3f} ms/step of host time; loss {float(loss):.5f}")
+print(f"graph: {ms:.2f} ms/step on the device, {host:.3f} ms/step of host time; loss {float(loss.detach()):.5f}")
+
+# marginal cost of each kernel family inside the pipeline: the same step captured with that family's launches skipped
+from iswm_b200 import _lib
+eng = model.engine()
+for inline in (False, True):
+    eng.async_wgrad = not inline
+    res = {}
+    for name, mask in (("all", 0), ("no conv_igemm", 1), ("no conv_wgrad", 2), ("no BatchNorm kernels", 4), ("no conv at all", 3), ("only glue + loss + SGD", 7)):
+        _lib.lib().iswm_debug_set_skip(mask)
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg):
+            step()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            gg.replay()
+        res[name], _ = timed(gg.replay, 5)
+        _lib.lib().iswm_debug_set_skip(0)
+    print(f"weight gradients {'in line' if inline else 'on the side stream'}: " + "; ".join(f"{k} {v:.2f} ms" for k, v in res.items()))
