@@ -511,9 +511,20 @@ def run_ours(args):
     x_dev, y_dev = synth_batch(B, H, W, rank, device=dev)
     x_host, y_host = synth_batch(B, H, W, rank, pinned=True)
 
+    # single GPU: the step is captured once and replayed as ONE CUDA graph launch (iswm_b200.graphs.GraphedTrainStep, the
+    # recommended API; ISWM_BENCH_GRAPH=0 times the eager ~430-launch step instead). Data-parallel steps stay eager.
+    use_graph = world == 1 and os.environ.get("ISWM_BENCH_GRAPH", "1") != "0"
+    stepper = None
+    if use_graph:
+        from iswm_b200.graphs import GraphedTrainStep
+        stepper = GraphedTrainStep(model, crit, opt)
+    eager_only = [False]
+
     def step(x, y):
         if dp is not None:
             return dp.train_step(x, y, opt)
+        if stepper is not None and not eager_only[0]:
+            return stepper(x, y)
         logits = model(x)
         loss = crit(logits, y)
         opt.zero_grad()
@@ -548,6 +559,8 @@ def run_ours(args):
     barrier()
     w1 = time.time()
     launches = _lib.launch_count() - launches0
+    if stepper is not None:
+        launches += args.steps * stepper.launches_per_replay      # kernels inside the replayed graph (counted at capture)
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     # ---- timed region 2: end to end through the public API with HOST buffers ("e2e"): every step's images and
@@ -586,6 +599,7 @@ def run_ours(args):
     # the SMs with the kernel being timed, its CUDA events measure the contention, not the kernel
     async_wgrad = eng.async_wgrad
     eng.async_wgrad = False
+    eager_only[0] = True                    # per-kernel events need the eager launch path
     host_head_start()
     step(x_dev, y_dev)
     barrier()
@@ -643,6 +657,7 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": train_workload_name(args.backbone, args.output_stride, H, W, B),
                    "parallelism": f"dp{world}", "global_batch": B * world,
+                   "launch": "one CUDA graph replay per step (GraphedTrainStep)" if stepper is not None else "eager launches",
                    "l2": "no explicit flush: each step streams > 2 GB of activations (>> 126 MB L2)",
                    "e2e_note": "per step: images+labels H2D from pinned memory (HostBatchPrefetcher, copy of batch i+1 under step i) and the loss D2H (DeferredLoss: read on the host one step later, last one before the timer stops)",
                    "whole_step_tensor_frac": (gflop * 1e9 * B * world * args.steps / (ms * 1e-3) / 1e12 / world / peaks().get("bf16_tflops_sustained", 1400.0)) if gflop else None,

@@ -204,12 +204,15 @@ int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stri
  * network/_deeplab.py:38,46,49,125,135,150,163): from per-channel sum/sum^2
  * (conv epilogue STATS) compute batch mean / biased var, write
  * out = [relu]( gamma*(x-mean)*invstd + beta [+ residual] ) with optional dropout,
- * save mean/invstd for backward, update running stats (momentum, unbiased var). */
+ * save mean/invstd for backward, update running stats (momentum, unbiased var).
+ * Dropout (network/_deeplab.py:165 nn.Dropout(0.1)) is counter-based: element i is kept iff hash(seed_eff, i) >= p with
+ * seed_eff = (drop_seed + 1000003 * *d_drop_step) mod 2^48; d_drop_step (int64 on the DEVICE, or NULL = 0) lets a
+ * train step captured in a CUDA graph draw a fresh mask on every replay. The backward kernels take the same pair. */
 int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,
                         const float* d_gamma, const float* d_beta, float eps, float momentum,
                         float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                         float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld, int relu,
-                        float drop_p, uint64_t drop_seed, void* d_out, int out_ld, void* stream);
+                        float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, void* d_out, int out_ld, void* stream);
 
 /* eval-mode BN folding: scale = gamma / sqrt(running_var + eps), shift = beta - mean*scale */
 int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean, const float* d_var,
@@ -223,13 +226,13 @@ int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_l
                        const void* d_out_act, int act_ld, int64_t M, int C,
                        const float* d_save_mean, const float* d_save_invstd,
                        const float* d_gamma, const float* d_beta, int relu,
-                       float drop_p, uint64_t drop_seed, double* d_sums, void* stream);
+                       float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, double* d_sums, void* stream);
 /* pass 2: dx = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzxhat/M); dgamma += , dbeta += ;
  * optionally writes dz (the pre-activation gradient, used by the residual identity path). */
 int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                       const void* d_out_act, int act_ld, int64_t M, int C,
                       const float* d_gamma, const float* d_beta, const float* d_save_mean,
-                      const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                      const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step,
                       void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                       float* d_dgamma, float* d_dbeta, void* stream);
 
@@ -240,7 +243,7 @@ int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld
 int iswm_bn_bwd(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                 const void* d_out_act, int act_ld, int64_t M, int C,
                 const float* d_gamma, const float* d_beta, const float* d_save_mean,
-                const float* d_save_invstd, double* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                const float* d_save_invstd, double* d_sums, int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step,
                 void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                 float* d_dgamma, float* d_dbeta, void* stream);
 
@@ -287,15 +290,17 @@ int iswm_bias_grad_nchw(const float* d_dout, int B, int C, int64_t HW, float* d_
 int iswm_scale_by_device_scalar(void* d_x, int dtype, int64_t n, const float* d_scalar, void* stream);
 
 /* fused multi-tensor SGD(momentum, nesterov, weight decay) step (train.py:421-431, :1049) on a flat fp32 buffer */
+/* d_lr: optional DEVICE float overriding `lr` (a step replayed from a CUDA graph follows the LR schedule through it) */
 int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr, float momentum,
-                  float weight_decay, int nesterov, int first_step, void* stream);
+                  float weight_decay, int nesterov, int first_step, const float* d_lr, void* stream);
 
 /* fused Adam / AdamW step on a flat fp32 buffer: torch.optim.Adam(weight_decay) and torch.optim.AdamW(weight_decay)
  * as train.py:432-441 builds them (torch defaults lr 1e-3, betas (0.9, 0.999), eps 1e-8), stepped at train.py:1049.
- * adamw = 0: L2 decay added to the gradient; 1: decoupled decay. step = 1 on the first update (bias correction). */
+ * adamw = 0: L2 decay added to the gradient; 1: decoupled decay. step = 1 on the first update (bias correction).
+ * d_lr / d_step: optional DEVICE float / int64 overriding `lr` / `step` (CUDA-graph replays). */
 int iswm_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int adamw,
-                   int64_t step, void* stream);
+                   int64_t step, const float* d_lr, const int64_t* d_step, void* stream);
 
 /* ---- the step before the hot path: device input pipeline ---------------- */
 /* ExtRandomCrop (window origin per image, no padding) + ExtRandomHorizontalFlip + ExtToTensor + ExtNormalize

@@ -201,6 +201,16 @@ pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
 // Row walk shared by the three kernels: thread (tx, ty) owns channels [8tx, 8tx+8) of rows r0+ty, r0+ty+ny, ...
 // of its block; pointers advance by a fixed stride (no per-row 64-bit multiplies) and the main loop handles U rows
 // per trip without bounds checks (U independent 16-byte loads per tensor in flight), a scalar tail the rest.
+// dropout seed of one launch: a by-value part plus an optional per-step counter read from DEVICE memory, so that a train
+// step captured in a CUDA graph draws a fresh mask on every replay (effective seed = seed + 1000003 * *step, 48 bits)
+struct DropSeed {
+  uint64_t seed;
+  const long long* step;
+  __device__ __forceinline__ uint64_t resolve() const {
+    return (seed + (step ? (uint64_t)(*step) * 1000003ull : 0ull)) & 0xFFFFFFFFFFFFull;
+  }
+};
+
 struct RowWalk {
   int64_t first;      // first row of this thread
   int n;              // rows this thread owns
@@ -222,10 +232,11 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
                       float eps, float momentum, float* running_mean, float* running_var,
                       long long* nbt, float* save_mean, float* save_invstd,
                       const __nv_bfloat16* __restrict__ res, int res_ld, float drop_p,
-                      uint64_t drop_seed, __nv_bfloat16* __restrict__ out, int out_ld, int nx, int ny,
+                      DropSeed drop_seed_in, __nv_bfloat16* __restrict__ out, int out_ld, int nx, int ny,
                       int rows_per_block) {
   pdl_wait();
   pdl_launch();
+  const uint64_t drop_seed = DROP ? drop_seed_in.resolve() : 0ull;
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
@@ -339,10 +350,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                      const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float drop_p, uint64_t drop_seed, double* __restrict__ sums, int nx, int ny,
+                     float drop_p, DropSeed drop_seed_in, double* __restrict__ sums, int nx, int ny,
                      int rows_per_block) {
   pdl_wait();
   pdl_launch();
+  const uint64_t drop_seed = DROP ? drop_seed_in.resolve() : 0ull;
   __shared__ float s_red[kT * 16];
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
@@ -450,11 +462,12 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const double* __restrict__ sums,
-                    float drop_p, uint64_t drop_seed, __nv_bfloat16* __restrict__ dx, int dx_ld,
+                    float drop_p, DropSeed drop_seed_in, __nv_bfloat16* __restrict__ dx, int dx_ld,
                     __nv_bfloat16* __restrict__ dz, int dz_ld, float* dgamma, float* dbeta, int nx,
                     int ny, int rows_per_block) {
   pdl_wait();
   pdl_launch();
+  const uint64_t drop_seed = DROP ? drop_seed_in.resolve() : 0ull;
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   if (ty >= ny) return;
   const int c0 = tx << 3;
@@ -574,11 +587,12 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
                     const __nv_bfloat16* __restrict__ x, int x_ld,
                     const __nv_bfloat16* __restrict__ act, int act_ld, int64_t M, int C,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, double* sums, float drop_p, uint64_t drop_seed,
+                    const float* __restrict__ invstd, double* sums, float drop_p, DropSeed drop_seed_in,
                     __nv_bfloat16* __restrict__ dx, int dx_ld, __nv_bfloat16* __restrict__ dz, int dz_ld,
                     float* dgamma, float* dbeta, int nx, int ny, int rows_per_block, int* abort_flag) {
   pdl_wait();
   pdl_launch();
+  const uint64_t drop_seed = DROP ? drop_seed_in.resolve() : 0ull;
   __shared__ float s_red[kT * 16];
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   const int c0 = tx << 3;
@@ -1230,9 +1244,10 @@ nchw_f32_to_nhwc_kernel(const float* __restrict__ x, int B, int64_t HW, int C,
 // fused SGD(momentum, nesterov, weight decay) over a flat fp32 buffer (torch.optim.SGD rule)
 __global__ void __launch_bounds__(kT)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, int64_t n,
-                float lr, float momentum, float wd, int nesterov, int first) {
+                float lr, float momentum, float wd, int nesterov, int first, const float* __restrict__ d_lr) {
   pdl_wait();
   pdl_launch();
+  if (d_lr) lr = *d_lr;                  // learning rate from device memory (CUDA-graph replays follow the scheduler)
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
     float grad = g[i];
     const float w = p[i];
@@ -1254,9 +1269,21 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
 __global__ void __launch_bounds__(kT)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, float lr, float b1, float b2, float eps, float wd, int adamw, float step_size,
-                 float inv_sqrt_bc2) {
+                 float inv_sqrt_bc2, const float* __restrict__ d_lr, const long long* __restrict__ d_step) {
   pdl_wait();
   pdl_launch();
+  if (d_lr || d_step) {                  // device-resident schedule state (CUDA-graph replays): redo the host's scalar math
+    const double lr_host = (double)lr;
+    const double lr_d = d_lr ? (double)*d_lr : lr_host;
+    if (d_step) {
+      const double t = (double)*d_step;
+      step_size = (float)(lr_d / (1.0 - pow((double)b1, t)));
+      inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+    } else {
+      step_size = (float)((double)step_size * (lr_d / lr_host));
+    }
+    lr = (float)lr_d;
+  }
   auto one = [&](float& w, float grad, float& mm, float& vv) {
     if (adamw) w = w * (1.f - lr * wd);
     else if (wd != 0.f) grad = fmaf(wd, w, grad);
@@ -1423,7 +1450,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
                                    const float* d_gamma, const float* d_beta, float eps, float momentum,
                                    float* d_running_mean, float* d_running_var, int64_t* d_nbt,
                                    float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld,
-                                   int relu, float drop_p, uint64_t drop_seed, void* d_out, int out_ld,
+                                   int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, void* d_out, int out_ld,
                                    void* stream) {
   if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_train_apply"); REQ_LD8(x_ld, "bn_train_apply"); REQ_LD8(out_ld, "bn_train_apply");
@@ -1440,7 +1467,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
 #define ISWM_BN_APPLY(R, L, D)                                                                                     \
   launch_k(bn_train_apply_kernel<R, L, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, d_stats, M, C,    \
            d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var, reinterpret_cast<long long*>(d_nbt),      \
-           d_save_mean, d_save_invstd, BF(d_res), res_ld, drop_p, drop_seed, BFW(d_out), out_ld, nx, ny, rpb)
+           d_save_mean, d_save_invstd, BF(d_res), res_ld, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, BFW(d_out), out_ld, nx, ny, rpb)
   if (has_drop) {
     if (has_res) { if (relu) ISWM_BN_APPLY(true, true, true); else ISWM_BN_APPLY(true, false, true); }
     else         { if (relu) ISWM_BN_APPLY(false, true, true); else ISWM_BN_APPLY(false, false, true); }
@@ -1463,7 +1490,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
                                   const void* d_out_act, int act_ld, int64_t M, int C,
                                   const float* d_save_mean, const float* d_save_invstd,
                                   const float* d_gamma, const float* d_beta, int relu,
-                                  float drop_p, uint64_t drop_seed, double* d_sums, void* stream) {
+                                  float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, double* d_sums, void* stream) {
   if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
@@ -1476,7 +1503,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
   const bool has_drop = drop_p > 0.f;
 #define ISWM_BN_RED(MK, D)                                                                                          \
   launch_k(bn_bwd_reduce_kernel<MK, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,   \
-           BF(d_out_act), act_ld, M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, drop_p, drop_seed, d_sums, nx, \
+           BF(d_out_act), act_ld, M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, d_sums, nx, \
            ny, rows_per_block)
   if (has_drop) { if (mask == 0) ISWM_BN_RED(0, true); else if (mask == 1) ISWM_BN_RED(1, true); else ISWM_BN_RED(2, true); }
   else          { if (mask == 0) ISWM_BN_RED(0, false); else if (mask == 1) ISWM_BN_RED(1, false); else ISWM_BN_RED(2, false); }
@@ -1486,7 +1513,7 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
 extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                                  const void* d_out_act, int act_ld, int64_t M, int C,
                                  const float* d_gamma, const float* d_beta, const float* d_save_mean,
-                                 const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                                 const float* d_save_invstd, const double* d_sums, int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step,
                                  void* d_dx, int dx_ld, void* d_dz, int dz_ld, float* d_dgamma,
                                  float* d_dbeta, void* stream) {
   if (debug_skip(ISWM_SKIP_BN)) return 0;
@@ -1503,7 +1530,7 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   const bool has_drop = drop_p > 0.f, has_dz = d_dz != nullptr;
 #define ISWM_BN_BAP(MK, D, Z)                                                                                          \
   launch_k(bn_bwd_apply_kernel<MK, D, Z>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,    \
-           BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean, d_save_invstd, d_sums, drop_p, drop_seed,        \
+           BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean, d_save_invstd, d_sums, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)},        \
            BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta, nx, ny, rpb)
 #define ISWM_BN_BAP_M(D, Z) \
   do { if (mask == 0) ISWM_BN_BAP(0, D, Z); else if (mask == 1) ISWM_BN_BAP(1, D, Z); else ISWM_BN_BAP(2, D, Z); } while (0)
@@ -1519,7 +1546,7 @@ namespace iswm { int* abort_flag_ptr(); }   // tc_host.cu
 extern "C" int iswm_bn_bwd(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                            const void* d_out_act, int act_ld, int64_t M, int C,
                            const float* d_gamma, const float* d_beta, const float* d_save_mean,
-                           const float* d_save_invstd, double* d_sums, int relu, float drop_p, uint64_t drop_seed,
+                           const float* d_save_invstd, double* d_sums, int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step,
                            void* d_dx, int dx_ld, void* d_dz, int dz_ld, float* d_dgamma,
                            float* d_dbeta, void* stream) {
   REQ_C8(C, "bn_bwd"); REQ_LD8(dout_ld, "bn_bwd"); REQ_LD8(x_ld, "bn_bwd"); REQ_LD8(dx_ld, "bn_bwd");
@@ -1536,7 +1563,7 @@ extern "C" int iswm_bn_bwd(const void* d_dout, int dout_ld, const void* d_x, int
   const bool has_drop = drop_p > 0.f, has_dz = d_dz != nullptr;
 #define ISWM_BN_F(MK, D, Z)                                                                                             \
   launch_k(bn_bwd_fused_kernel<MK, D, Z>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,     \
-           BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean, d_save_invstd, d_sums, drop_p, drop_seed,         \
+           BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean, d_save_invstd, d_sums, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)},         \
            BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta, nx, ny, rpb, abort_flag)
 #define ISWM_BN_F_M(D, Z) \
   do { if (mask == 0) ISWM_BN_F(0, D, Z); else if (mask == 1) ISWM_BN_F(1, D, Z); else ISWM_BN_F(2, D, Z); } while (0)
@@ -1674,10 +1701,10 @@ extern "C" int iswm_nchw_f32_to_nhwc(const float* d_x, int B, int64_t HW, int C,
   return check_launch("nchw_f32_to_nhwc");
 }
 extern "C" int iswm_sgd_step(float* d_param, const float* d_grad, float* d_mom, int64_t n, float lr,
-                             float momentum, float weight_decay, int nesterov, int first_step, void* stream) {
+                             float momentum, float weight_decay, int nesterov, int first_step, const float* d_lr, void* stream) {
   ISWM_REQUIRE(d_param && d_grad && (momentum == 0.f || d_mom), "sgd_step: null");
   if (n == 0) return 0;
-  launch_k(sgd_step_kernel, dim3(grid_for(n)), dim3(kT), 0, ST(stream), d_param, d_grad, d_mom, n, lr, momentum, weight_decay, nesterov, first_step);
+  launch_k(sgd_step_kernel, dim3(grid_for(n)), dim3(kT), 0, ST(stream), d_param, d_grad, d_mom, n, lr, momentum, weight_decay, nesterov, first_step, d_lr);
   return check_launch("sgd_step");
 }
 
@@ -1708,9 +1735,10 @@ extern "C" int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int tot
 
 extern "C" int iswm_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int adamw,
-                              int64_t step, void* stream) {
+                              int64_t step, const float* d_lr, const int64_t* d_step, void* stream) {
   ISWM_REQUIRE(d_param && d_grad && d_exp_avg && d_exp_avg_sq, "adam_step: null");
-  ISWM_REQUIRE(step >= 1, "adam_step: step=%lld must be >= 1 (1 on the first update)", (long long)step);
+  ISWM_REQUIRE(step >= 1 || d_step, "adam_step: step=%lld must be >= 1 (1 on the first update)", (long long)step);
+  if (step < 1) step = 1;
   ISWM_REQUIRE(((reinterpret_cast<uintptr_t>(d_param) | reinterpret_cast<uintptr_t>(d_grad) | reinterpret_cast<uintptr_t>(d_exp_avg) |
                  reinterpret_cast<uintptr_t>(d_exp_avg_sq)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
   if (n == 0) return 0;
@@ -1719,7 +1747,7 @@ extern "C" int iswm_adam_step(float* d_param, const float* d_grad, float* d_exp_
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   launch_k(adam_step_kernel, dim3(grid_for(n, kT * 4)), dim3(kT), 0, ST(stream), d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1, beta2,
-           eps, weight_decay, adamw, step_size, inv_sqrt_bc2);
+           eps, weight_decay, adamw, step_size, inv_sqrt_bc2, d_lr, reinterpret_cast<const long long*>(d_step));
   return check_launch("adam_step");
 }
 

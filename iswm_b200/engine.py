@@ -356,13 +356,16 @@ class Engine:
             out = Act.new(B, Ho, Wo, Cout, self.device)
         save = self._save_slot(2 * Cout)
         bn = s.bn
-        seed = (self.seed + self.step * 1000003 + len(self.tape)) & 0xFFFFFFFFFFFF
+        # dropout seed = by-value part (unit position) + 1000003 * the DEVICE step counter: identical masks in forward and
+        # backward of one step, a fresh one every step, and valid inside a replayed CUDA graph (iswm_b200.graphs)
+        seed = (self.seed + len(self.tape)) & 0xFFFFFFFFFFFF
+        step_ptr = self._step_dev.data_ptr() if drop_p > 0.0 else None
         ev = self._prof_begin()
         check(L.iswm_bn_train_apply(raw.data_ptr(), Cout, stats.data_ptr(), M, Cout, bn.weight.data_ptr(), bn.bias.data_ptr(),
                                     BN_EPS, BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                     bn.num_batches_tracked.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(),
                                     None if residual is None else residual.ptr, 0 if residual is None else residual.ld,
-                                    1 if relu else 0, drop_p, seed, out.ptr, out.ld, _st()), "bn_train_apply " + s.name)
+                                    1 if relu else 0, drop_p, seed, step_ptr, out.ptr, out.ld, _st()), "bn_train_apply " + s.name)
         # HBM-bound kernels are recorded with their algorithmic BYTES in the flops slot (kernel name prefixed "hbm:")
         self._prof_end(ev, "hbm:bn_train_apply", 2.0 * M * Cout * (3 if residual is not None else 2), "bn_apply " + s.name)
         self._tap(s.name, out)
@@ -399,7 +402,7 @@ class Engine:
                 # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
                 check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                     bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
-                                    1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                    1 if use_mask else 0, drop_p, seed, step_ptr, dy.data_ptr(), Cout, dz_ptr, dz_ld,
                                     self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd " + s.name)
             else:
@@ -407,12 +410,12 @@ class Engine:
                 ev = self._prof_begin()
                 check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                            save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                           1 if use_mask else 0, drop_p, seed, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+                                           1 if use_mask else 0, drop_p, seed, step_ptr, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
                 self._prof_end(ev, "hbm:bn_bwd_reduce", 2.0 * M * Cout * (2 + nmask), "bn_bwd_reduce " + s.name)
                 ev = self._prof_begin()
                 check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                           bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
-                                          1 if use_mask else 0, drop_p, seed, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                          1 if use_mask else 0, drop_p, seed, step_ptr, dy.data_ptr(), Cout, dz_ptr, dz_ld,
                                           self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd_apply " + s.name)
                 self._prof_end(ev, "hbm:bn_bwd_apply", 2.0 * M * Cout * (3 + nmask + (1 if dz_ptr is not None else 0)), "bn_bwd_apply " + s.name)
@@ -609,6 +612,9 @@ class Engine:
         if train:
             self._ensure_grad_buffers()
             self.step += 1
+            if getattr(self, "_step_dev", None) is None or self._step_dev.device != self.device:
+                self._step_dev = torch.full((1,), self.step - 1, dtype=torch.int64, device=self.device)
+            self._step_dev.add_(1)          # on the stream (and in the graph, when captured): == self.step in eager mode
         unit = self._unit_train if train else self._unit_eval
         B, _, H, W = x.shape
         dev = self.device
@@ -720,7 +726,7 @@ class Engine:
         bn = s.bn
         check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                     BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
-                                    save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, out.ptr, 64, _st()), "bn_train_apply stem")
+                                    save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, None, out.ptr, 64, _st()), "bn_train_apply stem")
         self._tap(s.name, out)
 
         def backward():
@@ -728,7 +734,7 @@ class Engine:
             sums = self._stats_slot(130)
             dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
             check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
-                                save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, dy.data_ptr(), 64, None, 0,
+                                save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, None, dy.data_ptr(), 64, None, 0,
                                 self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd stem")
             out.grad = None
             off, n = self.wacc_off[s.name]

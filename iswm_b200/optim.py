@@ -21,6 +21,26 @@ class FusedSGD:
         self.param_groups = [{"lr": lr, "momentum": momentum, "weight_decay": weight_decay, "nesterov": nesterov}]
         self._mom = None
         self._steps = 0
+        self.lr_dev = None                 # device copy of the learning rate (enable_device_state: CUDA-graph replays)
+        self.step_dev = None
+
+    def enable_device_state(self):
+        """Keep the schedule state the kernels read (learning rate, step count) in DEVICE memory, so that an optimiser
+        step captured in a CUDA graph (iswm_b200.graphs.GraphedTrainStep) follows `param_groups[0]['lr']` and counts
+        its own replays. `sync_device_state()` pushes the current host-side learning rate (one 4-byte async copy)."""
+        dev = next(iter(self.engine._param_list())).device
+        if self.lr_dev is None or self.lr_dev.device != dev:
+            self.lr_dev = torch.tensor([self.param_groups[0]["lr"]], dtype=torch.float32, device=dev)
+            self.step_dev = torch.tensor([self._steps], dtype=torch.int64, device=dev)
+            self._lr_host = torch.empty(1, dtype=torch.float32).pin_memory()
+            self._lr_pushed = None
+
+    def sync_device_state(self):
+        lr = float(self.param_groups[0]["lr"])
+        if self.lr_dev is not None and lr != self._lr_pushed:
+            self._lr_host[0] = lr
+            self.lr_dev.copy_(self._lr_host, non_blocking=True)
+            self._lr_pushed = lr
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.engine._param_list():
@@ -41,7 +61,8 @@ class FusedSGD:
         lr = self.param_groups[0]["lr"]
         _lib.check(_lib.lib().iswm_sgd_step(flat_w.data_ptr(), flat_g.data_ptr(), self._mom.data_ptr(), flat_w.numel(),
                                             lr, self.momentum, self.weight_decay, 1 if self.nesterov else 0,
-                                            1 if self._steps == 0 else 0, torch.cuda.current_stream().cuda_stream), "sgd_step")
+                                            1 if self._steps == 0 else 0, None if self.lr_dev is None else self.lr_dev.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "sgd_step")
         self._steps += 1
         eng.invalidate_packed()
 
@@ -65,8 +86,12 @@ class FusedAdam:
         self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay}]
         self._m = self._v = None
         self._steps = 0
+        self.lr_dev = None
+        self.step_dev = None
 
     zero_grad = FusedSGD.zero_grad
+    enable_device_state = FusedSGD.enable_device_state
+    sync_device_state = FusedSGD.sync_device_state
 
     def step(self):
         eng = self.engine
@@ -79,10 +104,14 @@ class FusedAdam:
             self._steps = 0
         self._steps += 1
         g = self.param_groups[0]
+        if self.step_dev is not None:
+            self.step_dev.add_(1)          # counted on the stream: a replayed graph advances the bias correction itself
         _lib.check(_lib.lib().iswm_adam_step(flat_w.data_ptr(), flat_g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
                                              flat_w.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
-                                             1 if self.decoupled else 0, self._steps, torch.cuda.current_stream().cuda_stream),
-                   "adam_step")
+                                             1 if self.decoupled else 0, self._steps,
+                                             None if self.lr_dev is None else self.lr_dev.data_ptr(),
+                                             None if self.step_dev is None else self.step_dev.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "adam_step")
         eng.invalidate_packed()
 
     def state_dict(self):

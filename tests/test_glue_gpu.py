@@ -67,7 +67,7 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     resd = nhwc(res).to(DEV) if with_res else None
     check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, rmd.data_ptr(), rvd.data_ptr(),
                                   nbt.data_ptr(), save.data_ptr(), save[C:].data_ptr(), None if resd is None else resd.data_ptr(), C,
-                                  1 if relu else 0, 0.0, 0, out.data_ptr(), C, st()))
+                                  1 if relu else 0, 0.0, 0, None, out.data_ptr(), C, st()))
     close(nchw(out), y.detach(), 1e-2, 2e-2)
     close(rmd, rm_ref, 1e-4, 1e-5)
     close(rvd, rv_ref, 1e-3, 1e-4)
@@ -77,18 +77,18 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     # units without a residual recompute the ReLU mask from x (act = NULL); residual units read the block output
     act_ptr = out.data_ptr() if with_res else None
     check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, save.data_ptr(), save[C:].data_ptr(),
-                                 gd.data_ptr(), bd.data_ptr(), 1 if relu else 0, 0.0, 0, sums.data_ptr(), st()))
+                                 gd.data_ptr(), bd.data_ptr(), 1 if relu else 0, 0.0, 0, None, sums.data_ptr(), st()))
     if relu and not with_res:                       # both mask sources must agree bit for bit
         sums2 = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
         check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, out.data_ptr(), C, M, C, save.data_ptr(), save[C:].data_ptr(),
-                                     gd.data_ptr(), bd.data_ptr(), 1, 0.0, 0, sums2.data_ptr(), st()))
+                                     gd.data_ptr(), bd.data_ptr(), 1, 0.0, 0, None, sums2.data_ptr(), st()))
         assert torch.equal(sums.float(), sums2.float())   # fp64 accumulators: atomics order is invisible in fp32
     dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     dg = torch.zeros(C, dtype=torch.float32, device=DEV)
     db = torch.zeros(C, dtype=torch.float32, device=DEV)
     check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
-                                sums.data_ptr(), 1 if relu else 0, 0.0, 0, dx.data_ptr(), C, dz.data_ptr(), C, dg.data_ptr(), db.data_ptr(), st()))
+                                sums.data_ptr(), 1 if relu else 0, 0.0, 0, None, dx.data_ptr(), C, dz.data_ptr(), C, dg.data_ptr(), db.data_ptr(), st()))
     scale = float(xr.grad.abs().max())
     close(nchw(dx), xr.grad, 2e-2, 2e-2 * scale)
     close(dg, gr.grad, 2e-2, 5e-2)
@@ -100,7 +100,7 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     dx_f = torch.empty_like(dx); dz_f = torch.empty_like(dz)
     dg_f = torch.zeros(C, dtype=torch.float32, device=DEV); db_f = torch.zeros(C, dtype=torch.float32, device=DEV)
     check(L().iswm_bn_bwd(dd.data_ptr(), C, xd.data_ptr(), C, act_ptr, C, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
-                          sums_f.data_ptr(), 1 if relu else 0, 0.0, 0, dx_f.data_ptr(), C, dz_f.data_ptr() if with_res else None, C,
+                          sums_f.data_ptr(), 1 if relu else 0, 0.0, 0, None, dx_f.data_ptr(), C, dz_f.data_ptr() if with_res else None, C,
                           dg_f.data_ptr(), db_f.data_ptr(), st()))
     torch.cuda.synchronize()
     from iswm_b200 import ops
@@ -292,5 +292,5 @@ def test_sgd_step_matches_torch():
         grad = torch.randn(10007, generator=g)
         p_ref.grad = grad.clone()
         opt.step()
-        check(L().iswm_sgd_step(p.data_ptr(), grad.to(DEV).data_ptr(), mom.data_ptr(), p.numel(), 1e-3, 0.9, 1e-4, 1, 1 if step == 0 else 0, st()))
+        check(L().iswm_sgd_step(p.data_ptr(), grad.to(DEV).data_ptr(), mom.data_ptr(), p.numel(), 1e-3, 0.9, 1e-4, 1, 1 if step == 0 else 0, None, st()))
     close(p, p_ref.detach(), 1e-6, 1e-7)

@@ -1,0 +1,121 @@
+"""CUDA-graph train step (iswm_b200.graphs) and the device-resident step state it relies on (dropout step counter,
+learning rate / Adam step count read by the optimiser kernels from device memory)."""
+import numpy as np
+import pytest
+import torch
+
+from iswm_b200 import _lib
+from iswm_b200.graphs import GraphedTrainStep
+from iswm_b200.network import modeling
+from iswm_b200.optim import CosineAnnealingLR, FusedAdamW, FusedSGD
+from iswm_b200.utils.loss import CrossEntropyLoss
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _batches(n, B=2, S=96):
+    g = torch.Generator().manual_seed(3)
+    out = []
+    for _ in range(n):
+        x = torch.randn((B, 3, S, S), generator=g)
+        y = (torch.rand((B, S, S), generator=g) < 0.1).long()
+        y[torch.rand((B, S, S), generator=g) < 0.02] = 255
+        out.append((x.to(DEV), y.to(DEV)))
+    return out
+
+
+def _model():
+    torch.manual_seed(0)
+    return modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(DEV).train()
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_graphed_step_equals_eager(opt_name):
+    """Same batches, same seeds, Dropout ON, cosine LR stepped every iteration: the replayed graph must walk the same
+    trajectory as the eager loop (weight gradients differ only by fp32 atomics order)."""
+    batches = _batches(4)
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    runs = {}
+    for mode in ("eager", "graph"):
+        m = _model()
+        opt = FusedSGD(m, lr=1e-2, momentum=0.9, weight_decay=1e-4) if opt_name == "sgd" else FusedAdamW(m, lr=1e-3, weight_decay=1e-2)
+        sched = CosineAnnealingLR(opt, T_max=8, eta_min=1e-4)
+        stepper = GraphedTrainStep(m, crit, opt) if mode == "graph" else None
+        losses = []
+        for x, y in batches:
+            if stepper is not None:
+                losses.append(float(stepper(x, y)))
+            else:
+                loss = crit(m(x), y)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+            sched.step()
+        eng = m.engine()
+        runs[mode] = (losses, eng.flat_w.clone(), [b.detach().clone() for b in m.buffers()], opt._steps, eng.step)
+    le, we, be, se, ee = runs["eager"]
+    lg, wg, bg, sg, eg = runs["graph"]
+    assert se == sg == 4 and ee == eg == 4
+    np.testing.assert_allclose(lg, le, rtol=2e-4)
+    rel = float((wg - we).norm() / (we.norm()))
+    upd = float((we - _model().engine().flatten_parameters()).norm() / we.norm())
+    assert rel <= 2e-2 * upd + 1e-7, (rel, upd)          # trajectories agree to a small fraction of the distance travelled
+    for a, b in zip(be, bg):                                # BatchNorm running stats / num_batches_tracked
+        assert torch.allclose(a.float(), b.float(), rtol=1e-3, atol=1e-5)
+
+
+def test_graphed_step_then_eval_uses_fresh_weights():
+    m = _model()
+    crit = CrossEntropyLoss().to(DEV)
+    opt = FusedSGD(m, lr=5e-2, momentum=0.9)
+    stepper = GraphedTrainStep(m, crit, opt)
+    (x, y), = _batches(1)
+    m.eval()
+    with pytest.raises(RuntimeError):
+        stepper(x, y)
+    m.train()
+    for _ in range(2):
+        stepper(x, y)
+    m.eval()
+    with torch.no_grad():
+        a = m(x).clone()
+    m.engine().invalidate_packed()                          # force a repack: must change nothing if the cache was fresh
+    with torch.no_grad():
+        b = m(x)
+    assert torch.equal(a, b)
+    assert stepper.launches_per_replay > 300
+    with pytest.raises(ValueError):
+        stepper(x[:1], y[:1])
+
+
+def test_dropout_mask_follows_device_step_counter():
+    """bn_train_apply with Dropout: seed_eff = seed + 1000003 * *d_step - equal to passing that seed by value, a
+    different mask for another step, keep fraction ~ 1 - p, survivors scaled by 1/(1-p)."""
+    M, C, p = 4096, 64, 0.25
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((M, C), generator=g).to(torch.bfloat16).to(DEV)
+    stats = torch.stack([x.double().sum(0), (x.double() ** 2).sum(0)]).reshape(-1).contiguous()
+    gm, bt = torch.ones(C, device=DEV), torch.full((C,), 3.0, device=DEV)     # shift keeps every output away from 0
+    save = torch.empty(2 * C, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(seed, step):
+        out = torch.empty_like(x)
+        sp = None if step is None else torch.tensor([step], dtype=torch.int64, device=DEV)
+        _lib.check(_lib.lib().iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), M, C, gm.data_ptr(), bt.data_ptr(), 1e-5, 0.1, None, None, None,
+                                                  save.data_ptr(), save[C:].data_ptr(), None, C, 0, p, seed, None if sp is None else sp.data_ptr(),
+                                                  out.data_ptr(), C, st), "bn_train_apply")
+        torch.cuda.synchronize()
+        return out.float()
+
+    base = run(77, None)
+    assert torch.equal(run(77, 0), base)
+    s5 = run(77, 5)
+    assert torch.equal(s5, run(77 + 5 * 1000003, None)) and not torch.equal(s5, base)
+    keep = (s5 != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01
+    nodrop = run(77, None) * 0 + (x.float() - x.float().mean(0)) / x.float().var(0, unbiased=False).add(1e-5).sqrt() + 3.0
+    kept = s5 != 0
+    assert torch.allclose(s5[kept], (nodrop / (1 - p))[kept], rtol=2e-2, atol=2e-2)

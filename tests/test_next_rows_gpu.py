@@ -125,7 +125,7 @@ def test_adam_step_vs_torch_golden(nr, name, adamw, wd):
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     for t, g in enumerate(nr["adam_grads"], 1):
         gd = torch.from_numpy(g).to(DEV)
-        _lib.check(_lib.lib().iswm_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8, wd, adamw, t,
+        _lib.check(_lib.lib().iswm_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8, wd, adamw, t, None, None,
                                              torch.cuda.current_stream().cuda_stream), "adam_step")
     np.testing.assert_allclose(p.cpu().numpy(), nr[f"{name}_wd{wd:g}"], rtol=2e-6, atol=2e-7)
 
@@ -142,7 +142,7 @@ def test_adam_ragged_length_vs_torch():
         buf = torch.zeros(((n + 3) // 4) * 4 * 4, device=DEV)             # 16-byte aligned slabs
         p, g, m, v = (buf[i * ((n + 3) // 4) * 4: i * ((n + 3) // 4) * 4 + n] for i in range(4))
         p.copy_(p0); g.copy_(gr)
-        _lib.check(_lib.lib().iswm_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 1, 1,
+        _lib.check(_lib.lib().iswm_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 1, 1, None, None,
                                              torch.cuda.current_stream().cuda_stream), "adam_step")
         np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=2e-6, atol=2e-7)
 
