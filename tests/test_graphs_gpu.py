@@ -30,40 +30,60 @@ def _model():
     return modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(DEV).train()
 
 
+def _state(m, opt):
+    eng = m.engine()
+    st = {"w": eng.flat_w, "buffers": list(m.buffers())}
+    for k in ("_mom", "_m", "_v"):
+        if getattr(opt, k, None) is not None:
+            st[k] = getattr(opt, k)
+    return st
+
+
 @pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
 def test_graphed_step_equals_eager(opt_name):
-    """Same batches, same seeds, Dropout ON, cosine LR stepped every iteration: the replayed graph must walk the same
-    trajectory as the eager loop (weight gradients differ only by fp32 atomics order)."""
+    """Every replay against the eager step FROM THE SAME STATE (the eager model's state is copied into the graphed one
+    before each step, so that the chaotic amplification of the ~1e-7 weight-gradient atomics noise over several steps -
+    BatchNorm over the 2-sample pooled ASPP branch flips signs - stays out of the comparison): Dropout ON, a new batch
+    every step, cosine LR stepped every iteration. The forward is bit-reproducible, so the losses must agree to fp32
+    noise and the updated weights to the atomics noise."""
     batches = _batches(4)
     crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
-    runs = {}
-    for mode in ("eager", "graph"):
+
+    def make():
         m = _model()
         opt = FusedSGD(m, lr=1e-2, momentum=0.9, weight_decay=1e-4) if opt_name == "sgd" else FusedAdamW(m, lr=1e-3, weight_decay=1e-2)
-        sched = CosineAnnealingLR(opt, T_max=8, eta_min=1e-4)
-        stepper = GraphedTrainStep(m, crit, opt) if mode == "graph" else None
-        losses = []
-        for x, y in batches:
-            if stepper is not None:
-                losses.append(float(stepper(x, y)))
-            else:
-                loss = crit(m(x), y)
-                opt.zero_grad()
-                loss.backward()
-                opt.step()
-                losses.append(float(loss.detach()))
-            sched.step()
-        eng = m.engine()
-        runs[mode] = (losses, eng.flat_w.clone(), [b.detach().clone() for b in m.buffers()], opt._steps, eng.step)
-    le, we, be, se, ee = runs["eager"]
-    lg, wg, bg, sg, eg = runs["graph"]
-    assert se == sg == 4 and ee == eg == 4
-    np.testing.assert_allclose(lg, le, rtol=2e-4)
-    rel = float((wg - we).norm() / (we.norm()))
-    upd = float((we - _model().engine().flatten_parameters()).norm() / we.norm())
-    assert rel <= 2e-2 * upd + 1e-7, (rel, upd)          # trajectories agree to a small fraction of the distance travelled
-    for a, b in zip(be, bg):                                # BatchNorm running stats / num_batches_tracked
-        assert torch.allclose(a.float(), b.float(), rtol=1e-3, atol=1e-5)
+        return m, opt, CosineAnnealingLR(opt, T_max=8, eta_min=1e-4)
+
+    me, oe, se = make()
+    mg, og, sg = make()
+    stepper = GraphedTrainStep(mg, crit, og)
+    for i, (x, y) in enumerate(batches):
+        if i > 0:                                   # same starting state for this step
+            a, b = _state(me, oe), _state(mg, og)
+            assert a.keys() == b.keys()
+            with torch.no_grad():
+                for k in a:
+                    if k == "buffers":
+                        for u, v in zip(a[k], b[k]):
+                            v.copy_(u)
+                    else:
+                        b[k].copy_(a[k])
+            mg.engine().invalidate_packed()
+        loss = crit(me(x), y)
+        oe.zero_grad()
+        loss.backward()
+        oe.step()
+        lg = float(stepper(x, y))
+        le = float(loss.detach())
+        assert abs(lg - le) <= 1e-6 * max(1.0, abs(le)), (i, le, lg)
+        we, wg = me.engine().flat_w, mg.engine().flat_w
+        assert float((wg - we).norm() / we.norm()) <= 1e-6, i
+        for u, v in zip(me.buffers(), mg.buffers()):      # BatchNorm running statistics / num_batches_tracked
+            assert torch.allclose(u.float(), v.float(), rtol=1e-6, atol=1e-7)
+        assert abs(oe.param_groups[0]["lr"] - og.param_groups[0]["lr"]) == 0.0
+        se.step()
+        sg.step()
+    assert oe._steps == og._steps == 4 and me.engine().step == mg.engine().step == 4
 
 
 def test_graphed_step_then_eval_uses_fresh_weights():

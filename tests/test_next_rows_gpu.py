@@ -31,7 +31,7 @@ def test_focal_vs_reference_golden(nr, i):
     loss = crit(x, y)
     loss.backward()
     ref = float(nr[f"focal_loss_{i}"])
-    assert abs(float(loss) - ref) <= 1e-5 * max(1.0, abs(ref))          # fp32 kernel vs fp32 torch
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * max(1.0, abs(ref))          # fp32 kernel vs fp32 torch
     np.testing.assert_allclose(x.grad.cpu().numpy(), nr[f"focal_grad_{i}"], rtol=2e-3, atol=2e-6)
 
 
