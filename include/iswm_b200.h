@@ -207,12 +207,16 @@ int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stri
  * save mean/invstd for backward, update running stats (momentum, unbiased var).
  * Dropout (network/_deeplab.py:165 nn.Dropout(0.1)) is counter-based: element i is kept iff hash(seed_eff, i) >= p with
  * seed_eff = (drop_seed + 1000003 * *d_drop_step) mod 2^48; d_drop_step (int64 on the DEVICE, or NULL = 0) lets a
- * train step captured in a CUDA graph draw a fresh mask on every replay. The backward kernels take the same pair. */
+ * train step captured in a CUDA graph draw a fresh mask on every replay. The backward kernels take the same pair.
+ * d_relu_bits (optional, with relu): uint8 [M, C/8], bit j of byte (row, g) = output channel 8g+j is positive. The
+ * backward kernels of residual units read these bits (relu mode 2, passed in d_out_act) instead of the 16-byte
+ * activation row: the mask of relu(bn(x) + residual) cannot be recomputed from x alone. */
 int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,
                         const float* d_gamma, const float* d_beta, float eps, float momentum,
                         float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                         float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld, int relu,
-                        float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, void* d_out, int out_ld, void* stream);
+                        float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, void* d_out, int out_ld,
+                        uint8_t* d_relu_bits, void* stream);
 
 /* eval-mode BN folding: scale = gamma / sqrt(running_var + eps), shift = beta - mean*scale */
 int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean, const float* d_var,
@@ -221,7 +225,9 @@ int iswm_bn_fold(const float* d_gamma, const float* d_beta, const float* d_mean,
 /* BatchNorm backward, pass 1: dz = dout * [out>0 if relu] * dropmask;
  * sums[c] = sum dz, sums[C+c] = sum dz * xhat. d_out_act = post-activation output (for the ReLU mask);
  * pass NULL for a unit WITHOUT a residual add and the mask is recomputed from d_x with the forward
- * kernel's own arithmetic, gamma*invstd*x + (beta - mean*gamma*invstd) > 0 (one tensor read less). */
+ * kernel's own arithmetic, gamma*invstd*x + (beta - mean*gamma*invstd) > 0 (one tensor read less).
+ * relu: 0 = no mask, 1 = as above, 2 = d_out_act points at the packed sign bits written by iswm_bn_train_apply
+ * (uint8 [M, C/8], act_ld ignored): 1 byte instead of 16 per 8 channels on residual units. Same in iswm_bn_bwd_apply. */
 int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                        const void* d_out_act, int act_ld, int64_t M, int C,
                        const float* d_save_mean, const float* d_save_invstd,

@@ -233,7 +233,7 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
                       long long* nbt, float* save_mean, float* save_invstd,
                       const __nv_bfloat16* __restrict__ res, int res_ld, float drop_p,
                       DropSeed drop_seed_in, __nv_bfloat16* __restrict__ out, int out_ld, int nx, int ny,
-                      int rows_per_block) {
+                      int rows_per_block, uint8_t* __restrict__ relu_bits) {
   pdl_wait();
   pdl_launch();
   const uint64_t drop_seed = DROP ? drop_seed_in.resolve() : 0ull;
@@ -284,7 +284,11 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
   const int64_t so = (int64_t)ny * out_ld;
   uint64_t didx = (uint64_t)w.first * C + c0;                 // dropout counter of this thread's first element
   const uint64_t sd = (uint64_t)ny * C;
-  auto one = [&](const uint4& f4, const uint4& r4, __nv_bfloat16* o, uint64_t di) {
+  // ReLU sign bits of this thread's 8 channels, one byte per (row, channel group): the backward kernels of residual
+  // units read it instead of the 16-byte activation (the mask cannot be recomputed from x alone there)
+  uint8_t* pb = relu_bits ? relu_bits + w.first * (C >> 3) + tx : nullptr;
+  const int64_t sb = (int64_t)ny * (C >> 3);
+  auto one = [&](const uint4& f4, const uint4& r4, __nv_bfloat16* o, uint64_t di, uint8_t* ob) {
     F8 f = unpack8(f4);
 #pragma unroll
     for (int j = 0; j < 8; j++) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
@@ -294,6 +298,12 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
       for (int j = 0; j < 8; j++) f.v[j] += r.v[j];
     }
     if (RELU) {
+      if (ob) {
+        unsigned bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) bits |= (f.v[j] > 0.f) ? (1u << j) : 0u;
+        *ob = (uint8_t)bits;
+      }
 #pragma unroll
       for (int j = 0; j < 8; j++) f.v[j] = fmaxf(f.v[j], 0.f);
     }
@@ -313,17 +323,19 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) one(fr[u], rr[u], po + u * so, didx + u * sd);
+    for (int u = 0; u < U; u++) one(fr[u], rr[u], po + u * so, didx + u * sd, pb ? pb + u * sb : nullptr);
     px += U * sx; po += U * so; didx += U * sd;
     if (RES) pr += U * sr;
+    if (pb) pb += U * sb;
   }
   for (; i < w.n; i++) {
     const uint4 f4 = load_raw(px);
     uint4 r4 = f4;
     if (RES) r4 = load_raw(pr);
-    one(f4, r4, po, didx);
+    one(f4, r4, po, didx, pb);
     px += sx; po += so; didx += sd;
     if (RES) pr += sr;
+    if (pb) pb += sb;
   }
 }
 
@@ -365,6 +377,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
   const __nv_bfloat16* px = x + w.first * x_ld + c0;
   const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
+  const uint8_t* pm = (MASK == 3) ? reinterpret_cast<const uint8_t*>(act) + w.first * (C >> 3) + tx : nullptr;
+  const int64_t sm_ = (int64_t)ny * (C >> 3);
   const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa = (int64_t)ny * act_ld;
   uint4 gr[U], xr[U], orr[U];
   if (w.n >= U) {
@@ -372,7 +386,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     for (int u = 0; u < U; u++) {
       gr[u] = load_raw(pg + u * sg);
       xr[u] = load_raw(px + u * sx);
-      if (MASK == 1) orr[u] = load_raw(pa + u * sa); else orr[u] = gr[u];
+      if (MASK == 1) orr[u] = load_raw(pa + u * sa); else if (MASK == 3) { orr[u] = gr[u]; orr[u].x = pm[u * sm_]; } else orr[u] = gr[u];
     }
   }
   float a[8], b[8], sc[8], sh[8];
@@ -396,6 +410,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
         const F8 o = unpack8(orr);
 #pragma unroll
         for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+      } else if (MASK == 3) {
+        const unsigned bits = orr.x;
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.v[j] = ((bits >> j) & 1u) ? g.v[j] : 0.f;
       } else if (MASK == 2) {
 #pragma unroll
         for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], sc[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
@@ -417,21 +435,24 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
         for (int u = 0; u < U; u++) {
           gr[u] = load_raw(pg + u * sg);
           xr[u] = load_raw(px + u * sx);
-          if (MASK == 1) orr[u] = load_raw(pa + u * sa); else orr[u] = gr[u];
+          if (MASK == 1) orr[u] = load_raw(pa + u * sa); else if (MASK == 3) { orr[u] = gr[u]; orr[u].x = pm[u * sm_]; } else orr[u] = gr[u];
         }
       }
 #pragma unroll
       for (int u = 0; u < U; u++) one(gr[u], xr[u], orr[u], didx + u * sd);
       pg += U * sg; px += U * sx; didx += U * sd;
       if (MASK == 1) pa += U * sa;
+      if (MASK == 3) pm += U * sm_;
     }
     for (; i < w.n; i++) {
       const uint4 g1 = load_raw(pg), x1 = load_raw(px);
       uint4 o1 = g1;
       if (MASK == 1) o1 = load_raw(pa);
+      if (MASK == 3) o1.x = *pm;
       one(g1, x1, o1, didx);
       pg += sg; px += sx; didx += sd;
       if (MASK == 1) pa += sa;
+      if (MASK == 3) pm += sm_;
     }
   }
 #pragma unroll
@@ -477,6 +498,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
   const __nv_bfloat16* px = x + w.first * x_ld + c0;
   const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
+  const uint8_t* pm = (MASK == 3) ? reinterpret_cast<const uint8_t*>(act) + w.first * (C >> 3) + tx : nullptr;
+  const int64_t sm_ = (int64_t)ny * (C >> 3);
   const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa_ = (int64_t)ny * act_ld;
   uint4 gr[U], xr[U], orr[U];
   if (w.n >= U) {
@@ -484,7 +507,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
     for (int u = 0; u < U; u++) {
       gr[u] = load_raw(pg + u * sg);
       xr[u] = load_raw(px + u * sx);
-      if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else orr[u] = gr[u];
+      if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else if (MASK == 3) { orr[u] = gr[u]; orr[u].x = pm[u * sm_]; } else orr[u] = gr[u];
     }
   }
   const float invM = 1.0f / (float)M;
@@ -519,6 +542,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       const F8 o = unpack8(orr);
 #pragma unroll
       for (int j = 0; j < 8; j++) g.v[j] = (o.v[j] > 0.f) ? g.v[j] : 0.f;
+    } else if (MASK == 3) {
+      const unsigned bits = orr.x;
+#pragma unroll
+      for (int j = 0; j < 8; j++) g.v[j] = ((bits >> j) & 1u) ? g.v[j] : 0.f;
     } else if (MASK == 2) {
 #pragma unroll
       for (int j = 0; j < 8; j++) g.v[j] = (fmaf(xv.v[j], kk[j], sh[j]) > 0.f) ? g.v[j] : 0.f;
@@ -540,22 +567,25 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       for (int u = 0; u < U; u++) {
         gr[u] = load_raw(pg + u * sg);
         xr[u] = load_raw(px + u * sx);
-        if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else orr[u] = gr[u];
+        if (MASK == 1) orr[u] = load_raw(pa + u * sa_); else if (MASK == 3) { orr[u] = gr[u]; orr[u].x = pm[u * sm_]; } else orr[u] = gr[u];
       }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) one(gr[u], xr[u], orr[u], pdx + u * sdx, DZ ? pdz + u * sdz : nullptr, didx + u * sd);
     pg += U * sg; px += U * sx; pdx += U * sdx; didx += U * sd;
     if (MASK == 1) pa += U * sa_;
+    if (MASK == 3) pm += U * sm_;
     if (DZ) pdz += U * sdz;
   }
   for (; i < w.n; i++) {
     const uint4 g1 = load_raw(pg), x1 = load_raw(px);
     uint4 o1 = g1;
     if (MASK == 1) o1 = load_raw(pa);
+      if (MASK == 3) o1.x = *pm;
     one(g1, x1, o1, pdx, pdz, didx);
     pg += sg; px += sx; pdx += sdx; didx += sd;
     if (MASK == 1) pa += sa_;
+    if (MASK == 3) pm += sm_;
     if (DZ) pdz += sdz;
   }
 }
@@ -1451,7 +1481,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
                                    float* d_running_mean, float* d_running_var, int64_t* d_nbt,
                                    float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld,
                                    int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step, void* d_out, int out_ld,
-                                   void* stream) {
+                                   uint8_t* d_relu_bits, void* stream) {
   if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_train_apply"); REQ_LD8(x_ld, "bn_train_apply"); REQ_LD8(out_ld, "bn_train_apply");
   ISWM_REQUIRE(d_x && d_stats && d_gamma && d_beta && d_out && M > 0, "bn_train_apply: null/empty");
@@ -1467,7 +1497,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
 #define ISWM_BN_APPLY(R, L, D)                                                                                     \
   launch_k(bn_train_apply_kernel<R, L, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, d_stats, M, C,    \
            d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var, reinterpret_cast<long long*>(d_nbt),      \
-           d_save_mean, d_save_invstd, BF(d_res), res_ld, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, BFW(d_out), out_ld, nx, ny, rpb)
+           d_save_mean, d_save_invstd, BF(d_res), res_ld, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, BFW(d_out), out_ld, nx, ny, rpb, relu ? d_relu_bits : nullptr)
   if (has_drop) {
     if (has_res) { if (relu) ISWM_BN_APPLY(true, true, true); else ISWM_BN_APPLY(true, false, true); }
     else         { if (relu) ISWM_BN_APPLY(false, true, true); else ISWM_BN_APPLY(false, false, true); }
@@ -1494,19 +1524,21 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
   if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_bwd_reduce"); REQ_LD8(dout_ld, "bn_bwd_reduce"); REQ_LD8(x_ld, "bn_bwd_reduce");
   ISWM_REQUIRE(d_dout && d_x && d_save_mean && d_save_invstd && d_sums && M > 0, "bn_bwd_reduce: null/empty");
-  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_gamma && d_beta),
+  ISWM_REQUIRE(relu >= 0 && relu <= 2, "bn_bwd_reduce: relu mode %d", relu);
+  ISWM_REQUIRE(relu != 1 || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_gamma && d_beta),
                "bn_bwd_reduce: relu needs the activation (or gamma and beta to recompute the mask)");
+  ISWM_REQUIRE(relu != 2 || d_out_act, "bn_bwd_reduce: relu mode 2 needs the packed sign bits in d_out_act");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
   int nx, ny, rows_per_block, blocks;
   bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 3);   // one wave: every block ends with fp64 atomics on the same 2C addresses
-  const int mask = !relu ? 0 : (d_out_act ? 1 : 2);
+  const int mask = !relu ? 0 : (relu == 2 ? 3 : (d_out_act ? 1 : 2));
   const bool has_drop = drop_p > 0.f;
 #define ISWM_BN_RED(MK, D)                                                                                          \
   launch_k(bn_bwd_reduce_kernel<MK, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,   \
            BF(d_out_act), act_ld, M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, d_sums, nx, \
            ny, rows_per_block)
-  if (has_drop) { if (mask == 0) ISWM_BN_RED(0, true); else if (mask == 1) ISWM_BN_RED(1, true); else ISWM_BN_RED(2, true); }
-  else          { if (mask == 0) ISWM_BN_RED(0, false); else if (mask == 1) ISWM_BN_RED(1, false); else ISWM_BN_RED(2, false); }
+  if (has_drop) { if (mask == 0) ISWM_BN_RED(0, true); else if (mask == 1) ISWM_BN_RED(1, true); else if (mask == 2) ISWM_BN_RED(2, true); else ISWM_BN_RED(3, true); }
+  else          { if (mask == 0) ISWM_BN_RED(0, false); else if (mask == 1) ISWM_BN_RED(1, false); else if (mask == 2) ISWM_BN_RED(2, false); else ISWM_BN_RED(3, false); }
 #undef ISWM_BN_RED
   return check_launch("bn_bwd_reduce");
 }
@@ -1519,21 +1551,23 @@ extern "C" int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_
   if (debug_skip(ISWM_SKIP_BN)) return 0;
   REQ_C8(C, "bn_bwd_apply"); REQ_LD8(dout_ld, "bn_bwd_apply"); REQ_LD8(x_ld, "bn_bwd_apply"); REQ_LD8(dx_ld, "bn_bwd_apply");
   ISWM_REQUIRE(d_dout && d_x && d_gamma && d_save_mean && d_save_invstd && d_sums && d_dx && M > 0, "bn_bwd_apply: null/empty");
-  ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_beta),
+  ISWM_REQUIRE(relu >= 0 && relu <= 2, "bn_bwd_apply: relu mode %d", relu);
+  ISWM_REQUIRE(relu != 1 || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_beta),
                "bn_bwd_apply: relu needs the activation (or beta to recompute the mask)");
+  ISWM_REQUIRE(relu != 2 || d_out_act, "bn_bwd_apply: relu mode 2 needs the packed sign bits in d_out_act");
   ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd_apply: dz_ld");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_apply: C=%d > 2048 not supported", C);
   int nx, ny, rpb, blocks;
   static const int env_waves = [] { const char* e = getenv("ISWM_BN_WAVES"); return e ? atoi(e) : 3; }();   // see iswm_bn_train_apply
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks, env_waves);
-  const int mask = !relu ? 0 : (d_out_act ? 1 : 2);
+  const int mask = !relu ? 0 : (relu == 2 ? 3 : (d_out_act ? 1 : 2));
   const bool has_drop = drop_p > 0.f, has_dz = d_dz != nullptr;
 #define ISWM_BN_BAP(MK, D, Z)                                                                                          \
   launch_k(bn_bwd_apply_kernel<MK, D, Z>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,    \
            BF(d_out_act), act_ld, M, C, d_gamma, d_beta, d_save_mean, d_save_invstd, d_sums, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)},        \
            BFW(d_dx), dx_ld, BFW(d_dz), dz_ld, d_dgamma, d_dbeta, nx, ny, rpb)
 #define ISWM_BN_BAP_M(D, Z) \
-  do { if (mask == 0) ISWM_BN_BAP(0, D, Z); else if (mask == 1) ISWM_BN_BAP(1, D, Z); else ISWM_BN_BAP(2, D, Z); } while (0)
+  do { if (mask == 0) ISWM_BN_BAP(0, D, Z); else if (mask == 1) ISWM_BN_BAP(1, D, Z); else if (mask == 2) ISWM_BN_BAP(2, D, Z); else ISWM_BN_BAP(3, D, Z); } while (0)
   if (has_drop) { if (has_dz) ISWM_BN_BAP_M(true, true); else ISWM_BN_BAP_M(true, false); }
   else          { if (has_dz) ISWM_BN_BAP_M(false, true); else ISWM_BN_BAP_M(false, false); }
 #undef ISWM_BN_BAP_M
@@ -1551,6 +1585,7 @@ extern "C" int iswm_bn_bwd(const void* d_dout, int dout_ld, const void* d_x, int
                            float* d_dbeta, void* stream) {
   REQ_C8(C, "bn_bwd"); REQ_LD8(dout_ld, "bn_bwd"); REQ_LD8(x_ld, "bn_bwd"); REQ_LD8(dx_ld, "bn_bwd");
   ISWM_REQUIRE(d_dout && d_x && d_gamma && d_save_mean && d_save_invstd && d_sums && d_dx && M > 0, "bn_bwd: null/empty");
+  ISWM_REQUIRE(relu == 0 || relu == 1, "bn_bwd: relu mode %d (the packed-bit mask is a two-kernel feature)", relu);
   ISWM_REQUIRE(!relu || (d_out_act && (act_ld % 8) == 0) || (!d_out_act && d_beta),
                "bn_bwd: relu needs the activation (or beta to recompute the mask)");
   ISWM_REQUIRE(!d_dz || (dz_ld % 8) == 0, "bn_bwd: dz_ld");

@@ -123,6 +123,7 @@ class Engine:
         # (tensor-core) kernels overlap the HBM-bound BatchNorm kernels and the launch / fill / drain gaps of the
         # data-gradient chain; ISWM_ASYNC_WGRAD=0 puts them back in line
         self.async_wgrad = __import__("os").environ.get("ISWM_ASYNC_WGRAD", "1") != "0"
+        self.relu_bits = __import__("os").environ.get("ISWM_RELU_BITS", "1") != "0"
         self._wstream = None
         self._wgrad_keep = []
         self.profile = None           # list of (kernel, algorithmic_flops, start_event, end_event) when profiling
@@ -360,14 +361,18 @@ class Engine:
         # backward of one step, a fresh one every step, and valid inside a replayed CUDA graph (iswm_b200.graphs)
         seed = (self.seed + len(self.tape)) & 0xFFFFFFFFFFFF
         step_ptr = self._step_dev.data_ptr() if drop_p > 0.0 else None
+        # residual units: the ReLU sign bits go out as one byte per 8 channels, read back by the backward kernels
+        # instead of the block output (ISWM_RELU_BITS=0 restores the activation read)
+        bits = torch.empty((M, Cout // 8), dtype=torch.uint8, device=self.device) if (relu and residual is not None and self.relu_bits) else None
         ev = self._prof_begin()
         check(L.iswm_bn_train_apply(raw.data_ptr(), Cout, stats.data_ptr(), M, Cout, bn.weight.data_ptr(), bn.bias.data_ptr(),
                                     BN_EPS, BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                     bn.num_batches_tracked.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(),
                                     None if residual is None else residual.ptr, 0 if residual is None else residual.ld,
-                                    1 if relu else 0, drop_p, seed, step_ptr, out.ptr, out.ld, _st()), "bn_train_apply " + s.name)
+                                    1 if relu else 0, drop_p, seed, step_ptr, out.ptr, out.ld,
+                                    None if bits is None else bits.data_ptr(), _st()), "bn_train_apply " + s.name)
         # HBM-bound kernels are recorded with their algorithmic BYTES in the flops slot (kernel name prefixed "hbm:")
-        self._prof_end(ev, "hbm:bn_train_apply", 2.0 * M * Cout * (3 if residual is not None else 2), "bn_apply " + s.name)
+        self._prof_end(ev, "hbm:bn_train_apply", 2.0 * M * Cout * (3 if residual is not None else 2) + (M * Cout / 8 if bits is not None else 0), "bn_apply " + s.name)
         self._tap(s.name, out)
         if self.debug_taps is not None:
             self.debug_taps[s.name + ":raw"] = raw.float().permute(0, 3, 1, 2).cpu()
@@ -388,6 +393,9 @@ class Engine:
             # the ReLU mask is read from the block output only where a residual was added; otherwise the
             # kernel recomputes it from raw (one tensor read less in each pass)
             act_ptr = out.ptr if (use_mask and residual is not None) else None
+            relu_mode = 1 if use_mask else 0
+            if bits is not None:
+                act_ptr, relu_mode = bits.data_ptr(), 2
             dy = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
             dz_ptr, dz_ld, dz_tmp = None, 0, None
             if residual is not None:
@@ -398,7 +406,7 @@ class Engine:
                     assert residual.grad.ld == residual.C
                     dz_tmp = torch.empty_like(residual.grad.t)
                     dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
-            if M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems:
+            if bits is None and (M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems):
                 # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
                 check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                     bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
@@ -406,16 +414,16 @@ class Engine:
                                     self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd " + s.name)
             else:
-                nmask = 1 if act_ptr is not None else 0
+                nmask = (1.0 / 16 if bits is not None else 1) if act_ptr is not None else 0
                 ev = self._prof_begin()
                 check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                            save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                           1 if use_mask else 0, drop_p, seed, step_ptr, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+                                           relu_mode, drop_p, seed, step_ptr, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
                 self._prof_end(ev, "hbm:bn_bwd_reduce", 2.0 * M * Cout * (2 + nmask), "bn_bwd_reduce " + s.name)
                 ev = self._prof_begin()
                 check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                           bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
-                                          1 if use_mask else 0, drop_p, seed, step_ptr, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                          relu_mode, drop_p, seed, step_ptr, dy.data_ptr(), Cout, dz_ptr, dz_ld,
                                           self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd_apply " + s.name)
                 self._prof_end(ev, "hbm:bn_bwd_apply", 2.0 * M * Cout * (3 + nmask + (1 if dz_ptr is not None else 0)), "bn_bwd_apply " + s.name)
@@ -726,7 +734,7 @@ class Engine:
         bn = s.bn
         check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                     BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
-                                    save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, None, out.ptr, 64, _st()), "bn_train_apply stem")
+                                    save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, None, out.ptr, 64, None, _st()), "bn_train_apply stem")
         self._tap(s.name, out)
 
         def backward():

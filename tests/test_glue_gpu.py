@@ -67,7 +67,7 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     resd = nhwc(res).to(DEV) if with_res else None
     check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, rmd.data_ptr(), rvd.data_ptr(),
                                   nbt.data_ptr(), save.data_ptr(), save[C:].data_ptr(), None if resd is None else resd.data_ptr(), C,
-                                  1 if relu else 0, 0.0, 0, None, out.data_ptr(), C, st()))
+                                  1 if relu else 0, 0.0, 0, None, out.data_ptr(), C, None, st()))
     close(nchw(out), y.detach(), 1e-2, 2e-2)
     close(rmd, rm_ref, 1e-4, 1e-5)
     close(rvd, rv_ref, 1e-3, 1e-4)
@@ -95,6 +95,24 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     close(db, br.grad, 2e-2, 5e-2)
     if with_res:
         close(nchw(dz), resr.grad, 1e-2, 1e-2)
+    if relu and with_res:
+        # packed ReLU sign bits (one byte per 8 channels) instead of the activation: identical sums and gradients
+        bits = torch.zeros((M, C // 8), dtype=torch.uint8, device=DEV)
+        out_b = torch.empty_like(out)
+        check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+                                      save.data_ptr(), save[C:].data_ptr(), resd.data_ptr(), C, 1, 0.0, 0, None, out_b.data_ptr(), C, bits.data_ptr(), st()))
+        assert torch.equal(out_b, out)
+        want = (out.float().reshape(M, C // 8, 8) > 0).to(torch.int32) * (2 ** torch.arange(8, device=DEV, dtype=torch.int32))
+        assert torch.equal(bits.to(torch.int32), want.sum(-1))
+        sums_b = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+        check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, bits.data_ptr(), 0, M, C, save.data_ptr(), save[C:].data_ptr(),
+                                     gd.data_ptr(), bd.data_ptr(), 2, 0.0, 0, None, sums_b.data_ptr(), st()))
+        assert torch.equal(sums_b.float(), sums.float())
+        dx_b = torch.empty_like(dx); dz_b = torch.empty_like(dz)
+        dg_b = torch.zeros(C, dtype=torch.float32, device=DEV); db_b = torch.zeros(C, dtype=torch.float32, device=DEV)
+        check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, bits.data_ptr(), 0, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
+                                    sums.data_ptr(), 2, 0.0, 0, None, dx_b.data_ptr(), C, dz_b.data_ptr(), C, dg_b.data_ptr(), db_b.data_ptr(), st()))
+        assert torch.equal(dx_b, dx) and torch.equal(dz_b, dz) and torch.equal(dg_b, dg) and torch.equal(db_b, db)
     # the single-launch version (pass 1, grid barrier, pass 2) must reproduce the two-kernel result bit for bit
     sums_f = torch.zeros(2 * C + 2, dtype=torch.float64, device=DEV)
     dx_f = torch.empty_like(dx); dz_f = torch.empty_like(dz)
