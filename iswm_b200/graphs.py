@@ -17,7 +17,8 @@ What makes the replay a TRAINING step rather than a recording of one:
   * the packed bf16 weights are refreshed at the START of the captured step (weights changed at the end of the
     previous one); after a replay the engine is told so, and an eager eval forward repacks.
 The returned loss is a static 0-dim device tensor, overwritten by the next call (copy it, or use DeferredLoss).
-Single process / single GPU; the data-parallel step (iswm_b200.parallel) stays eager.
+Single process / single GPU; the data-parallel step (iswm_b200.parallel) stays eager: capturing its NCCL all-reduces
+(issued with async_op from the backward hooks) was tried on 2 B200s and hung at the first replay, so it is refused.
 """
 from __future__ import annotations
 
