@@ -104,7 +104,10 @@ class_hist_small_kernel(const T* __restrict__ labels, int64_t n, int n_classes,
   pdl_wait();
   pdl_launch();
   constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte load
-  constexpr int UNROLL = 4;
+#ifndef ISWM_HIST_UNROLL
+#define ISWM_HIST_UNROLL 4
+#endif
+  constexpr int UNROLL = ISWM_HIST_UNROLL;
   unsigned cnt[4] = {0, 0, 0, 0};
   const int64_t nvec = n / VEC;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -177,7 +180,7 @@ static int launch_class_hist(const void* labels, int64_t n, int n_classes, int64
   const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
   if (n_classes <= 4 && aligned) {
     constexpr int VEC = 16 / sizeof(T);
-    int64_t want = (n / VEC + kThreads * 4 - 1) / (kThreads * 4);
+    int64_t want = (n / VEC + kThreads * ISWM_HIST_UNROLL - 1) / (kThreads * ISWM_HIST_UNROLL);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)resident_grid(class_hist_small_kernel<T>, kThreads));
     launch_k(class_hist_small_kernel<T>, dim3(grid), dim3(kThreads), 0, st, p, n, n_classes, h);
   } else {
