@@ -370,14 +370,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
   __shared__ float s_red[kT * 16];
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
   const float keep_scale = DROP ? 1.f / (1.f - drop_p) : 1.f;
-  const int c0 = tx << 3;
+  // blockIdx.y = channel group of nx*8 channels: wide layers are cut into 256-channel groups so that a block ends with
+  // 2*256 fp64 atomics instead of 2*C (C = 2048: 1.8 M same-address-heavy atomics per launch were a 10-20 us tail)
+  const int cbase = blockIdx.y * (nx << 3);
+  const int c0 = cbase + (tx << 3);
   constexpr int U = 4;
   // first batch of rows requested before the per-channel constants are loaded (overlapping latencies)
-  const RowWalk w = (ty < ny) ? row_walk(M, rows_per_block, ty, ny) : RowWalk{0, 0};
+  const bool live = (ty < ny) && (c0 < C);
+  const RowWalk w = live ? row_walk(M, rows_per_block, ty, ny) : RowWalk{0, 0};
   const __nv_bfloat16* pg = dout + w.first * dout_ld + c0;
   const __nv_bfloat16* px = x + w.first * x_ld + c0;
   const __nv_bfloat16* pa = (MASK == 1) ? act + w.first * act_ld + c0 : nullptr;
-  const uint8_t* pm = (MASK == 3) ? reinterpret_cast<const uint8_t*>(act) + w.first * (C >> 3) + tx : nullptr;
+  const uint8_t* pm = (MASK == 3) ? reinterpret_cast<const uint8_t*>(act) + w.first * (C >> 3) + (c0 >> 3) : nullptr;
   const int64_t sm_ = (int64_t)ny * (C >> 3);
   const int64_t sg = (int64_t)ny * dout_ld, sx = (int64_t)ny * x_ld, sa = (int64_t)ny * act_ld;
   uint4 gr[U], xr[U], orr[U];
@@ -393,14 +397,14 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     a[j] = 0.f; b[j] = 0.f;
-    if (MASK == 2) {
+    if (MASK == 2 && live) {
       sc[j] = gamma[c0 + j] * invstd[c0 + j];
       sh[j] = fmaf(-mean[c0 + j], sc[j], beta[c0 + j]);
     } else {
       sc[j] = 0.f; sh[j] = 0.f;
     }
   }
-  if (ty < ny) {
+  if (live) {
     uint64_t didx = (uint64_t)w.first * C + c0;
     const uint64_t sd = (uint64_t)ny * C;
     auto one = [&](const uint4& gr, const uint4& xr, const uint4& orr, uint64_t di) {
@@ -469,9 +473,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
       ta += s_red[(y * nx + gx) * 16 + j];
       tb += s_red[(y * nx + gx) * 16 + 8 + j];
     }
-    const int c = (gx << 3) + j;
-    atomicAdd(sums + c, (double)ta);
-    atomicAdd(sums + C + c, (double)invstd[c] * ((double)tb - (double)mean[c] * (double)ta));
+    const int c = cbase + (gx << 3) + j;
+    if (c < C) {
+      atomicAdd(sums + c, (double)ta);
+      atomicAdd(sums + C + c, (double)invstd[c] * ((double)tb - (double)mean[c] * (double)ta));
+    }
   }
 }
 
@@ -1529,12 +1535,23 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
                "bn_bwd_reduce: relu needs the activation (or gamma and beta to recompute the mask)");
   ISWM_REQUIRE(relu != 2 || d_out_act, "bn_bwd_reduce: relu mode 2 needs the packed sign bits in d_out_act");
   ISWM_REQUIRE(C <= 2048, "bn_bwd_reduce: C=%d > 2048 not supported", C);
-  int nx, ny, rows_per_block, blocks;
-  bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 3);   // one wave: every block ends with fp64 atomics on the same 2C addresses
+  int nx, ny, rows_per_block, blocks, groups = 1;
+  static const int env_groups = [] { const char* e = getenv("ISWM_BN_RED_GROUPS"); return e ? atoi(e) : 1; }();
+  if (env_groups && C > 256) {
+    // channel groups of 256 (32 threads x 8 channels, 512 contiguous bytes per row) x row blocks, one resident wave in all
+    nx = 32; ny = kT / nx;
+    groups = (C / 8 + nx - 1) / nx;
+    int64_t want = (M + (int64_t)ny * 8 - 1) / ((int64_t)ny * 8);
+    want = std::max<int64_t>(1, std::min<int64_t>(want, std::max(1, num_sms() * 3 / groups)));
+    rows_per_block = (int)((M + want - 1) / want);
+    blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+  } else {
+    bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 3);   // one wave: every block ends with fp64 atomics on the same 2C addresses
+  }
   const int mask = !relu ? 0 : (relu == 2 ? 3 : (d_out_act ? 1 : 2));
   const bool has_drop = drop_p > 0.f;
 #define ISWM_BN_RED(MK, D)                                                                                          \
-  launch_k(bn_bwd_reduce_kernel<MK, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,   \
+  launch_k(bn_bwd_reduce_kernel<MK, D>, dim3(blocks, groups), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, BF(d_x), x_ld,   \
            BF(d_out_act), act_ld, M, C, d_save_mean, d_save_invstd, d_gamma, d_beta, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, d_sums, nx, \
            ny, rows_per_block)
   if (has_drop) { if (mask == 0) ISWM_BN_RED(0, true); else if (mask == 1) ISWM_BN_RED(1, true); else if (mask == 2) ISWM_BN_RED(2, true); else ISWM_BN_RED(3, true); }

@@ -35,7 +35,8 @@ def rnd(shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("B,C,H,W,relu,with_res", [(2, 64, 9, 7, True, False), (3, 48, 8, 8, True, True), (2, 256, 5, 5, False, False), (2, 2048, 4, 4, True, True),
-                                                    (4, 64, 96, 96, True, False), (4, 256, 48, 48, True, True)])
+                                                    (4, 64, 96, 96, True, False), (4, 256, 48, 48, True, True), (2, 1024, 9, 11, True, False),
+                                                    (3, 304, 7, 5, True, True), (2, 512, 16, 16, False, True)])
 def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     x = rnd((B, C, H, W), 1, 2.0)
     res = rnd((B, C, H, W), 2) if with_res else None
