@@ -160,3 +160,19 @@ def test_conv_wgrad(B, Cin, H, W, Cout, k, dil):
     ops.unpack_wgrad(dw, grad)
     torch.cuda.synchronize()
     assert _rel_err(grad.cpu(), wr.grad) < 5e-3
+
+
+@pytest.mark.parametrize("Cout,Cin,RS", [(3, 8, 9), (64, 64, 9), (5, 304, 9), (7, 1111, 9), (2, 2048, 9), (4, 16, 4), (6, 24, 1)])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_unpack_wgrad_exact(Cout, Cin, RS, beta):
+    """[Cout][tap][Cin] accumulator -> OIHW gradient (tiled shared-memory transpose for k x k, generic otherwise): a pure
+    permutation, so bit-exact; beta = 1 accumulates."""
+    g = torch.Generator().manual_seed(Cout * 131 + Cin)
+    dw = torch.randn((Cout, RS, Cin), generator=g)
+    base = torch.randn((Cout, Cin, RS), generator=g)
+    out = base.clone().to(DEV)
+    from iswm_b200 import _lib
+    _lib.check(_lib.lib().iswm_unpack_wgrad(dw.to(DEV).data_ptr(), Cout, Cin, RS, Cin, RS * Cin, beta, out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "unpack_wgrad")
+    want = dw.permute(0, 2, 1) + (base if beta else 0)
+    assert torch.equal(out.cpu(), want)
