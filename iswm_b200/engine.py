@@ -124,6 +124,8 @@ class Engine:
         # data-gradient chain; ISWM_ASYNC_WGRAD=0 puts them back in line
         self.async_wgrad = __import__("os").environ.get("ISWM_ASYNC_WGRAD", "1") != "0"
         self.relu_bits = __import__("os").environ.get("ISWM_RELU_BITS", "1") != "0"
+        self.fwd_overlap = __import__("os").environ.get("ISWM_FWD_OVERLAP", "1") != "0"
+        self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
         self.profile = None           # list of (kernel, algorithmic_flops, start_event, end_event) when profiling
@@ -542,6 +544,40 @@ class Engine:
         self._wgrad_keep.extend(keep_alive)
         return Engine._SideCtx(self._wstream)
 
+    class _HandleCtx:
+        """Launch the library kernels issued inside on `stream` WITHOUT changing torch's current stream: tensors are still
+        allocated from (and returned to) the main stream's pool, so they must stay referenced until the join."""
+
+        def __init__(self, stream):
+            self.handle = stream.cuda_stream
+
+        def __enter__(self):
+            self.prev = _StreamCache.handle
+            _StreamCache.handle = self.handle
+            return self
+
+        def __exit__(self, *a):
+            _StreamCache.handle = self.prev
+            return False
+
+    def _fwd_fork(self):
+        """Context for a forward branch nothing on the main chain consumes for a while (low-level projection, pooled ASPP
+        branch): its launches go to the side stream after everything enqueued so far, and run under the main chain's
+        convolutions (which leave 20 of the 148 SMs idle at 128 tiles). `_fwd_join()` makes the main stream wait."""
+        if not (self.async_wgrad and self.fwd_overlap) or self.profile is not None or self.debug_units is not None or self.debug_taps is not None:
+            return Engine._NullCtx()
+        if self._wstream is None or self._wstream.device != self.device:
+            self._wstream = torch.cuda.Stream(self.device)
+        self._wstream.wait_event(torch.cuda.current_stream(self.device).record_event())
+        self._fwd_forked = True
+        return Engine._HandleCtx(self._wstream)
+
+    def _fwd_join(self):
+        if getattr(self, "_fwd_forked", False):
+            torch.cuda.current_stream(self.device).wait_stream(self._wstream)
+            self._fwd_forked = False
+        self._fwd_keep = []
+
     def _wgrad_join(self):
         if self.async_wgrad and self._wstream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._wstream)
@@ -650,6 +686,7 @@ class Engine:
         # ---- residual layers (resnet.py:99-120, :176-198)
         a = pooled
         low_level = None
+        cat2 = low_slice = None
         for li, blocks in enumerate(self.layers):
             for (c1, c2, c3, ds) in blocks:
                 idt = a if ds is None else unit(ds, a, relu=False)
@@ -658,19 +695,24 @@ class Engine:
                 a = unit(c3, y, relu=True, residual=idt)
             if li == 0:
                 low_level = a
+                # head, part 1 (_deeplab.py:56): the low-level projection only needs layer1's output; it is issued now,
+                # on the side stream, and runs under layers 2-4 (its consumer is the decoder, ~40 launches later)
+                h4, w4 = low_level.H, low_level.W
+                cat2 = Act.new(B, h4, w4, 304, dev)
+                low_slice = cat2.slice(0, 48)
+                with self._fwd_fork():
+                    unit(self.low_proj, low_level, out=low_slice)
         feat = a
 
-        # ---- head (_deeplab.py:55-61): low-level projection and ASPP write straight into concat buffers
-        h4, w4 = low_level.H, low_level.W
-        cat2 = Act.new(B, h4, w4, 304, dev)
-        low_slice = cat2.slice(0, 48)
-        unit(self.low_proj, low_level, out=low_slice)
+        # ---- head (_deeplab.py:55-61): ASPP branches write straight into the concat buffer
         hf, wf = feat.H, feat.W
         cat1 = Act.new(B, hf, wf, 1280, dev)
         br_slices = [cat1.slice(256 * i, 256) for i in range(5)]
+        with self._fwd_fork():                               # four tiny latency-bound launches under the big branch convs
+            self._aspp_pool(feat, br_slices[4], train)
         for i, s in enumerate(self.aspp_branches):
             unit(s, feat, out=br_slices[i])
-        self._aspp_pool(feat, br_slices[4], train)
+        self._fwd_join()
         if train:
             self._slice_grad_split(cat1, [(br_slices[i], 256 * i) for i in range(5)])
             aspp_out = self._unit_train(self.aspp_proj, cat1, drop_p=self.dropout_p)
@@ -786,6 +828,7 @@ class Engine:
         else:
             v = self._unit_eval(self.aspp_pool, pooled)
         check(L.iswm_broadcast_hw(v.ptr, B, HW, 256, dst.ptr, dst.ld, _st()), "broadcast_hw")
+        self._fwd_keep.extend((pooled.t, v.t))               # may be running on the side stream: alive until the join
         if train:
             def bc_bwd():
                 g = dst.grad

@@ -258,3 +258,41 @@ def test_predict_mask_matches_reference_semantics(golden_dir):
     assert np.abs(conf.cpu().numpy().astype(np.int32) - ref_conf.astype(np.int32)).max() <= 1     # uint8(p*255) at a rounding edge
     ref_cm = O.fast_hist(g["y"].reshape(-1), ref_pred.reshape(-1), 2)
     assert sm.confusion_matrix.astype(np.int64).tolist() == ref_cm.tolist()
+
+
+def test_forward_branch_overlap_changes_nothing():
+    """The low-level projection and the pooled ASPP branch run on the side stream under the main chain
+    (Engine._fwd_fork): the forward must stay BIT-identical to the in-line order (train and eval), the gradients equal
+    up to the weight-gradient atomics noise."""
+    m, sd = build("resnet50", 16, seed=21)
+    m.to(DEV)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((4, 3, 96, 80), generator=g).to(DEV)
+    y = synth_labels((4, 96, 80), seed=9, fg=0.2, ign=0.05).to(DEV)
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    eng = m.engine()
+    eng.dropout_p = 0.1
+    outs = {}
+    for overlap in (False, True, True):
+        eng.fwd_overlap = overlap
+        eng.step = 0
+        eng._step_dev = None                       # same Dropout mask in every run
+        for p in m.parameters():
+            p.grad = None
+        bufs = [b.detach().clone() for b in m.buffers()]
+        m.train()
+        logits = m(x)
+        loss = crit(logits, y)
+        loss.backward()
+        m.eval()
+        with torch.no_grad():
+            ev = m(x).clone()
+        torch.cuda.synchronize()
+        outs.setdefault(overlap, []).append((logits.detach().clone(), eng.flat_g.clone(), ev))
+        with torch.no_grad():
+            for b, v in zip(m.buffers(), bufs):    # BatchNorm running statistics back to the start
+                b.copy_(v)
+    (l0, g0, e0), = outs[False]
+    for l1, g1, e1 in outs[True]:
+        assert torch.equal(l0, l1) and torch.equal(e0, e1)
+        assert rel_l2(g1, g0) <= 1e-5

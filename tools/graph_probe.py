@@ -75,3 +75,16 @@ for inline in (False, True):
         res[name], _ = timed(gg.replay, 5)
         _lib.lib().iswm_debug_set_skip(0)
     print(f"weight gradients {'in line' if inline else 'on the side stream'}: " + "; ".join(f"{k} {v:.2f} ms" for k, v in res.items()))
+
+# forward branches on the side stream (Engine._fwd_fork) on / off, same process, graph replays
+eng.async_wgrad = True
+for ov in (False, True, False, True):
+    eng.fwd_overlap = ov
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg):
+        step()
+    torch.cuda.synchronize()
+    for _ in range(2):
+        gg.replay()
+    t, _ = timed(gg.replay, 8)
+    print(f"forward branch overlap {'on ' if ov else 'off'}: {t:.3f} ms/step")
