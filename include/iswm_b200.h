@@ -277,7 +277,10 @@ int iswm_bilinear_bwd(const void* d_dout, int dout_ld, int B, int Hi, int Wi, in
 /* final upsample (network/utils.py:22): NHWC fp32 [B,h,w,C] logits -> NCHW fp32 [B,C,H,W]; and adjoint
  * NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels C..dx_ld-1 zero-filled) */
 int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C, int Ho, int Wo, float* d_out, void* stream);
-int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld, void* stream);
+/* d_bias_grad (optional, float[C], ACCUMULATED into): the classifier bias gradient sum_{b,y,x} dlogits[b,c,y,x]
+ * (network/_deeplab.py:51 Conv2d(256, C, 1) bias) from the same sweep over dlogits */
+int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld,
+                       float* d_bias_grad, void* stream);
 /* strided helpers for stride-2 convolutions */
 int iswm_phase_split(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream);   /* -> [4][B][ceil(H/2)][ceil(W/2)][C], phase = (h&1)*2 + (w&1) */
 int iswm_subsample2(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream);    /* -> [B][ceil(H/2)][ceil(W/2)][C] */

@@ -91,7 +91,7 @@ SIGNATURES = {
     "iswm_bilinear_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "iswm_bilinear_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "iswm_logits_up_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "iswm_logits_up_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "iswm_logits_up_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "iswm_phase_split": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_subsample2": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_zero_stuff2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -843,16 +843,21 @@ stem_im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, 
   const int koct = Kpad >> 3;
   const int npx = min(kStemStrip, Wo - wo0);
   const int64_t m0 = ((int64_t)b * Ho + ho) * Wo + wo0;
-  for (int i = threadIdx.x; i < npx * koct; i += kT) {
-    const int px = i / koct, ko = i - px * koct;
-    const float* pp = patch + 2 * px;
-    F8 f;
+  // thread -> one 16-byte chunk position ko of the im2col row (its 8 patch offsets live in registers) and a pixel lane:
+  // consecutive threads write consecutive chunks of one row (coalesced), and the inner loop is 8 shared-memory loads per
+  // 16-byte store instead of 16 (the offset table is not re-read per pixel)
+  const int ko = threadIdx.x % koct, pl = threadIdx.x / koct, npl = kT / koct;
+  if (pl < npl) {
+    int offs[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int off = koff[ko * 8 + jj];
-      f.v[jj] = off >= 0 ? pp[off] : 0.f;
+    for (int jj = 0; jj < 8; jj++) offs[jj] = koff[ko * 8 + jj];
+    for (int px = pl; px < npx; px += npl) {
+      const float* pp = patch + 2 * px;
+      F8 f;
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) f.v[jj] = offs[jj] >= 0 ? pp[offs[jj]] : 0.f;
+      store8(out + (m0 + px) * Kpad + ko * 8, f);
     }
-    store8(out + (m0 + px) * Kpad + ko * 8, f);
   }
 }
 
@@ -1069,43 +1074,96 @@ __device__ __forceinline__ void bil_range(int i, float rscale, int out, int& lo,
   hi = hi > out - 1 ? out - 1 : hi;
 }
 
-// adjoint (gather form): one grid row per INPUT image row
+// adjoint, separable: a block owns one INPUT row yi of one image and a 64-channel chunk. Pass 1 folds the <= ~12
+// output rows that touch yi into ONE row v[ox][c] in shared memory (coalesced 16-byte loads, each output element is
+// read by the 2 input rows it feeds instead of the 4 pixels of the gather form); pass 2 folds v along x. The gather
+// form spent its time recomputing source coordinates inside a ~100-iteration loop (109 us at cfg2).
+constexpr int kBilChunk = 64;
+constexpr int kBilRows = 64;                                 // capacity of the per-block row list (scale ratios up to ~14)
+// rows oy in [lo, hi] with weight wy(oy -> yi) != 0 (or owned for the bias sum): built once per block by thread 0, so the
+// row loops below are short, branch-free and can keep several loads in flight
+__device__ __forceinline__ void bil_row_list(int yi, int lo, int hi, float sh, int Hi, int own_lo, int own_hi,
+                                             int* s_oy, float* s_wy, int* s_n) {
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int oy = lo; oy <= hi && n < kBilRows; oy++) {
+      int y0, y1; float ly;
+      bil_src(oy, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+      const bool mine = oy >= own_lo && oy < own_hi;
+      if (wy != 0.f || mine) { s_oy[n] = mine ? (oy | 0x40000000) : oy; s_wy[n] = wy; n++; }
+    }
+    *s_n = n;
+  }
+  __syncthreads();
+}
 __global__ void __launch_bounds__(kT)
 bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int B, int Hi, int Wi,
                     int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx, int dx_ld) {
   pdl_wait();
   pdl_launch();
-  const int nvec = C >> 3;
+  extern __shared__ float s_v[];                              // [Wo][kBilChunk]
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
   const int yi = blockIdx.x % Hi, b = blockIdx.x / Hi;
+  const int cb = blockIdx.y * kBilChunk;
+  const int nvec = min(kBilChunk, C - cb) >> 3;
   int ylo, yhi;
   bil_range(yi, rh, Ho, ylo, yhi);
-  const __nv_bfloat16* base = dout + (int64_t)b * Ho * Wo * dout_ld;
-  __nv_bfloat16* orow = dx + ((int64_t)b * Hi + yi) * Wi * dx_ld;
-  const int total = Wi * nvec;
-  for (int i = blockIdx.y * kT + threadIdx.x; i < total; i += gridDim.y * kT) {
+  __shared__ int s_oy[kBilRows];
+  __shared__ float s_wy[kBilRows];
+  __shared__ int s_n;
+  bil_row_list(yi, ylo, yhi, sh, Hi, 0, 0, s_oy, s_wy, &s_n);
+  const int nrows = s_n;
+  const __nv_bfloat16* base = dout + (int64_t)b * Ho * Wo * dout_ld + cb;
+  for (int i = threadIdx.x; i < Wo * nvec; i += kT) {
+    const int ox = i / nvec, c8 = (i - ox * nvec) << 3;
+    const __nv_bfloat16* col = base + (int64_t)ox * dout_ld + c8;
+    const int64_t rs = (int64_t)Wo * dout_ld;
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc.v[j] = 0.f;
+    int r = 0;
+    for (; r + 4 <= nrows; r += 4) {                          // four independent 16-byte loads in flight
+      uint4 g[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) g[u] = load_raw(col + s_oy[r + u] * rs);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const F8 f = unpack8(g[u]);
+        const float wy = s_wy[r + u];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc.v[j] = fmaf(wy, f.v[j], acc.v[j]);
+      }
+    }
+    for (; r < nrows; r++) {
+      const F8 f = load8(col + s_oy[r] * rs);
+      const float wy = s_wy[r];
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc.v[j] = fmaf(wy, f.v[j], acc.v[j]);
+    }
+    float4* d = reinterpret_cast<float4*>(s_v + ox * kBilChunk + c8);
+    d[0] = make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+    d[1] = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  }
+  __syncthreads();
+  __nv_bfloat16* orow = dx + ((int64_t)b * Hi + yi) * Wi * dx_ld + cb;
+  for (int i = threadIdx.x; i < Wi * nvec; i += kT) {
     const int xi = i / nvec, c8 = (i - xi * nvec) << 3;
     int xlo, xhi;
     bil_range(xi, rw, Wo, xlo, xhi);
     F8 acc;
 #pragma unroll
     for (int j = 0; j < 8; j++) acc.v[j] = 0.f;
-    for (int oy = ylo; oy <= yhi; oy++) {
-      int y0, y1; float ly;
-      bil_src(oy, sh, Hi, y0, y1, ly);
-      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
-      if (wy == 0.f) continue;
-      for (int ox = xlo; ox <= xhi; ox++) {
-        int x0, x1; float lx;
-        bil_src(ox, sw, Wi, x0, x1, lx);
-        const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
-        if (wx == 0.f) continue;
-        const F8 g = load8(base + ((int64_t)oy * Wo + ox) * dout_ld + c8);
-        const float w = wy * wx;
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc.v[j] = fmaf(w, g.v[j], acc.v[j]);
-      }
+    for (int ox = xlo; ox <= xhi; ox++) {
+      int x0, x1; float lx;
+      bil_src(ox, sw, Wi, x0, x1, lx);
+      const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+      if (wx == 0.f) continue;
+      const float4* v = reinterpret_cast<const float4*>(s_v + ox * kBilChunk + c8);
+      const float4 a = v[0], c = v[1];
+      acc.v[0] = fmaf(wx, a.x, acc.v[0]); acc.v[1] = fmaf(wx, a.y, acc.v[1]); acc.v[2] = fmaf(wx, a.z, acc.v[2]); acc.v[3] = fmaf(wx, a.w, acc.v[3]);
+      acc.v[4] = fmaf(wx, c.x, acc.v[4]); acc.v[5] = fmaf(wx, c.y, acc.v[5]); acc.v[6] = fmaf(wx, c.z, acc.v[6]); acc.v[7] = fmaf(wx, c.w, acc.v[7]);
     }
     store8(orow + (int64_t)xi * dx_ld + c8, acc);
   }
@@ -1139,37 +1197,85 @@ logits_up_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, 
     }
   }
 }
-// adjoint: NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels >= C zero-filled); grid row = (image, input row)
+// adjoint: NCHW fp32 dlogits -> NHWC bf16 [B,h,w,dx_ld] (channels >= C zero-filled); a block owns one INPUT row yi of one
+// image: pass 1 folds the output rows that touch yi into v[c][ox] in shared memory (coalesced reads along W), pass 2
+// folds v along x. Optionally the same pass accumulates the classifier bias gradient sum_{b,y,x} dlogits[b,c,y,x]
+// (each output row counted by the ONE input row floor(oy*Hi/Ho) that owns it), replacing a second sweep over dlogits.
 __global__ void __launch_bounds__(kT)
 logits_up_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, int C, int Ho, int Wo,
-                     __nv_bfloat16* __restrict__ dx, int dx_ld) {
+                     __nv_bfloat16* __restrict__ dx, int dx_ld, float* __restrict__ bias_grad) {
   pdl_wait();
   pdl_launch();
+  extern __shared__ float s_v[];                              // [C][Wo], then [C] bias partials
+  float* s_bias = s_v + C * Wo;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
   const float rh = (float)Ho / (float)Hi, rw = (float)Wo / (float)Wi;
   const int yi = blockIdx.x % Hi, b = blockIdx.x / Hi;
   int ylo, yhi;
   bil_range(yi, rh, Ho, ylo, yhi);
-  const int total = Wi * C;
-  for (int i = blockIdx.y * kT + threadIdx.x; i < total; i += gridDim.y * kT) {
+  if (bias_grad) {
+    for (int c = threadIdx.x; c < C; c += kT) s_bias[c] = 0.f;
+    __syncthreads();
+  }
+  // rows [own_lo, own_hi) of the output belong to this input row for the bias sum (a partition of [0, Ho))
+  const int own_lo = (int)(((int64_t)yi * Ho + Hi - 1) / Hi), own_hi = (int)(((int64_t)(yi + 1) * Ho + Hi - 1) / Hi);
+  __shared__ int s_oy[kBilRows];
+  __shared__ float s_wy[kBilRows];
+  __shared__ int s_n;
+  bil_row_list(yi, min(ylo, own_lo), max(yhi, own_hi - 1), sh, Hi, bias_grad ? own_lo : 0, bias_grad ? own_hi : 0, s_oy, s_wy, &s_n);
+  const int nrows = s_n;
+  for (int i0 = 0; i0 < C * Wo; i0 += kT) {                 // uniform trip count: the warp shuffles below need all lanes
+    const int i = i0 + threadIdx.x;
+    const bool in = i < C * Wo;
+    const int c = in ? i / Wo : -1, ox = in ? i - c * Wo : 0;
+    float acc = 0.f, own = 0.f;
+    if (in) {
+      const float* col = dout + ((int64_t)b * C + c) * Ho * Wo + ox;
+      int r = 0;
+      for (; r + 4 <= nrows; r += 4) {
+        float g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) g[u] = __ldg(col + (int64_t)(s_oy[r + u] & 0x3fffffff) * Wo);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          acc = fmaf(s_wy[r + u], g[u], acc);
+          if (s_oy[r + u] & 0x40000000) own += g[u];
+        }
+      }
+      for (; r < nrows; r++) {
+        const float g = __ldg(col + (int64_t)(s_oy[r] & 0x3fffffff) * Wo);
+        acc = fmaf(s_wy[r], g, acc);
+        if (s_oy[r] & 0x40000000) own += g;
+      }
+      s_v[i] = acc;
+    }
+    if (bias_grad) {
+      // segmented warp sum: lanes hold consecutive i, so c is non-decreasing across the warp; the first lane of every
+      // run of equal c ends up with the run's total and adds it to the block's per-class partial
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_down_sync(0xffffffffu, own, o);
+        const int oc = __shfl_down_sync(0xffffffffu, c, o);
+        if ((int)(threadIdx.x & 31) + o < 32 && oc == c) own += other;
+      }
+      const int pc = __shfl_up_sync(0xffffffffu, c, 1);
+      if (in && ((threadIdx.x & 31) == 0 || pc != c)) atomicAdd(s_bias + c, own);
+    }
+  }
+  __syncthreads();
+  if (bias_grad)
+    for (int c = threadIdx.x; c < C; c += kT) atomicAdd(bias_grad + c, s_bias[c]);
+  for (int i = threadIdx.x; i < Wi * C; i += kT) {
     const int xi = i / C, c = i - xi * C;
     int xlo, xhi;
     bil_range(xi, rw, Wo, xlo, xhi);
-    const float* base = dout + ((int64_t)b * C + c) * Ho * Wo;
+    const float* v = s_v + c * Wo;
     float acc = 0.f;
-    for (int oy = ylo; oy <= yhi; oy++) {
-      int y0, y1; float ly;
-      bil_src(oy, sh, Hi, y0, y1, ly);
-      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
-      if (wy == 0.f) continue;
-      float rowacc = 0.f;
-      for (int ox = xlo; ox <= xhi; ox++) {
-        int x0, x1; float lx;
-        bil_src(ox, sw, Wi, x0, x1, lx);
-        const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
-        if (wx != 0.f) rowacc = fmaf(wx, __ldg(base + (int64_t)oy * Wo + ox), rowacc);
-      }
-      acc = fmaf(wy, rowacc, acc);
+    for (int ox = xlo; ox <= xhi; ox++) {
+      int x0, x1; float lx;
+      bil_src(ox, sw, Wi, x0, x1, lx);
+      const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+      if (wx != 0.f) acc = fmaf(wx, v[ox], acc);
     }
     const int64_t m = ((int64_t)b * Hi + yi) * Wi + xi;
     dx[m * dx_ld + c] = __float2bfloat16_rn(acc);
@@ -1726,7 +1832,14 @@ extern "C" int iswm_bilinear_bwd(const void* d_dout, int dout_ld, int B, int Hi,
                                  void* d_dx, int dx_ld, void* stream) {
   REQ_C8(C, "bilinear_bwd"); REQ_LD8(dout_ld, "bilinear_bwd"); REQ_LD8(dx_ld, "bilinear_bwd");
   ISWM_REQUIRE(d_dout && d_dx, "bilinear_bwd: null");
-  launch_k(bilinear_bwd_kernel, dim3((unsigned)(B * Hi), (unsigned)std::min(8, (Wi * (C / 8) + kT - 1) / kT)), dim3(kT), 0, ST(stream), BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  ISWM_REQUIRE(Ho <= 14 * Hi, "bilinear_bwd: scale ratio %d/%d above the row-list capacity", Ho, Hi);
+  const size_t smem = (size_t)Wo * kBilChunk * sizeof(float);
+  ISWM_REQUIRE(smem <= 200 * 1024, "bilinear_bwd: output width %d too large for the shared-memory row", Wo);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(bilinear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ISWM_REQUIRE(e == cudaSuccess, "bilinear_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  launch_k(bilinear_bwd_kernel, dim3((unsigned)(B * Hi), (unsigned)((C + kBilChunk - 1) / kBilChunk)), dim3(kT), smem, ST(stream), BF(d_dout), dout_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
   return check_launch("bilinear_bwd");
 }
 extern "C" int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C, int Ho, int Wo, float* d_out, void* stream) {
@@ -1734,9 +1847,17 @@ extern "C" int iswm_logits_up_fwd(const float* d_x, int B, int Hi, int Wi, int C
   launch_k(logits_up_fwd_kernel, dim3((unsigned)(B * Ho), (unsigned)std::min(8, (Wo + kT - 1) / kT)), dim3(kT), 0, ST(stream), d_x, B, Hi, Wi, C, Ho, Wo, d_out);
   return check_launch("logits_up_fwd");
 }
-extern "C" int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld, void* stream) {
+extern "C" int iswm_logits_up_bwd(const float* d_dout, int B, int Hi, int Wi, int C, int Ho, int Wo, void* d_dx, int dx_ld,
+                                  float* d_bias_grad, void* stream) {
   ISWM_REQUIRE(d_dout && d_dx && C >= 1 && dx_ld >= C, "logits_up_bwd: bad args");
-  launch_k(logits_up_bwd_kernel, dim3((unsigned)(B * Hi), (unsigned)std::min(8, (Wi * C + kT - 1) / kT)), dim3(kT), 0, ST(stream), d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld);
+  ISWM_REQUIRE(Ho <= 14 * Hi, "logits_up_bwd: scale ratio %d/%d above the row-list capacity", Ho, Hi);
+  const size_t smem = ((size_t)C * Wo + C) * sizeof(float);
+  ISWM_REQUIRE(smem <= 200 * 1024, "logits_up_bwd: C * output width = %d x %d too large for the shared-memory row", C, Wo);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(logits_up_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ISWM_REQUIRE(e == cudaSuccess, "logits_up_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  launch_k(logits_up_bwd_kernel, dim3((unsigned)(B * Hi)), dim3(kT), smem, ST(stream), d_dout, B, Hi, Wi, C, Ho, Wo, BFW(d_dx), dx_ld, d_bias_grad);
   return check_launch("logits_up_bwd");
 }
 extern "C" int iswm_phase_split(const void* d_x, int x_ld, int B, int H, int W, int C, void* d_out, void* stream) {

@@ -783,9 +783,12 @@ class Engine:
             dout = out.grad
             sums = self._stats_slot(130)
             dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
-            check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
-                                save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, None, dy.data_ptr(), 64, None, 0,
-                                self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd stem")
+            # two launches: the single-launch grid-barrier version costs more than the boundary it saves
+            check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, save.data_ptr(), save[64:].data_ptr(),
+                                       bn.weight.data_ptr(), bn.bias.data_ptr(), 1, 0.0, 0, None, sums.data_ptr(), _st()), "bn_bwd_reduce stem")
+            check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
+                                      save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, None, dy.data_ptr(), 64, None, 0,
+                                      self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd_apply stem")
             out.grad = None
             off, n = self.wacc_off[s.name]
             acc = self.wacc[off:off + n]
@@ -874,10 +877,11 @@ class Engine:
         self.wacc.zero_()
         # classifier: bias grad, low-res logits gradient, weight grad, data grad
         cls = self.cls
-        check(L.iswm_bias_grad_nchw(dlogits.data_ptr(), B, ncls, H * W, self.grad_views[id(cls.conv.bias)].data_ptr(), _st()), "bias_grad")
         ldp = 8 * ((ncls + 7) // 8)
         dlo = torch.empty((B, h4, w4, ldp), dtype=torch.bfloat16, device=dev)
-        check(L.iswm_logits_up_bwd(dlogits.data_ptr(), B, h4, w4, ncls, H, W, dlo.data_ptr(), ldp, _st()), "logits_up_bwd")
+        # adjoint of the final upsample; the classifier bias gradient (sum of dlogits per class) rides on the same sweep
+        check(L.iswm_logits_up_bwd(dlogits.data_ptr(), B, h4, w4, ncls, H, W, dlo.data_ptr(), ldp,
+                                   self.grad_views[id(cls.conv.bias)].data_ptr(), _st()), "logits_up_bwd")
         d = ops.make_conv_desc(B, h4, w4, y.C, y.ld, B, h4, w4, ncls, ldp, [(0, 0, 0)])
         with self._wgrad_ctx(dlo, y.t):
             check(L.iswm_conv_wgrad(C.byref(d), y.ptr, dlo.data_ptr(), self.grad_views[id(cls.conv.weight)].data_ptr(), _st()), "conv_wgrad cls")

@@ -150,7 +150,7 @@ def test_maxpool_fwd_bwd():
     close(nchw(dx), xr.grad, 1e-2, 1e-2)
 
 
-@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(4, 4, 16, 16), (13, 13, 50, 50), (8, 6, 17, 23), (1, 1, 5, 5)])
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(4, 4, 16, 16), (13, 13, 50, 50), (8, 6, 17, 23), (1, 1, 5, 5), (7, 5, 25, 17), (32, 32, 128, 128)])
 def test_bilinear_fwd_bwd(Hi, Wi, Ho, Wo):
     B, C = 2, 16
     x = rnd((B, C, Hi, Wi), 7)
@@ -168,7 +168,7 @@ def test_bilinear_fwd_bwd(Hi, Wi, Ho, Wo):
     close(nchw(dx), xr.grad, 1e-2, 2e-2 * float(xr.grad.abs().max()))
 
 
-@pytest.mark.parametrize("Hi,Wi,Ho,Wo,C", [(16, 16, 64, 64, 2), (13, 11, 50, 41, 3)])
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo,C", [(16, 16, 64, 64, 2), (13, 11, 50, 41, 3), (25, 17, 97, 65, 2), (7, 9, 7, 9, 5), (3, 5, 31, 77, 7)])
 def test_logits_up_fwd_bwd(Hi, Wi, Ho, Wo, C):
     B = 2
     g = torch.Generator().manual_seed(9)
@@ -181,9 +181,15 @@ def test_logits_up_fwd_bwd(Hi, Wi, Ho, Wo, C):
     check(L().iswm_logits_up_fwd(nhwc(x).to(DEV).data_ptr(), B, Hi, Wi, C, Ho, Wo, out.data_ptr(), st()))
     close(out, y.detach(), 1e-5, 1e-5)
     dx = torch.empty((B, Hi, Wi, 8), dtype=torch.bfloat16, device=DEV)
-    check(L().iswm_logits_up_bwd(dout.to(DEV).data_ptr(), B, Hi, Wi, C, Ho, Wo, dx.data_ptr(), 8, st()))
+    check(L().iswm_logits_up_bwd(dout.to(DEV).data_ptr(), B, Hi, Wi, C, Ho, Wo, dx.data_ptr(), 8, None, st()))
     close(nchw(dx[..., :C]), xr.grad, 1e-2, 1e-2 * float(xr.grad.abs().max()))
     assert torch.count_nonzero(dx[..., C:]).item() == 0
+    # the same sweep with the classifier bias gradient riding along (accumulated into a non-zero start)
+    dx2 = torch.empty_like(dx)
+    bias2 = torch.full((C,), 0.5, dtype=torch.float32, device=DEV)
+    check(L().iswm_logits_up_bwd(dout.to(DEV).data_ptr(), B, Hi, Wi, C, Ho, Wo, dx2.data_ptr(), 8, bias2.data_ptr(), st()))
+    assert torch.equal(dx2, dx)
+    close(bias2 - 0.5, dout.sum((0, 2, 3)), 1e-4, 1e-3)
     bias = torch.zeros(C, dtype=torch.float32, device=DEV)
     check(L().iswm_bias_grad_nchw(dout.to(DEV).data_ptr(), B, C, Ho * Wo, bias.data_ptr(), st()))
     close(bias, dout.sum((0, 2, 3)), 1e-4, 1e-3)
