@@ -878,17 +878,30 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int
     int arg[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { best[j] = -INFINITY; arg[j] = 0; }
+    // all nine 16-byte loads are issued first (from clamped, always valid addresses), then compared in window order:
+    // nine independent loads in flight instead of a load -> compare chain
+    const __nv_bfloat16* img = x + (int64_t)b * H * W * C + cg * 8;
+    uint4 raw[9];
+    bool ok[9];
+#pragma unroll
     for (int r = 0; r < 3; r++) {
       const int hi = 2 * ho + r - 1;
-      if (hi < 0 || hi >= H) continue;
-      for (int s = 0; s < 3; s++) {
-        const int wi = 2 * wo + s - 1;
-        if (wi < 0 || wi >= W) continue;
-        const F8 v = load8(x + (((int64_t)b * H + hi) * W + wi) * C + cg * 8);
+      const int hc = min(max(hi, 0), H - 1);
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-          if (v.v[j] > best[j]) { best[j] = v.v[j]; arg[j] = r * 3 + s; }
+      for (int s2 = 0; s2 < 3; s2++) {
+        const int wi = 2 * wo + s2 - 1;
+        const int wc = min(max(wi, 0), W - 1);
+        ok[r * 3 + s2] = (hi >= 0 && hi < H && wi >= 0 && wi < W);
+        raw[r * 3 + s2] = load_raw(img + ((int64_t)hc * W + wc) * C);
       }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      if (!ok[t]) continue;
+      const F8 v = unpack8(raw[t]);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (v.v[j] > best[j]) { best[j] = v.v[j]; arg[j] = t; }
     }
     F8 o;
 #pragma unroll
