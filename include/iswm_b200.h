@@ -198,6 +198,17 @@ int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int total_blocks, 
 int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stride, int row_ld,
                       float beta, float* d_grad_oihw, void* stream);
 
+/* All k x k (2 <= RS <= 9, dense rows) accumulators of a step in ONE launch (dst += src permuted): the
+ * caller lists its jobs in a device array and deals blocks to them, job j owning blocks
+ * [blk_begin, blk_begin + Cout * chunks) with chunks = ceil(Cin / 512). */
+typedef struct {
+  const float* src;           /* [Cout][RS][Cin] accumulator */
+  float* dst;                 /* [Cout][Cin][RS] = OIHW gradient */
+  int32_t Cout, Cin, RS, chunks;
+  int32_t blk_begin, pad_;
+} iswm_unpack_job;
+int iswm_unpack_wgrad_batched(const void* d_jobs, int n_jobs, int total_blocks, void* stream);
+
 /* ---- HBM-bound glue kernels (see src for reference citations) ---------- */
 
 /* BatchNorm2d training forward, second half (network/backbone/resnet.py:92-110 bn1..bn3,

@@ -40,6 +40,24 @@ class PackJob(C.Structure):
                 ("pad", C.c_int32), ("row_ld", C.c_int32), ("mode", C.c_int32), ("blk_begin", C.c_int32), ("blk_count", C.c_int32)]
 
 
+class UnpackJob(C.Structure):
+    """Mirror of iswm_unpack_job."""
+
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32), ("RS", C.c_int32),
+                ("chunks", C.c_int32), ("blk_begin", C.c_int32), ("pad_", C.c_int32)]
+
+
+def fill_unpack_jobs(jobs):
+    """jobs: list of (src_ptr, dst_ptr, Cout, Cin, RS) -> (ctypes array, total_blocks)."""
+    arr = (UnpackJob * len(jobs))()
+    begin = 0
+    for i, (src, dst, Cout, Cin, RS) in enumerate(jobs):
+        chunks = (Cin + 511) // 512
+        arr[i].src, arr[i].dst, arr[i].Cout, arr[i].Cin, arr[i].RS, arr[i].chunks, arr[i].blk_begin = src, dst, Cout, Cin, RS, chunks, begin
+        begin += Cout * chunks
+    return arr, begin
+
+
 def fill_pack_jobs(jobs):
     """jobs: list of (w_ptr, dst_ptr, Cout, Cin, RS, pad, row_ld, mode) -> (ctypes array, total_blocks); thread
     blocks are dealt to jobs in proportion to their element count (one per 16 Ki elements, 1..256)."""
@@ -76,6 +94,7 @@ SIGNATURES = {
     "iswm_pack_weight_dgrad": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weights_batched": (_i, [_p, _i, _i, _p]),
     "iswm_unpack_wgrad": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
+    "iswm_unpack_wgrad_batched": (_i, [_p, _i, _i, _p]),
     "iswm_bn_train_apply": (_i, [_p, _i, _p, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _p, _i, _p, _p]),
     "iswm_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "iswm_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _p]),

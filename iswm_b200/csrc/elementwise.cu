@@ -115,6 +115,41 @@ unpack_wgrad_tiled_kernel(const float* __restrict__ dw, int Cin, int RS, float b
   }
 }
 
+// every k x k convolution's weight-gradient accumulator unpacked in ONE launch at the end of the backward sweep (22
+// per-layer launches were mostly launch boundaries on the weight-gradient stream); blocks find their job by binary search
+struct UnpackJob {
+  const float* src;
+  float* dst;
+  int Cout, Cin, RS, chunks;
+  int blk_begin, pad_;
+};
+__global__ void __launch_bounds__(kT)
+unpack_wgrad_batched_kernel(const UnpackJob* __restrict__ jobs, int n_jobs) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float s_t[9][kUnpackChunk + 1];
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const UnpackJob jb = jobs[lo];
+  const int local = blockIdx.x - jb.blk_begin;
+  const int o = local / jb.chunks, cb = (local - o * jb.chunks) * kUnpackChunk;
+  if (o >= jb.Cout) return;
+  const int nc = min(kUnpackChunk, jb.Cin - cb);
+  const float* src = jb.src + (int64_t)o * jb.RS * jb.Cin + cb;
+  for (int t = 0; t < jb.RS; t++)
+    for (int c = threadIdx.x; c < nc; c += kT) s_t[t][c] = src[(int64_t)t * jb.Cin + c];
+  __syncthreads();
+  float* dst = jb.dst + ((int64_t)o * jb.Cin + cb) * jb.RS;
+  const int n = nc * jb.RS;
+  for (int i = threadIdx.x; i < n; i += kT) {
+    const int c = i / jb.RS, t = i - c * jb.RS;
+    dst[i] += s_t[t][c];                 // gradients ACCUMULATE into .grad (zeroed by the sweep when it is fresh)
+  }
+}
+
 // all convolutions' weights packed in ONE launch. Blocks are dealt to jobs in proportion to their size
 // (blk_begin / blk_count, filled in by the host); a block finds its job by binary search.
 struct PackJob {
@@ -1991,4 +2026,11 @@ extern "C" int iswm_crop_flip_u8(const uint8_t* d_src, int B, int Hs, int Ws, co
   dim3 grid((unsigned)(B * H), (unsigned)std::max(1, std::min(8, (W + kT - 1) / kT)));
   launch_k(crop_flip_u8_kernel, grid, dim3(kT), 0, ST(stream), d_src, Hs, Ws, d_origin_xy, d_flip, H, W, d_out);
   return check_launch("crop_flip_u8");
+}
+
+extern "C" int iswm_unpack_wgrad_batched(const void* d_jobs, int n_jobs, int total_blocks, void* stream) {
+  ISWM_REQUIRE(d_jobs && n_jobs >= 1 && total_blocks >= 1, "unpack_wgrad_batched: empty job list");
+  static_assert(sizeof(UnpackJob) == 40, "iswm_unpack_job layout");
+  launch_k(unpack_wgrad_batched_kernel, dim3((unsigned)total_blocks), dim3(kT), 0, ST(stream), static_cast<const UnpackJob*>(d_jobs), n_jobs);
+  return check_launch("unpack_wgrad_batched");
 }

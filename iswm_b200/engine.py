@@ -125,6 +125,7 @@ class Engine:
         self.async_wgrad = __import__("os").environ.get("ISWM_ASYNC_WGRAD", "1") != "0"
         self.relu_bits = __import__("os").environ.get("ISWM_RELU_BITS", "1") != "0"
         self.fwd_overlap = __import__("os").environ.get("ISWM_FWD_OVERLAP", "1") != "0"
+        self.batch_unpack = __import__("os").environ.get("ISWM_BATCH_UNPACK", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -459,7 +460,8 @@ class Engine:
                 acc = self.wacc[off:off + n]
                 check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
                 self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k, "wgrad " + s.name)
-                check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
+                if not self._batched_unpack():
+                    check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
             # notifications are issued in the same context: a bucket all-reduce launched from here orders itself after
             # this stream, which has seen everything the main stream produced up to this unit (BatchNorm gradients too)
             self._notify(s.conv.weight)
@@ -489,6 +491,26 @@ class Engine:
             else:
                 assert x.grad.ld == Cin
                 check(L.iswm_scatter2_add(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "scatter2_add")
+
+    def _batched_unpack(self) -> bool:
+        """k x k weight gradients leave their [Cout][tap][Cin] accumulators in ONE launch at the end of the sweep -
+        unless somebody consumes gradients tensor by tensor (data-parallel bucket hooks, the unit-replay recorder)."""
+        return self.batch_unpack and self.grad_ready_hook is None and self.debug_units is None
+
+    def _unpack_all(self):
+        import numpy as np  # noqa: F401
+        sig = (self.wacc.data_ptr(), self.flat_g.data_ptr())
+        if getattr(self, "_unpack_sig", None) != sig:
+            jobs = []
+            for s in self.specs:
+                if s.k > 1 and not s.is_stem:
+                    off, n = self.wacc_off[s.name]
+                    jobs.append((self.wacc.data_ptr() + 4 * off, self.grad_views[id(s.conv.weight)].data_ptr(), s.cout, s.cin, s.k * s.k))
+            arr, self._unpack_blocks = _lib.fill_unpack_jobs(jobs)
+            self._unpack_jobs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(self.device)
+            self._unpack_njobs = len(jobs)
+            self._unpack_sig = sig
+        check(_lib.lib().iswm_unpack_wgrad_batched(self._unpack_jobs.data_ptr(), self._unpack_njobs, self._unpack_blocks, _st()), "unpack_wgrad_batched")
 
     def _dgrad_into(self, s: ConvSpec, x: Act, dy: torch.Tensor, dy_ld: int, Hi, Wi, dtaps, Ho, Wo):
         L = _lib.lib()
@@ -895,6 +917,9 @@ class Engine:
         # reverse sweep
         for fn in reversed(self.tape):
             fn()
+        if self._batched_unpack():
+            with self._wgrad_ctx():              # after every weight-gradient kernel of the sweep, on their stream
+                self._unpack_all()
         self._wgrad_join()                       # the optimiser / all-reduce tail sees every weight gradient
         self.tape = []
         self._saved = None

@@ -296,3 +296,32 @@ def test_forward_branch_overlap_changes_nothing():
     for l1, g1, e1 in outs[True]:
         assert torch.equal(l0, l1) and torch.equal(e0, e1)
         assert rel_l2(g1, g0) <= 1e-5
+
+
+def test_batched_unpack_equals_per_layer_and_accumulates():
+    """k x k weight gradients unpacked in one launch at the end of the sweep == the per-layer unpack (to the atomics
+    noise of wgrad), and a second backward without zeroing accumulates (.grad semantics of train.py:1047-1048)."""
+    m, sd = build("resnet50", 16, seed=31)
+    m.to(DEV).train()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((3, 3, 64, 80), generator=g).to(DEV)
+    y = synth_labels((3, 64, 80), seed=5, fg=0.2, ign=0.05).to(DEV)
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    eng = m.engine()
+    eng.dropout_p = 0.0
+    grads = {}
+    for mode in (False, True):
+        eng.batch_unpack = mode
+        bufs = [b.detach().clone() for b in m.buffers()]
+        for p in m.parameters():
+            p.grad = None
+        crit(m(x), y).backward()
+        g1 = eng.flat_g.clone()
+        crit(m(x), y).backward()                      # no zero_grad in between: accumulates
+        grads[mode] = (g1, eng.flat_g.clone())
+        with torch.no_grad():
+            for b, v in zip(m.buffers(), bufs):
+                b.copy_(v)
+    assert rel_l2(grads[True][0], grads[False][0]) <= 1e-5
+    assert rel_l2(grads[True][1], 2 * grads[True][0]) <= 1e-3     # second pass: running statistics moved nothing in train mode
+    assert rel_l2(grads[True][1], grads[False][1]) <= 1e-5
