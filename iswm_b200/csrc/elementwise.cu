@@ -1033,7 +1033,19 @@ reduce_hw_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int64_t HW, int 
   for (int j = 0; j < 8; j++) a[j] = 0.f;
   if (cg < nvec && ty < ny) {
     const __nv_bfloat16* xp = x + (int64_t)b * HW * x_ld + cg * 8;
-    for (int64_t r = ty; r < HW; r += ny) {
+    int64_t r = ty;
+    for (; r + 3 * ny < HW; r += 4 * ny) {        // four independent 16-byte loads in flight (was a load -> add chain)
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) q[u] = load_raw(xp + (r + (int64_t)u * ny) * x_ld);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const F8 v = unpack8(q[u]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] += v.v[j];
+      }
+    }
+    for (; r < HW; r += ny) {
       const F8 v = load8(xp + r * x_ld);
 #pragma unroll
       for (int j = 0; j < 8; j++) a[j] += v.v[j];
