@@ -498,7 +498,6 @@ class Engine:
         return self.batch_unpack and self.grad_ready_hook is None and self.debug_units is None
 
     def _unpack_all(self):
-        import numpy as np  # noqa: F401
         sig = (self.wacc.data_ptr(), self.flat_g.data_ptr())
         if getattr(self, "_unpack_sig", None) != sig:
             jobs = []
