@@ -517,7 +517,13 @@ def run_ours(args):
     stepper = None
     if use_graph:
         from iswm_b200.graphs import GraphedTrainStep
-        stepper = GraphedTrainStep(model, crit, opt)
+        try:
+            stepper = GraphedTrainStep(model, crit, opt)
+            stepper(x_dev, y_dev)           # capture now (its warm-up state is restored; then one real step)
+            torch.cuda.synchronize()
+        except Exception as e:              # never lose the measurement to the launch mode: fall back to eager launches
+            print(f"[bench] CUDA graph capture failed ({e!r}); timing the eager step instead", file=sys.stderr)
+            stepper = None
     eager_only = [False]
 
     def step(x, y):
