@@ -662,6 +662,8 @@ class Engine:
         """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]; with `lowres` (eval only) the
         classifier's fp32 NHWC [B,H/4,W/4,num_classes] output, for consumers that fuse the final upsample
         (ops.predict_epilogue)."""
+        if not x.is_cuda:                    # before any CUDA call: the message must be ours, not the driver's
+            raise RuntimeError("iswm_b200 runs on CUDA only: move the model and the input to a B200 (no CPU fallback)")
         with _StreamScope():
             return self._forward(x, train, lowres)
 
