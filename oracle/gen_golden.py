@@ -11,6 +11,7 @@ Imports /root/reference through oracle/ref_import.py and records, for fixed seed
                     and train mode on a 2x3x64x64 input with seeded weights: logits, loss, a few
                     gradients, BN running stats after one step; plus the seed recipe so the test
                     can rebuild the same weights without the reference;
+  model_r50_os8.npz   deeplabv3plus_resnet50(output_stride=8) (rates 12/24/36, layers 3 and 4 dilated), eval only;
   model_r101_os8.npz  same for _load_model('deeplabv3plus','resnet101',2,output_stride=8), eval only.
 Weights themselves are not stored (160 MB); they are regenerated from the seed through the
 state_dict key order, which the fixture also pins (names + shapes).
@@ -181,6 +182,8 @@ def main():
     gen_loss_metric(ref_metrics)
     gen_model(modeling, "model_r50_os16.npz",
               lambda: modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False), 96, 96, True)
+    gen_model(modeling, "model_r50_os8.npz",
+              lambda: modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=8, pretrained_backbone=False), 56, 72, False)
     gen_model(modeling, "model_r101_os8.npz",
               lambda: modeling._load_model("deeplabv3plus", "resnet101", 2, output_stride=8, pretrained_backbone=False), 48, 40, False)
 

@@ -135,6 +135,14 @@ def test_r101_os8_eval_matches_reference_golden(golden_dir):
     logits_close(out.cpu(), g["eval_logits"])
 
 
+def test_r50_os8_eval_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_r50_os8.npz"))
+    m, _ = build("resnet50", 8)
+    m.to(DEV).eval()
+    out = m(torch.tensor(g["x"]).to(DEV))
+    logits_close(out.cpu(), g["eval_logits"])
+
+
 def test_r50_os16_train_step_matches_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "model_r50_os16.npz"))
     m, sd = build("resnet50", 16)
