@@ -104,6 +104,7 @@ class Engine:
         self._build_specs()
         self.tape: List[Callable[[], None]] = []
         self.step = 0
+        self.generation = 0           # train-mode forwards issued so far (a backward must belong to the latest one)
         self.flat_g = None            # fp32 flat gradient buffer (all parameters, registration order)
         self.grad_views = {}
         self.wacc = None              # fp32 scratch for k>1 weight gradients
@@ -323,7 +324,11 @@ class Engine:
     # ------------------------------------------------------------------ eval-mode unit: conv + folded BN (+res, relu)
     def _fold(self, s: ConvSpec):
         bn = s.bn
-        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
+        # running statistics are updated by kernels through raw pointers and the affine through the flat master buffer
+        # (fused optimisers, graph replays): neither bumps a tensor version, so the key also carries the engine's own
+        # counters - `step` moves with every train-mode forward / graph replay, `weights_epoch` with every fused step
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               self.weights_epoch, self.step)
         if s.fold_scale is None or s.fold_version != key or s.fold_scale.device != self.device:
             s.fold_scale = torch.empty(s.cout, dtype=torch.float32, device=self.device)
             s.fold_shift = torch.empty(s.cout, dtype=torch.float32, device=self.device)
@@ -674,9 +679,13 @@ class Engine:
         x = x.contiguous().float()
         self._image = x if self.debug_units is not None else None
         L = _lib.lib()
-        self.tape = []
-        self._begin_scratch()
         if train:
+            # an eval / predict forward between a train forward and its backward leaves the pending tape, the BatchNorm
+            # accumulators and the saved head tensors alone; a second TRAIN forward supersedes the first (generation
+            # counter: the stale autograd node raises instead of sweeping the wrong tape)
+            self.tape = []
+            self.generation += 1
+            self._begin_scratch()
             self._ensure_grad_buffers()
             self.step += 1
             if getattr(self, "_step_dev", None) is None or self._step_dev.device != self.device:

@@ -5,8 +5,13 @@ arithmetic follow the reference exactly (integer counts bit-exact, ratios in flo
 eps=1e-7); counts are produced by the CUDA confusion kernel and kept ON DEVICE as int64 until
 a result is read. The per-image shape / temporal / front-tracking evaluators of the reference
 (metrics/region_metrics.py, temporal_metrics.py, front_tracking_metrics.py — cv2/scipy CPU
-heuristics) are outside the accelerated hot path: their result
-keys are present with neutral values so callers that read the dict keep working.
+heuristics) are outside the accelerated hot path. They are PLUG-INS
+here: assign objects with the reference's evaluator interface (`update(pred, gt)`, `reset()`,
+`get_mean_score()` / `get_mean_error()`) to `temporal_evaluator`, `region_evaluator`,
+`front_tracking_evaluator` (the reference's own classes work unchanged) and `update()` feeds them
+exactly as stream_metrics.py:104-118 does. While a slot is empty its result key is NaN ("not
+measured") and the weighted score is taken over the measured terms with the reference's weights
+renormalised - a constant 0.0 would read as a perfect Front Tracking Error and add +0.25 to every score.
 """
 from __future__ import annotations
 
@@ -16,6 +21,10 @@ import numpy as np
 import torch
 
 from .. import ops
+
+
+def _to_host(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
 
 
 def _to_device_labels(a, device):
@@ -37,6 +46,10 @@ class StreamMetrics:
         self.FOREGROUND_CLASS = 1
         self.sequence_length, self.temporal_stride, self.threshold = sequence_length, temporal_stride, threshold
         self.best_score = {"weighted_score": 0.0}
+        # optional CPU evaluators with the reference's interface (stream_metrics.py:16-22); None = not measured
+        self.temporal_evaluator = None
+        self.region_evaluator = None
+        self.front_tracking_evaluator = None
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         self._cm_dev: Optional[torch.Tensor] = None
         self.process_group = None          # set by iswm_b200.parallel to all-reduce counts in get_results
@@ -69,14 +82,31 @@ class StreamMetrics:
 
     def update(self, label_trues, label_preds, sequence_data=True):
         """stream_metrics.py:102-138: with sequence_data only the LAST frame of the window reaches the
-        confusion matrix (:113-114)."""
+        confusion matrix (:113-114); like the reference, every call re-evaluates the running results and
+        refreshes `best_score` (:124-137) - one device->host read of the n x n counters per call, which is what the
+        reference's numpy accumulator costs too. `update_cuda` is the non-synchronising path."""
         if sequence_data:
+            if self.temporal_evaluator is not None:
+                self.temporal_evaluator.update(label_preds, label_trues)
             t, p = label_trues[-1], label_preds[-1]
         else:
             t, p = label_trues, label_preds
+        if self.region_evaluator is not None:
+            self.region_evaluator.update(_to_host(p), _to_host(t))
+        if self.front_tracking_evaluator is not None:
+            self.front_tracking_evaluator.update(_to_host(p), _to_host(t))
         t = _to_device_labels(t, self.device).reshape(-1)
         p = _to_device_labels(p, self.device).reshape(-1)
         ops.confusion(t, p, self.n_classes, out=self._cm())
+        current = self.get_results(update_best=False)
+        score = self._calculate_weighted_score(current)
+        if score > self.best_score["weighted_score"]:
+            self.best_score["weighted_score"] = score
+            self.best_score.update({
+                "miou": current["MIoU"], "foreground_iou": current["Foreground IoU"], "foreground_f1": current["Foreground F1"],
+                "temporal_consistency": current["Temporal Consistency"], "front_tracking_error": current["Front Tracking Error"],
+                "region_continuity": current["Region Continuity"],
+            })
 
     @property
     def confusion_matrix(self) -> np.ndarray:
@@ -114,19 +144,38 @@ class StreamMetrics:
         return miou, foreground_iou, precision, recall, f1_score
 
     def _calculate_weighted_score(self, results):
-        """stream_metrics.py:65-100."""
-        norm_front_error = 1.0 - min(results["Front Tracking Error"] / 10.0, 1.0)
-        return (0.05 * results["MIoU"] + 0.25 * results["Foreground IoU"] + 0.25 * results["Foreground F1"]
-                + 0.25 * norm_front_error + 0.10 * results["Temporal Consistency"] + 0.10 * results["Region Continuity"])
+        """stream_metrics.py:65-100 (weights 0.05 / 0.25 / 0.25 / 0.25 / 0.10 / 0.10); terms whose evaluator is not
+        plugged in (NaN) are left out and the remaining weights renormalised."""
+        fte = results["Front Tracking Error"]
+        terms = [(0.05, results["MIoU"]), (0.25, results["Foreground IoU"]), (0.25, results["Foreground F1"]),
+                 (0.25, float("nan") if fte != fte else 1.0 - min(fte / 10.0, 1.0)),
+                 (0.10, results["Temporal Consistency"]), (0.10, results["Region Continuity"])]
+        live = [(w, v) for (w, v) in terms if v == v]
+        wsum = sum(w for w, _ in live)
+        if len(live) == len(terms):
+            return sum(w * v for w, v in live)
+        return sum(w * v for w, v in live) / wsum if wsum > 0 else 0.0
 
     def get_results(self, update_best=True):
         """stream_metrics.py:140-189 (the one device->host read of the int64 counters happens here)."""
         miou, fiou, precision, recall, f1 = self._calculate_foreground_metrics(self.confusion_matrix)
+        nan = float("nan")
+        te, re_, fe = self.temporal_evaluator, self.region_evaluator, self.front_tracking_evaluator
         results = {
             "MIoU": miou, "Foreground IoU": fiou, "Foreground F1": f1,
-            "Temporal Consistency": 0.0, "Front Tracking Error": 0.0, "Region Continuity": 0.0,   # CPU heuristics: out of scope
+            "Temporal Consistency": nan if te is None else te.get_mean_score(),
+            "Front Tracking Error": nan if fe is None else fe.get_mean_error(),
+            "Region Continuity": nan if re_ is None else re_.get_mean_score(),
             "Precision": precision, "Recall": recall,
         }
+        if te is not None and hasattr(te, "get_detailed_statistics"):
+            st = te.get_detailed_statistics()
+            results.update({"Transition Accuracy": st["mean_transition"], "Stability Score": st["mean_stability"],
+                            "Motion Consistency": st["mean_motion"], "Wave Segment Score": st["mean_wave_segment"]})
+        if re_ is not None and hasattr(re_, "get_statistics"):
+            rs = re_.get_statistics()
+            if "valid_ratio" in rs:
+                results["Region Valid Ratio"] = rs["valid_ratio"]
         if update_best:
             score = self._calculate_weighted_score(results)
             if score > self.best_score["weighted_score"]:
@@ -145,3 +194,6 @@ class StreamMetrics:
         """stream_metrics.py:191-195."""
         if self._cm_dev is not None:
             self._cm_dev.zero_()
+        for ev in (self.temporal_evaluator, self.region_evaluator, self.front_tracking_evaluator):
+            if ev is not None:
+                ev.reset()

@@ -19,10 +19,15 @@ class _EngineFn(torch.autograd.Function):
     def forward(ctx, x, engine, anchor, *params):
         ctx.engine = engine
         ctx.n_params = len(params)
-        return engine.forward(x, train=True)
+        out = engine.forward(x, train=True)
+        ctx.generation = engine.generation
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
+        if ctx.generation != ctx.engine.generation:
+            raise RuntimeError("backward() of a forward pass that a later train-mode forward superseded: the engine keeps "
+                               "ONE pending tape (no gradient accumulation over several forwards, like the reference loop)")
         ctx.engine.backward(dlogits)
         return (None, None, None) + (None,) * ctx.n_params
 

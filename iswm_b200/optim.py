@@ -67,11 +67,31 @@ class FusedSGD:
         eng.invalidate_packed()
 
     def state_dict(self):
+        """Flat layout (ONE momentum buffer over the engine's flat parameter buffer). A checkpoint's `optimizer_state`
+        written by the reference's torch.optim objects (per-parameter `state` dict, train.py:569) is NOT loadable here
+        and vice versa; model / scheduler states are interchangeable."""
         return {"momentum_buffer": self._mom, "steps": self._steps, "param_groups": self.param_groups}
 
+    def _adopt(self, name: str, t):
+        """validate a loaded flat state buffer against the engine's flat parameter buffer"""
+        if t is None:
+            return None
+        flat_w = self.engine.flatten_parameters()
+        if not isinstance(t, torch.Tensor) or t.numel() != flat_w.numel():
+            raise ValueError(f"{type(self).__name__}.load_state_dict: '{name}' does not match the model's {flat_w.numel()} "
+                             "parameters (a reference torch.optim state_dict is not loadable, see state_dict())")
+        return t.detach().to(device=flat_w.device, dtype=torch.float32).contiguous().clone()
+
+    def _resync_device_state(self):
+        if self.lr_dev is not None:
+            self.step_dev.fill_(self._steps)
+            self._lr_pushed = None
+            self.sync_device_state()
+
     def load_state_dict(self, sd):
-        self._mom, self._steps = sd["momentum_buffer"], sd["steps"]
-        self.param_groups = sd["param_groups"]
+        self._mom, self._steps = self._adopt("momentum_buffer", sd["momentum_buffer"]), int(sd["steps"])
+        self.param_groups = [dict(g) for g in sd["param_groups"]]
+        self._resync_device_state()
 
 
 class FusedAdam:
@@ -90,6 +110,8 @@ class FusedAdam:
         self.step_dev = None
 
     zero_grad = FusedSGD.zero_grad
+    _adopt = FusedSGD._adopt
+    _resync_device_state = FusedSGD._resync_device_state
     enable_device_state = FusedSGD.enable_device_state
     sync_device_state = FusedSGD.sync_device_state
 
@@ -118,8 +140,10 @@ class FusedAdam:
         return {"exp_avg": self._m, "exp_avg_sq": self._v, "steps": self._steps, "param_groups": self.param_groups}
 
     def load_state_dict(self, sd):
-        self._m, self._v, self._steps = sd["exp_avg"], sd["exp_avg_sq"], sd["steps"]
-        self.param_groups = sd["param_groups"]
+        self._m, self._v = self._adopt("exp_avg", sd["exp_avg"]), self._adopt("exp_avg_sq", sd["exp_avg_sq"])
+        self._steps = int(sd["steps"])
+        self.param_groups = [dict(g) for g in sd["param_groups"]]
+        self._resync_device_state()
 
 
 class FusedAdamW(FusedAdam):
@@ -167,3 +191,15 @@ class CosineAnnealingLR:
 
     def get_last_lr(self):
         return [self.opt.param_groups[0]["lr"]]
+
+    def state_dict(self):
+        """Same keys torch's scheduler saves (train.py:570 stores it in every checkpoint, :1016 restores it)."""
+        return {"T_max": self.T_max, "eta_min": self.eta_min, "base_lrs": [self.base_lr], "last_epoch": self.last_epoch,
+                "_step_count": self.last_epoch + 1, "_last_lr": self.get_last_lr()}
+
+    def load_state_dict(self, sd):
+        self.T_max, self.eta_min = sd["T_max"], sd["eta_min"]
+        self.base_lr = sd["base_lrs"][0] if "base_lrs" in sd else sd["base_lr"]
+        self.last_epoch = sd["last_epoch"]
+        if "_last_lr" in sd:
+            self.opt.param_groups[0]["lr"] = sd["_last_lr"][0]

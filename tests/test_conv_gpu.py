@@ -48,6 +48,13 @@ CASES = [
     (2, 256, 9, 11, 2, 1, 1),
     (3, 64, 25, 25, 128, 3, 1),
     (2, 1024, 8, 8, 2048, 1, 1),
+    # large dilations with taps that land INSIDE the image (OS16 rate 18, OS8 rates 24 / 36 of network/modeling.py:27-33);
+    # a wrong tap offset cannot hide behind the zero padding here
+    (1, 128, 48, 48, 64, 3, 18),
+    (1, 128, 80, 80, 64, 3, 24),
+    (1, 128, 80, 80, 64, 3, 36),
+    (2, 64, 50, 77, 64, 3, 36),
+    (1, 192, 40, 40, 256, 3, 12),
 ]
 
 
@@ -121,7 +128,9 @@ def test_conv_stride2_via_phases():
     assert _rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) < 1e-2
 
 
-@pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", [(2, 64, 16, 16, 128, 3, 1), (1, 256, 8, 8, 512, 3, 2), (2, 256, 16, 16, 64, 1, 1), (2, 256, 9, 11, 2, 1, 1)])
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", [(2, 64, 16, 16, 128, 3, 1), (1, 256, 8, 8, 512, 3, 2), (2, 256, 16, 16, 64, 1, 1), (2, 256, 9, 11, 2, 1, 1),
+                                                   (1, 128, 48, 48, 64, 3, 18), (1, 128, 80, 80, 64, 3, 24), (1, 128, 80, 80, 64, 3, 36),
+                                                   (2, 64, 50, 77, 64, 3, 36)])
 def test_conv_dgrad(B, Cin, H, W, Cout, k, dil):
     x, w = _mk(B, Cin, H, W, Cout, k, seed=7)
     g = torch.Generator().manual_seed(8)
@@ -142,7 +151,9 @@ def test_conv_dgrad(B, Cin, H, W, Cout, k, dil):
 
 @pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", [(2, 64, 16, 16, 64, 1, 1), (2, 64, 16, 16, 128, 3, 1), (1, 512, 8, 8, 256, 3, 2),
                                                    (2, 304, 16, 16, 256, 3, 1), (2, 256, 9, 11, 2, 1, 1), (4, 2048, 8, 8, 256, 3, 6),
-                                                   (2, 256, 32, 32, 48, 1, 1)])
+                                                   (2, 256, 32, 32, 48, 1, 1),
+                                                   (1, 128, 48, 48, 64, 3, 18), (1, 128, 80, 80, 64, 3, 24), (1, 128, 80, 80, 64, 3, 36),
+                                                   (2, 64, 50, 77, 64, 3, 36)])
 def test_conv_wgrad(B, Cin, H, W, Cout, k, dil):
     x, w = _mk(B, Cin, H, W, Cout, k, seed=9)
     g = torch.Generator().manual_seed(10)

@@ -319,3 +319,58 @@ def test_sgd_step_matches_torch():
         opt.step()
         check(L().iswm_sgd_step(p.data_ptr(), grad.to(DEV).data_ptr(), mom.data_ptr(), p.numel(), 1e-3, 0.9, 1e-4, 1, 1 if step == 0 else 0, None, st()))
     close(p, p_ref.detach(), 1e-6, 1e-7)
+
+
+@pytest.mark.parametrize("B,C,H,W,p", [(4, 256, 16, 16, 0.1), (2, 64, 9, 7, 0.5), (3, 256, 32, 32, 0.25)])
+def test_bn_backward_with_dropout_against_torch_with_the_kernels_own_mask(B, C, H, W, p):
+    """ASPP projection unit (network/_deeplab.py:163-166: conv -> BN -> ReLU -> Dropout(0.1)): the forward kernel's keep
+    mask is recovered from its output (kept elements are y / (1 - p), dropped ones 0 where relu(y) > 0) and INJECTED into a
+    torch fp32 restatement y * mask / (1 - p); bn_bwd_reduce / bn_bwd_apply with drop_p > 0 (which regenerate the mask from
+    the counter-based hash) must then produce torch's gradients. SURVEY 7 'hard parts': Dropout parity by mask injection."""
+    x = rnd((B, C, H, W), 11, 2.0)
+    g = torch.Generator().manual_seed(12)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    dout = rnd((B, C, H, W), 13)
+    M = B * H * W
+    seed, step = 0x5EED + 41, torch.tensor([7], dtype=torch.int64, device=DEV)
+    xd = nhwc(x).to(DEV)
+    stats = torch.stack([x.double().sum((0, 2, 3)), (x.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    save = torch.empty(2 * C, dtype=torch.float32, device=DEV)
+    gd, bd = gamma.to(DEV), beta.to(DEV)
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+                                  save.data_ptr(), save[C:].data_ptr(), None, C, 1, p, seed, step.data_ptr(), out.data_ptr(), C, None, st()))
+    # torch: the same unit without dropout, then the mask read off the kernel's output
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5))
+    got = nchw(out).float().cpu()
+    live = y.detach() > 1e-3                          # away from the ReLU edge (bf16 rounding may flip the sign there)
+    keep = got != 0
+    frac = float(keep[live].float().mean())
+    assert abs(frac - (1 - p)) < 0.02, f"keep fraction {frac:.4f} vs 1-p = {1 - p}"
+    close(got[live & keep], (y.detach() / (1 - p))[live & keep], 1e-2, 2e-2)
+    mask = (keep | ~live).float()                      # dropped = live but zero in the kernel's output
+    (y * mask / (1 - p)).backward(dout.float())
+    dd = nhwc(dout).to(DEV)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, None, C, M, C, save.data_ptr(), save[C:].data_ptr(),
+                                 gd.data_ptr(), bd.data_ptr(), 1, p, seed, step.data_ptr(), sums.data_ptr(), st()))
+    dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    dg = torch.zeros(C, dtype=torch.float32, device=DEV)
+    db = torch.zeros(C, dtype=torch.float32, device=DEV)
+    check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, None, C, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
+                                sums.data_ptr(), 1, p, seed, step.data_ptr(), dx.data_ptr(), C, None, 0, dg.data_ptr(), db.data_ptr(), st()))
+    scale = float(xr.grad.abs().max())
+    # elements within 1e-3 of the ReLU edge may carry a flipped mask: compare everything, with that small population tolerated
+    err = (nchw(dx).float().cpu() - xr.grad).abs()
+    assert float((err > 2e-2 * scale + 2e-2 * xr.grad.abs()).float().mean()) < 2e-3
+    close(dg, gr.grad, 3e-2, 8e-2)
+    close(db, br.grad, 3e-2, 8e-2)
+    # a different step counter draws a different mask (the graph-replayed step advances it on the device)
+    out2 = torch.empty_like(out)
+    step2 = torch.tensor([8], dtype=torch.int64, device=DEV)
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+                                  save.data_ptr(), save[C:].data_ptr(), None, C, 1, p, seed, step2.data_ptr(), out2.data_ptr(), C, None, st()))
+    assert not torch.equal(out2, out)

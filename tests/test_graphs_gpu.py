@@ -139,3 +139,70 @@ def test_dropout_mask_follows_device_step_counter():
     nodrop = run(77, None) * 0 + (x.float() - x.float().mean(0)) / x.float().var(0, unbiased=False).add(1e-5).sqrt() + 3.0
     kept = s5 != 0
     assert torch.allclose(s5[kept], (nodrop / (1 - p))[kept], rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("mode", ["eager_fused", "graphed", "torch_optim"])
+def test_eval_after_training_refolds_batchnorm(mode):
+    """validate_and_save / predict between training iterations (train.py:620-745): eval -> train 2 steps -> eval. The
+    second eval must see the NEW running statistics and affine parameters, i.e. equal a fresh model loaded from the same
+    state_dict. (The folded eval-mode scale / shift are cached per unit; the kernels update running_mean / var through raw
+    pointers and the fused optimisers update gamma / beta through the flat master buffer, so no tensor version moves.)"""
+    batches = _batches(2)
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    m = _model()
+    xe = batches[0][0]
+    m.eval()
+    with torch.no_grad():
+        before = m(xe).clone()
+    m.train()
+    if mode == "torch_optim":
+        opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9)
+    else:
+        opt = FusedSGD(m, lr=1e-2, momentum=0.9)
+    stepper = GraphedTrainStep(m, crit, opt) if mode == "graphed" else None
+    for x, y in batches:
+        if stepper is not None:
+            stepper(x, y)
+        else:
+            loss = crit(m(x), y)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    m.eval()
+    with torch.no_grad():
+        after = m(xe).clone()
+    fresh = modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False)
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    fresh.to(DEV).eval()
+    with torch.no_grad():
+        want = fresh(xe)
+    assert torch.equal(after, want), float((after - want).abs().max())
+    assert not torch.equal(after, before)
+    assert int(m.state_dict()["backbone.bn1.num_batches_tracked"]) == 2
+
+
+def test_eval_forward_between_forward_and_backward_keeps_the_tape():
+    """An eval / predict forward issued between a train forward and its loss.backward() (periodic visualisation hooks do
+    that) must not destroy the pending tape; a second TRAIN forward supersedes the first one and its stale backward raises."""
+    (x, y), (x2, _) = _batches(2)
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    ma, mb = _model(), _model()
+    for m in (ma, mb):
+        m.engine().dropout_p = 0.0
+    la = crit(ma(x), y)
+    la.backward()
+    lb = crit(mb(x), y)
+    mb.eval()
+    with torch.no_grad():
+        mb(x2)
+        mb.forward_lowres(x2)
+    mb.train()
+    lb.backward()
+    torch.cuda.synchronize()
+    assert float(la) == float(lb)
+    ga, gb = ma.engine().flat_g, mb.engine().flat_g
+    assert float((ga - gb).norm() / ga.norm()) <= 1e-5
+    stale = crit(mb(x), y)
+    crit(mb(x2), y)
+    with pytest.raises(RuntimeError, match="superseded"):
+        stale.backward()

@@ -44,9 +44,21 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-def logits_close(got, ref):
+def report(name, **vals):
+    """Every parity test prints what it MEASURED (pytest -rP / -s shows it) and appends it to gpurun_out/parity_measured.txt
+    when that directory exists (copied to profiles/ per round)."""
+    line = "PARITY " + name + " " + " ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}" for k, v in vals.items())
+    print(line)
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_measured.txt"), "a") as f:
+            f.write(line + "\n")
+
+
+def logits_close(got, ref, name="logits", l2_max=2e-2, mx_max=4e-2):
     l2, mx = rel_l2(got, ref), rel_max(got, ref)
-    assert l2 <= 2e-2 and mx <= 4e-2, f"logits: rel L2 {l2:.4g} (<=2e-2), max/range {mx:.4g} (<=4e-2)"
+    report(name, rel_l2=l2, max_over_range=mx, gate_l2=l2_max, gate_max=mx_max)
+    assert l2 <= l2_max and mx <= mx_max, f"{name}: rel L2 {l2:.4g} (<={l2_max}), max/range {mx:.4g} (<={mx_max})"
 
 
 def train_reference(backbone, os_, sd, x, y, w):
@@ -69,6 +81,8 @@ def check_train_against_noise_floor(logits, loss, ref):
     f32_logits, f32_loss = ref["fp32"][0], ref["fp32"][1]
     floor = rel_l2(ref["matched"][0], f32_logits)
     mine = rel_l2(logits, f32_logits)
+    report("train_vs_fp32", logits_rel_l2=mine, matched_oracle_floor=floor, loss=float(loss), loss_fp32=f32_loss.item(),
+           loss_rel=abs(loss - f32_loss.item()) / abs(f32_loss.item()), loss_floor_rel=abs(ref["matched"][1].item() - f32_loss.item()) / abs(f32_loss.item()))
     assert mine <= 1.5 * floor + 5e-3, f"train logits {mine:.4g} from fp32; bf16 noise floor (matched oracle) {floor:.4g}"
     # scalar loss: the batch-2 golden case normalises the ASPP pooling branch over TWO samples, so bf16
     # rounding is amplified by 1/sqrt(eps); the precision-matched oracle's own distance from fp32 is the floor
@@ -95,7 +109,7 @@ def test_r50_os16_eval_matches_reference_golden(golden_dir):
     m.to(DEV).eval()
     out = m(torch.tensor(g["x"]).to(DEV))
     assert out.dtype == torch.float32 and tuple(out.shape) == g["eval_logits"].shape
-    logits_close(out.cpu(), g["eval_logits"])
+    logits_close(out.cpu(), g["eval_logits"], "r50_os16_eval_vs_reference_golden")
 
 
 def test_r50_os16_eval_loss_vs_reference(golden_dir):
@@ -132,7 +146,7 @@ def test_r101_os8_eval_matches_reference_golden(golden_dir):
     m, _ = build("resnet101", 8)
     m.to(DEV).eval()
     out = m(torch.tensor(g["x"]).to(DEV))
-    logits_close(out.cpu(), g["eval_logits"])
+    logits_close(out.cpu(), g["eval_logits"], "r101_os8_eval_vs_reference_golden")
 
 
 def test_r50_os8_eval_matches_reference_golden(golden_dir):
@@ -140,7 +154,31 @@ def test_r50_os8_eval_matches_reference_golden(golden_dir):
     m, _ = build("resnet50", 8)
     m.to(DEV).eval()
     out = m(torch.tensor(g["x"]).to(DEV))
-    logits_close(out.cpu(), g["eval_logits"])
+    logits_close(out.cpu(), g["eval_logits"], "r50_os8_eval_vs_reference_golden")
+
+
+def test_r50_os8_320_eval_matches_reference_golden(golden_dir):
+    """ResNet-50 at output stride 8 on a 320 x 320 tile: the 40 x 40 feature map is larger than every ASPP rate
+    (12 / 24 / 36, network/modeling.py:27-33; layer3 d=2, layer4 d=4), so EVERY tap of the dilated branches reads pixels inside
+    the image - a wrong tap offset at d=24 / d=36 cannot hide behind the zero padding as it can in the small fixtures.
+    Golden: oracle/gen_golden_r2.py (the real reference); full-resolution map additionally vs the fp32 oracle."""
+    from oracle.gen_golden_r2 import golden_input
+    g = np.load(os.path.join(golden_dir, "model_r50_os8_320.npz"))
+    x = golden_input()
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-6 and np.array_equal(x.flatten()[:16].numpy(), g["x_head"])
+    m, sd = build("resnet50", 8)
+    m.to(DEV).eval()
+    out = m(x.to(DEV)).cpu()
+    logits_close(out[:, :, ::4, ::4], g["logits_s4"], "r50_os8_320_eval_vs_reference_golden(stride-4 lattice)")
+    got = out.flatten(2)[0][:, torch.tensor(g["pos"])]
+    logits_close(got, g["logits_at_pos"], "r50_os8_320_eval_vs_reference_golden(4096 samples)")
+    o = TM.oracle_model("resnet50", 2, 8)
+    o.load_state_dict(sd)
+    o.eval()
+    with torch.no_grad():
+        ref = o(x)
+    assert rel_l2(ref[:, :, ::4, ::4], g["logits_s4"]) <= 1e-4          # the oracle is pinned to the reference here too
+    logits_close(out, ref, "r50_os8_320_eval_vs_fp32_oracle(full map)")
 
 
 def test_r50_os16_train_step_matches_reference_golden(golden_dir):
