@@ -476,6 +476,151 @@ def run_lossmetric(args, dev, world, rank, local):
         "cpu_baseline": cpu}))
 
 
+def dp_parity_check(dev, world, rank):
+    """Multi-rank parity INSIDE the driver's own run (every --gpus N > 1 call, before the timed region): one train step of
+    DeepLabV3+ R50-OS16 on a fixed global batch sharded over the ranks (6 images of 128x128 per rank, very different class
+    mixes per shard, Dropout off) through iswm_b200.parallel.DataParallel, against rank 0's single-GPU restatement of
+    nn.DataParallel's semantics (train.py:970, :1045-1048): per-shard forward / backward with per-shard
+    BatchNorm, loss normalised by the GLOBAL class histogram, gradients SUMMED. Also the data-parallel confusion matrix:
+    every rank updates StreamMetrics with its shard, the all-reduced matrix must equal the one computed over the whole
+    batch bit for bit. Returns {"rel_grad", "rel_loss", "cm_equal", ...} on rank 0 (None elsewhere)."""
+    import torch.distributed as dist
+    from iswm_b200 import ops
+    from iswm_b200.metrics import StreamMetrics
+    from iswm_b200.network import modeling
+    from iswm_b200.parallel import DataParallel
+    from iswm_b200.utils.loss import CrossEntropyLoss
+    Bs, H, W = 6, 128, 128
+    g = torch.Generator().manual_seed(4242)
+    x = torch.randn((world * Bs, 3, H, W), generator=g)
+    y = torch.empty((world * Bs, H, W), dtype=torch.int64)
+    for r in range(world):                               # foreground fraction 5 % .. 85 % across the shards
+        fg = 0.05 + 0.8 * r / max(1, world - 1)
+        yy = (torch.rand((Bs, H, W), generator=g) < fg).long()
+        yy[torch.rand((Bs, H, W), generator=g) < 0.02] = 255
+        y[r * Bs:(r + 1) * Bs] = yy
+    w = torch.tensor([1.0, 4.0])
+
+    def build():
+        torch.manual_seed(1)
+        m = modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(dev).train()
+        m.engine().dropout_p = 0.0
+        return m
+
+    model = build()
+    crit = CrossEntropyLoss(weight=w, ignore_index=255).to(dev)
+    sm = StreamMetrics(2, device=dev)
+    dp = DataParallel(model, crit, bucket_bytes=8 << 20, metrics=sm)
+    xs, ys = x[rank * Bs:(rank + 1) * Bs].to(dev), y[rank * Bs:(rank + 1) * Bs].to(dev)
+    loss = dp.train_step(xs, ys, optimizer=None)
+    torch.cuda.synchronize()
+    flat = model.engine().flat_g.clone()
+    model.eval()
+    with torch.no_grad():
+        sm.update_cuda(ys, model(xs))                    # argmax predictions of this rank's shard
+    cm = sm.confusion_matrix                             # all-reduce(SUM) of the int64 counters: every rank calls it
+    out = None
+    if rank == 0:
+        hist = torch.zeros(2, dtype=torch.int64, device=dev)
+        ops.class_hist(y.to(dev), 2, out=hist)
+        ref_grad, num = None, 0.0
+        ref_cm = StreamMetrics(2, device=dev)
+        m2 = build()
+        sd0 = {k: v.clone() for k, v in m2.state_dict().items()}
+        for r in range(world):
+            m2.load_state_dict(sd0)                      # every replica starts from the same parameters AND buffers
+            m2.train()
+            for p in m2.parameters():
+                p.grad = None
+            c2 = CrossEntropyLoss(weight=w, ignore_index=255).to(dev)
+            c2.hist_hook = lambda h: h.copy_(hist)       # the global (all-reduced) histogram
+            xr, yr = x[r * Bs:(r + 1) * Bs].to(dev), y[r * Bs:(r + 1) * Bs].to(dev)
+            l2 = c2(m2(xr), yr)
+            l2.backward()
+            torch.cuda.synchronize()
+            gr = m2.engine().flat_g.clone()
+            ref_grad = gr if ref_grad is None else ref_grad + gr
+            num += float(l2)
+            m2.eval()
+            with torch.no_grad():
+                ref_cm.update_cuda(yr, m2(xr))
+        rel = float((flat - ref_grad).norm() / ref_grad.norm())
+        out = {"rel_grad": rel, "rel_loss": abs(float(loss) - num) / abs(num), "loss": float(loss), "ref_loss": num,
+               "cm_equal": bool((cm == ref_cm.confusion_matrix).all()), "cm_total": float(cm.sum()),
+               "buckets": len(dp.bucketer.bounds), "case": f"R50-OS16, {Bs} x {H}x{W} per rank, {world} ranks, fg 5-85 % per shard"}
+    model.engine().grad_ready_hook = None
+    dist.barrier()
+    del dp, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_extras(dev):
+    """Compact cfg5 / cfg4 results measured in the SAME process as the headline (so that the driver's own run times
+    them): the three loss / metric kernels at 16x2x1024x1024 (median of 10 launches, L2 flushed between them) and the predict
+    path at 8 x 2048x2048 (3 steps after 3 warm-ups)."""
+    from iswm_b200 import ops
+    from iswm_b200.metrics import StreamMetrics
+    from iswm_b200.network import modeling
+    from iswm_b200.predict import predict_mask
+    pk = peaks()
+    extra = {}
+    B, H, W = 16, 1024, 1024
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn((B, 2, H, W), generator=g).to(dev)
+    labels = (torch.rand((B, H, W), generator=g) < 0.02).long()
+    labels[torch.rand((B, H, W), generator=g) < 0.01] = 255
+    labels = labels.to(dev)
+    wts = torch.tensor([1.0, 7.0], device=dev)
+    N = B * H * W
+    hist = ops.class_hist(labels, 2)
+    cm = torch.zeros(5, dtype=torch.int64, device=dev)
+    fns = {"class_hist": (lambda: ops.class_hist(labels, 2, out=hist), N * 8),
+           "wce_fwd_bwd": (lambda: ops.wce_fwd_bwd(logits, labels, wts, hist), 2 * N * 2 * 4 + N * 8),
+           "argmax_confusion": (lambda: ops.argmax_confusion(logits, labels, mode=1, threshold=0.5, out=cm), N * 2 * 4 + N * 8)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    k5 = {}
+    for name, (fn, nbytes) in fns.items():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        us = ts[len(ts) // 2] * 1e3
+        k5[name] = {"us": us, "algorithmic_bytes": nbytes, "frac_of_hbm_peak": nbytes / (us * 1e-6) / 1e9 / pk["hbm_gbs"],
+                    "traffic": traffic_from_profiles("cfg5:" + name)}
+    extra["cfg5"] = {"workload": "16x2x1024x1024 fp32 logits, int64 labels; median of 10 launches, 256 MB L2 flush between", "kernels": k5}
+    del logits, labels, flush
+    torch.cuda.empty_cache()
+    torch.manual_seed(0)
+    model = modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(dev).eval()
+    metrics = StreamMetrics(2, device=dev)
+    x, y = synth_batch(8, 2048, 2048, 0, device=dev)
+    for _ in range(3):
+        predict_mask(model, x, 0.5, y, metrics, fused=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        predict_mask(model, x, 0.5, y, metrics, fused=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    extra["cfg4"] = {"workload": "predict path, R50-OS16 eval, 8 x 2048x2048, fused upsample+softmax+threshold+confusion; 3 steps after 3 warm-ups",
+                     "img_per_s": 8 / (ms * 1e-3), "ms_per_step": ms,
+                     "whole_step_tensor_frac": FWD_GFLOP_PER_IMG[("resnet50", 16, 2048)] * 8e9 / (ms * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)}
+    del model, x, y
+    torch.cuda.empty_cache()
+    return extra
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
@@ -499,6 +644,7 @@ def run_ours(args):
     if args.workload == "lossmetric":
         return run_lossmetric(args, dev, world, rank, local)
     B, H, W = args.batch, args.size, args.size
+    dp_parity = dp_parity_check(dev, world, rank) if (world > 1 and not args.no_dp_parity) else None
     torch.manual_seed(0)
     ctor = modeling.deeplabv3plus_resnet50 if args.backbone == "resnet50" else modeling.deeplabv3plus_resnet101
     model = ctor(num_classes=2, output_stride=args.output_stride, pretrained_backbone=False).to(dev).train()
@@ -662,6 +808,14 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "img/s", "cores": n, "kind": "port",
                "sample": f"1 warm-up + 2 timed steps of batch 2, {H}x{W}, R50-OS16 fwd+CE+bwd+SGD, fp32 torch oracle on the host"}
     gflop = TRAIN_GFLOP_PER_IMG.get((args.backbone, args.output_stride, H))
+    extra = None
+    if world == 1 and not args.no_extras and (args.backbone, args.output_stride, H, B) == ("resnet50", 16, 512, 16):
+        del model, opt, stepper, x_dev, y_dev
+        torch.cuda.empty_cache()
+        try:
+            extra = run_extras(dev)
+        except Exception as e:                           # the headline must survive a failure of the side measurements
+            extra = {"error": repr(e)}
     line = {
         "metric": f"train img/s DeepLabV3+ {'R50' if args.backbone == 'resnet50' else 'R101'} {H}^2", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -672,7 +826,7 @@ def run_ours(args):
                    "l2": "no explicit flush: each step streams > 2 GB of activations (>> 126 MB L2)",
                    "e2e_note": "per step: images+labels H2D from pinned memory (HostBatchPrefetcher, copy of batch i+1 under step i) and the loss D2H (DeferredLoss: read on the host one step later, last one before the timer stops)",
                    "whole_step_tensor_frac": (gflop * 1e9 * B * world * args.steps / (ms * 1e-3) / 1e12 / world / peaks().get("bf16_tflops_sustained", 1400.0)) if gflop else None,
-                   "loss": last},
+                   "loss": last, "dp_parity": dp_parity, "extra": extra},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
                 "ms_per_step": ms_e2e / args.steps},
@@ -699,6 +853,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 16 train, 8 predict, 16 lossmetric)")
     ap.add_argument("--size", type=int, default=0, help="tile edge (default: 512 train, 2048 predict, 1024 lossmetric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N=1 cfg2 only: skip the compact cfg5 / cfg4 side measurements (config.extra)")
+    ap.add_argument("--no-dp-parity", action="store_true", help="N>1 only: skip the multi-rank parity step before the timed region (config.dp_parity)")
     ap.add_argument("--profile-detail", default="", help="write the per-launch table of the instrumented step here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

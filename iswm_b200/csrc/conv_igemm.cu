@@ -43,6 +43,8 @@ struct ConvKParams {
   int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
   int BN, kchunks, cin_pad, ntaps, stages, flags;
   int n_img_per_phase;
+  int step, s_nt, s_tw, s_th, s_tb;   // grid size and its mixed-radix digits over (tiles_n, tiles_w, tiles_h, tiles_b): tile decode without divisions
+  int nprod;                     // producer warps (1 or 2) taking alternate k-blocks of the CTA's schedule
   int out_ld, res_ld;
   int use_tma_out;               // bf16 output through smem staging + TMA store
   int res_prefetch;              // residual rows prefetched into shared memory one chunk ahead (short-K convolutions)
@@ -55,6 +57,36 @@ struct ConvKParams {
   int* abort_flag;
 };
 
+// A CTA's tile schedule (tile = blockIdx.x, += gridDim.x ...) decoded into (n tile, w / h / image tile) coordinates. The decode
+// of the first tile uses integer divisions once; every later tile adds the precomputed mixed-radix digits of the grid size with
+// carries (each digit < its radix, so one conditional subtraction per digit) - the per-tile divisions used to cost each of
+// the three roles ~100 issue slots per tile, which showed on the short-K convolutions (1-9 k-blocks per tile).
+struct TileIter {
+  int tile, nt, tw, th, tb;
+  __device__ __forceinline__ void init(const ConvKParams& p, int t0) {
+    tile = t0;
+    const int mt = t0 / p.tiles_n;
+    nt = t0 - mt * p.tiles_n;
+    tw = mt % p.tiles_w;
+    const int r = mt / p.tiles_w;
+    th = r % p.tiles_h;
+    tb = r / p.tiles_h;
+  }
+  __device__ __forceinline__ void next(const ConvKParams& p) {
+    tile += p.step;
+    nt += p.s_nt;
+    int c = nt >= p.tiles_n ? 1 : 0;
+    nt -= c ? p.tiles_n : 0;
+    tw += p.s_tw + c;
+    c = tw >= p.tiles_w ? 1 : 0;
+    tw -= c ? p.tiles_w : 0;
+    th += p.s_th + c;
+    c = th >= p.tiles_h ? 1 : 0;
+    th -= c ? p.tiles_h : 0;
+    tb += p.s_tb + c;
+  }
+};
+
 // NWG = number of epilogue warpgroups: 2 (384 threads, up to 168 registers each) for long-K convolutions whose epilogue
 // hides under the MMA main loop, 3 (512 threads, 128 registers) for short-K ones that are bound by the epilogue.
 template <int NWG>
@@ -63,6 +95,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
+#ifdef ISWM_EPI_TIMING
+  unsigned long long gt_entry, gt_prol = 0, gt_dep = 0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
+#endif
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
   const uint32_t ring = (raw_addr + 1023u) & ~1023u;     // swizzle-128B tiles need 1 KiB alignment
   uint8_t* smem = smem_raw + (ring - raw_addr);
@@ -112,110 +148,125 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef ISWM_EPI_TIMING
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_prol));
+#endif
   // prologue done (barriers, TMEM, descriptor prefetch touch no global data): wait for the producer grid, then let
   // the next kernel of the stream start its own prologue under our main loop
   pdl_wait();
   pdl_launch();
+#ifdef ISWM_EPI_TIMING
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_dep));
+#endif
 
   const int kblocks = p.ntaps * p.kchunks;
   const int BW = 1 << p.lgBW, BH = 1 << p.lgBH;
   const int BB = kTileM >> (p.lgBW + p.lgBH);
 
-  // The producer and MMA warps walk their schedules with ALL 32 lanes (warp-uniform control flow and operands, so
-  // descriptors / coordinates live in uniform registers) and elect one lane only for the issue instructions; a
-  // lane-0-only loop makes the compiler wrap every UTMALDG / UTCHMMA in a register->uniform "waterfall" loop,
-  // which costs more than a 128 x 64 x 16 MMA itself.
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    bool ok = true;
+  // Producer and MMA roles: ONE elected thread runs the whole schedule (elect.sync: the compiler sees a single active
+  // thread, so TMA / MMA operands move to uniform registers with plain R2UR - no waterfall loop, and no per-iteration
+  // vote / shuffle / reconvergence as in the earlier all-lanes-walk-elect-to-issue form, whose ~80-instruction serial loop
+  // body cost ~700-900 cycles per k-block: 5x the MMA time of a 128x64x64 block, ncu profiles/r2a). Two producer warps
+  // (0 and 3) take alternate k-blocks of the CTA's linear (tile, tap, channel slice) schedule, which halves the issue
+  // latency per k-block again for the short-K convolutions.
+  if (warp == 0 || (warp == 3 && p.nprod == 2)) {
+    // ===================== TMA producers =====================
+    if (tc::elect_one()) {
+      const int me = (warp == 0) ? 0 : 1;
+      const int np = p.nprod;
+      int g = 0;                                  // global k-block counter at the start of the current tile
+      int stage = me % p.stages;
+      uint32_t phase = (uint32_t)((me / p.stages) & 1);
+      bool ok = true;
 #ifdef ISWM_EPI_TIMING
-    long long pw = 0, pt0 = clock64();
+      long long pw = 0, pt0 = clock64();
+      int pn = 0;
 #endif
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h,
-                tb = mt / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB, n0 = nt * p.BN;
-      for (int t = 0; t < p.ntaps && ok; t++) {
-        const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
-        for (int kc = 0; kc < p.kchunks; kc++) {
+      TileIter ti;
+      ti.init(p, blockIdx.x);
+      for (; ti.tile < p.total_tiles && ok; ti.next(p)) {
+        const int w0 = ti.tw * BW, h0 = ti.th * BH, b0 = ti.tb * BB, n0 = ti.nt * p.BN;
+        // first k-block of this tile that is mine: (g + kb) % np == me
+        int kb = me - (g % np);
+        if (kb < 0) kb += np;
+        int t = kb / p.kchunks, kc = kb - t * p.kchunks;
+        for (; kb < kblocks; kb += np) {
 #ifdef ISWM_EPI_TIMING
           const long long w0c = clock64();
 #endif
-          ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 1) ? 1 : 0, 0) != 0;
+          ok = tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 1);
           if (!ok) break;
 #ifdef ISWM_EPI_TIMING
-          pw += clock64() - w0c;
+          pw += clock64() - w0c; pn++;
 #endif
+          const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
           const uint32_t a_dst = ring + stage * stage_bytes;
-          if (tc::elect_one()) {
-            tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
-            tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, kc * kKBlock, cw, ch, cb);
-            tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage,
-                            t * p.cin_pad + kc * kKBlock, n0);
-          }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
+          tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, kc * kKBlock, cw, ch, cb);
+          tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage, t * p.cin_pad + kc * kKBlock, n0);
+          stage += np;
+          if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+          kc += np;
+          while (kc >= p.kchunks) { kc -= p.kchunks; t++; }
         }
+        g += kblocks;
       }
-    }
 #ifdef ISWM_EPI_TIMING
-    if (blockIdx.x == 0 && lane == 0) printf("producer: total %lld  waiting for a free stage %lld  (stages %d, kblocks/tile %d)\n", clock64() - pt0, pw, p.stages, kblocks);
+      if (blockIdx.x == 0) printf("producer %d: total %lld  waiting for a free stage %lld  k-blocks issued %d (stages %d, kblocks/tile %d, nprod %d)\n", me, clock64() - pt0, pw, pn, p.stages, kblocks, np);
 #endif
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 0, 0);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int stage = 0, as = 0;
-    uint32_t phase = 0, aphase = 0;
-    bool ok = true;
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      bool ok = true;
 #ifdef ISWM_EPI_TIMING
-    long long mw_acc = 0, mw_full = 0, mt0 = clock64();
+      long long mw_acc = 0, mw_full = 0, mt0 = clock64(), c0;
+      int ntl = 0;
 #endif
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += p.step) {
 #ifdef ISWM_EPI_TIMING
-      long long c0 = clock64();
+        c0 = clock64(); ntl++;
 #endif
-      ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 2) ? 1 : 0, 0) != 0;
-      if (!ok) break;
-      tc::tc_fence_after();
-#ifdef ISWM_EPI_TIMING
-      mw_acc += clock64() - c0;
-#endif
-      const uint32_t d_tmem = tmem_u + (uint32_t)(as * p.BN);
-      for (int kb = 0; kb < kblocks; kb++) {
-#ifdef ISWM_EPI_TIMING
-        c0 = clock64();
-#endif
-        ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 3) ? 1 : 0, 0) != 0;
+        ok = tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 2);
         if (!ok) break;
         tc::tc_fence_after();
 #ifdef ISWM_EPI_TIMING
-        mw_full += clock64() - c0;
+        mw_acc += clock64() - c0;
 #endif
-        const uint32_t a_addr = ring + stage * stage_bytes;
-        const uint64_t da = tc::make_smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t db = tc::make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
-        if (tc::elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        for (int kb = 0; kb < kblocks; kb++) {
+#ifdef ISWM_EPI_TIMING
+          c0 = clock64();
+#endif
+          ok = tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 3);
+          if (!ok) break;
+          tc::tc_fence_after();
+#ifdef ISWM_EPI_TIMING
+          mw_full += clock64() - c0;
+#endif
+          const uint32_t a_addr = ring + stage * stage_bytes;
+          const uint64_t da = tc::make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = tc::make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kKBlock / 16; k++)
             tc::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           tc::umma_commit(bar_empty + 8 * stage);     // frees this smem stage when the MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (!ok) break;
+        tc::umma_commit(bar_tfull + 8 * as);          // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
       }
-      if (!ok) break;
-      if (tc::elect_one()) tc::umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
-      __syncwarp();
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
-    }
 #ifdef ISWM_EPI_TIMING
-    if (blockIdx.x == 0 && lane == 0) printf("mma: total %lld  waiting for operands %lld  waiting for a free accumulator %lld\n", clock64() - mt0, mw_full, mw_acc);
+      if (blockIdx.x == 0) printf("mma: total %lld  waiting for operands %lld  waiting for a free accumulator %lld  (tiles %d)\n", clock64() - mt0, mw_full, mw_acc, ntl);
 #endif
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue: two warpgroups, 64-channel chunks alternate between them =====================
     const int nchunk64 = (p.BN + 63) >> 6;
@@ -235,7 +286,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool f_aff = p.flags & ISWM_EPI_AFFINE, f_relu = p.flags & ISWM_EPI_RELU,
                f_res = p.flags & ISWM_EPI_RESIDUAL, f_stats = p.flags & ISWM_EPI_STATS,
                f_f32 = p.flags & ISWM_EPI_OUT_F32;
-    const bool issuer = (row == 0);                     // issues this warpgroup's TMA stores
+    // Each epilogue WARP is independent between channel-tile changes: it stages its own 32 rows (a 4 KiB, 1 KiB-aligned
+    // slice of the warpgroup's staging tile), issues its own TMA store (a 32-pixel sub-box of the tile) and sums its own
+    // rows for the statistics - __syncwarp() instead of three 128-thread named barriers per chunk, so the eight warps
+    // drift apart and hide each other's TMEM-load / shared-memory latencies (the epilogue bounds every short-K convolution).
+    const bool issuer = (lane == 0);                    // issues this warp's TMA stores
+    const int srow = q * 32;                            // first tile row of this warp: its sub-box origin inside the tile
+    const int sub_b = srow >> (p.lgBW + p.lgBH), sub_h = (srow >> p.lgBW) & (BH - 1), sub_w = srow & (BW - 1);
     const uint32_t ob = obuf + (uint32_t)wg * kStageBuf; // this warpgroup's 128 x 64 bf16 staging tile
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);            // 128B swizzle: 16-byte chunk index ^= row % 8
@@ -251,7 +308,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // fixed order, then ONE fp64 atomic per channel and component leaves the CTA (fp64: the order in which CTAs
     // arrive does not show up in the fp32 mean / variance, so a training step is reproducible bit for bit)
     auto flush_stats = [&](int n0f) {
-      if (issuer) tc::tma_store_wait_read<0>();
+      if (issuer) tc::tma_store_wait_read<0>();        // every warp's stores have left the staging tile
       asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
 #pragma unroll
       for (int slot = 0; slot < NSLOT; slot++)
@@ -295,27 +352,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // issuing thread reads it back, so no barrier is involved.
     const uint32_t rb_row = rbuf + (uint32_t)wg * kStageBuf + row_off;
     const bool res_pf_ok = f_res && p.res_prefetch != 0;
-    auto chunk_owner_ok = [&](int tile_, int it_, int c_) -> bool {
+    auto chunk_owner_ok = [&](const TileIter& ti_, int it_, int c_) -> bool {
       if (owner_of(it_, c_) != wg) return false;
-      const int n0_ = (tile_ % p.tiles_n) * p.BN;
-      return n0_ + c_ * 64 < p.Cout;
+      return ti_.nt * p.BN + c_ * 64 < p.Cout;
     };
-    // advance (tile_, it_, c_) to the next chunk this warpgroup owns; false when the CTA's schedule is exhausted
-    auto next_chunk = [&](int& tile_, int& it_, int& c_) -> bool {
+    // advance (ti_, it_, c_) to the next chunk this warpgroup owns; false when the CTA's schedule is exhausted
+    auto next_chunk = [&](TileIter& ti_, int& it_, int& c_) -> bool {
       c_++;
-      while (tile_ < p.total_tiles) {
+      while (ti_.tile < p.total_tiles) {
         for (; c_ < nchunk64; c_++)
-          if (chunk_owner_ok(tile_, it_, c_)) return true;
-        tile_ += gridDim.x; it_++; c_ = 0;
+          if (chunk_owner_ok(ti_, it_, c_)) return true;
+        ti_.next(p); it_++; c_ = 0;
       }
       return false;
     };
-    // issue the prefetch of chunk (tile_, c_); returns whether the vector path applies to it for this thread
-    auto prefetch_res = [&](int tile_, int c_) -> bool {
-      const int mt_ = tile_ / p.tiles_n, nt_ = tile_ - mt_ * p.tiles_n;
-      const int tw_ = mt_ % p.tiles_w, th_ = (mt_ / p.tiles_w) % p.tiles_h, tb_ = mt_ / (p.tiles_w * p.tiles_h);
-      const int w_ = tw_ * BW + ww, h_ = th_ * BH + hh, b_ = tb_ * BB + bb;
-      const int nc_ = nt_ * p.BN + c_ * 64;
+    // issue the prefetch of chunk (ti_, c_); returns whether the vector path applies to it for this thread
+    auto prefetch_res = [&](const TileIter& ti_, int c_) -> bool {
+      const int w_ = ti_.tw * BW + ww, h_ = ti_.th * BH + hh, b_ = ti_.tb * BB + bb;
+      const int nc_ = ti_.nt * p.BN + c_ * 64;
       const bool ok_ = (b_ < p.B) && (h_ < p.Ho) && (w_ < p.Wo) && min(p.BN - c_ * 64, p.Cout - nc_) >= 64;
       if (ok_) {
         const __nv_bfloat16* rp = p.res + (((size_t)b_ * p.Ho + h_) * p.Wo + w_) * (size_t)p.res_ld + nc_;
@@ -326,11 +380,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       asm volatile("cp.async.commit_group;" ::: "memory");
       return ok_;
     };
-    int pf_tile = blockIdx.x, pf_it = 0, pf_c = -1;
+    TileIter pf_ti;
+    pf_ti.init(p, blockIdx.x);
+    int pf_it = 0, pf_c = -1;
     bool pf_more = false, pf_vec = false;
     if (res_pf_ok) {
-      pf_more = next_chunk(pf_tile, pf_it, pf_c);
-      if (pf_more) pf_vec = prefetch_res(pf_tile, pf_c);
+      pf_more = next_chunk(pf_ti, pf_it, pf_c);
+      if (pf_more) pf_vec = prefetch_res(pf_ti, pf_c);
     }
     int as = 0, it = 0, cur_n0 = -1;
     uint32_t aphase = 0;
@@ -341,10 +397,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #else
 #define TMARK(i)
 #endif
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB, n0 = nt * p.BN;
+    TileIter ti;
+    ti.init(p, blockIdx.x);
+    for (; ti.tile < p.total_tiles; ti.next(p), it++) {
+      const int w0 = ti.tw * BW, h0 = ti.th * BH, b0 = ti.tb * BB, n0 = ti.nt * p.BN;
       const int w = w0 + ww, h = h0 + hh, b = b0 + bb;
       const bool valid = (b < p.B) && (h < p.Ho) && (w < p.Wo);
       const size_t pix = ((size_t)b * p.Ho + h) * p.Wo + w;
@@ -381,7 +437,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 8; j++) rr[j] = rp[j];
         }
-        if (res_pf_ok) {                                   // (pf_tile, pf_c) == (tile, c64) by construction
+        if (res_pf_ok) {                                   // (pf_ti.tile, pf_c) == (ti.tile, c64) by construction
           asm volatile("cp.async.wait_group 0;" ::: "memory");
           if (res_vec) {
 #pragma unroll
@@ -389,8 +445,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[j].x), "=r"(rr[j].y), "=r"(rr[j].z), "=r"(rr[j].w)
                            : "r"(rb_row + ((((uint32_t)j) ^ sw) << 4)));
           }
-          pf_more = next_chunk(pf_tile, pf_it, pf_c);      // the row is in registers: refill the tile for the next chunk
-          if (pf_more) pf_vec = prefetch_res(pf_tile, pf_c);
+          pf_more = next_chunk(pf_ti, pf_it, pf_c);        // the row is in registers: refill the tile for the next chunk
+          if (pf_more) pf_vec = prefetch_res(pf_ti, pf_c);
         }
         tc::tmem_ld_wait();
         TMARK(2)
@@ -445,16 +501,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // statistics readers, who arrive at this barrier after their loop)
           TMARK(0)
           if (issuer) tc::tma_store_wait_read<0>();
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
+          __syncwarp();
           TMARK(3)
 #pragma unroll
           for (int j = 0; j < 8; j++)
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ob + row_off + ((((uint32_t)j) ^ sw) << 4)),
                          "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
           tc::fence_proxy_async();                        // staging writes -> visible to the TMA engine
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
+          __syncwarp();
           if (issuer) {
-            tc::tma_store_4d(&tmap_out, ob, nc, w0, h0, b0);
+            tc::tma_store_4d(&tmap_out, ob + (uint32_t)srow * 128u, nc, w0 + sub_w, h0 + sub_h, b0 + sub_b);
             tc::tma_store_commit();
           }
           TMARK(4)
@@ -479,7 +535,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
               }
             }
-            st[slot][0] += s0; st[slot][1] += s1; st[slot][2] += q0; st[slot][3] += q1;
+            // predicated adds on statically indexed registers (a runtime index put the array in local memory)
+#pragma unroll
+            for (int sl = 0; sl < NSLOT; sl++) {
+              const bool mine = (sl == slot);
+              st[sl][0] += mine ? s0 : 0.f; st[sl][1] += mine ? s1 : 0.f; st[sl][2] += mine ? q0 : 0.f; st[sl][3] += mine ? q1 : 0.f;
+            }
             TMARK(5)
           }
         } else if (valid) {
@@ -522,6 +583,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_base, kTmemCols);
+#ifdef ISWM_EPI_TIMING
+  if (threadIdx.x == 0) {
+    unsigned long long gt_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_end));
+    printf("CTA %d entry %llu prologue +%llu dep +%llu end +%llu\n", blockIdx.x, gt_entry, gt_prol - gt_entry, gt_dep - gt_entry, gt_end - gt_entry);
+  }
+#endif
 }
 
 static int ilog2_ceil(int v) {
@@ -636,7 +704,9 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   CUtensorMap tmap_out = tmap_a;                         // placeholder when unused
   if (p.use_tma_out) {
     const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
-    const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};
+    // one store per epilogue warp: the 32 consecutive tile rows of a warp are a sub-box of the 128-pixel tile
+    const int sBW = std::min(BW, 32), sBH = std::min(BH, 32 / sBW), sBB = 32 / (sBW * sBH);
+    const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)sBW, (uint32_t)sBH, (uint32_t)sBB};
     const uint64_t str[4] = {1, (uint64_t)d->out_ld, (uint64_t)Wo * d->out_ld, (uint64_t)Ho * Wo * d->out_ld};
     if (int rc = encode_tmap_bf16(&tmap_out, d_out, 4, dims, str, box)) return rc;
   }
@@ -650,6 +720,20 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, num_sms());
+  {
+    // mixed-radix digits of the grid size over (tiles_n, tiles_w, tiles_h, tiles_b) for TileIter::next
+    int r = grid;
+    p.step = grid;
+    p.s_nt = r % p.tiles_n; r /= p.tiles_n;
+    p.s_tw = r % p.tiles_w; r /= p.tiles_w;
+    p.s_th = r % p.tiles_h; r /= p.tiles_h;
+    p.s_tb = r;
+  }
+  // second producer warp: pays off when a k-block's MMA time (128 x BN x 64) is short against the ~300-cycle issue path of
+  // one producer thread, i.e. for narrow N tiles; ISWM_CONV_NPROD=1/2 forces it
+  static const int env_np = [] { const char* e = getenv("ISWM_CONV_NPROD"); return e ? atoi(e) : 0; }();
+  p.nprod = (env_np == 1 || env_np == 2) ? env_np : ((BN <= 128 && p.stages >= 4 && nwg == 2) ? 2 : 1);
+  if (nwg != 2) p.nprod = 1;                              // with three epilogue warpgroups warp 3 does not exist as a spare
   if (nwg == 3)
     launch_k(conv_igemm_kernel<3>, dim3(grid), dim3(512), smem_bytes, static_cast<cudaStream_t>(stream), tmap_a, tmap_b, tmap_out, p);
   else

@@ -14,6 +14,7 @@
 // produced by loss.backward() at train.py:1048.
 #include "tc_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace iswm {
 
@@ -35,6 +36,7 @@ struct WgradKParams {
   long long kblocks_per_cta;      // stream-K mode: equal contiguous ranges of the linearised (tile, pixel block) space
   int splits, split_len;          // split mode (splits > 0): CTA = (tile, split); same-split CTAs walk the same pixels
   int vec_red;
+  int nprod;                      // producer warps (1 or 2) taking alternate pixel blocks
   int n_img_per_phase;
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   float* dwgt;
@@ -112,79 +114,89 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
     range_hi = min(range_lo + p.kblocks_per_cta, p.total_kblocks);
   }
 
-  // producer / MMA warps: warp-uniform loops, one elected lane issues (see conv_igemm.cu)
-  if (warp == 0) {
-    int stage = 0;
-    uint32_t phase = 0;
-    bool ok = true;
-    for (long long cur = range_lo; cur < range_hi && ok;) {
-      const int tile = (int)(cur / p.pix_blocks);
-      const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
-      const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
-      int mt, tap, nt;
-      decode(tile, mt, tap, nt);
-      const int m0 = mt * kWTileM, n0 = nt * p.BN;
-      for (int pb = pb0; pb < pb1; pb++) {
-        const int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h,
-                  tb = pb / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB;
-        ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 11) ? 1 : 0, 0) != 0;
-        if (!ok) break;
-        const uint32_t dst = ring + stage * stage_bytes;
-        const uint32_t bar = bar_full + 8 * stage;
-        const int xw = w0 + p.dw[tap], xh = h0 + p.dh[tap],
-                  xb = p.phase[tap] * p.n_img_per_phase + b0;
-        if (tc::elect_one()) {
+  // producer / MMA roles: ONE elected thread runs the whole schedule (see conv_igemm.cu); producer warps 0 and 3 take
+  // alternate k-blocks (pixel blocks) of the CTA's range; pixel-block coordinates advance incrementally (no divisions
+  // inside the k loop)
+  if (warp == 0 || (warp == 3 && p.nprod == 2)) {
+    if (tc::elect_one()) {
+      const int me = (warp == 0) ? 0 : 1;
+      const int np = p.nprod;
+      int stage = me % p.stages;
+      uint32_t phase = 0;
+      long long q0 = 0;                         // k-blocks of this CTA issued before the current segment
+      bool ok = true;
+      for (long long cur = range_lo; cur < range_hi && ok;) {
+        const int tile = (int)(cur / p.pix_blocks);
+        const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+        const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+        int mt, tap, nt;
+        decode(tile, mt, tap, nt);
+        const int m0 = mt * kWTileM, n0 = nt * p.BN;
+        int off = me - (int)(q0 % np);
+        if (off < 0) off += np;
+        int pb = pb0 + off;
+        int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h, tb = pb / (p.tiles_w * p.tiles_h);
+        const int ddw = p.dw[tap], ddh = p.dh[tap], dph = p.phase[tap] * p.n_img_per_phase;
+        for (; pb < pb1; pb += np) {
+          const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB;
+          ok = tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 11);
+          if (!ok) break;
+          const uint32_t dst = ring + stage * stage_bytes;
+          const uint32_t bar = bar_full + 8 * stage;
+          const int xw = w0 + ddw, xh = h0 + ddh, xb = dph + b0;
           tc::mbar_expect_tx(bar, stage_bytes);
           tc::tma_load_4d(dst, &tmap_dy, bar, m0, w0, h0, b0);
           tc::tma_load_4d(dst + kChunkBytes, &tmap_dy, bar, m0 + 64, w0, h0, b0);
           for (int j = 0; j < p.nchunks_b; j++)
             tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, n0 + 64 * j, xw, xh, xb);
+          stage += np;
+          if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+          tw += np;
+          while (tw >= p.tiles_w) { tw -= p.tiles_w; th++; }
+          while (th >= p.tiles_h) { th -= p.tiles_h; tb++; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        q0 += pb1 - pb0;
+        cur += pb1 - pb0;
       }
-      cur += pb1 - pb0;
     }
+    __syncwarp();
   } else if (warp == 1) {
-    const uint32_t idesc = tc::make_idesc_bf16(kWTileM, p.BN, 1, 1);   // both operands MN-major
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int stage = 0, as = 0;
-    uint32_t phase = 0, aphase = 0;
-    bool ok = true;
-    for (long long cur = range_lo; cur < range_hi && ok;) {
-      const int tile = (int)(cur / p.pix_blocks);
-      const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
-      const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
-      ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 12) ? 1 : 0, 0) != 0;
-      if (!ok) break;
-      tc::tc_fence_after();
-      const uint32_t d_tmem = tmem_u + (uint32_t)(as * p.BN);
-      for (int pb = pb0; pb < pb1; pb++) {
-        ok = __shfl_sync(0xffffffffu, tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 13) ? 1 : 0, 0) != 0;
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(kWTileM, p.BN, 1, 1);   // both operands MN-major
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      bool ok = true;
+      for (long long cur = range_lo; cur < range_hi && ok;) {
+        const int tile = (int)(cur / p.pix_blocks);
+        const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
+        const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+        ok = tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 12);
         if (!ok) break;
         tc::tc_fence_after();
-        const uint32_t a_addr = ring + stage * stage_bytes;
-        // MN-major SW128: LBO = byte stride between 64-channel chunks, SBO = 8 pixel rows
-        const uint64_t da = tc::make_smem_desc_sw128(a_addr, kChunkBytes, 1024);
-        const uint64_t db = tc::make_smem_desc_sw128(a_addr + a_bytes, kChunkBytes, 1024);
-        const uint32_t first = (pb > pb0) ? 1u : 0u;
-        if (tc::elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        for (int pb = pb0; pb < pb1; pb++) {
+          ok = tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 13);
+          if (!ok) break;
+          tc::tc_fence_after();
+          const uint32_t a_addr = ring + stage * stage_bytes;
+          // MN-major SW128: LBO = byte stride between 64-channel chunks, SBO = 8 pixel rows
+          const uint64_t da = tc::make_smem_desc_sw128(a_addr, kChunkBytes, 1024);
+          const uint64_t db = tc::make_smem_desc_sw128(a_addr + a_bytes, kChunkBytes, 1024);
+          const uint32_t first = (pb > pb0) ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < kPixBlock / 16; k++)     // 16 pixel rows = 2048 bytes per MMA
             tc::umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, first | (uint32_t)(k > 0));
           tc::umma_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (!ok) break;
+        tc::umma_commit(bar_tfull + 8 * as);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+        cur += pb1 - pb0;
       }
-      if (!ok) break;
-      if (tc::elect_one()) tc::umma_commit(bar_tfull + 8 * as);
-      __syncwarp();
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
-      cur += pb1 - pb0;
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
@@ -312,6 +324,8 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
   const int stage_bytes = (2 + p.nchunks_b) * kChunkBytes;
   p.stages = std::max(2, std::min(kWStages, kWSmemBudget / stage_bytes));
   p.n_img_per_phase = B;
+  static const int env_np = [] { const char* e = getenv("ISWM_WGRAD_NPROD"); return e ? atoi(e) : 0; }();
+  p.nprod = (env_np == 1 || env_np == 2) ? env_np : (p.stages >= 4 ? 2 : 1);
   for (int t = 0; t < d->ntaps; t++) { p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t]; }
   p.dwgt = d_dw;
   p.abort_flag = abort_flag;

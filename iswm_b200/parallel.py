@@ -84,7 +84,7 @@ class GradBucketer:
 class DataParallel:
     """Wraps an iswm_b200 DeepLabV3 model + criterion for multi-rank training (see module docstring)."""
 
-    def __init__(self, model, criterion, bucket_bytes: int = 25 << 20, group=None):
+    def __init__(self, model, criterion, bucket_bytes: int = 25 << 20, group=None, metrics=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (backend 'nccl', one process per GPU)")
         self.model, self.criterion, self.group = model, criterion, group
@@ -99,6 +99,15 @@ class DataParallel:
         criterion.hist_hook = self._allreduce_hist
         self.engine.grad_ready_hook = self._grad_ready
         self._index = {id(p): i for i, p in enumerate(model.parameters())}
+        if metrics is not None:
+            self.attach_metrics(metrics)
+
+    def attach_metrics(self, metrics):
+        """Validation under data parallelism (SURVEY 8e "Metric"): every rank accumulates the confusion counts of ITS shard on
+        the device; `metrics.get_results()` / `.confusion_matrix` then all-reduce (SUM) the n*n int64 counters once, so every
+        rank reports the whole validation set's numbers - bit-exact by construction (metrics/stream_metrics.py:122)."""
+        metrics.process_group = self.group if self.group is not None else dist.group.WORLD
+        return metrics
 
     def _allreduce_hist(self, hist: torch.Tensor):
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)

@@ -341,17 +341,20 @@ def test_bn_backward_with_dropout_against_torch_with_the_kernels_own_mask(B, C, 
     gd, bd = gamma.to(DEV), beta.to(DEV)
     check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
                                   save.data_ptr(), save[C:].data_ptr(), None, C, 1, p, seed, step.data_ptr(), out.data_ptr(), C, None, st()))
-    # torch: the same unit without dropout, then the mask read off the kernel's output
+    # the keep mask depends on (seed, step, element index) only: the same launch WITHOUT the ReLU leaves bn(x) * keep / (1 - p),
+    # which is zero exactly where the element was dropped (bn(x) == 0 itself has measure zero)
+    probe = torch.empty_like(out)
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+                                  save.data_ptr(), save[C:].data_ptr(), None, C, 0, p, seed, step.data_ptr(), probe.data_ptr(), C, None, st()))
+    mask = (nchw(probe).float().cpu() != 0).float()
+    frac = float(mask.mean())
+    assert abs(frac - (1 - p)) < 0.02, f"keep fraction {frac:.4f} vs 1-p = {1 - p}"
+    # torch: the same unit with that mask injected
     xr = x.float().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     y = F.relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5))
     got = nchw(out).float().cpu()
-    live = y.detach() > 1e-3                          # away from the ReLU edge (bf16 rounding may flip the sign there)
-    keep = got != 0
-    frac = float(keep[live].float().mean())
-    assert abs(frac - (1 - p)) < 0.02, f"keep fraction {frac:.4f} vs 1-p = {1 - p}"
-    close(got[live & keep], (y.detach() / (1 - p))[live & keep], 1e-2, 2e-2)
-    mask = (keep | ~live).float()                      # dropped = live but zero in the kernel's output
+    close(got, (y * mask / (1 - p)).detach(), 1e-2, 2e-2)
     (y * mask / (1 - p)).backward(dout.float())
     dd = nhwc(dout).to(DEV)
     sums = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
@@ -363,11 +366,11 @@ def test_bn_backward_with_dropout_against_torch_with_the_kernels_own_mask(B, C, 
     check(L().iswm_bn_bwd_apply(dd.data_ptr(), C, xd.data_ptr(), C, None, C, M, C, gd.data_ptr(), bd.data_ptr(), save.data_ptr(), save[C:].data_ptr(),
                                 sums.data_ptr(), 1, p, seed, step.data_ptr(), dx.data_ptr(), C, None, 0, dg.data_ptr(), db.data_ptr(), st()))
     scale = float(xr.grad.abs().max())
-    # elements within 1e-3 of the ReLU edge may carry a flipped mask: compare everything, with that small population tolerated
+    # an element whose bn(x) lies within bf16 rounding of the ReLU edge may carry a flipped ReLU mask: tolerated as a tiny population
     err = (nchw(dx).float().cpu() - xr.grad).abs()
     assert float((err > 2e-2 * scale + 2e-2 * xr.grad.abs()).float().mean()) < 2e-3
-    close(dg, gr.grad, 3e-2, 8e-2)
-    close(db, br.grad, 3e-2, 8e-2)
+    close(dg, gr.grad, 3e-2, 2e-2 * float(gr.grad.abs().max()))
+    close(db, br.grad, 3e-2, 2e-2 * float(br.grad.abs().max()))
     # a different step counter draws a different mask (the graph-replayed step advances it on the device)
     out2 = torch.empty_like(out)
     step2 = torch.tensor([8], dtype=torch.int64, device=DEV)

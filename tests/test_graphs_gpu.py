@@ -199,7 +199,7 @@ def test_eval_forward_between_forward_and_backward_keeps_the_tape():
     mb.train()
     lb.backward()
     torch.cuda.synchronize()
-    assert float(la) == float(lb)
+    assert float(la.detach()) == float(lb.detach())
     ga, gb = ma.engine().flat_g, mb.engine().flat_g
     assert float((ga - gb).norm() / ga.norm()) <= 1e-5
     stale = crit(mb(x), y)

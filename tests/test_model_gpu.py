@@ -4,9 +4,11 @@ run on the host CPU with identical weights.
 
 Stated tolerances (north_star asks for "a stated bf16 tolerance, e.g. <= 1e-2 on logits, <= 1e-3 on
 the scalar loss vs the fp32 reference"):
-  * eval mode (BatchNorm folded): logits relative L2 <= 2e-2 and worst logit within 4e-2 of the
-    logit range. Measured 0.7-1.4e-2 (R50) / 1.4e-2 (R101): bf16 storage through 53-104 layers,
-    2^-9 per rounding, random walk.
+  * eval mode (BatchNorm folded) against the REFERENCE's golden logits: relative L2 <= 1e-2 (north_star's figure) and
+    worst logit within 2e-2 of the logit range for ResNet-50 at OS16 / OS8 (measured on B200, r2b: 7.5e-3 / 6.0e-3 /
+    8.4e-3 at 320x320 with every ASPP tap in-image); ResNet-101 OS8 <= 1.5e-2 (measured 1.0e-2: 104 convolutions of bf16
+    storage, 2^-9 per rounding, random walk). Odd-size cases on other weights: within 1.25x the precision-matched
+    CPU oracle's own distance from fp32, never below the 1e-2 gate. Every test prints what it measured (PARITY lines).
   * train mode (batch statistics): bf16 rounding of the pre-BN conv outputs is amplified by every
     batch normalisation (noise relative to |x| becomes noise relative to |x - mean|), so ANY bf16
     implementation drifts several percent from fp32 on these random-weight nets — the
@@ -109,7 +111,7 @@ def test_r50_os16_eval_matches_reference_golden(golden_dir):
     m.to(DEV).eval()
     out = m(torch.tensor(g["x"]).to(DEV))
     assert out.dtype == torch.float32 and tuple(out.shape) == g["eval_logits"].shape
-    logits_close(out.cpu(), g["eval_logits"], "r50_os16_eval_vs_reference_golden")
+    logits_close(out.cpu(), g["eval_logits"], "r50_os16_eval_vs_reference_golden", 1e-2, 2e-2)
 
 
 def test_r50_os16_eval_loss_vs_reference(golden_dir):
@@ -146,7 +148,7 @@ def test_r101_os8_eval_matches_reference_golden(golden_dir):
     m, _ = build("resnet101", 8)
     m.to(DEV).eval()
     out = m(torch.tensor(g["x"]).to(DEV))
-    logits_close(out.cpu(), g["eval_logits"], "r101_os8_eval_vs_reference_golden")
+    logits_close(out.cpu(), g["eval_logits"], "r101_os8_eval_vs_reference_golden", 1.5e-2, 3e-2)   # 104 convolutions deep: measured 1.0e-2
 
 
 def test_r50_os8_eval_matches_reference_golden(golden_dir):
@@ -154,7 +156,7 @@ def test_r50_os8_eval_matches_reference_golden(golden_dir):
     m, _ = build("resnet50", 8)
     m.to(DEV).eval()
     out = m(torch.tensor(g["x"]).to(DEV))
-    logits_close(out.cpu(), g["eval_logits"], "r50_os8_eval_vs_reference_golden")
+    logits_close(out.cpu(), g["eval_logits"], "r50_os8_eval_vs_reference_golden", 1e-2, 2e-2)
 
 
 def test_r50_os8_320_eval_matches_reference_golden(golden_dir):
@@ -169,16 +171,16 @@ def test_r50_os8_320_eval_matches_reference_golden(golden_dir):
     m, sd = build("resnet50", 8)
     m.to(DEV).eval()
     out = m(x.to(DEV)).cpu()
-    logits_close(out[:, :, ::4, ::4], g["logits_s4"], "r50_os8_320_eval_vs_reference_golden(stride-4 lattice)")
+    logits_close(out[:, :, ::4, ::4], g["logits_s4"], "r50_os8_320_eval_vs_reference_golden(stride-4 lattice)", 1e-2, 2e-2)
     got = out.flatten(2)[0][:, torch.tensor(g["pos"])]
-    logits_close(got, g["logits_at_pos"], "r50_os8_320_eval_vs_reference_golden(4096 samples)")
+    logits_close(got, g["logits_at_pos"], "r50_os8_320_eval_vs_reference_golden(4096 samples)", 1e-2, 2e-2)
     o = TM.oracle_model("resnet50", 2, 8)
     o.load_state_dict(sd)
     o.eval()
     with torch.no_grad():
         ref = o(x)
     assert rel_l2(ref[:, :, ::4, ::4], g["logits_s4"]) <= 1e-4          # the oracle is pinned to the reference here too
-    logits_close(out, ref, "r50_os8_320_eval_vs_fp32_oracle(full map)")
+    logits_close(out, ref, "r50_os8_320_eval_vs_fp32_oracle(full map)", 1e-2, 2e-2)
 
 
 def test_r50_os16_train_step_matches_reference_golden(golden_dir):
@@ -253,7 +255,13 @@ def test_eval_odd_sizes_vs_oracle(H, W):
         ref = oracle(x)
     m.to(DEV).eval()
     out = m(x.to(DEV))
-    logits_close(out.cpu(), ref)
+    # seed-3 weights, unlike the golden seed, leave these logits with a small range: the precision-matched CPU oracle (bf16
+    # storage at the engine's rounding points) is itself ~1.3e-2 from fp32 here, reported next to the measurement
+    from oracle import torch_model_q as TQ
+    with torch.no_grad():
+        floor = rel_l2(TQ.forward_q(oracle, x, False), ref)
+    report(f"eval_odd_{H}x{W}_matched_oracle_floor", rel_l2=floor)
+    logits_close(out.cpu(), ref, f"eval_odd_{H}x{W}_vs_fp32_oracle", max(1e-2, 1.25 * floor), 4e-2)
 
 
 def test_state_dict_roundtrip_and_dataparallel_prefix():
