@@ -126,7 +126,7 @@ int iswm_focal_fwd_bwd(const void* d_logits, int logit_dtype, const void* d_labe
 
 /* ---- convolution as implicit GEMM on tcgen05 / TMEM / TMA -------------- */
 
-#define ISWM_MAX_TAPS 16
+#define ISWM_MAX_TAPS 32
 
 /* epilogue flags */
 enum {
@@ -138,8 +138,10 @@ enum {
 };
 
 /* Geometry of one implicit-GEMM convolution over NHWC bf16 activations.
- * out[b,ho,wo,n] = sum_t sum_c in[img(t,b), ho + dh[t], wo + dw[t], c] * wgt[n, t, c]
- * with zero fill outside [0,Hi)x[0,Wi). Strided convolutions are expressed
+ * out[b,ho,wo,n] = sum_t sum_c in[img(t,b), ho + dh[t], wo + dw[t], coff[t] + c] * wgt[n, t, c]
+ * with zero fill outside [0,Hi)x[0,Wi). coff[t] (a multiple of 8, 0 for an ordinary convolution) selects a channel slice
+ * of a wider input buffer per tap: several convolutions that read different slices of one buffer and sum into the same
+ * output run as ONE K-concatenated GEMM (the four ASPP branches' input gradients, iswm_aspp_bwd). Strided convolutions are expressed
  * over the 4 parity phases of the input (phase-major [4][B][Hi][Wi][C]),
  * img(t,b) = phase[t]*B + b.
  * Replaces nn.Conv2d at network/backbone/resnet.py:27-35 (conv3x3/conv1x1),
@@ -154,6 +156,7 @@ typedef struct {
   int32_t res_ld;             /* residual row pitch in elements                */
   int32_t ntaps;
   int8_t  dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
+  int16_t coff[ISWM_MAX_TAPS]; /* per-tap channel offset into the input buffer (elements)  */
   int32_t flags;
 } iswm_conv_desc;
 
@@ -165,6 +168,17 @@ typedef struct {
 int iswm_conv_igemm(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt,
                     void* d_out, const float* d_scale, const float* d_shift,
                     const void* d_res, double* d_stats, void* stream);
+
+/* ASPP backward, data-gradient half (network/_deeplab.py:143-172: the 1x1 branch and the three dilated 3x3 branches all
+ * read the SAME 2048-channel feature map): ONE K-concatenated implicit GEMM
+ *   dfeat[b,h,w,c] (+)= sum_{branch i} sum_{tap t of i} dy_i[b, h - dh_t, w - dw_t, :] . W_i[:, c, t]
+ * over K = (1 + 9 + 9 + 9) taps x Cb channels instead of four data-gradient launches with three read-modify-write passes over
+ * the feature gradient. d_dycat: bf16 [B,H,W,dy_ld], branch i's BatchNorm-backward output in channels [i*Cb, (i+1)*Cb);
+ * d_wcat: bf16 [Cfeat][28][Cb] = the branches' dgrad operands concatenated along the tap axis (iswm_pack_weights_batched,
+ * mode 1, row_ld = 28); rates[3] = the dilations of branches 1..3; d_dfeat bf16 [B,H,W,dfeat_ld]; accumulate != 0 adds to
+ * what d_dfeat holds (e.g. the pooled branch's gradient). Cb %% 64 == 0. */
+int iswm_aspp_bwd(const void* d_dycat, int dy_ld, const void* d_wcat, int B, int H, int W, int Cb, int Cfeat,
+                  const int* rates, void* d_dfeat, int dfeat_ld, int accumulate, void* stream);
 
 /* Weight gradient: dW[n, t, c] += sum_{b,ho,wo} dy[b,ho,wo,n] * in[img(t,b), ho+dh[t], wo+dw[t], c]
  * desc as for the forward conv (Cout = channels of dy). d_dw: float [Cout][ntaps][Cin],
@@ -182,7 +196,9 @@ int iswm_pack_weight_dgrad(const float* d_w, int Cout, int Cin, int RS, int cout
                            void* stream);
 /* One launch for many weight tensors (after an optimiser step): d_jobs is a DEVICE array of n_jobs
  * records; mode 0 = forward operand (as iswm_pack_weight_fwd, pad = cin_pad), mode 1 = dgrad operand
- * (as iswm_pack_weight_dgrad, pad = cout_pad, row_ld unused). The caller deals thread blocks to jobs in
+ * (as iswm_pack_weight_dgrad, pad = cout_pad; row_ld = 0, or the number of taps of a K-CONCATENATED row of which this
+ * tensor's R*S taps are a slice starting at dst: row (c, t) is written at c * row_ld + t, the layout iswm_aspp_bwd
+ * reads). The caller deals thread blocks to jobs in
  * proportion to their size: job i owns blocks [blk_begin, blk_begin + blk_count), blk_begin ascending and
  * contiguous from 0; total_blocks = sum of blk_count. */
 typedef struct {

@@ -49,6 +49,7 @@ struct ConvKParams {
   int use_tma_out;               // bf16 output through smem staging + TMA store
   int res_prefetch;              // residual rows prefetched into shared memory one chunk ahead (short-K convolutions)
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
+  int16_t coff[ISWM_MAX_TAPS];   // per-tap channel offset into the input buffer (K-concatenated convolutions)
   void* out;
   const float* scale;
   const float* shift;
@@ -202,7 +203,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
           const uint32_t a_dst = ring + stage * stage_bytes;
           tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
-          tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, kc * kKBlock, cw, ch, cb);
+          tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, p.coff[t] + kc * kKBlock, cw, ch, cb);
           tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage, t * p.cin_pad + kc * kKBlock, n0);
           stage += np;
           if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
@@ -681,7 +682,14 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   p.n_img_per_phase = B;
   p.out_ld = d->out_ld;
   p.res_ld = d->res_ld;
-  for (int t = 0; t < d->ntaps; t++) { p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t]; }
+  int in_c = d->Cin;                                       // channels the input tensor map must span
+  for (int t = 0; t < d->ntaps; t++) {
+    p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t]; p.coff[t] = d->coff[t];
+    ISWM_REQUIRE(d->coff[t] >= 0 && (d->coff[t] % 8) == 0 && d->coff[t] + d->Cin <= d->in_ld,
+                 "conv_igemm: tap %d channel offset %d (must be a multiple of 8 with offset + Cin <= in_ld)", t, (int)d->coff[t]);
+    ISWM_REQUIRE(d->coff[t] == 0 || (d->Cin % kKBlock) == 0, "conv_igemm: channel-offset taps need Cin %% 64 == 0 (the K tail is zero-filled by the tensor map's edge)");
+    in_c = std::max(in_c, d->coff[t] + d->Cin);
+  }
   p.out = d_out; p.scale = d_scale; p.shift = d_shift;
   p.res = static_cast<const __nv_bfloat16*>(d_res);
   p.stats = d_stats;
@@ -689,7 +697,7 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
 
   CUtensorMap tmap_a, tmap_b;
   {
-    const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)n_img};
+    const uint64_t dims[4] = {(uint64_t)in_c, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)n_img};
     const uint64_t str[4] = {1, (uint64_t)d->in_ld, (uint64_t)Wi * d->in_ld, (uint64_t)Hi * Wi * d->in_ld};
     const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};
     if (int rc = encode_tmap_bf16(&tmap_a, d_in, 4, dims, str, box)) return rc;
@@ -739,4 +747,27 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   else
     launch_k(conv_igemm_kernel<2>, dim3(grid), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), tmap_a, tmap_b, tmap_out, p);
   return check_launch("conv_igemm");
+}
+
+extern "C" int iswm_aspp_bwd(const void* d_dycat, int dy_ld, const void* d_wcat, int B, int H, int W, int Cb, int Cfeat,
+                             const int* rates, void* d_dfeat, int dfeat_ld, int accumulate, void* stream) {
+  ISWM_REQUIRE(d_dycat && d_wcat && d_dfeat && rates, "aspp_bwd: null argument");
+  ISWM_REQUIRE(Cb >= 64 && (Cb % 64) == 0 && 4 * Cb <= dy_ld, "aspp_bwd: Cb=%d must be a multiple of 64 with 4*Cb <= dy_ld=%d", Cb, dy_ld);
+  iswm_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.Hi = H; d.Wi = W; d.Cin = Cb; d.in_ld = dy_ld; d.n_img = B;
+  d.Ho = H; d.Wo = W; d.Cout = Cfeat; d.out_ld = dfeat_ld; d.res_ld = dfeat_ld;
+  int t = 0;
+  d.dh[t] = 0; d.dw[t] = 0; d.phase[t] = 0; d.coff[t] = 0; t++;            // branch 0: 1x1
+  for (int i = 0; i < 3; i++) {
+    const int r = rates[i];
+    ISWM_REQUIRE(r >= 1 && r <= 127, "aspp_bwd: rate %d out of range", r);
+    for (int a = -1; a <= 1; a++)
+      for (int b = -1; b <= 1; b++) {                                          // data gradient: negated forward taps, forward tap ORDER
+        d.dh[t] = (int8_t)(-a * r); d.dw[t] = (int8_t)(-b * r); d.phase[t] = 0; d.coff[t] = (int16_t)((i + 1) * Cb); t++;
+      }
+  }
+  d.ntaps = t;
+  d.flags = accumulate ? ISWM_EPI_RESIDUAL : 0;
+  return iswm_conv_igemm(&d, d_dycat, d_wcat, d_dfeat, nullptr, nullptr, accumulate ? d_dfeat : nullptr, nullptr, stream);
 }

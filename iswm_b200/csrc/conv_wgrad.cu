@@ -326,7 +326,10 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
   p.n_img_per_phase = B;
   static const int env_np = [] { const char* e = getenv("ISWM_WGRAD_NPROD"); return e ? atoi(e) : 0; }();
   p.nprod = (env_np == 1 || env_np == 2) ? env_np : (p.stages >= 4 ? 2 : 1);
-  for (int t = 0; t < d->ntaps; t++) { p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t]; }
+  for (int t = 0; t < d->ntaps; t++) {
+    p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t];
+    ISWM_REQUIRE(d->coff[t] == 0, "conv_wgrad: per-tap channel offsets are a forward / data-gradient feature");
+  }
   p.dwgt = d_dw;
   p.abort_flag = abort_flag;
 

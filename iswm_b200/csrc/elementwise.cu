@@ -246,7 +246,10 @@ pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
           F8 v;
 #pragma unroll
           for (int k = 0; k < 8; k++) v.v[k] = tile[(o + k) * 65 + f];
-          store8(j.dst + (int64_t)(f0 + f) * j.pad + o0 + o, v);
+          // row_ld > 0: this tensor's RS taps are a slice of a K-CONCATENATED row of row_ld taps (dst points at the slice's
+          // first tap): row (c, t) lands at c * row_ld + t instead of c * RS + t
+          const int64_t rowi = j.row_ld > 0 ? (int64_t)((f0 + f) / j.RS) * j.row_ld + (f0 + f) % j.RS : (int64_t)(f0 + f);
+          store8(j.dst + rowi * j.pad + o0 + o, v);
         }
       }
     }

@@ -127,6 +127,9 @@ class Engine:
         self.relu_bits = __import__("os").environ.get("ISWM_RELU_BITS", "1") != "0"
         self.fwd_overlap = __import__("os").environ.get("ISWM_FWD_OVERLAP", "1") != "0"
         self.batch_unpack = __import__("os").environ.get("ISWM_BATCH_UNPACK", "1") != "0"
+        # ASPP backward: one K-concatenated data-gradient GEMM over the four conv branches (iswm_aspp_bwd) instead of four
+        # launches with three read-modify-write passes over the 2048-channel feature gradient
+        self.aspp_fused_bwd = __import__("os").environ.get("ISWM_ASPP_FUSED_BWD", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -207,7 +210,16 @@ class Engine:
                 if s.packed_fwd is None or s.packed_fwd.numel() != Cout * row_ld or s.packed_fwd.device != w.device:
                     s.packed_fwd = torch.empty(Cout * row_ld, dtype=torch.bfloat16, device=w.device)
                 jobs.append((w.data_ptr(), s.packed_fwd.data_ptr(), Cout, Cin, RS, cin_pad, row_ld, 0))
-                if need_dgrad and not s.is_stem:
+                if need_dgrad and s.name in self._aspp_cat_slot():
+                    # the four ASPP conv branches share ONE K-concatenated dgrad operand [Cfeat][28 taps][256]
+                    # (iswm_aspp_bwd): each branch's taps are a slice of the concatenated row
+                    tap_off, taps_total = self._aspp_cat_slot()[s.name]
+                    cout_pad = ((Cout + 63) // 64) * 64
+                    n = Cin * taps_total * cout_pad
+                    if getattr(self, "aspp_wcat", None) is None or self.aspp_wcat.numel() != n or self.aspp_wcat.device != w.device:
+                        self.aspp_wcat = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                    jobs.append((w.data_ptr(), self.aspp_wcat.data_ptr() + 2 * tap_off * cout_pad, Cout, Cin, RS, cout_pad, taps_total, 1))
+                elif need_dgrad and not s.is_stem:
                     cout_pad = ((Cout + 63) // 64) * 64
                     n = Cin * RS * cout_pad
                     if s.packed_dgrad is None or s.packed_dgrad.numel() != n or s.packed_dgrad.device != w.device:
@@ -223,6 +235,24 @@ class Engine:
             w = s.conv.weight
             s.version = (w._version, self.weights_epoch, w.data_ptr())
             s.has_dgrad = need_dgrad and not s.is_stem
+
+    def _aspp_cat_slot(self):
+        """name -> (first tap, total taps) of the ASPP conv branches inside the concatenated dgrad operand; empty when the
+        fused ASPP backward is off (ISWM_ASPP_FUSED_BWD=0) or the branch widths do not allow it."""
+        d = getattr(self, "_aspp_slots", None)
+        if d is None:
+            d = {}
+            br = self.aspp_branches
+            ok = self.aspp_fused_bwd and self.batched_pack and len(br) == 4 and all(b.cout == br[0].cout and b.cin == br[0].cin for b in br) \
+                and br[0].cout % 64 == 0 and br[0].k == 1 and all(b.k == 3 for b in br[1:])
+            if ok:
+                total = sum(b.k * b.k for b in br)
+                off = 0
+                for b in br:
+                    d[b.name] = (off, total)
+                    off += b.k * b.k
+            self._aspp_slots = d
+        return d
 
     def _pack(self, s: ConvSpec, need_dgrad: bool):
         w = s.conv.weight
@@ -351,7 +381,9 @@ class Engine:
 
     # ------------------------------------------------------------------ train-mode unit: conv(+stats) -> BN apply, taped
     def _unit_train(self, s: ConvSpec, x: Act, relu=True, residual: Optional[Act] = None, out: Optional[Act] = None,
-                    drop_p: float = 0.0, need_dx: bool = True) -> Act:
+                    drop_p: float = 0.0, need_dx: bool = True, dy_into: Optional[Callable[[], torch.Tensor]] = None) -> Act:
+        """`dy_into`: called in backward, returns the [B,Ho,Wo,Cout] (possibly channel-sliced) view the BatchNorm backward
+        writes this unit's pre-activation gradient into instead of a private buffer (ASPP: slices of one concatenated buffer)."""
         L = _lib.lib()
         self._pack(s, need_dx)
         xin, taps, n_img, Ho, Wo = self._prep_input(s, x)
@@ -404,7 +436,8 @@ class Engine:
             relu_mode = 1 if use_mask else 0
             if bits is not None:
                 act_ptr, relu_mode = bits.data_ptr(), 2
-            dy = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
+            dy = dy_into() if dy_into is not None else torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
+            dy_ld = dy.stride(2)
             dz_ptr, dz_ld, dz_tmp = None, 0, None
             if residual is not None:
                 if residual.grad is None:
@@ -418,7 +451,7 @@ class Engine:
                 # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
                 check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                     bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
-                                    1 if use_mask else 0, drop_p, seed, step_ptr, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                    1 if use_mask else 0, drop_p, seed, step_ptr, dy.data_ptr(), dy_ld, dz_ptr, dz_ld,
                                     self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd " + s.name)
             else:
@@ -431,7 +464,7 @@ class Engine:
                 ev = self._prof_begin()
                 check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                           bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
-                                          relu_mode, drop_p, seed, step_ptr, dy.data_ptr(), Cout, dz_ptr, dz_ld,
+                                          relu_mode, drop_p, seed, step_ptr, dy.data_ptr(), dy_ld, dz_ptr, dz_ld,
                                           self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()),
                       "bn_bwd_apply " + s.name)
                 self._prof_end(ev, "hbm:bn_bwd_apply", 2.0 * M * Cout * (3 + nmask + (1 if dz_ptr is not None else 0)), "bn_bwd_apply " + s.name)
@@ -452,7 +485,7 @@ class Engine:
         """Weight gradient into the flat fp32 buffer and data gradient into x.grad (assign or accumulate)."""
         L = _lib.lib()
         B, Cout = x.B, s.cout
-        dy_ld = dy.shape[-1]
+        dy_ld = dy.stride(-2) if dy.dim() >= 2 else dy.shape[-1]          # a channel slice of a wider buffer keeps that buffer's pitch
         gview = self.grad_views[id(s.conv.weight)]
         d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps)
         with self._wgrad_ctx(dy, xin.t):
@@ -742,8 +775,36 @@ class Engine:
         br_slices = [cat1.slice(256 * i, 256) for i in range(5)]
         with self._fwd_fork():                               # four tiny latency-bound launches under the big branch convs
             self._aspp_pool(feat, br_slices[4], train)
-        for i, s in enumerate(self.aspp_branches):
-            unit(s, feat, out=br_slices[i])
+        fused_aspp_bwd = train and bool(self._aspp_cat_slot()) and self.debug_units is None   # the unit-replay recorder wants per-unit dx
+        if fused_aspp_bwd:
+            cb = self.aspp_branches[0].cout
+            dycat = [None]
+
+            def dy_slice(i):
+                def get():
+                    if dycat[0] is None:
+                        dycat[0] = torch.empty((B, hf, wf, 4 * cb), dtype=torch.bfloat16, device=dev)
+                    return dycat[0][..., i * cb:(i + 1) * cb]
+                return get
+
+            def aspp_dgrad():
+                # runs after the four branch closures (reverse tape order): every slice of dycat is written
+                first = feat.grad is None
+                if first:
+                    feat.new_grad()
+                g = feat.grad
+                rates = (C.c_int * 3)(*[b.dilation for b in self.aspp_branches[1:]])
+                ev = self._prof_begin()
+                check(L.iswm_aspp_bwd(dycat[0].data_ptr(), 4 * cb, self.aspp_wcat.data_ptr(), B, hf, wf, cb, feat.C, rates,
+                                      g.ptr, g.ld, 0 if first else 1, _st()), "aspp_bwd")
+                self._prof_end(ev, "conv_igemm", 2.0 * B * hf * wf * feat.C * cb * 28, "dgrad classifier.aspp.convs.0-3 (fused)")
+                dycat[0] = None
+            self.tape.append(aspp_dgrad)
+            for i, s in enumerate(self.aspp_branches):
+                self._unit_train(s, feat, out=br_slices[i], need_dx=False, dy_into=dy_slice(i))
+        else:
+            for i, s in enumerate(self.aspp_branches):
+                unit(s, feat, out=br_slices[i])
         self._fwd_join()
         if train:
             self._slice_grad_split(cat1, [(br_slices[i], 256 * i) for i in range(5)])

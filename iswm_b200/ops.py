@@ -196,8 +196,9 @@ def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, H
     d.ntaps = len(taps)
     if d.ntaps > _lib.MAX_TAPS:
         raise ValueError("too many taps")
-    for i, (dh, dw, ph) in enumerate(taps):
-        d.dh[i], d.dw[i], d.phase[i] = dh, dw, ph
+    for i, tap in enumerate(taps):                    # (dh, dw, phase) or (dh, dw, phase, channel offset)
+        d.dh[i], d.dw[i], d.phase[i] = tap[0], tap[1], tap[2]
+        d.coff[i] = tap[3] if len(tap) > 3 else 0
     d.flags = flags
     return d
 
@@ -207,6 +208,15 @@ def conv_igemm(desc: ConvDesc, x: torch.Tensor, wgt: torch.Tensor, out: torch.Te
                res: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
     check(_lib.lib().iswm_conv_igemm(C.byref(desc), _ptr(x), _ptr(wgt), _ptr(out), _ptr(scale),
                                      _ptr(shift), _ptr(res), _ptr(stats), _stream()), "conv_igemm")
+
+
+def aspp_bwd(dycat: torch.Tensor, wcat: torch.Tensor, rates: Sequence[int], dfeat: torch.Tensor, accumulate: bool = False) -> None:
+    """K-concatenated data gradient of the four ASPP conv branches (iswm_aspp_bwd): dycat bf16 [B,H,W,4*Cb], wcat the concatenated
+    dgrad operand [Cfeat][28][Cb], dfeat bf16 [B,H,W,Cfeat] written (or accumulated into)."""
+    B, H, W, C4 = dycat.shape
+    r = (C.c_int * 3)(*[int(v) for v in rates])
+    check(_lib.lib().iswm_aspp_bwd(_ptr(dycat), dycat.stride(2), _ptr(wcat), B, H, W, C4 // 4, dfeat.shape[-1], r, _ptr(dfeat),
+                                   dfeat.stride(2), 1 if accumulate else 0, _stream()), "aspp_bwd")
 
 
 def conv_wgrad(desc: ConvDesc, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor) -> None:

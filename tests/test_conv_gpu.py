@@ -187,3 +187,45 @@ def test_unpack_wgrad_exact(Cout, Cin, RS, beta):
                                             torch.cuda.current_stream().cuda_stream), "unpack_wgrad")
     want = dw.permute(0, 2, 1) + (base if beta else 0)
     assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("B,H,W,Cf,Cb,rates", [(2, 24, 24, 128, 64, (6, 12, 18)), (1, 40, 40, 256, 64, (12, 24, 36)), (2, 9, 11, 128, 128, (6, 12, 18))])
+def test_aspp_bwd_k_concatenated_dgrad(B, H, W, Cf, Cb, rates):
+    """iswm_aspp_bwd: ONE data-gradient GEMM over the 1x1 branch and the three dilated 3x3 branches of ASPP
+    (network/_deeplab.py:143-172), K = 28 taps x Cb, against torch autograd of the four convolutions summed; also the
+    accumulate form and the concatenated operand written by the batched packer (mode 1, row_ld = 28)."""
+    g = torch.Generator().manual_seed(31)
+    feat = torch.randn((B, Cf, H, W), generator=g).to(torch.bfloat16)
+    ws = [torch.randn((Cb, Cf, 1, 1), generator=g) * (2.0 / Cf) ** 0.5] + [torch.randn((Cb, Cf, 3, 3), generator=g) * (2.0 / (9 * Cf)) ** 0.5 for _ in rates]
+    dys = [torch.randn((B, Cb, H, W), generator=g).to(torch.bfloat16) for _ in range(4)]
+    fr = feat.float().requires_grad_(True)
+    outs = [F.conv2d(fr, ws[0].to(torch.bfloat16).float())] + [F.conv2d(fr, ws[i + 1].to(torch.bfloat16).float(), padding=r, dilation=r) for i, r in enumerate(rates)]
+    torch.autograd.backward(outs, [d.float() for d in dys])
+    # concatenated operand through the batched packer
+    wd = [w.to(DEV) for w in ws]
+    wcat = torch.zeros(Cf * 28 * Cb, dtype=torch.bfloat16, device=DEV)
+    jobs, off = [], 0
+    for w in wd:
+        rs = w.shape[2] * w.shape[3]
+        jobs.append((w.data_ptr(), wcat.data_ptr() + 2 * off * Cb, Cb, Cf, rs, Cb, 28, 1))
+        off += rs
+    arr, nblk = _lib.fill_pack_jobs(jobs)
+    jd = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(DEV)
+    _lib.check(_lib.lib().iswm_pack_weights_batched(jd.data_ptr(), len(jobs), nblk, torch.cuda.current_stream().cuda_stream), "pack")
+    # the slice of each branch equals its stand-alone dgrad packing
+    cat = wcat.view(Cf, 28, Cb)
+    off = 0
+    for w in wd:
+        rs = w.shape[2] * w.shape[3]
+        assert torch.equal(cat[:, off:off + rs, :].contiguous().view(-1), ops.pack_weight_dgrad(w))
+        off += rs
+    dycat = torch.cat([_nhwc(d) for d in dys], dim=-1).contiguous().to(DEV)
+    dfeat = torch.zeros((B, H, W, Cf), dtype=torch.bfloat16, device=DEV)
+    ops.aspp_bwd(dycat, wcat, rates, dfeat)
+    _assert_healthy()
+    assert _rel_err(dfeat.float().cpu().permute(0, 3, 1, 2), fr.grad) < 1e-2
+    base = torch.randn((B, H, W, Cf), generator=g).to(torch.bfloat16)
+    acc = base.clone().to(DEV)
+    ops.aspp_bwd(dycat, wcat, rates, acc, accumulate=True)
+    _assert_healthy()
+    assert _rel_err(acc.float().cpu().permute(0, 3, 1, 2), fr.grad + base.float().permute(0, 3, 1, 2)) < 1e-2

@@ -379,3 +379,34 @@ def test_batched_unpack_equals_per_layer_and_accumulates():
     assert rel_l2(grads[True][0], grads[False][0]) <= 1e-5
     assert rel_l2(grads[True][1], 2 * grads[True][0]) <= 1e-3     # second pass: running statistics moved nothing in train mode
     assert rel_l2(grads[True][1], grads[False][1]) <= 1e-5
+
+
+def test_fused_aspp_backward_matches_the_four_launch_form():
+    """ASPP backward as one K-concatenated data-gradient GEMM (iswm_aspp_bwd, the default) against the four separate
+    launches (ISWM_ASPP_FUSED_BWD=0 semantics: engine.aspp_fused_bwd = False): same loss bit for bit (the forward is
+    untouched); the fused form accumulates the four branches in fp32 where the unfused one rounds to bf16 three times, so the
+    parameter gradients agree to bf16 noise."""
+    x = torch.randn((4, 3, 96, 96), generator=torch.Generator().manual_seed(5))
+    y = synth_labels((4, 96, 96), seed=6, fg=0.2, ign=0.05)
+    w = torch.tensor([1.0, 3.0])
+    res = []
+    for fused in (True, False):
+        m, _ = build("resnet50", 16, seed=77)
+        m.to(DEV).train()
+        eng = m.engine()
+        eng.dropout_p = 0.0
+        eng.aspp_fused_bwd = fused
+        crit = CrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
+        loss = crit(m(x.to(DEV)), y.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        assert bool(eng._aspp_cat_slot()) == fused
+        res.append((float(loss.detach()), eng.flat_g.clone(), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    assert res[0][0] == res[1][0]
+    rel = rel_l2(res[0][1], res[1][1])
+    cos = cosine(res[0][1], res[1][1])
+    report("fused_aspp_bwd_vs_unfused", flat_grad_rel_l2=rel, cosine=cos)
+    assert rel <= 3e-2 and cos >= 0.999
+    # the ASPP branches' own weight gradients do not depend on the data-gradient path at all
+    for n in ("classifier.aspp.convs.0.0.weight", "classifier.aspp.convs.2.0.weight"):
+        assert rel_l2(res[0][2][n], res[1][2][n]) <= 1e-5
