@@ -657,26 +657,32 @@ def run_ours(args):
     x_dev, y_dev = synth_batch(B, H, W, rank, device=dev)
     x_host, y_host = synth_batch(B, H, W, rank, pinned=True)
 
-    # single GPU: the step is captured once and replayed as ONE CUDA graph launch (iswm_b200.graphs.GraphedTrainStep, the
-    # recommended API; ISWM_BENCH_GRAPH=0 times the eager ~430-launch step instead). Data-parallel steps stay eager.
-    use_graph = world == 1 and os.environ.get("ISWM_BENCH_GRAPH", "1") != "0"
+    # the step is captured once and replayed as ONE CUDA graph launch (iswm_b200.graphs.GraphedTrainStep, the recommended
+    # API; ISWM_BENCH_GRAPH=0 times the eager ~430-launch step instead). Data-parallel steps are captured too when the
+    # peer-memory transport is up (every exchange is a plain kernel); on the torch.distributed transport they stay eager.
+    use_graph = os.environ.get("ISWM_BENCH_GRAPH", "1") != "0" and (world == 1 or dp.comm_mode == "peer")
     stepper = None
     if use_graph:
         from iswm_b200.graphs import GraphedTrainStep
         try:
-            stepper = GraphedTrainStep(model, crit, opt)
+            stepper = GraphedTrainStep(model, crit, opt, dp=dp)
             stepper(x_dev, y_dev)           # capture now (its warm-up state is restored; then one real step)
             torch.cuda.synchronize()
         except Exception as e:              # never lose the measurement to the launch mode: fall back to eager launches
             print(f"[bench] CUDA graph capture failed ({e!r}); timing the eager step instead", file=sys.stderr)
             stepper = None
+        if world > 1:                       # every rank must take the same path (a rank replaying against ranks launching eagerly would deadlock)
+            okf = torch.tensor([1 if stepper is not None else 0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf) == 0:
+                stepper = None
     eager_only = [False]
 
     def step(x, y):
-        if dp is not None:
-            return dp.train_step(x, y, opt)
         if stepper is not None and not eager_only[0]:
             return stepper(x, y)
+        if dp is not None:
+            return dp.train_step(x, y, opt)
         logits = model(x)
         loss = crit(logits, y)
         opt.zero_grad()
@@ -823,6 +829,8 @@ def run_ours(args):
         "config": {"workload": train_workload_name(args.backbone, args.output_stride, H, W, B),
                    "parallelism": f"dp{world}", "global_batch": B * world,
                    "launch": "one CUDA graph replay per step (GraphedTrainStep)" if stepper is not None else "eager launches",
+                   "comm": None if dp is None else ("peer-memory kernels over NVLink (iswm_b200.peer): histogram / gradient buckets / loss, captured in the graph"
+                                                    if dp.comm_mode == "peer" else "torch.distributed NCCL collectives"),
                    "l2": "no explicit flush: each step streams > 2 GB of activations (>> 126 MB L2)",
                    "e2e_note": "per step: images+labels H2D from pinned memory (HostBatchPrefetcher, copy of batch i+1 under step i) and the loss D2H (DeferredLoss: read on the host one step later, last one before the timer stops)",
                    "whole_step_tensor_frac": (gflop * 1e9 * B * world * args.steps / (ms * 1e-3) / 1e12 / world / peaks().get("bf16_tflops_sustained", 1400.0)) if gflop else None,

@@ -157,7 +157,16 @@ typedef struct {
   int32_t ntaps;
   int8_t  dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   int16_t coff[ISWM_MAX_TAPS]; /* per-tap channel offset into the input buffer (elements)  */
+  int8_t  wtap[ISWM_MAX_TAPS]; /* 0: tap t reads weight tap t; k > 0: weight tap k - 1 (a SUBSET of a packed tensor's taps:
+                                  the per-phase data gradients of a stride-2 convolution)   */
   int32_t flags;
+  /* strided output (all 0 = dense [B,Ho,Wo] rows of out_ld): element strides between consecutive output pixels along w, h and
+   * images, e.g. 2*ld, 2*W*ld, H*W*ld writes one parity phase of a [B,H,W] tensor. The residual, when present, has the
+   * same geometry (its strides are these scaled by res_ld / out_ld; res_ld == out_ld in strided mode). bf16 TMA output only. */
+  int32_t out_ws, out_hs;
+  int64_t out_bs;
+  int32_t w_ntaps;            /* taps per row of the packed weight tensor when wtap[] selects a subset (0 = ntaps) */
+  int32_t reserved_;
 } iswm_conv_desc;
 
 /* d_in: bf16 activations; d_wgt: packed bf16 [Cout][ntaps][Cin_pad] (Cin_pad =
@@ -179,6 +188,21 @@ int iswm_conv_igemm(const iswm_conv_desc* desc, const void* d_in, const void* d_
  * what d_dfeat holds (e.g. the pooled branch's gradient). Cb %% 64 == 0. */
 int iswm_aspp_bwd(const void* d_dycat, int dy_ld, const void* d_wcat, int B, int H, int W, int Cb, int Cfeat,
                   const int* rates, void* d_dfeat, int dfeat_ld, int accumulate, void* stream);
+
+/* ---- data-parallel exchanges over NVLink / NVSwitch PEER MEMORY (csrc/peer_allreduce.cu) --------------------------------
+ * Replaces nn.DataParallel's gradient reduce-add (train.py:970) and the small per-step reductions of SURVEY 8e. All pointer
+ * arrays are HOST arrays of `world` device pointers: rank q's buffer as mapped into THIS rank's address space (symmetric
+ * memory; q == rank is the local buffer). Plain stream-ordered kernels, no host synchronisation: capturable in a CUDA graph.
+ * iswm_peer_barrier: all ranks have reached this point of their streams and everything they wrote before it is visible
+ *   (flag_ptrs[q]: uint32[8] zero-initialised symmetric flags of rank q; d_epoch: this rank's private uint32 barrier count).
+ * iswm_peer_allreduce_f32: buf[offset, offset+n) = sum over ranks, identical bits on every rank (fixed rank order); rank r
+ *   reduces slice r (pull) and stores it to every rank (push). Callers bracket it with two barriers (data ready / stores landed).
+ * iswm_peer_small_publish / _sum: all-reduce of up to 64 int64 or double values through per-rank symmetric slots
+ *   (publish -> barrier -> sum); slot_off (8-byte elements) selects the slot region of a call site. */
+int iswm_peer_barrier(const void* const* flag_ptrs, int rank, int world, uint32_t* d_epoch, void* stream);
+int iswm_peer_allreduce_f32(const void* const* buf_ptrs, int rank, int world, int64_t offset, int64_t n, int max_blocks, void* stream);
+int iswm_peer_small_publish(const void* const* slot_ptrs, int rank, int world, const void* d_src, int n, int slot_off, int is_f64, void* stream);
+int iswm_peer_small_sum(const void* const* slot_ptrs, int world, void* d_dst, int n, int slot_off, int is_f64, void* stream);
 
 /* Weight gradient: dW[n, t, c] += sum_{b,ho,wo} dy[b,ho,wo,n] * in[img(t,b), ho+dh[t], wo+dw[t], c]
  * desc as for the forward conv (Cout = channels of dy). d_dw: float [Cout][ntaps][Cin],

@@ -50,6 +50,9 @@ struct ConvKParams {
   int res_prefetch;              // residual rows prefetched into shared memory one chunk ahead (short-K convolutions)
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   int16_t coff[ISWM_MAX_TAPS];   // per-tap channel offset into the input buffer (K-concatenated convolutions)
+  int8_t wtap[ISWM_MAX_TAPS];    // weight tap each tap reads (a subset of a packed tensor's taps)
+  long long o_ws, o_hs, o_bs;    // output element strides along w / h / image (dense or a strided view)
+  long long r_ws, r_hs, r_bs;    // residual, same geometry
   void* out;
   const float* scale;
   const float* shift;
@@ -204,7 +207,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t a_dst = ring + stage * stage_bytes;
           tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
           tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, p.coff[t] + kc * kKBlock, cw, ch, cb);
-          tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage, t * p.cin_pad + kc * kKBlock, n0);
+          tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage, p.wtap[t] * p.cin_pad + kc * kKBlock, n0);
           stage += np;
           if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
           kc += np;
@@ -373,7 +376,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int nc_ = ti_.nt * p.BN + c_ * 64;
       const bool ok_ = (b_ < p.B) && (h_ < p.Ho) && (w_ < p.Wo) && min(p.BN - c_ * 64, p.Cout - nc_) >= 64;
       if (ok_) {
-        const __nv_bfloat16* rp = p.res + (((size_t)b_ * p.Ho + h_) * p.Wo + w_) * (size_t)p.res_ld + nc_;
+        const __nv_bfloat16* rp = p.res + ((long long)b_ * p.r_bs + (long long)h_ * p.r_hs + (long long)w_ * p.r_ws) + nc_;
 #pragma unroll
         for (int j = 0; j < 8; j++)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rb_row + ((((uint32_t)j) ^ sw) << 4)), "l"(rp + 8 * j) : "memory");
@@ -404,7 +407,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int w0 = ti.tw * BW, h0 = ti.th * BH, b0 = ti.tb * BB, n0 = ti.nt * p.BN;
       const int w = w0 + ww, h = h0 + hh, b = b0 + bb;
       const bool valid = (b < p.B) && (h < p.Ho) && (w < p.Wo);
-      const size_t pix = ((size_t)b * p.Ho + h) * p.Wo + w;
+      const long long opix = (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)w * p.o_ws;   // element offsets
+      const long long rpix = (long long)b * p.r_bs + (long long)h * p.r_hs + (long long)w * p.r_ws;
       if (n0 != cur_n0) {
         if (f_stats && cur_n0 >= 0) flush_stats(cur_n0);
         if (f_aff) {
@@ -434,7 +438,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint4 rr[8];
         const bool res_vec = res_pf_ok ? pf_vec : (f_res && valid && ncols == 64 && (p.res_ld & 7) == 0);
         if (f_res && !res_pf_ok && res_vec) {             // long-K convolution: direct loads, issued under the TMEM read
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * (size_t)p.res_ld + nc);
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix + nc);
 #pragma unroll
           for (int j = 0; j < 8; j++) rr[j] = rp[j];
         }
@@ -480,7 +484,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
           } else if (valid) {
-            const __nv_bfloat16* rp = p.res + pix * (size_t)p.res_ld + nc;
+            const __nv_bfloat16* rp = p.res + rpix + nc;
 #pragma unroll
             for (int j = 0; j < 64; j++)
               if (j < ncols) f[j] += __bfloat162float(rp[j]);
@@ -546,7 +550,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         } else if (valid) {
           if (f_f32) {
-            float* op = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + nc;
+            float* op = reinterpret_cast<float*>(p.out) + opix + nc;
             if (ncols == 64 && (p.out_ld & 3) == 0) {
 #pragma unroll
               for (int j = 0; j < 16; j++)
@@ -557,7 +561,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (j < ncols) op[j] = f[j];
             }
           } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + nc;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + nc;
 #pragma unroll
             for (int j = 0; j < 64; j++)
               if (j < ncols) op[j] = __float2bfloat16_rn(f[j]);
@@ -621,8 +625,9 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   ConvKParams p;
   memset(&p, 0, sizeof(p));
   int B = d->B, Hi = d->Hi, Wi = d->Wi, Ho = d->Ho, Wo = d->Wo, n_img = d->n_img;
+  const bool strided_out = d->out_ws != 0 || d->out_hs != 0 || d->out_bs != 0;
   bool pointwise = (d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->phase[0] == 0 &&
-                    Hi == Ho && Wi == Wo && n_img == B);
+                    Hi == Ho && Wi == Wo && n_img == B && !strided_out);
   if (pointwise) {  // a 1x1 convolution is a plain GEMM over all pixels: no tile-edge waste
     const int64_t M = (int64_t)B * Ho * Wo;
     if (M < (1ll << 31)) {
@@ -682,9 +687,21 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   p.n_img_per_phase = B;
   p.out_ld = d->out_ld;
   p.res_ld = d->res_ld;
+  ISWM_REQUIRE(!strided_out || (d->out_ws >= d->out_ld && d->out_hs > 0 && d->out_bs > 0 && (d->out_ws % 8) == 0 && (d->out_hs % 8) == 0 && (d->out_bs % 8) == 0),
+               "conv_igemm: strided output needs positive strides that are multiples of 8 elements (ws=%d hs=%d bs=%lld)", d->out_ws, d->out_hs, (long long)d->out_bs);
+  ISWM_REQUIRE(!strided_out || p.use_tma_out, "conv_igemm: a strided output view needs the bf16 TMA output path");
+  ISWM_REQUIRE(!strided_out || !(d->flags & ISWM_EPI_RESIDUAL) || d->res_ld == d->out_ld, "conv_igemm: strided residual must share the output geometry");
+  if (strided_out) {
+    p.o_ws = d->out_ws; p.o_hs = d->out_hs; p.o_bs = d->out_bs;
+    p.r_ws = p.o_ws; p.r_hs = p.o_hs; p.r_bs = p.o_bs;
+  } else {
+    p.o_ws = d->out_ld; p.o_hs = (long long)Wo * d->out_ld; p.o_bs = (long long)Ho * Wo * d->out_ld;
+    p.r_ws = d->res_ld; p.r_hs = (long long)Wo * d->res_ld; p.r_bs = (long long)Ho * Wo * d->res_ld;
+  }
   int in_c = d->Cin;                                       // channels the input tensor map must span
   for (int t = 0; t < d->ntaps; t++) {
     p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.phase[t] = d->phase[t]; p.coff[t] = d->coff[t];
+    p.wtap[t] = d->wtap[t] > 0 ? (int8_t)(d->wtap[t] - 1) : (int8_t)t;
     ISWM_REQUIRE(d->coff[t] >= 0 && (d->coff[t] % 8) == 0 && d->coff[t] + d->Cin <= d->in_ld,
                  "conv_igemm: tap %d channel offset %d (must be a multiple of 8 with offset + Cin <= in_ld)", t, (int)d->coff[t]);
     ISWM_REQUIRE(d->coff[t] == 0 || (d->Cin % kKBlock) == 0, "conv_igemm: channel-offset taps need Cin %% 64 == 0 (the K tail is zero-filled by the tensor map's edge)");
@@ -703,7 +720,10 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
     if (int rc = encode_tmap_bf16(&tmap_a, d_in, 4, dims, str, box)) return rc;
   }
   {
-    const uint64_t ktot = (uint64_t)d->ntaps * p.cin_pad;
+    const int w_ntaps = d->w_ntaps > 0 ? d->w_ntaps : d->ntaps;
+    for (int t = 0; t < d->ntaps; t++)
+      ISWM_REQUIRE(p.wtap[t] >= 0 && p.wtap[t] < w_ntaps, "conv_igemm: tap %d reads weight tap %d of %d", t, (int)p.wtap[t], w_ntaps);
+    const uint64_t ktot = (uint64_t)w_ntaps * p.cin_pad;
     const uint64_t dims[2] = {ktot, (uint64_t)d->Cout};
     const uint64_t str[2] = {1, ktot};
     const uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)BN};
@@ -715,7 +735,7 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
     // one store per epilogue warp: the 32 consecutive tile rows of a warp are a sub-box of the 128-pixel tile
     const int sBW = std::min(BW, 32), sBH = std::min(BH, 32 / sBW), sBB = 32 / (sBW * sBH);
     const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)sBW, (uint32_t)sBH, (uint32_t)sBB};
-    const uint64_t str[4] = {1, (uint64_t)d->out_ld, (uint64_t)Wo * d->out_ld, (uint64_t)Ho * Wo * d->out_ld};
+    const uint64_t str[4] = {1, (uint64_t)p.o_ws, (uint64_t)p.o_hs, (uint64_t)p.o_bs};
     if (int rc = encode_tmap_bf16(&tmap_out, d_out, 4, dims, str, box)) return rc;
   }
   const int smem_bytes = p.stages * stage_bytes + fixed;

@@ -106,6 +106,7 @@ class Engine:
         self.step = 0
         self.generation = 0           # train-mode forwards issued so far (a backward must belong to the latest one)
         self.flat_g = None            # fp32 flat gradient buffer (all parameters, registration order)
+        self.ext_flat_g = None        # set by iswm_b200.parallel: a symmetric-memory allocation to use as flat_g
         self.grad_views = {}
         self.wacc = None              # fp32 scratch for k>1 weight gradients
         self.grad_ready_hook: Optional[Callable[[torch.nn.Parameter], None]] = None
@@ -304,8 +305,13 @@ class Engine:
     def _ensure_grad_buffers(self):
         params = self._param_list()
         total = sum(p.numel() for p in params)
+        ext = self.ext_flat_g
+        if ext is not None and (self.flat_g is None or self.flat_g.data_ptr() != ext.data_ptr()):
+            if ext.numel() < total or ext.device != self.device or ext.dtype != torch.float32:
+                raise RuntimeError("external gradient buffer does not fit the model")
+            self.flat_g = None
         if self.flat_g is None or self.flat_g.numel() != total or self.flat_g.device != self.device:
-            self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.flat_g = ext[:total] if ext is not None else torch.zeros(total, dtype=torch.float32, device=self.device)
             self.grad_views = {}
             off = 0
             for p in params:
@@ -513,22 +519,45 @@ class Engine:
             dtaps = [(-a, -b, 0) for (a, b, _) in taps]
             self._dgrad_into(s, x, dy, dy_ld, x.H, x.W, dtaps, x.H, x.W)
         elif s.k == 3:
-            dyz = torch.empty((B, x.H, x.W, Cout), dtype=torch.bfloat16, device=self.device)
-            check(L.iswm_zero_stuff2(dy.data_ptr(), B, Ho, Wo, Cout, x.H, x.W, dyz.data_ptr(), _st()), "zero_stuff2")
-            dtaps = [(-a, -b, 0) for (a, b, _) in ops.conv_taps(3, 1)]
-            self._dgrad_into(s, x, dyz, Cout, x.H, x.W, dtaps, x.H, x.W)
-        else:
-            dsub = torch.empty((B, Ho, Wo, Cin), dtype=torch.bfloat16, device=self.device)
-            dd = ops.make_conv_desc(B, Ho, Wo, Cout, dy_ld, B, Ho, Wo, Cin, Cin, [(0, 0, 0)])
-            ev = self._prof_begin()
-            check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), dsub.data_ptr(), None, None, None, None, _st()), "dgrad " + s.name)
-            self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin, "dgrad " + s.name)
-            if x.grad is None:
+            # stride-2 3x3: each of the four PARITY PHASES of dx is its own small convolution over dy with a subset of the taps
+            # (dx[2a+pu, 2b+pv] = sum over taps r = pu+1 (mod 2), s = pv+1 (mod 2) of dy[a + (r==0), b + (s==0)] . w[r,s]):
+            # 1 + 2 + 2 + 4 taps instead of 9 taps over a zero-stuffed tensor (4x dead MACs and a helper pass)
+            fresh = x.grad is None
+            if fresh:
                 x.new_grad()
-                check(L.iswm_zero_stuff2(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "zero_stuff2")
-            else:
-                assert x.grad.ld == Cin
-                check(L.iswm_scatter2_add(dsub.data_ptr(), B, Ho, Wo, Cin, x.H, x.W, x.grad.ptr, _st()), "scatter2_add")
+            g = x.grad
+            H, W = x.H, x.W
+            flags, res_ld = (0, 0) if fresh else (_lib.EPI_RESIDUAL, g.ld)
+            for pu in (0, 1):
+                rs = [(1, 0)] if pu == 0 else [(0, 1), (2, 0)]            # (forward tap row r, dy row offset)
+                for pv in (0, 1):
+                    ss = [(1, 0)] if pv == 0 else [(0, 1), (2, 0)]
+                    Hp, Wp = (H - pu + 1) // 2, (W - pv + 1) // 2
+                    if Hp <= 0 or Wp <= 0:
+                        continue
+                    ptaps = [(di, dj, 0) for (r, di) in rs for (sx, dj) in ss]
+                    wt = [r * 3 + sx for (r, di) in rs for (sx, dj) in ss]
+                    dd = ops.make_conv_desc(B, Ho, Wo, Cout, dy_ld, B, Hp, Wp, Cin, g.ld, ptaps, flags, res_ld, wtaps=wt,
+                                            out_strides=(2 * g.ld, 2 * W * g.ld, H * W * g.ld), w_ntaps=9)
+                    base = g.ptr + 2 * (pu * W + pv) * g.ld
+                    ev = self._prof_begin()
+                    check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), base, None, None,
+                                            None if fresh else base, None, _st()), "dgrad (phase) " + s.name)
+                    # algorithmic FLOPs of the whole data gradient = those of the forward conv; booked on the last phase
+                    self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin * 9 if (pu, pv) == (1, 1) else 0.0, "dgrad " + s.name)
+        else:
+            # stride-2 1x1 (downsample branch): the data gradient lives on the even-even phase of x only
+            fresh = x.grad is None
+            if fresh:
+                x.new_grad()
+                x.grad.t.zero_()
+            g = x.grad
+            H, W = x.H, x.W
+            dd = ops.make_conv_desc(B, Ho, Wo, Cout, dy_ld, B, Ho, Wo, Cin, g.ld, [(0, 0, 0)], _lib.EPI_RESIDUAL, g.ld,
+                                    out_strides=(2 * g.ld, 2 * W * g.ld, H * W * g.ld))
+            ev = self._prof_begin()
+            check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, None, None, g.ptr, None, _st()), "dgrad " + s.name)
+            self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin, "dgrad " + s.name)
 
     def _batched_unpack(self) -> bool:
         """k x k weight gradients leave their [Cout][tap][Cin] accumulators in ONE launch at the end of the sweep -

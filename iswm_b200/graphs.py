@@ -17,8 +17,11 @@ What makes the replay a TRAINING step rather than a recording of one:
   * the packed bf16 weights are refreshed at the START of the captured step (weights changed at the end of the
     previous one); after a replay the engine is told so, and an eager eval forward repacks.
 The returned loss is a static 0-dim device tensor, overwritten by the next call (copy it, or use DeferredLoss).
-Single process / single GPU; the data-parallel step (iswm_b200.parallel) stays eager: capturing its NCCL all-reduces
-(issued with async_op from the backward hooks) was tried on 2 B200s and hung at the first replay, so it is refused.
+Data parallel: `GraphedTrainStep(model, criterion, optimizer, dp=DataParallel(...))` captures the multi-GPU step too - on
+the peer-memory transport every exchange (class histogram, gradient buckets, loss) is a plain kernel over NVLink peer memory
+on an event-ordered communication stream (iswm_b200.peer), so there is nothing un-capturable in it. (Capturing the
+torch.distributed / NCCL all-reduces issued with async_op from the backward hooks hung at the first replay on 2 B200s in
+round 1; that transport stays eager and is refused here.)
 """
 from __future__ import annotations
 
@@ -26,17 +29,26 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, warmup_steps: int = 2):
+    def __init__(self, model, criterion, optimizer, warmup_steps: int = 2, dp=None):
+        """`dp`: an iswm_b200.parallel.DataParallel on the peer-memory transport - its step (histogram / gradient-bucket /
+        loss exchanges are plain kernels on event-ordered streams) is captured like the single-GPU one; the returned loss is
+        then the GLOBAL loss. Every rank must construct and call the stepper in lockstep."""
         self.model = getattr(model, "module", model)
         self.criterion, self.optimizer = criterion, optimizer
         self.engine = self.model.engine()
         self.warmup_steps = max(1, warmup_steps)
         self.graph = None
         self.images = self.labels = self.loss = None
-        if self.engine.grad_ready_hook is not None:
-            raise RuntimeError("GraphedTrainStep is single-GPU: the data-parallel gradient hooks launch NCCL from Python")
+        self.dp = dp
+        if dp is not None and getattr(dp, "comm_mode", "nccl") != "peer":
+            raise RuntimeError("GraphedTrainStep(dp=...) needs the peer-memory transport (torch.distributed collectives issued from "
+                               "Python hooks are not captured); construct DataParallel(..., comm='peer')")
+        if dp is None and self.engine.grad_ready_hook is not None:
+            raise RuntimeError("this model is wrapped by iswm_b200.parallel.DataParallel: pass it as GraphedTrainStep(..., dp=dp)")
 
     def _eager(self, x, y):
+        if self.dp is not None:
+            return self.dp.train_step(x, y, self.optimizer).detach()
         logits = self.model(x)
         loss = self.criterion(logits, y)
         self.optimizer.zero_grad()

@@ -189,7 +189,8 @@ def crop_flip_u8(src: torch.Tensor, size: Optional[Tuple[int, int]] = None, orig
 
 def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,
                    Cout: int, out_ld: int, taps: Sequence[Tuple[int, int, int]], flags: int = 0,
-                   res_ld: int = 0) -> ConvDesc:
+                   res_ld: int = 0, wtaps: Optional[Sequence[int]] = None,
+                   out_strides: Optional[Tuple[int, int, int]] = None, w_ntaps: int = 0) -> ConvDesc:
     d = ConvDesc()
     d.B, d.Hi, d.Wi, d.Cin, d.in_ld, d.n_img = B, Hi, Wi, Cin, in_ld, n_img
     d.Ho, d.Wo, d.Cout, d.out_ld, d.res_ld = Ho, Wo, Cout, out_ld, res_ld
@@ -199,7 +200,11 @@ def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, H
     for i, tap in enumerate(taps):                    # (dh, dw, phase) or (dh, dw, phase, channel offset)
         d.dh[i], d.dw[i], d.phase[i] = tap[0], tap[1], tap[2]
         d.coff[i] = tap[3] if len(tap) > 3 else 0
+        d.wtap[i] = 0 if wtaps is None else wtaps[i] + 1
     d.flags = flags
+    d.w_ntaps = w_ntaps
+    if out_strides is not None:                      # (w, h, image) element strides of a strided output view
+        d.out_ws, d.out_hs, d.out_bs = out_strides
     return d
 
 

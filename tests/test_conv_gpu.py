@@ -229,3 +229,35 @@ def test_aspp_bwd_k_concatenated_dgrad(B, H, W, Cf, Cb, rates):
     ops.aspp_bwd(dycat, wcat, rates, acc, accumulate=True)
     _assert_healthy()
     assert _rel_err(acc.float().cpu().permute(0, 3, 1, 2), fr.grad + base.float().permute(0, 3, 1, 2)) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout", [(2, 128, 16, 16, 128), (2, 64, 17, 13, 128), (1, 256, 9, 9, 64)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_stride2_3x3_dgrad_by_parity_phases(B, Cin, H, W, Cout, accumulate):
+    """Data gradient of a 3x3 / stride 2 / pad 1 convolution (network/backbone/resnet.py:27-30, first block of layers 2-3) as four
+    small convolutions, one per parity phase of dx, each over a SUBSET of the packed weight taps with a strided output view
+    (iswm_conv_desc.wtap / out_ws / out_hs / out_bs): 1 + 2 + 2 + 4 taps, no zero-stuffed tensor. Odd sizes included."""
+    x, w = _mk(B, Cin, H, W, Cout, 3, seed=17)
+    g = torch.Generator().manual_seed(18)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    dy = torch.randn((B, Cout, Ho, Wo), generator=g).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    F.conv2d(xr, w.to(torch.bfloat16).float(), stride=2, padding=1).backward(dy.float())
+    dyd = _nhwc(dy).to(DEV)
+    wd = ops.pack_weight_dgrad(w.to(DEV))
+    base = torch.randn((B, H, W, Cin), generator=g).to(torch.bfloat16)
+    dx = base.clone().to(DEV) if accumulate else torch.full((B, H, W, Cin), 7.0, dtype=torch.bfloat16, device=DEV)
+    for pu in (0, 1):
+        rs = [(1, 0)] if pu == 0 else [(0, 1), (2, 0)]
+        for pv in (0, 1):
+            ss = [(1, 0)] if pv == 0 else [(0, 1), (2, 0)]
+            Hp, Wp = (H - pu + 1) // 2, (W - pv + 1) // 2
+            taps = [(di, dj, 0) for (r, di) in rs for (s, dj) in ss]
+            wt = [r * 3 + s for (r, di) in rs for (s, dj) in ss]
+            d = ops.make_conv_desc(B, Ho, Wo, Cout, Cout, B, Hp, Wp, Cin, Cin, taps, _lib.EPI_RESIDUAL if accumulate else 0, Cin if accumulate else 0,
+                                   wtaps=wt, out_strides=(2 * Cin, 2 * W * Cin, H * W * Cin), w_ntaps=9)
+            view = dx.view(-1)[(pu * W + pv) * Cin:]
+            ops.conv_igemm(d, dyd, wd, view, res=view if accumulate else None)
+    _assert_healthy()
+    want = xr.grad + (base.float().permute(0, 3, 1, 2) if accumulate else 0)
+    assert _rel_err(dx.float().cpu().permute(0, 3, 1, 2), want) < 1e-2

@@ -44,13 +44,20 @@ y[: B // 2] = synth_labels((B // 2, H, W), seed=13, fg=0.85)       # very differ
 w = torch.tensor([1.0, 4.0])
 xs, ys = x.chunk(world)[rank].to(dev), y.chunk(world)[rank].to(dev)
 
+COMM = os.environ.get("ISWM_TEST_COMM", "peer")
 model = build()
 crit = CrossEntropyLoss(weight=w).to(dev)
-dp = DataParallel(model, crit, bucket_bytes=4 << 20)
+dp = DataParallel(model, crit, bucket_bytes=4 << 20, comm=COMM)
+assert dp.comm_mode == COMM, dp.comm_mode
 loss = dp.train_step(xs, ys, optimizer=None)
 torch.cuda.synchronize()
 flat = model.engine().flat_g.clone()
 nb = len(dp.bucketer.bounds)
+# every rank holds the SAME reduced gradient bits (fixed-order sums of the peer transport; NCCL's ring order is also rank-independent)
+chk = flat.double().sum().reshape(1)
+lst = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(lst, chk)
+assert all(float(a) == float(lst[0]) for a in lst), [float(a) for a in lst]
 
 if rank == 0:
     # single-GPU restatement: per-shard forward/backward with the global denominator, gradients summed
@@ -74,15 +81,42 @@ if rank == 0:
     assert abs(float(loss) - num) <= 1e-6 * abs(num), (float(loss), num)
     assert nb > 1
 dist.barrier()
+if COMM == "peer":
+    # the data-parallel step replayed from ONE CUDA graph against the same steps launched eagerly, from the same state
+    from iswm_b200.graphs import GraphedTrainStep
+    from iswm_b200.optim import FusedSGD
+    res = []
+    for graphed in (False, True):
+        m = build()
+        c = CrossEntropyLoss(weight=w).to(dev)
+        d = DataParallel(m, c, bucket_bytes=4 << 20, comm="peer")
+        opt = FusedSGD(m, lr=1e-2, momentum=0.9, weight_decay=1e-4)
+        stepper = GraphedTrainStep(m, c, opt, dp=d) if graphed else None
+        losses = []
+        for _ in range(2):
+            l = stepper(xs, ys) if graphed else d.train_step(xs, ys, opt)
+            losses.append(float(l))
+        torch.cuda.synchronize()
+        res.append((losses, m.engine().flat_w.clone()))
+        m.engine().grad_ready_hook = None
+        dist.barrier()
+    (le, we), (lg, wg) = res
+    relw = float((wg - we).norm() / we.norm())
+    if rank == 0:
+        print(f"GRAPH_DP losses eager={le} graph={lg} rel_w={relw:.3e}")
+    assert abs(le[0] - lg[0]) <= 1e-6 * abs(le[0]), (le, lg)
+    assert relw <= 1e-5, relw
+dist.barrier()
 dist.destroy_process_group()
 '''
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_dataparallel_two_ranks_match_per_shard_restatement(tmp_path):
+@pytest.mark.parametrize("comm", ["peer", "nccl"])
+def test_dataparallel_two_ranks_match_per_shard_restatement(tmp_path, comm):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, ISWM_ROOT=ROOT)
+    env = dict(os.environ, ISWM_ROOT=ROOT, ISWM_TEST_COMM=comm)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
