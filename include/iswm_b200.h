@@ -134,7 +134,8 @@ enum {
   ISWM_EPI_RELU     = 2,
   ISWM_EPI_RESIDUAL = 4,  /* y += residual (bf16, same geometry, own ld)      */
   ISWM_EPI_STATS    = 8,  /* accumulate per-channel fp32 sum / sum^2 of the STORED bf16 outputs (needs bf16 out, out_ld % 8 == 0) */
-  ISWM_EPI_OUT_F32  = 16  /* write fp32 instead of bf16                       */
+  ISWM_EPI_OUT_F32  = 16, /* write fp32 instead of bf16                       */
+  ISWM_EPI_RES_MASK = 32  /* the residual is gated by packed ReLU sign bits (iswm_conv_igemm_ex): y += res * bit  */
 };
 
 /* Geometry of one implicit-GEMM convolution over NHWC bf16 activations.
@@ -177,6 +178,13 @@ typedef struct {
 int iswm_conv_igemm(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt,
                     void* d_out, const float* d_scale, const float* d_shift,
                     const void* d_res, double* d_stats, void* stream);
+/* Same, plus d_res_mask for ISWM_EPI_RES_MASK: uint8 [B*Ho*Wo][Cout/8] ReLU sign bits as written by iswm_bn_train_apply; the
+ * residual element of channel c is added only where bit c is set. Used by the backward of a bottleneck block: the block
+ * input's gradient = conv1's data gradient + (block output gradient where the block's ReLU was active), so the identity
+ * path's gradient (resnet.py:112-118) is never written out as a tensor of its own. */
+int iswm_conv_igemm_ex(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt,
+                       void* d_out, const float* d_scale, const float* d_shift,
+                       const void* d_res, double* d_stats, const uint8_t* d_res_mask, void* stream);
 
 /* ASPP backward, data-gradient half (network/_deeplab.py:143-172: the 1x1 branch and the three dilated 3x3 branches all
  * read the SAME 2048-channel feature map): ONE K-concatenated implicit GEMM

@@ -57,6 +57,7 @@ struct ConvKParams {
   const float* scale;
   const float* shift;
   const __nv_bfloat16* res;
+  const uint8_t* mask;           // ISWM_EPI_RES_MASK: ReLU sign bits [pixels][Cout/8] gating the residual (dz = dout . mask)
   double* stats;                 // fp64 accumulators: cross-CTA summation order no longer shows up in fp32 results
   int* abort_flag;
 };
@@ -288,7 +289,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int hh = (row >> p.lgBW) & (BH - 1);
     const int ww = row & (BW - 1);
     const bool f_aff = p.flags & ISWM_EPI_AFFINE, f_relu = p.flags & ISWM_EPI_RELU,
-               f_res = p.flags & ISWM_EPI_RESIDUAL, f_stats = p.flags & ISWM_EPI_STATS,
+               f_res = p.flags & ISWM_EPI_RESIDUAL, f_stats = p.flags & ISWM_EPI_STATS, f_mask = p.flags & ISWM_EPI_RES_MASK,
                f_f32 = p.flags & ISWM_EPI_OUT_F32;
     // Each epilogue WARP is independent between channel-tile changes: it stages its own 32 rows (a 4 KiB, 1 KiB-aligned
     // slice of the warpgroup's staging tile), issues its own TMA store (a 32-pixel sub-box of the tile) and sums its own
@@ -453,6 +454,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           pf_more = next_chunk(pf_ti, pf_it, pf_c);        // the row is in registers: refill the tile for the next chunk
           if (pf_more) pf_vec = prefetch_res(pf_ti, pf_c);
         }
+        unsigned long long mbits = ~0ull;                 // residual gate: bit j = channel nc + j of this pixel
+        if (f_mask && valid && ncols == 64)
+          mbits = *reinterpret_cast<const unsigned long long*>(p.mask + (((size_t)b * p.Ho + h) * p.Wo + w) * (size_t)(p.Cout >> 3) + (nc >> 3));
         tc::tmem_ld_wait();
         TMARK(2)
         float f[64];
@@ -479,6 +483,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               for (int k = 0; k < 4; k++) {
                 float lo, hi;
                 unpack_bf16x2(r4[k], lo, hi);
+                if (f_mask) {
+                  lo = ((mbits >> (8 * j + 2 * k)) & 1ull) ? lo : 0.f;
+                  hi = ((mbits >> (8 * j + 2 * k + 1)) & 1ull) ? hi : 0.f;
+                }
                 f[8 * j + 2 * k] += lo;
                 f[8 * j + 2 * k + 1] += hi;
               }
@@ -487,7 +495,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const __nv_bfloat16* rp = p.res + rpix + nc;
 #pragma unroll
             for (int j = 0; j < 64; j++)
-              if (j < ncols) f[j] += __bfloat162float(rp[j]);
+              if (j < ncols && ((mbits >> j) & 1ull)) f[j] += __bfloat162float(rp[j]);
           }
         }
         if (f_relu) {
@@ -610,7 +618,16 @@ using namespace iswm;
 extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const void* d_wgt,
                                void* d_out, const float* d_scale, const float* d_shift,
                                const void* d_res, double* d_stats, void* stream) {
+  return iswm_conv_igemm_ex(d, d_in, d_wgt, d_out, d_scale, d_shift, d_res, d_stats, nullptr, stream);
+}
+
+extern "C" int iswm_conv_igemm_ex(const iswm_conv_desc* d, const void* d_in, const void* d_wgt,
+                                  void* d_out, const float* d_scale, const float* d_shift,
+                                  const void* d_res, double* d_stats, const uint8_t* d_res_mask, void* stream) {
   if (debug_skip(ISWM_SKIP_CONV_IGEMM)) return 0;
+  ISWM_REQUIRE(!(d && (d->flags & ISWM_EPI_RES_MASK)) || (d_res_mask && (d->flags & ISWM_EPI_RESIDUAL) && (d->Cout % 64) == 0 &&
+                                                          d->out_ws == 0 && d->out_hs == 0 && d->out_bs == 0),
+               "conv_igemm: RES_MASK needs RESIDUAL, the bit tensor, Cout %% 64 == 0 and a dense output");
   ISWM_REQUIRE(d && d_in && d_wgt && d_out, "conv_igemm: null argument");
   ISWM_REQUIRE(d->ntaps >= 1 && d->ntaps <= ISWM_MAX_TAPS, "conv_igemm: ntaps=%d", d->ntaps);
   ISWM_REQUIRE(d->Cin >= 1 && d->Cout >= 1 && d->B >= 1 && d->Ho >= 1 && d->Wo >= 1, "conv_igemm: bad dims");
@@ -709,6 +726,7 @@ extern "C" int iswm_conv_igemm(const iswm_conv_desc* d, const void* d_in, const 
   }
   p.out = d_out; p.scale = d_scale; p.shift = d_shift;
   p.res = static_cast<const __nv_bfloat16*>(d_res);
+  p.mask = d_res_mask;
   p.stats = d_stats;
   p.abort_flag = abort_flag;
 

@@ -53,11 +53,15 @@ class _StreamScope:
 class Act:
     """NHWC bf16 activation: `t` is a [B,H,W,C] view whose row pitch is `ld` elements."""
 
-    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad")
+    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad", "pending", "masked_ok")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, Cc: int, ld: int):
         self.t, self.B, self.H, self.W, self.C, self.ld = t, B, H, W, Cc, ld
         self.grad: Optional["Act"] = None             # gradient w.r.t. this activation (same geometry)
+        # identity-path gradient of a bottleneck block that has NOT been written out: (block-output gradient, ReLU sign bits);
+        # the block's conv1 data gradient adds it, gated by the bits, in its epilogue (ISWM_EPI_RES_MASK)
+        self.pending = None
+        self.masked_ok = False                        # set on block inputs whose only other consumer is that conv1
 
     @property
     def M(self) -> int:
@@ -131,6 +135,9 @@ class Engine:
         # ASPP backward: one K-concatenated data-gradient GEMM over the four conv branches (iswm_aspp_bwd) instead of four
         # launches with three read-modify-write passes over the 2048-channel feature gradient
         self.aspp_fused_bwd = __import__("os").environ.get("ISWM_ASPP_FUSED_BWD", "1") != "0"
+        # identity-path gradient of non-first bottleneck blocks folded into the block's conv1 data-gradient epilogue
+        # (ISWM_EPI_RES_MASK) instead of a tensor written by bn_bwd_apply and read back (ISWM_MASKED_IDENTITY=0: old form)
+        self.masked_identity = __import__("os").environ.get("ISWM_MASKED_IDENTITY", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -425,6 +432,12 @@ class Engine:
 
         def backward():
             dout = out.grad
+            pend_bits = None
+            if dout is None and out.pending is not None:
+                # this unit's output was the identity operand of a block-closing add + ReLU (downsample branch): its gradient is
+                # the block-output gradient gated by the block's ReLU sign bits, which the kernels apply on the fly (mode 2)
+                dout, pend_bits = out.pending
+                out.pending = None
             assert dout is not None, f"no gradient reached {s.name}"
             use_mask = relu  # residual units: the mask comes from the block output (post add + ReLU)
             rec = None
@@ -442,10 +455,19 @@ class Engine:
             relu_mode = 1 if use_mask else 0
             if bits is not None:
                 act_ptr, relu_mode = bits.data_ptr(), 2
+            if pend_bits is not None:
+                assert not relu and bits is None
+                act_ptr, relu_mode = pend_bits.data_ptr(), 2
             dy = dy_into() if dy_into is not None else torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
             dy_ld = dy.stride(2)
             dz_ptr, dz_ld, dz_tmp = None, 0, None
-            if residual is not None:
+            defer_dz = (residual is not None and residual.grad is None and residual.masked_ok and bits is not None and drop_p == 0.0
+                        and self.masked_identity and self.debug_units is None and residual.ld == residual.C and dout.ld == Cout and Cout % 64 == 0)
+            if defer_dz:
+                # the identity path's gradient dz = dout . relu_mask is NOT written: the block's conv1 data gradient (the only
+                # other contribution to the block input's gradient) reads dout and the sign bits in its epilogue instead
+                residual.pending = (dout, bits)
+            elif residual is not None:
                 if residual.grad is None:
                     residual.new_grad()
                     dz_ptr, dz_ld = residual.grad.ptr, residual.C
@@ -453,7 +475,7 @@ class Engine:
                     assert residual.grad.ld == residual.C
                     dz_tmp = torch.empty_like(residual.grad.t)
                     dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
-            if bits is None and (M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems):
+            if bits is None and pend_bits is None and (M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems):
                 # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
                 check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                     bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
@@ -581,16 +603,21 @@ class Engine:
     def _dgrad_into(self, s: ConvSpec, x: Act, dy: torch.Tensor, dy_ld: int, Hi, Wi, dtaps, Ho, Wo):
         L = _lib.lib()
         B, Cin, Cout = x.B, s.cin, s.cout
-        flags, res = 0, None
+        flags, res, mask = 0, None, None
         if x.grad is None:
             x.new_grad()
+            if x.pending is not None:              # + (block-output gradient where the block's ReLU was active)
+                res, mbits = x.pending
+                x.pending = None
+                flags, mask = _lib.EPI_RESIDUAL | _lib.EPI_RES_MASK, mbits
         else:
+            assert x.pending is None
             flags, res = _lib.EPI_RESIDUAL, x.grad
         g = x.grad
-        dd = ops.make_conv_desc(B, Hi, Wi, Cout, dy_ld, B, Ho, Wo, Cin, g.ld, dtaps, flags, g.ld)
+        dd = ops.make_conv_desc(B, Hi, Wi, Cout, dy_ld, B, Ho, Wo, Cin, g.ld, dtaps, flags, g.ld if res is None else res.ld)
         ev = self._prof_begin()
-        check(L.iswm_conv_igemm(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, None, None,
-                                None if res is None else res.ptr, None, _st()), "dgrad " + s.name)
+        check(L.iswm_conv_igemm_ex(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, None, None,
+                                   None if res is None else res.ptr, None, None if mask is None else mask.data_ptr(), _st()), "dgrad " + s.name)
         # algorithmic FLOPs of a data gradient = those of the forward conv it differentiates (no credit
         # for the zero-stuffed positions of the stride-2 case)
         fwd_pix = B * (Ho // s.stride if s.stride > 1 else Ho) * (Wo // s.stride if s.stride > 1 else Wo)
@@ -783,7 +810,11 @@ class Engine:
         cat2 = low_slice = None
         for li, blocks in enumerate(self.layers):
             for (c1, c2, c3, ds) in blocks:
+                if ds is None and c1.k == 1 and c1.stride == 1:
+                    a.masked_ok = True            # consumers of this block input: conv1 and the identity add, nothing else
                 idt = a if ds is None else unit(ds, a, relu=False)
+                if ds is not None:
+                    idt.masked_ok = True          # the downsample output feeds the block-closing add only
                 y = unit(c1, a)
                 y = unit(c2, y)
                 a = unit(c3, y, relu=True, residual=idt)

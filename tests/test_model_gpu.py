@@ -410,3 +410,30 @@ def test_fused_aspp_backward_matches_the_four_launch_form():
     # the ASPP branches' own weight gradients do not depend on the data-gradient path at all
     for n in ("classifier.aspp.convs.0.0.weight", "classifier.aspp.convs.2.0.weight"):
         assert rel_l2(res[0][2][n], res[1][2][n]) <= 1e-5
+
+
+def test_masked_identity_gradient_equals_the_materialised_form():
+    """Backward of non-first bottleneck blocks (resnet.py:99-120): the identity path's gradient dz = dout . relu_mask folded
+    into conv1's data-gradient epilogue (ISWM_EPI_RES_MASK, the default) against bn_bwd_apply writing dz as a tensor that the
+    epilogue reads back. Same arithmetic (the mask is 0/1, dz is dout's own bf16 value), so every activation gradient is
+    bit-identical; parameter gradients differ only by the weight-gradient kernels' fp32 atomics order."""
+    x = torch.randn((4, 3, 96, 96), generator=torch.Generator().manual_seed(15))
+    y = synth_labels((4, 96, 96), seed=16, fg=0.2, ign=0.05)
+    w = torch.tensor([1.0, 3.0])
+    res = []
+    for masked in (True, False):
+        m, _ = build("resnet50", 16, seed=78)
+        m.to(DEV).train()
+        eng = m.engine()
+        eng.dropout_p = 0.0
+        eng.masked_identity = masked
+        crit = CrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
+        loss = crit(m(x.to(DEV)), y.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((float(loss.detach()), eng.flat_g.clone(), m.backbone.bn1.weight.grad.clone()))
+    assert res[0][0] == res[1][0]
+    rel = rel_l2(res[0][1], res[1][1])
+    report("masked_identity_vs_materialised", flat_grad_rel_l2=rel)
+    assert rel <= 1e-5
+    assert rel_l2(res[0][2], res[1][2]) <= 1e-5          # the very last gradient of the sweep (stem BatchNorm weight)
