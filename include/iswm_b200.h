@@ -135,7 +135,8 @@ enum {
   ISWM_EPI_RESIDUAL = 4,  /* y += residual (bf16, same geometry, own ld)      */
   ISWM_EPI_STATS    = 8,  /* accumulate per-channel fp32 sum / sum^2 of the STORED bf16 outputs (needs bf16 out, out_ld % 8 == 0) */
   ISWM_EPI_OUT_F32  = 16, /* write fp32 instead of bf16                       */
-  ISWM_EPI_RES_MASK = 32  /* the residual is gated by packed ReLU sign bits (iswm_conv_igemm_ex): y += res * bit  */
+  ISWM_EPI_RES_MASK = 32, /* the residual is gated by packed ReLU sign bits (iswm_conv_igemm_ex): y += res * bit  */
+  ISWM_EPI_BN_DZ    = 64  /* BatchNorm-backward pass 1 rides on this data gradient's epilogue (iswm_conv_igemm_bn) */
 };
 
 /* Geometry of one implicit-GEMM convolution over NHWC bf16 activations.
@@ -185,6 +186,26 @@ int iswm_conv_igemm(const iswm_conv_desc* desc, const void* d_in, const void* d_
 int iswm_conv_igemm_ex(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt,
                        void* d_out, const float* d_scale, const float* d_shift,
                        const void* d_res, double* d_stats, const uint8_t* d_res_mask, void* stream);
+
+/* Data gradient + the FIRST pass of the BatchNorm backward of the unit whose activation gradient it produces
+ * (conv -> BatchNorm -> ReLU, network/backbone/resnet.py:99-108, network/_deeplab.py:44-50: autograd's
+ * threshold_backward + the two per-channel reductions of native_batch_norm_backward). The launch computes the data gradient
+ * dout of a convolution whose INPUT was that unit's activation, and in its epilogue
+ *   dz = dout where the unit's ReLU was active (mask recomputed from `raw`, the unit's pre-BN bf16 output, with the
+ *        forward kernel's own fma), 0 elsewhere                                   -> written to d_out instead of dout,
+ *   sums[c] += sum(dz), sums[Cout + c] += sum(dz * xhat)                          -> what iswm_bn_bwd_reduce would produce,
+ * so that tensor is not re-read for the reduction: the unit's backward continues with iswm_bn_bwd_apply(relu_mode = 0) on dz.
+ * Dense bf16 output with Cout %% 64 == 0; desc->flags must be 0 or ISWM_EPI_BN_DZ. */
+typedef struct {
+  const void*  raw;     /* bf16 [B*Ho*Wo][Cout]: pre-BatchNorm output of the unit (iswm_conv_igemm with ISWM_EPI_STATS) */
+  const float* mean;    /* float[Cout] saved batch mean   (iswm_bn_train_apply) */
+  const float* invstd;  /* float[Cout] saved 1/sqrt(var + eps)                  */
+  const float* gamma;   /* float[Cout] BatchNorm weight                         */
+  const float* beta;    /* float[Cout] BatchNorm bias                           */
+  double*      sums;    /* double[2*Cout], ACCUMULATED (zero it first)          */
+} iswm_bn_dz;
+int iswm_conv_igemm_bn(const iswm_conv_desc* desc, const void* d_in, const void* d_wgt, void* d_out,
+                       const iswm_bn_dz* bn, void* stream);
 
 /* ASPP backward, data-gradient half (network/_deeplab.py:143-172: the 1x1 branch and the three dilated 3x3 branches all
  * read the SAME 2048-channel feature map): ONE K-concatenated implicit GEMM

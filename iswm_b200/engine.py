@@ -53,7 +53,7 @@ class _StreamScope:
 class Act:
     """NHWC bf16 activation: `t` is a [B,H,W,C] view whose row pitch is `ld` elements."""
 
-    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad", "pending", "masked_ok")
+    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad", "pending", "masked_ok", "bn_fold", "bn_sums")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, Cc: int, ld: int):
         self.t, self.B, self.H, self.W, self.C, self.ld = t, B, H, W, Cc, ld
@@ -62,6 +62,11 @@ class Act:
         # the block's conv1 data gradient adds it, gated by the bits, in its epilogue (ISWM_EPI_RES_MASK)
         self.pending = None
         self.masked_ok = False                        # set on block inputs whose only other consumer is that conv1
+        # BatchNorm-backward pass 1 folded into the producer of this activation's gradient (ISWM_EPI_BN_DZ): `bn_fold` =
+        # (raw, save, bn) is set by the unit that owns the activation when its ONLY consumer is a stride-1 convolution,
+        # `bn_sums` by that consumer's data gradient once it has written dz (not dout) into `grad` and accumulated the sums
+        self.bn_fold = None
+        self.bn_sums = None
 
     @property
     def M(self) -> int:
@@ -138,6 +143,12 @@ class Engine:
         # identity-path gradient of non-first bottleneck blocks folded into the block's conv1 data-gradient epilogue
         # (ISWM_EPI_RES_MASK) instead of a tensor written by bn_bwd_apply and read back (ISWM_MASKED_IDENTITY=0: old form)
         self.masked_identity = __import__("os").environ.get("ISWM_MASKED_IDENTITY", "1") != "0"
+        # BatchNorm-backward reductions (sum dz, sum dz.xhat) of conv -> BN -> ReLU units with a single stride-1 consumer can ride
+        # on that consumer's data-gradient epilogue (iswm_conv_igemm_bn) instead of a bn_bwd_reduce pass. OFF by default: kernel by
+        # kernel it saves 4-27 us per unit (tools/prof_bndz.py), but inside the step it LOSES (cfg2 12.95 -> 13.17 ms): the eight
+        # epilogue warps pay ~800 extra instructions per 128x64 chunk, and the longer persistent data-gradient kernels leave the
+        # weight-gradient stream fewer HBM-bound BatchNorm windows to run under (ISWM_BN_DZ_FOLD=1 enables)
+        self.bn_dz_fold = __import__("os").environ.get("ISWM_BN_DZ_FOLD", "0") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -394,8 +405,11 @@ class Engine:
 
     # ------------------------------------------------------------------ train-mode unit: conv(+stats) -> BN apply, taped
     def _unit_train(self, s: ConvSpec, x: Act, relu=True, residual: Optional[Act] = None, out: Optional[Act] = None,
-                    drop_p: float = 0.0, need_dx: bool = True, dy_into: Optional[Callable[[], torch.Tensor]] = None) -> Act:
-        """`dy_into`: called in backward, returns the [B,Ho,Wo,Cout] (possibly channel-sliced) view the BatchNorm backward
+                    drop_p: float = 0.0, need_dx: bool = True, dy_into: Optional[Callable[[], torch.Tensor]] = None,
+                    single_consumer: bool = False) -> Act:
+        """`single_consumer`: the caller promises that exactly one convolution reads this unit's output (so that convolution's
+        data gradient IS the whole gradient of the activation and may carry the BatchNorm-backward reductions).
+        `dy_into`: called in backward, returns the [B,Ho,Wo,Cout] (possibly channel-sliced) view the BatchNorm backward
         writes this unit's pre-activation gradient into instead of a private buffer (ASPP: slices of one concatenated buffer)."""
         L = _lib.lib()
         self._pack(s, need_dx)
@@ -429,17 +443,21 @@ class Engine:
         self._tap(s.name, out)
         if self.debug_taps is not None:
             self.debug_taps[s.name + ":raw"] = raw.float().permute(0, 3, 1, 2).cpu()
+        if (single_consumer and self.bn_dz_fold and relu and residual is None and drop_p == 0.0 and out.ld == Cout and Cout % 64 == 0
+                and self.debug_units is None):
+            out.bn_fold = (raw, save, bn)
 
         def backward():
             dout = out.grad
             pend_bits = None
+            folded_sums, out.bn_sums, out.bn_fold = out.bn_sums, None, None
             if dout is None and out.pending is not None:
                 # this unit's output was the identity operand of a block-closing add + ReLU (downsample branch): its gradient is
                 # the block-output gradient gated by the block's ReLU sign bits, which the kernels apply on the fly (mode 2)
                 dout, pend_bits = out.pending
                 out.pending = None
             assert dout is not None, f"no gradient reached {s.name}"
-            use_mask = relu  # residual units: the mask comes from the block output (post add + ReLU)
+            use_mask = relu and folded_sums is None   # residual units: the mask comes from the block output (post add + ReLU)
             rec = None
             if self.debug_units is not None:
                 rec = dict(name=s.name, k=s.k, stride=s.stride, dilation=s.dilation, relu=relu, x=x.t.clone(), raw=raw.clone(),
@@ -448,7 +466,8 @@ class Engine:
                            residual=None if residual is None else residual.t.clone(),
                            xgrad_before=None if x.grad is None else x.grad.t.clone(),
                            resgrad_before=None if (residual is None or residual.grad is None) else residual.grad.t.clone())
-            sums = self._stats_slot(2 * Cout + 2)        # + the grid barrier's arrival counter
+            # (folded: `dout` already holds dz and the sums were accumulated by the consumer's data-gradient epilogue)
+            sums = folded_sums if folded_sums is not None else self._stats_slot(2 * Cout + 2)        # + the grid barrier's arrival counter
             # the ReLU mask is read from the block output only where a residual was added; otherwise the
             # kernel recomputes it from raw (one tensor read less in each pass)
             act_ptr = out.ptr if (use_mask and residual is not None) else None
@@ -475,7 +494,7 @@ class Engine:
                     assert residual.grad.ld == residual.C
                     dz_tmp = torch.empty_like(residual.grad.t)
                     dz_ptr, dz_ld = dz_tmp.data_ptr(), residual.C
-            if bits is None and pend_bits is None and (M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems):
+            if folded_sums is None and bits is None and pend_bits is None and (M * Cout <= self.bn_fused_max_elems or M * Cout >= self.bn_fused_min_elems):
                 # small tensor (dout and raw stay in L2): reduce + apply in one launch, grid barrier between the passes
                 check(L.iswm_bn_bwd(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                     bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
@@ -484,11 +503,12 @@ class Engine:
                       "bn_bwd " + s.name)
             else:
                 nmask = (1.0 / 16 if bits is not None else 1) if act_ptr is not None else 0
-                ev = self._prof_begin()
-                check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
-                                           save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                           relu_mode, drop_p, seed, step_ptr, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
-                self._prof_end(ev, "hbm:bn_bwd_reduce", 2.0 * M * Cout * (2 + nmask), "bn_bwd_reduce " + s.name)
+                if folded_sums is None:
+                    ev = self._prof_begin()
+                    check(L.iswm_bn_bwd_reduce(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
+                                               save.data_ptr(), save[Cout:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                               relu_mode, drop_p, seed, step_ptr, sums.data_ptr(), _st()), "bn_bwd_reduce " + s.name)
+                    self._prof_end(ev, "hbm:bn_bwd_reduce", 2.0 * M * Cout * (2 + nmask), "bn_bwd_reduce " + s.name)
                 ev = self._prof_begin()
                 check(L.iswm_bn_bwd_apply(dout.ptr, dout.ld, raw.data_ptr(), Cout, act_ptr, out.ld, M, Cout,
                                           bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(), sums.data_ptr(),
@@ -604,6 +624,19 @@ class Engine:
         L = _lib.lib()
         B, Cin, Cout = x.B, s.cin, s.cout
         flags, res, mask = 0, None, None
+        if x.grad is None and x.pending is None and x.bn_fold is not None and x.ld == x.C and Cin == x.C:
+            # x = relu(bn(raw)) has no other consumer: write dz = dout . relu_mask and accumulate the BatchNorm-backward sums here
+            raw, save, bn = x.bn_fold
+            x.new_grad()
+            g = x.grad
+            sums = self._stats_slot(2 * Cin + 2)
+            dd = ops.make_conv_desc(B, Hi, Wi, Cout, dy_ld, B, Ho, Wo, Cin, g.ld, dtaps, _lib.EPI_BN_DZ, g.ld)
+            bnd = _lib.BnDz(raw.data_ptr(), save.data_ptr(), save[Cin:].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), sums.data_ptr())
+            ev = self._prof_begin()
+            check(L.iswm_conv_igemm_bn(C.byref(dd), dy.data_ptr(), s.packed_dgrad.data_ptr(), g.ptr, C.byref(bnd), _st()), "dgrad+bn " + s.name)
+            self._prof_end(ev, "conv_igemm", 2.0 * B * Ho * Wo * Cout * Cin * len(dtaps), "dgrad " + s.name)
+            x.bn_sums = sums
+            return
         if x.grad is None:
             x.new_grad()
             if x.pending is not None:              # + (block-output gradient where the block's ReLU was active)
@@ -815,8 +848,9 @@ class Engine:
                 idt = a if ds is None else unit(ds, a, relu=False)
                 if ds is not None:
                     idt.masked_ok = True          # the downsample output feeds the block-closing add only
-                y = unit(c1, a)
-                y = unit(c2, y)
+                kw = dict(single_consumer=True) if train else {}
+                y = unit(c1, a, **kw)
+                y = unit(c2, y, **kw)
                 a = unit(c3, y, relu=True, residual=idt)
             if li == 0:
                 low_level = a
@@ -857,7 +891,7 @@ class Engine:
                 ev = self._prof_begin()
                 check(L.iswm_aspp_bwd(dycat[0].data_ptr(), 4 * cb, self.aspp_wcat.data_ptr(), B, hf, wf, cb, feat.C, rates,
                                       g.ptr, g.ld, 0 if first else 1, _st()), "aspp_bwd")
-                self._prof_end(ev, "conv_igemm", 2.0 * B * hf * wf * feat.C * cb * 28, "dgrad classifier.aspp.convs.0-3 (fused)")
+                self._prof_end(ev, "conv_igemm", 2.0 * B * hf * wf * feat.C * cb * 28, "dgrad classifier.aspp.convs.0-3(fused)")
                 dycat[0] = None
             self.tape.append(aspp_dgrad)
             for i, s in enumerate(self.aspp_branches):
@@ -881,8 +915,9 @@ class Engine:
                 up.grad = None
             self.tape.append(up_bwd)
             self._slice_grad_split(cat2, [(low_slice, 0), (up, 48)])
-        y = unit(self.dec1, cat2)
-        y = unit(self.dec2, y)
+        kw = dict(single_consumer=True) if train else {}
+        y = unit(self.dec1, cat2, **kw)
+        y = unit(self.dec2, y, **kw)
 
         # ---- classifier 1x1 (+bias) -> fp32 NHWC low-res logits -> bilinear to input size (utils.py:22)
         ncls = self.cls.cout

@@ -27,6 +27,7 @@ import numpy as np
 import pytest
 import torch
 
+from iswm_b200 import _lib
 from iswm_b200.network import modeling
 from iswm_b200.utils.loss import CrossEntropyLoss
 from oracle import torch_model as TM
@@ -437,3 +438,32 @@ def test_masked_identity_gradient_equals_the_materialised_form():
     report("masked_identity_vs_materialised", flat_grad_rel_l2=rel)
     assert rel <= 1e-5
     assert rel_l2(res[0][2], res[1][2]) <= 1e-5          # the very last gradient of the sweep (stem BatchNorm weight)
+
+
+def test_bn_backward_reduction_folded_into_dgrad_matches_the_separate_pass():
+    """conv -> BN -> ReLU units with one stride-1 consumer (conv1 / conv2 of every bottleneck, both decoder 3x3s): the
+    BatchNorm-backward sums ride on the consumer's data-gradient epilogue (iswm_conv_igemm_bn, Engine.bn_dz_fold) against the separate
+    bn_bwd_reduce pass. Same summands (the stored bf16 dz and raw values), different fp32 partial-sum order: gradients agree
+    to that noise amplified by the occasional bf16 rounding flip downstream."""
+    x = torch.randn((4, 3, 96, 96), generator=torch.Generator().manual_seed(25))
+    y = synth_labels((4, 96, 96), seed=26, fg=0.2, ign=0.05)
+    w = torch.tensor([1.0, 3.0])
+    res = []
+    for fold in (True, False):
+        m, _ = build("resnet50", 16, seed=79)
+        m.to(DEV).train()
+        eng = m.engine()
+        eng.dropout_p = 0.0
+        eng.bn_dz_fold = fold
+        crit = CrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
+        n0 = _lib.launch_count()
+        loss = crit(m(x.to(DEV)), y.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((float(loss.detach()), eng.flat_g.clone(), _lib.launch_count() - n0))
+    assert res[0][0] == res[1][0]
+    rel = rel_l2(res[0][1], res[1][1])
+    cos = cosine(res[0][1], res[1][1])
+    report("bn_dz_fold_vs_separate_reduce", flat_grad_rel_l2=rel, cosine=cos, launches_folded=res[0][2], launches_separate=res[1][2])
+    assert res[1][2] - res[0][2] >= 30          # 16 conv1 + 16 conv2 (minus stride-2 consumers) + 2 decoder reductions are gone
+    assert rel <= 3e-2 and cos >= 0.999

@@ -17,11 +17,26 @@ def main(path, backbone="resnet50", os_=16):
         m = ctor(num_classes=2, output_stride=os_, pretrained_backbone=False)
     specs = {s.name: s for s in m.engine().specs}
     rows, bn = [], []
+    merged = {}                                    # several launches of one data gradient (parity phases) count as one
+    order = []
     for line in open(path):
         p = line.split()
-        kind, name, gf, us = p[0], p[1], float(p[2]), float(p[4])
+        kind, name, gf, us = p[0], p[1], float(p[-6]), float(p[-4])
+        key = (kind, name)
+        if kind.startswith("bn_") or key not in merged:
+            if not kind.startswith("bn_"):
+                merged[key] = len(order)
+            order.append([kind, name, gf, us])
+        else:
+            order[merged[key]][2] += gf
+            order[merged[key]][3] += us
+    for kind, name, gf, us in order:
         if kind.startswith("bn_"):                 # HBM-bound entries: the third column is algorithmic MB
             bn.append((us - gf * 1e6 / GBS * 1e6, kind, name, us, gf, gf * 1e6 / (us * 1e-6) / 1e9))
+            continue
+        if name not in specs:                      # fused launches (the K-concatenated ASPP data gradient): tensor floor only
+            t_tc = gf * 1e9 / TF * 1e6
+            rows.append((us - t_tc, kind, name, us, t_tc, 0.0, "tensor"))
             continue
         s = specs[name]
         taps = 49 if s.is_stem else s.k * s.k
