@@ -322,6 +322,41 @@ int iswm_bn_bwd_apply(const void* d_dout, int dout_ld, const void* d_x, int x_ld
                       void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                       float* d_dgamma, float* d_dbeta, void* stream);
 
+/* ---- the closing BatchNorm of a bottleneck block WITH a downsample branch, both branches per pass (csrc/bn_dual.cu) ----
+ *   out = relu( bn3(raw) + bn_ds(raw_ds) )        network/backbone/resnet.py:110-118 with `downsample` (:176-186)
+ * raw / raw_ds: bf16 [M][C] pre-BatchNorm outputs of conv3 and of the downsample convolution (iswm_conv_igemm with
+ * ISWM_EPI_STATS). The normalised shortcut is never written out, and in backward the block-output gradient and its
+ * ReLU sign bits are read once per pass for both BatchNorms instead of once per BatchNorm. One iswm_bn_side per BatchNorm:
+ * forward reads stats / gamma / beta, updates running_mean / running_var / num_batches_tracked (NULL = skip) and writes
+ * save_mean / save_invstd; the backward passes read gamma / save_mean / save_invstd. */
+typedef struct {
+  const double* stats;          /* double[2*C]: sum x, sum x^2 over the M rows (forward only) */
+  const float*  gamma;
+  const float*  beta;
+  float*        running_mean;
+  float*        running_var;
+  int64_t*      num_batches_tracked;
+  float*        save_mean;      /* float[C] */
+  float*        save_invstd;    /* float[C] */
+} iswm_bn_side;
+/* d_relu_bits (uint8 [M][C/8], may be NULL): sign bits of the block output, as iswm_bn_train_apply writes them. */
+int iswm_bn_dual_train_apply(const void* d_x, int x_ld, const iswm_bn_side* main_bn,
+                             const void* d_x_ds, int x_ds_ld, const iswm_bn_side* ds_bn,
+                             int64_t M, int C, float eps, float momentum,
+                             void* d_out, int out_ld, uint8_t* d_relu_bits, void* stream);
+/* pass 1: dz = dout where the bit is set; d_sums[c] += sum dz, d_sums[C+c] += sum dz.xhat (main), d_sums_ds likewise with
+ * the downsample branch's xhat (its first half equals d_sums'). double[2*C] each, zeroed by the caller. */
+int iswm_bn_dual_bwd_reduce(const void* d_dout, int dout_ld, const uint8_t* d_relu_bits,
+                            const void* d_x, int x_ld, const iswm_bn_side* main_bn,
+                            const void* d_x_ds, int x_ds_ld, const iswm_bn_side* ds_bn,
+                            int64_t M, int C, double* d_sums, double* d_sums_ds, void* stream);
+/* pass 2: d_dx = gradient w.r.t. raw, d_dx_ds = gradient w.r.t. raw_ds (bf16, own pitches); dgamma / dbeta ACCUMULATE. */
+int iswm_bn_dual_bwd_apply(const void* d_dout, int dout_ld, const uint8_t* d_relu_bits,
+                           const void* d_x, int x_ld, const iswm_bn_side* main_bn, const double* d_sums,
+                           const void* d_x_ds, int x_ds_ld, const iswm_bn_side* ds_bn, const double* d_sums_ds,
+                           int64_t M, int C, void* d_dx, int dx_ld, void* d_dx_ds, int dx_ds_ld,
+                           float* d_dgamma, float* d_dbeta, float* d_dgamma_ds, float* d_dbeta_ds, void* stream);
+
 /* Both passes in ONE launch (what the engine uses): pass 1, a grid-wide barrier, pass 2 over the same rows (served
  * from L2 for all but the largest tensors). d_sums: double[2*C + 1], zeroed by the caller; the extra cell is the
  * barrier's arrival counter. The grid is sized to be co-resident; the barrier wait is bounded

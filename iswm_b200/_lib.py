@@ -42,6 +42,13 @@ class BnDz(C.Structure):
                 ("beta", C.c_void_p), ("sums", C.c_void_p)]
 
 
+class BnSide(C.Structure):
+    """Mirror of iswm_bn_side."""
+
+    _fields_ = [("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p)]
+
+
 class PackJob(C.Structure):
     """Mirror of iswm_pack_job."""
 
@@ -115,6 +122,10 @@ SIGNATURES = {
     "iswm_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "iswm_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _p]),
     "iswm_bn_bwd_apply": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _i, _p, _i, _p, _p, _p]),
+    "iswm_bn_dual_train_apply": (_i, [_p, _i, C.POINTER(BnSide), _p, _i, C.POINTER(BnSide), _i64, _i, _f, _f, _p, _i, _p, _p]),
+    "iswm_bn_dual_bwd_reduce": (_i, [_p, _i, _p, _p, _i, C.POINTER(BnSide), _p, _i, C.POINTER(BnSide), _i64, _i, _p, _p, _p]),
+    "iswm_bn_dual_bwd_apply": (_i, [_p, _i, _p, _p, _i, C.POINTER(BnSide), _p, _p, _i, C.POINTER(BnSide), _p, _i64, _i, _p, _i, _p, _i,
+                                    _p, _p, _p, _p, _p]),
     "iswm_bn_bwd": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _i, _p, _i, _p, _p, _p]),
     "iswm_stem_im2col": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_maxpool_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

@@ -5,42 +5,11 @@
 // pitch (ld) so that channel slices of a concat buffer are read and written in place —
 // torch.cat (network/_deeplab.py:59, :171) never materialises.
 #include "common.cuh"
+#include "ew_common.cuh"
 #include <algorithm>
 #include <stdlib.h>
 
 namespace iswm {
-
-constexpr int kT = 256;
-
-struct F8 { float v[8]; };
-
-__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
-  const uint4 r = *reinterpret_cast<const uint4*>(p);
-  F8 o;
-  unpack_bf16x2(r.x, o.v[0], o.v[1]);
-  unpack_bf16x2(r.y, o.v[2], o.v[3]);
-  unpack_bf16x2(r.z, o.v[4], o.v[5]);
-  unpack_bf16x2(r.w, o.v[6], o.v[7]);
-  return o;
-}
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& f) {
-  uint4 r;
-  r.x = pack_bf16x2(f.v[0], f.v[1]);
-  r.y = pack_bf16x2(f.v[2], f.v[3]);
-  r.z = pack_bf16x2(f.v[4], f.v[5]);
-  r.w = pack_bf16x2(f.v[6], f.v[7]);
-  *reinterpret_cast<uint4*>(p) = r;
-}
-
-__device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ F8 unpack8(const uint4& r) {
-  F8 o;
-  unpack_bf16x2(r.x, o.v[0], o.v[1]);
-  unpack_bf16x2(r.y, o.v[2], o.v[3]);
-  unpack_bf16x2(r.z, o.v[4], o.v[5]);
-  unpack_bf16x2(r.w, o.v[6], o.v[7]);
-  return o;
-}
 
 static inline int grid_for(int64_t work, int per_block = kT, int waves = 8) {
   int64_t g = (work + per_block - 1) / per_block;
@@ -273,19 +242,6 @@ struct DropSeed {
     return (seed + (step ? (uint64_t)(*step) * 1000003ull : 0ull)) & 0xFFFFFFFFFFFFull;
   }
 };
-
-struct RowWalk {
-  int64_t first;      // first row of this thread
-  int n;              // rows this thread owns
-};
-__device__ __forceinline__ RowWalk row_walk(int64_t M, int rows_per_block, int ty, int ny) {
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(r0 + (int64_t)rows_per_block, M);
-  RowWalk w;
-  w.first = r0 + ty;
-  w.n = (w.first < r1) ? (int)((r1 - w.first + ny - 1) / ny) : 0;
-  return w;
-}
 
 // BatchNorm training forward: stats -> normalise (+residual, ReLU, dropout)
 template <bool RES, bool RELU, bool DROP>
@@ -1662,22 +1618,6 @@ extern "C" int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, i
   }
   launch_k(unpack_wgrad_kernel, dim3(grid_for((int64_t)Cout * Cin * RS)), dim3(kT), 0, ST(stream), d_dw, Cout, Cin, RS, cin_stride, row_ld, beta, d_grad_oihw);
   return check_launch("unpack_wgrad");
-}
-
-static void bn_red_shape(int C, int& nx, int& ny) {
-  const int nvec = C / 8;
-  nx = std::min(nvec, kT);
-  ny = std::max(1, kT / nx);
-}
-// rows per block: every thread walks >= min_rows rows (amortises the per-channel constant setup), but small
-// tensors still get several blocks per SM (the kernels are latency-bound below ~4 resident blocks per SM);
-// capped at 6 blocks per SM
-static void bn_row_grid(int C, int64_t M, int min_rows, int& nx, int& ny, int& rows_per_block, int& blocks, int blocks_per_sm = 6) {
-  bn_red_shape(C, nx, ny);
-  int64_t want = (M + (int64_t)ny * min_rows - 1) / ((int64_t)ny * min_rows);
-  want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * blocks_per_sm));
-  rows_per_block = (int)((M + want - 1) / want);
-  blocks = (int)((M + rows_per_block - 1) / rows_per_block);
 }
 
 extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,

@@ -149,6 +149,9 @@ class Engine:
         # epilogue warps pay ~800 extra instructions per 128x64 chunk, and the longer persistent data-gradient kernels leave the
         # weight-gradient stream fewer HBM-bound BatchNorm windows to run under (ISWM_BN_DZ_FOLD=1 enables)
         self.bn_dz_fold = __import__("os").environ.get("ISWM_BN_DZ_FOLD", "0") != "0"
+        # blocks with a downsample branch: the closing BatchNorm and the downsample BatchNorm run as ONE kernel per pass
+        # (csrc/bn_dual.cu; the normalised shortcut is never written, backward reads dout / sign bits once per pass for both)
+        self.dual_bn = __import__("os").environ.get("ISWM_DUAL_BN", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -529,6 +532,64 @@ class Engine:
         self.tape.append(backward)
         return out
 
+    def _conv_raw(self, s: ConvSpec, x: Act):
+        """Train-mode convolution alone: raw (pre-BN) bf16 output + its per-channel statistics; the BatchNorm comes later."""
+        self._pack(s, True)
+        xin, taps, n_img, Ho, Wo = self._prep_input(s, x)
+        raw = torch.empty((x.B, Ho, Wo, s.cout), dtype=torch.bfloat16, device=self.device)
+        stats = self._stats_slot(2 * s.cout)
+        self._conv(s, xin, raw, s.cout, Ho, Wo, taps, n_img, _lib.EPI_STATS, stats=stats)
+        return raw, stats, xin, taps, n_img, Ho, Wo
+
+    def _bn_side(self, bn, stats, save, Cc, train_fwd: bool):
+        return _lib.BnSide(stats.data_ptr() if stats is not None else None, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                           bn.running_mean.data_ptr() if train_fwd else None, bn.running_var.data_ptr() if train_fwd else None,
+                           bn.num_batches_tracked.data_ptr() if train_fwd else None, save.data_ptr(), save[Cc:].data_ptr())
+
+    def _unit_train_dual(self, s: ConvSpec, x: Act, sds: ConvSpec, xds: Act, dsc) -> Act:
+        """Closing unit of a bottleneck block with a downsample branch (resnet.py:110-118): out = relu(bn3(conv3(x)) +
+        bn_ds(conv_ds(xds))), both BatchNorms in one kernel per pass (csrc/bn_dual.cu). `dsc` = _conv_raw(sds, xds)."""
+        L = _lib.lib()
+        raw, stats, xin, taps, n_img, Ho, Wo = self._conv_raw(s, x)
+        raw_ds, stats_ds, xin_ds, taps_ds, n_img_ds, Ho_ds, Wo_ds = dsc
+        assert (Ho, Wo) == (Ho_ds, Wo_ds) and s.cout == sds.cout
+        B, Cout = x.B, s.cout
+        M = B * Ho * Wo
+        out = Act.new(B, Ho, Wo, Cout, self.device)
+        save, save_ds = self._save_slot(2 * Cout), self._save_slot(2 * Cout)
+        bits = torch.empty((M, Cout // 8), dtype=torch.uint8, device=self.device)
+        a_side, d_side = self._bn_side(s.bn, stats, save, Cout, True), self._bn_side(sds.bn, stats_ds, save_ds, Cout, True)
+        ev = self._prof_begin()
+        check(L.iswm_bn_dual_train_apply(raw.data_ptr(), Cout, C.byref(a_side), raw_ds.data_ptr(), Cout, C.byref(d_side), M, Cout,
+                                         BN_EPS, BN_MOMENTUM, out.ptr, out.ld, bits.data_ptr(), _st()), "bn_dual_train_apply " + s.name)
+        self._prof_end(ev, "hbm:bn_train_apply", 2.0 * M * Cout * 3 + M * Cout / 8, "bn_apply " + s.name + "+ds")
+
+        def backward():
+            dout = out.grad
+            assert dout is not None and dout.ld == Cout, f"no dense gradient reached {s.name}"
+            sums, sums_ds = self._stats_slot(2 * Cout + 2), self._stats_slot(2 * Cout + 2)
+            a_b, d_b = self._bn_side(s.bn, None, save, Cout, False), self._bn_side(sds.bn, None, save_ds, Cout, False)
+            dy = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
+            dy_ds = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
+            ev = self._prof_begin()
+            check(L.iswm_bn_dual_bwd_reduce(dout.ptr, Cout, bits.data_ptr(), raw.data_ptr(), Cout, C.byref(a_b), raw_ds.data_ptr(), Cout,
+                                            C.byref(d_b), M, Cout, sums.data_ptr(), sums_ds.data_ptr(), _st()), "bn_dual_bwd_reduce " + s.name)
+            self._prof_end(ev, "hbm:bn_bwd_reduce", 2.0 * M * Cout * 3 + M * Cout / 8, "bn_bwd_reduce " + s.name + "+ds")
+            gv = self.grad_views
+            ev = self._prof_begin()
+            check(L.iswm_bn_dual_bwd_apply(dout.ptr, Cout, bits.data_ptr(), raw.data_ptr(), Cout, C.byref(a_b), sums.data_ptr(),
+                                           raw_ds.data_ptr(), Cout, C.byref(d_b), sums_ds.data_ptr(), M, Cout,
+                                           dy.data_ptr(), Cout, dy_ds.data_ptr(), Cout,
+                                           gv[id(s.bn.weight)].data_ptr(), gv[id(s.bn.bias)].data_ptr(),
+                                           gv[id(sds.bn.weight)].data_ptr(), gv[id(sds.bn.bias)].data_ptr(), _st()), "bn_dual_bwd_apply " + s.name)
+            self._prof_end(ev, "hbm:bn_bwd_apply", 2.0 * M * Cout * 5 + M * Cout / 8, "bn_bwd_apply " + s.name + "+ds")
+            out.grad = None
+            self._conv_backward(s, x, xin, taps, n_img, Ho, Wo, dy, True)
+            self._conv_backward(sds, xds, xin_ds, taps_ds, n_img_ds, Ho, Wo, dy_ds, True)
+
+        self.tape.append(backward)
+        return out
+
     def _conv_backward(self, s: ConvSpec, x: Act, xin: Act, taps, n_img, Ho, Wo, dy: torch.Tensor, need_dx: bool):
         """Weight gradient into the flat fp32 buffer and data gradient into x.grad (assign or accumulate)."""
         L = _lib.lib()
@@ -845,10 +906,17 @@ class Engine:
             for (c1, c2, c3, ds) in blocks:
                 if ds is None and c1.k == 1 and c1.stride == 1:
                     a.masked_ok = True            # consumers of this block input: conv1 and the identity add, nothing else
+                kw = dict(single_consumer=True) if train else {}
+                if (ds is not None and train and self.dual_bn and self.relu_bits and self.debug_units is None and self.debug_taps is None
+                        and c3.cout % 8 == 0):
+                    dsc = self._conv_raw(ds, a)   # downsample convolution now; its BatchNorm rides on the block's closing one
+                    y = unit(c1, a, **kw)
+                    y = unit(c2, y, **kw)
+                    a = self._unit_train_dual(c3, y, ds, a, dsc)
+                    continue
                 idt = a if ds is None else unit(ds, a, relu=False)
                 if ds is not None:
                     idt.masked_ok = True          # the downsample output feeds the block-closing add only
-                kw = dict(single_consumer=True) if train else {}
                 y = unit(c1, a, **kw)
                 y = unit(c2, y, **kw)
                 a = unit(c3, y, relu=True, residual=idt)

@@ -377,3 +377,64 @@ def test_bn_backward_with_dropout_against_torch_with_the_kernels_own_mask(B, C, 
     check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
                                   save.data_ptr(), save[C:].data_ptr(), None, C, 1, p, seed, step2.data_ptr(), out2.data_ptr(), C, None, st()))
     assert not torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 256, 9, 7), (3, 64, 8, 8), (2, 2048, 4, 4), (4, 512, 24, 24), (2, 1024, 9, 11)])
+def test_dual_batchnorm_of_a_downsample_block_against_torch(B, C, H, W):
+    """csrc/bn_dual.cu: out = relu(bn3(raw) + bn_ds(raw_ds)) and its backward, both BatchNorms per pass, against torch autograd
+    (network/backbone/resnet.py:110-118 with a downsample branch) on the same bf16 inputs."""
+    from iswm_b200 import _lib
+    import ctypes as Ct
+    xa, xb = rnd((B, C, H, W), 11, 2.0), rnd((B, C, H, W), 12, 1.5)
+    g = torch.Generator().manual_seed(13)
+    ga, ba = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    gb, bb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    rma, rva = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    rmb, rvb = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    dout = rnd((B, C, H, W), 14)
+    # torch
+    xar, xbr = xa.float().requires_grad_(True), xb.float().requires_grad_(True)
+    gar, bar_, gbr, bbr = (t.clone().requires_grad_(True) for t in (ga, ba, gb, bb))
+    rma_r, rva_r, rmb_r, rvb_r = rma.clone(), rva.clone(), rmb.clone(), rvb.clone()
+    y = F.relu(F.batch_norm(xar, rma_r, rva_r, gar, bar_, True, 0.1, 1e-5) + F.batch_norm(xbr, rmb_r, rvb_r, gbr, bbr, True, 0.1, 1e-5))
+    y.backward(dout.float())
+    # ours
+    M = B * H * W
+    xad, xbd = nhwc(xa).to(DEV), nhwc(xb).to(DEV)
+    sta = torch.stack([xa.double().sum((0, 2, 3)), (xa.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    stb = torch.stack([xb.double().sum((0, 2, 3)), (xb.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    dev = lambda t: t.clone().to(DEV)
+    gad, bad, gbd, bbd, rmad, rvad, rmbd, rvbd = (dev(t) for t in (ga, ba, gb, bb, rma, rva, rmb, rvb))
+    nbta, nbtb = torch.zeros((), dtype=torch.long, device=DEV), torch.full((), 5, dtype=torch.long, device=DEV)
+    sva, svb = torch.empty(2 * C, device=DEV), torch.empty(2 * C, device=DEV)
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    bits = torch.zeros((M, C // 8), dtype=torch.uint8, device=DEV)
+    sa = _lib.BnSide(sta.data_ptr(), gad.data_ptr(), bad.data_ptr(), rmad.data_ptr(), rvad.data_ptr(), nbta.data_ptr(), sva.data_ptr(), sva[C:].data_ptr())
+    sb = _lib.BnSide(stb.data_ptr(), gbd.data_ptr(), bbd.data_ptr(), rmbd.data_ptr(), rvbd.data_ptr(), nbtb.data_ptr(), svb.data_ptr(), svb[C:].data_ptr())
+    check(L().iswm_bn_dual_train_apply(xad.data_ptr(), C, Ct.byref(sa), xbd.data_ptr(), C, Ct.byref(sb), M, C, 1e-5, 0.1, out.data_ptr(), C, bits.data_ptr(), st()))
+    close(nchw(out), y.detach(), 1e-2, 2e-2)
+    close(rmad, rma_r, 1e-4, 1e-5); close(rvad, rva_r, 1e-3, 1e-4); close(rmbd, rmb_r, 1e-4, 1e-5); close(rvbd, rvb_r, 1e-3, 1e-4)
+    assert nbta.item() == 1 and nbtb.item() == 6
+    want = (out.float().reshape(M, C // 8, 8) > 0).to(torch.int32) * (2 ** torch.arange(8, device=DEV, dtype=torch.int32))
+    assert torch.equal(bits.to(torch.int32), want.sum(-1))
+    dd = nhwc(dout).to(DEV)
+    s1, s2 = torch.zeros(2 * C, dtype=torch.float64, device=DEV), torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    check(L().iswm_bn_dual_bwd_reduce(dd.data_ptr(), C, bits.data_ptr(), xad.data_ptr(), C, Ct.byref(sa), xbd.data_ptr(), C, Ct.byref(sb), M, C,
+                                      s1.data_ptr(), s2.data_ptr(), st()))
+    # each half against the single-branch reduction with the same sign bits
+    for xd, sv, gd, bd, s in ((xad, sva, gad, bad, s1), (xbd, svb, gbd, bbd, s2)):
+        ref = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+        check(L().iswm_bn_bwd_reduce(dd.data_ptr(), C, xd.data_ptr(), C, bits.data_ptr(), 0, M, C, sv.data_ptr(), sv[C:].data_ptr(),
+                                     gd.data_ptr(), bd.data_ptr(), 2, 0.0, 0, None, ref.data_ptr(), st()))
+        mag = float(ref.abs().max()) + 1.0
+        np.testing.assert_allclose(s.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5 * mag)
+    dxa, dxb = torch.empty_like(out), torch.empty_like(out)
+    dga, dba, dgb, dbb = (torch.zeros(C, device=DEV) for _ in range(4))
+    check(L().iswm_bn_dual_bwd_apply(dd.data_ptr(), C, bits.data_ptr(), xad.data_ptr(), C, Ct.byref(sa), s1.data_ptr(), xbd.data_ptr(), C, Ct.byref(sb),
+                                     s2.data_ptr(), M, C, dxa.data_ptr(), C, dxb.data_ptr(), C, dga.data_ptr(), dba.data_ptr(), dgb.data_ptr(), dbb.data_ptr(), st()))
+    torch.cuda.synchronize()
+    for dx, xr_, dg, gr_, db, br_ in ((dxa, xar, dga, gar, dba, bar_), (dxb, xbr, dgb, gbr, dbb, bbr)):
+        scale = float(xr_.grad.abs().max())
+        close(nchw(dx), xr_.grad, 2e-2, 2e-2 * scale)
+        close(dg, gr_.grad, 2e-2, 5e-2)
+        close(db, br_.grad, 2e-2, 5e-2)

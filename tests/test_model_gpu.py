@@ -467,3 +467,46 @@ def test_bn_backward_reduction_folded_into_dgrad_matches_the_separate_pass():
     report("bn_dz_fold_vs_separate_reduce", flat_grad_rel_l2=rel, cosine=cos, launches_folded=res[0][2], launches_separate=res[1][2])
     assert res[1][2] - res[0][2] >= 30          # 16 conv1 + 16 conv2 (minus stride-2 consumers) + 2 decoder reductions are gone
     assert rel <= 3e-2 and cos >= 0.999
+
+
+def test_dual_batchnorm_blocks_match_the_two_kernel_form():
+    """First block of every ResNet layer (resnet.py:176-186): closing BatchNorm + downsample BatchNorm as one kernel per pass
+    (csrc/bn_dual.cu, the default) against the separate kernels. The fused forward adds the shortcut in fp32 instead of
+    rounding it to bf16 first; at this size a train-mode forward amplifies ANY bf16-level change to ~8 % of the logits (the
+    pooled ASPP branch normalises over 4 samples: see train_vs_fp32 / matched_oracle_floor), so the two forms are compared
+    through their distance to the fp32 oracle, which must not grow. The kernels themselves are checked against torch
+    autograd in tests/test_glue_gpu.py::test_dual_batchnorm_of_a_downsample_block_against_torch."""
+    x = torch.randn((4, 3, 96, 96), generator=torch.Generator().manual_seed(35))
+    y = synth_labels((4, 96, 96), seed=36, fg=0.2, ign=0.05)
+    w = torch.tensor([1.0, 3.0])
+    _, sd = build("resnet50", 16, seed=80)
+    ref = train_reference("resnet50", 16, sd, x, y, w)["fp32"]
+    ref_flat = torch.cat([ref[2][n].flatten() for n, _ in build("resnet50", 16, seed=80)[0].named_parameters()])
+    res = []
+    for dual in (True, False):
+        m, _ = build("resnet50", 16, seed=80)
+        m.to(DEV).train()
+        eng = m.engine()
+        eng.dropout_p = 0.0
+        eng.dual_bn = dual
+        crit = CrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
+        n0 = _lib.launch_count()
+        logits = m(x.to(DEV))
+        loss = crit(logits, y.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        flat = torch.cat([p.grad.flatten() for _, p in m.named_parameters()]).cpu()
+        res.append(dict(loss=float(loss.detach()), launches=_lib.launch_count() - n0, d_logits=rel_l2(logits.detach().cpu(), ref[0]),
+                        cos=cosine(flat, ref_flat), d_loss=abs(float(loss.detach()) - ref[1].item()) / abs(ref[1].item()),
+                        bufs={k: v.clone() for k, v in m.state_dict().items() if "downsample.1.running" in k or "num_batches" in k}))
+    d, s_ = res
+    report("dual_bn_vs_two_kernels", logits_to_fp32_dual=d["d_logits"], logits_to_fp32_separate=s_["d_logits"], loss_rel_dual=d["d_loss"],
+           loss_rel_separate=s_["d_loss"], grad_cos_to_fp32_dual=d["cos"], grad_cos_to_fp32_separate=s_["cos"],
+           launches_dual=d["launches"], launches_separate=s_["launches"])
+    assert s_["launches"] - d["launches"] == 12           # 4 blocks x (apply + reduce + bwd apply) fewer launches
+    assert d["d_logits"] <= 1.25 * s_["d_logits"] + 5e-3
+    assert d["d_loss"] <= 1.5 * s_["d_loss"] + 5e-3
+    assert d["cos"] >= s_["cos"] - 0.05
+    for k in d["bufs"]:                                   # running statistics / step counters of the downsample BatchNorms keep moving
+        a, b = d["bufs"][k].float(), s_["bufs"][k].float()
+        assert rel_l2(a, b) <= 2e-2, (k, rel_l2(a, b))
