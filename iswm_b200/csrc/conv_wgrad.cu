@@ -2,12 +2,18 @@
 //
 //   dW[cout, tap, cin] = sum_pixels dy[pixel, cout] * x[pixel + offset(tap), cin]
 //
-// GEMM view: M = cout (128 per tile), N = cin (<= 256 per tile), K = pixels. Both
+// GEMM view: M = cout (128 per tile), N = (tap, cin) columns, K = pixels. Both
 // operands are NHWC, i.e. the contraction index (pixel) is the slow one, so both are fed
 // to the MMA as MN-major 128B-swizzled tiles: a TMA box of {64 channels, 64 pixels} lands
 // as 64 rows (K) of 128 bytes (64 channels of M or N). The tap shift and the zero padding
 // come from the TMA coordinates exactly as in conv_igemm.cu. The pixel range is split
 // across CTAs (split-K) and partial tiles are reduced with fp32 atomics into dW.
+//
+// The N side of a tile is a run of up to 6 "column chunks" of the linearised (tap, 64-channel slice) axis, each loaded
+// with its own tap shift: narrow layers put several taps side by side behind ONE dy tile (3x3 64->64: three taps per
+// tile, N = 192, instead of nine N = 64 tiles that each re-read dy), and Cin = 304 runs as one 5-chunk tile per tap
+// (N = 192 + 112 as two MMAs into 320 TMEM columns) instead of two 160-column tiles. Tiles wider than 256 columns use a
+// single accumulator (each CTA owns one tile in split mode, so there is nothing to double-buffer against).
 //
 // Replaces the autograd weight gradients of every nn.Conv2d on the hot path
 // (network/backbone/resnet.py:27-35, network/_deeplab.py:37-51,124,134,149,162)
@@ -23,15 +29,19 @@ constexpr int kWTileM = 128;
 constexpr int kPixBlock = 64;               // pixels per k-block
 constexpr int kChunkBytes = 64 * 128;       // one {64 ch x 64 px} box = 8 KiB
 constexpr int kWTmemCols = 512;
-constexpr int kWSmemBudget = 196608;
+constexpr int kWSmemBudget = 232448 - 1024 - 256;   // opt-in limit minus alignment slack and barriers
+constexpr int kMaxG = 6;                            // column chunks per tile
 
 struct WgradKParams {
   int Cout, Cin, ntaps;
   int lgBW, lgBH;                 // pixel box: BW*BH*BB == 64
   int tiles_w, tiles_h, tiles_b;  // pixel blocks
   int pix_blocks;
-  int tiles_m, tiles_n, BN, nchunks_b, stages;
-  int n_tiles;                    // output tiles = tiles_m * ntaps * tiles_n
+  int tiles_m, tiles_n, stages;
+  int G, cchunks, T;              // chunks per tile, 64-channel slices per tap, total chunks = ntaps * cchunks
+  int tail_cols;                  // valid columns of a tap's last slice rounded up to 16 (64 when Cin % 64 == 0)
+  int acc_cols, nacc;             // TMEM columns per accumulator, accumulators (2 while 2 * 64 * G <= 512)
+  int n_tiles;                    // output tiles = tiles_m * tiles_n
   long long total_kblocks;        // n_tiles * pix_blocks
   long long kblocks_per_cta;      // stream-K mode: equal contiguous ranges of the linearised (tile, pixel block) space
   int splits, split_len;          // split mode (splits > 0): CTA = (tile, split); same-split CTAs walk the same pixels
@@ -51,7 +61,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
   const uint32_t ring = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (ring - raw_addr);
   const uint32_t a_bytes = 2 * kChunkBytes;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)p.nchunks_b * kChunkBytes;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)p.G * kChunkBytes;
   uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 4);
@@ -96,11 +106,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
   // Stream-K: the (output tile, pixel block) space is linearised and cut into equal contiguous
   // ranges, one per CTA; a CTA flushes its partial tile with fp32 reductions whenever its range
   // crosses a tile boundary. tile -> (m tile, tap, n tile), n fastest (neighbours share dy in L2).
-  auto decode = [&](int tile, int& mt, int& tap, int& nt) {
+  auto decode = [&](int tile, int& mt, int& nt) {
     nt = tile % p.tiles_n;
-    const int r = tile / p.tiles_n;
-    tap = r % p.ntaps;
-    mt = r / p.ntaps;
+    mt = tile / p.tiles_n;
+  };
+  // columns of n-tile nt: gc chunks starting at chunk g0 of the (tap, slice) axis; the MMA covers ncols of them (a trailing
+  // partial slice is trimmed to 16; partial slices in the middle of a tile run as zero columns)
+  auto tile_cols = [&](int nt, int& g0, int& gc, int& ncols) {
+    g0 = nt * p.G;
+    gc = min(p.G, p.T - g0);
+    const int last = g0 + gc - 1;
+    const bool tail = (last % p.cchunks) == p.cchunks - 1;
+    ncols = 64 * (gc - 1) + (tail ? p.tail_cols : 64);
   };
   long long range_lo, range_hi;
   if (p.splits > 0) {
@@ -129,26 +146,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
         const int tile = (int)(cur / p.pix_blocks);
         const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
         const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
-        int mt, tap, nt;
-        decode(tile, mt, tap, nt);
-        const int m0 = mt * kWTileM, n0 = nt * p.BN;
+        int mt, nt, g0, gc, ncols;
+        decode(tile, mt, nt);
+        tile_cols(nt, g0, gc, ncols);
+        const int m0 = mt * kWTileM;
+        // per-chunk tap shift and channel origin of this tile (registers; the k loop below only adds the pixel-block origin)
+        int c_dw[kMaxG], c_dh[kMaxG], c_db[kMaxG], c_ch[kMaxG];
+        {
+          int tap = g0 / p.cchunks, cc = g0 - tap * p.cchunks;
+#pragma unroll
+          for (int j = 0; j < kMaxG; j++) {
+            const int t_ = min(tap, p.ntaps - 1);
+            c_dw[j] = p.dw[t_]; c_dh[j] = p.dh[t_]; c_db[j] = p.phase[t_] * p.n_img_per_phase; c_ch[j] = cc * 64;
+            if (++cc == p.cchunks) { cc = 0; tap++; }
+          }
+        }
+        const uint32_t tx_bytes = a_bytes + (uint32_t)gc * kChunkBytes;
         int off = me - (int)(q0 % np);
         if (off < 0) off += np;
         int pb = pb0 + off;
         int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h, tb = pb / (p.tiles_w * p.tiles_h);
-        const int ddw = p.dw[tap], ddh = p.dh[tap], dph = p.phase[tap] * p.n_img_per_phase;
         for (; pb < pb1; pb += np) {
           const int w0 = tw * BW, h0 = th * BH, b0 = tb * BB;
           ok = tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.abort_flag, 11);
           if (!ok) break;
           const uint32_t dst = ring + stage * stage_bytes;
           const uint32_t bar = bar_full + 8 * stage;
-          const int xw = w0 + ddw, xh = h0 + ddh, xb = dph + b0;
-          tc::mbar_expect_tx(bar, stage_bytes);
+          tc::mbar_expect_tx(bar, tx_bytes);
           tc::tma_load_4d(dst, &tmap_dy, bar, m0, w0, h0, b0);
           tc::tma_load_4d(dst + kChunkBytes, &tmap_dy, bar, m0 + 64, w0, h0, b0);
-          for (int j = 0; j < p.nchunks_b; j++)
-            tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, n0 + 64 * j, xw, xh, xb);
+#pragma unroll
+          for (int j = 0; j < kMaxG; j++)
+            if (j < gc) tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, c_ch[j], w0 + c_dw[j], h0 + c_dh[j], b0 + c_db[j]);
           stage += np;
           if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
           tw += np;
@@ -162,7 +191,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
     __syncwarp();
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_bf16(kWTileM, p.BN, 1, 1);   // both operands MN-major
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       bool ok = true;
@@ -170,10 +198,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
         const int tile = (int)(cur / p.pix_blocks);
         const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
         const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
+        int mt, nt, g0, gc, ncols;
+        decode(tile, mt, nt);
+        tile_cols(nt, g0, gc, ncols);
+        // up to 256 columns per MMA: wider tiles run as two MMAs over the first h1 chunks and the rest
+        const int h1 = (ncols <= 256) ? gc : (gc + 1) / 2;
+        const int n1 = (ncols <= 256) ? ncols : 64 * h1, n2 = ncols - n1;
+        const uint32_t idesc1 = tc::make_idesc_bf16(kWTileM, n1, 1, 1);   // both operands MN-major
+        const uint32_t idesc2 = tc::make_idesc_bf16(kWTileM, n2 > 0 ? n2 : 16, 1, 1);
         ok = tc::mbar_wait(bar_tempty + 8 * as, aphase ^ 1, p.abort_flag, 12);
         if (!ok) break;
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_cols);
         for (int pb = pb0; pb < pb1; pb++) {
           ok = tc::mbar_wait(bar_full + 8 * stage, phase, p.abort_flag, 13);
           if (!ok) break;
@@ -185,14 +221,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
           const uint32_t first = (pb > pb0) ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < kPixBlock / 16; k++)     // 16 pixel rows = 2048 bytes per MMA
-            tc::umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, first | (uint32_t)(k > 0));
+            tc::umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc1, first | (uint32_t)(k > 0));
+          if (n2 > 0) {
+            const uint64_t db2 = tc::make_smem_desc_sw128(a_addr + a_bytes + (uint32_t)h1 * kChunkBytes, kChunkBytes, 1024);
+#pragma unroll
+            for (int k = 0; k < kPixBlock / 16; k++)
+              tc::umma_bf16(d_tmem + (uint32_t)n1, da + 128 * k, db2 + 128 * k, idesc2, first | (uint32_t)(k > 0));
+          }
           tc::umma_commit(bar_empty + 8 * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (!ok) break;
         tc::umma_commit(bar_tfull + 8 * as);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        if (++as == p.nacc) { as = 0; aphase ^= 1; }
         cur += pb1 - pb0;
       }
     }
@@ -206,38 +247,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
       const int tile = (int)(cur / p.pix_blocks);
       const int pb0 = (int)(cur - (long long)tile * p.pix_blocks);
       const int pb1 = (int)min((long long)p.pix_blocks, pb0 + (range_hi - cur));
-      int mt, tap, nt;
-      decode(tile, mt, tap, nt);
-      const int m = mt * kWTileM + row, n0 = nt * p.BN;
+      int mt, nt, g0, gc, ncols;
+      decode(tile, mt, nt);
+      tile_cols(nt, g0, gc, ncols);
+      const int m = mt * kWTileM + row;
       if (!tc::mbar_wait(bar_tfull + 8 * as, aphase, p.abort_flag, 14)) break;
       tc::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * p.BN);
-      float* orow = p.dwgt + ((size_t)m * p.ntaps + tap) * p.Cin;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        tc::tmem_ld16(t_row + c, v);
-        tc::tmem_ld_wait();
-        const int n = n0 + c;
-        if (m < p.Cout) {
-          if (p.vec_red && n + 16 <= p.Cin) {
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * p.acc_cols);
+      int tap = g0 / p.cchunks, cc = g0 - tap * p.cchunks;
+      for (int j = 0; j < gc; j++) {                     // one 64-channel slice of one tap per chunk
+        float* orow = p.dwgt + ((size_t)m * p.ntaps + tap) * p.Cin + cc * 64;
+        const int nvalid = min(64, p.Cin - cc * 64);     // channels of this slice that exist
+        const int ccols = min(64, ncols - 64 * j);       // columns of it the MMA produced
+        for (int c = 0; c < ccols; c += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(t_row + 64 * j + c, v);
+          tc::tmem_ld_wait();
+          if (m < p.Cout) {
+            if (p.vec_red && c + 16 <= nvalid) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + n + j),
-                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
-                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                           : "memory");
-          } else {
+              for (int i = 0; i < 16; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c + i),
+                             "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                             "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                             : "memory");
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; j++)
-              if (n + j < p.Cin) atomicAdd(orow + n + j, __uint_as_float(v[j]));
+              for (int i = 0; i < 16; i++)
+                if (c + i < nvalid) atomicAdd(orow + c + i, __uint_as_float(v[i]));
+            }
           }
         }
+        if (++cc == p.cchunks) { cc = 0; tap++; }
       }
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar_tempty + 8 * as);
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == p.nacc) { as = 0; aphase ^= 1; }
       cur += pb1 - pb0;
     }
   }
@@ -291,26 +337,55 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
   ISWM_REQUIRE(pbs < (1ll << 31), "conv_wgrad: too many pixel blocks");
   p.pix_blocks = (int)pbs;
   p.tiles_m = (d->Cout + kWTileM - 1) / kWTileM;
-  const int n_split_n = (d->Cin + 255) / 256;
-  p.BN = std::min(256, (((d->Cin + n_split_n - 1) / n_split_n + 15) / 16) * 16);
-  p.tiles_n = (d->Cin + p.BN - 1) / p.BN;
-  p.nchunks_b = (p.BN + 63) / 64;
-  const int64_t n_tiles = (int64_t)p.tiles_m * p.ntaps * p.tiles_n;
+  const int sms = num_sms();
+  p.cchunks = (d->Cin + 63) / 64;
+  p.T = d->ntaps * p.cchunks;
+  p.tail_cols = (d->Cin % 64) ? (((d->Cin % 64) + 15) / 16) * 16 : 64;
+  {
+    // chunks per tile, by a small cost model fitted to tools/wgrad_g_sweep.py: a CTA streams its share of the pixel blocks at
+    // max(MMA time, operand bytes at ~100 B/clk of L2 -> SM ingest) per block, then adds its partial tile into dW with
+    // red.global (~2 TB/s device-wide, and EVERY split flushes the whole tile): wide tiles re-read dy less but need more
+    // splits to fill the SMs, i.e. more reduction traffic - 1x1 and small 3x3 layers end up at 2 chunks, the decoder at 4-5.
+    static const int env_g = [] { const char* e = getenv("ISWM_WGRAD_G"); return e ? atoi(e) : 0; }();
+    int G = 1;
+    double best = 1e30;
+    for (int g = 1; g <= std::min(kMaxG, p.T); g++) {
+      const int64_t tiles = (int64_t)p.tiles_m * ((p.T + g - 1) / g);
+      double kb, flush_tiles;
+      if (tiles <= sms) {
+        const int64_t sp = std::max<int64_t>(1, std::min<int64_t>(pbs, sms / tiles));
+        kb = (double)((pbs + sp - 1) / sp);
+        flush_tiles = (double)(tiles * sp);
+      } else {
+        kb = (double)((tiles * pbs + sms - 1) / sms);
+        flush_tiles = (double)sms * (1.0 + kb / (double)pbs);
+      }
+      const double mma = 2.0 * 64 * g, load = 82.0 * (2 + g);                     // cycles per 64-pixel block
+      const double t_stream = kb * std::max(mma, load) / 1700.0;                  // us at ~1.7 GHz
+      const double t_flush = flush_tiles * std::min(128, d->Cout) * 64.0 * g * 4.0 / 2.0e6;
+      const double cost = t_stream + t_flush + ((p.T % g) ? 0.03 * t_stream : 0.0);
+      if (cost < best) { best = cost; G = g; }
+    }
+    if (env_g >= 1 && env_g <= kMaxG) G = std::min(env_g, p.T);
+    p.G = G;
+  }
+  p.tiles_n = (p.T + p.G - 1) / p.G;
+  p.acc_cols = 64 * p.G;
+  p.nacc = (2 * p.acc_cols <= kWTmemCols) ? 2 : 1;
+  const int64_t n_tiles = (int64_t)p.tiles_m * p.tiles_n;
   ISWM_REQUIRE(n_tiles < (1ll << 31), "conv_wgrad: too many output tiles");
   p.n_tiles = (int)n_tiles;
   p.total_kblocks = n_tiles * pbs;
   int grid;
-  const int sms = num_sms();
-  if (n_tiles <= 2 * sms) {
-    // split mode: pick the split count (each split >= ~4 pixel blocks) that fills whole waves of SMs best
-    const int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(pbs / 4, (4 * sms) / n_tiles));
-    int best = 1;
-    double best_eff = 0.0;
-    for (int sp = 1; sp <= max_splits; sp++) {
-      const int64_t ctas = n_tiles * sp;
-      const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms) - 1e-4 * sp;
-      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
-    }
+  if (n_tiles <= sms) {
+    // split mode, ONE resident wave: as many splits as fit on the SMs next to each other. More CTAs than SMs (the former
+    // "best fill of whole waves" rule picked e.g. 37 splits x 8 tiles = 2 waves) doubles the fp32 reduction traffic - every
+    // CTA ends by adding its whole 128 x BN partial tile into dW with red.global, ~2 TB/s device-wide - for no gain in
+    // parallelism; measured sweep (tools/wgrad_split_sweep.py): 1024->256 at 32x32 32.8 -> 22.5 us, 2048->256 55.3 -> 31.6,
+    // 1024->2048 86.0 -> 66.6
+    int best = (int)std::max<int64_t>(1, std::min<int64_t>(pbs, sms / n_tiles));
+    static const int env_sp = [] { const char* e = getenv("ISWM_WGRAD_SPLITS"); return e ? atoi(e) : 0; }();
+    if (env_sp > 0) best = (int)std::min<int64_t>(env_sp, std::max<int64_t>(1, pbs));
     p.split_len = (int)((pbs + best - 1) / best);
     p.splits = (int)((pbs + p.split_len - 1) / p.split_len);
     grid = (int)(n_tiles * p.splits);
@@ -321,7 +396,7 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
     grid = (int)((p.total_kblocks + p.kblocks_per_cta - 1) / p.kblocks_per_cta);
   }
   p.vec_red = ((reinterpret_cast<uintptr_t>(d_dw) & 15) == 0 && (d->Cin % 4) == 0) ? 1 : 0;
-  const int stage_bytes = (2 + p.nchunks_b) * kChunkBytes;
+  const int stage_bytes = (2 + p.G) * kChunkBytes;
   p.stages = std::max(2, std::min(kWStages, kWSmemBudget / stage_bytes));
   p.n_img_per_phase = B;
   static const int env_np = [] { const char* e = getenv("ISWM_WGRAD_NPROD"); return e ? atoi(e) : 0; }();

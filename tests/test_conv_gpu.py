@@ -153,7 +153,12 @@ def test_conv_dgrad(B, Cin, H, W, Cout, k, dil):
                                                    (2, 304, 16, 16, 256, 3, 1), (2, 256, 9, 11, 2, 1, 1), (4, 2048, 8, 8, 256, 3, 6),
                                                    (2, 256, 32, 32, 48, 1, 1),
                                                    (1, 128, 48, 48, 64, 3, 18), (1, 128, 80, 80, 64, 3, 24), (1, 128, 80, 80, 64, 3, 36),
-                                                   (2, 64, 50, 77, 64, 3, 36)])
+                                                   (2, 64, 50, 77, 64, 3, 36),
+                                                   # column-chunk tiles of the (tap, 64-channel slice) axis: partial slices in the middle of a
+                                                   # tile (Cin = 96: 18 chunks), at its end (Cin = 160, 304), 27 chunks (Cin = 192), a 6-chunk
+                                                   # 384-column tile as two MMAs (Cin = 128), Cout above one M tile
+                                                   (2, 96, 12, 12, 64, 3, 1), (2, 160, 16, 16, 64, 1, 1), (2, 192, 16, 16, 320, 3, 1),
+                                                   (2, 128, 16, 16, 128, 3, 1), (1, 304, 24, 24, 256, 3, 1), (2, 40, 10, 10, 72, 3, 1)])
 def test_conv_wgrad(B, Cin, H, W, Cout, k, dil):
     x, w = _mk(B, Cin, H, W, Cout, k, seed=9)
     g = torch.Generator().manual_seed(10)
