@@ -168,7 +168,10 @@ typedef struct {
   int32_t out_ws, out_hs;
   int64_t out_bs;
   int32_t w_ntaps;            /* taps per row of the packed weight tensor when wtap[] selects a subset (0 = ntaps) */
-  int32_t reserved_;
+  int32_t stats_replicas;     /* ISWM_EPI_STATS: d_stats holds this many copies of double[2*Cout] (0 / 1 = one); CTA i adds into copy
+                                 i % replicas and the consumer (iswm_bn_train_apply) sums the copies. With one copy every CTA of a
+                                 narrow layer ends on the same 2*Cout addresses: 296 same-address fp64 atomics per channel cost a
+                                 64-channel 3x3 convolution 14 of its 51 us (tools/prof_conv.py) */
 } iswm_conv_desc;
 
 /* d_in: bf16 activations; d_wgt: packed bf16 [Cout][ntaps][Cin_pad] (Cin_pad =
@@ -291,7 +294,7 @@ int iswm_unpack_wgrad_batched(const void* d_jobs, int n_jobs, int total_blocks, 
  * d_relu_bits (optional, with relu): uint8 [M, C/8], bit j of byte (row, g) = output channel 8g+j is positive. The
  * backward kernels of residual units read these bits (relu mode 2, passed in d_out_act) instead of the 16-byte
  * activation row: the mask of relu(bn(x) + residual) cannot be recomputed from x alone. */
-int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,
+int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int stats_replicas, int64_t M, int C,
                         const float* d_gamma, const float* d_beta, float eps, float momentum,
                         float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
                         float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld, int relu,
@@ -338,6 +341,7 @@ typedef struct {
   int64_t*      num_batches_tracked;
   float*        save_mean;      /* float[C] */
   float*        save_invstd;    /* float[C] */
+  int32_t       stats_replicas; /* copies of double[2*C] in `stats` to sum (0 / 1 = one; see iswm_conv_desc.stats_replicas) */
 } iswm_bn_side;
 /* d_relu_bits (uint8 [M][C/8], may be NULL): sign bits of the block output, as iswm_bn_train_apply writes them. */
 int iswm_bn_dual_train_apply(const void* d_x, int x_ld, const iswm_bn_side* main_bn,
@@ -367,6 +371,15 @@ int iswm_bn_bwd(const void* d_dout, int dout_ld, const void* d_x, int x_ld,
                 const float* d_save_invstd, double* d_sums, int relu, float drop_p, uint64_t drop_seed, const int64_t* d_drop_step,
                 void* d_dx, int dx_ld, void* d_dz, int dz_ld,
                 float* d_dgamma, float* d_dbeta, void* stream);
+
+/* Stem 7x7 / stride 2 / pad 3 (network/backbone/resnet.py:144), ROW-TAP form - what the engine runs. The fp32 NCHW image is
+ * unrolled along x only: d_out bf16 [2][B][Hh][Wo][kpitch], element [p][b][hh][wo][s*Cin + c] = img[b][c][2*hh + p][2*wo + s - 3]
+ * (zero outside the image and in the kpitch - 7*Cin padding channels), p = row parity, Hh = ceil(H/2), Wo = ceil(W/2). The
+ * convolution is then iswm_conv_igemm over that tensor with Cin = kpitch, n_img = 2*B and 7 taps r = 0..6 =
+ * (dh = (r - 3 - p)/2, dw = 0, phase p = (r + 1) & 1), weights packed by iswm_pack_weights_batched mode 2 ([Cout][7][64]);
+ * its weight gradient is iswm_conv_wgrad with the same descriptor ([Cout][7][kpitch] fp32) unpacked by iswm_unpack_wgrad_stem. */
+int iswm_stem_rows(const float* d_img, int B, int Cin, int H, int W, int Hh, int Wo, int kpitch, void* d_out, void* stream);
+int iswm_unpack_wgrad_stem(const float* d_dw, int Cout, int Cin, int ks, int kpitch, float beta, float* d_grad, void* stream);
 
 /* NCHW fp32 image -> stem im2col matrix bf16 [B*Ho*Wo][Kpad] for the 7x7/s2/p3 conv
  * (network/backbone/resnet.py:144); column = (r*7+s)*Cin + c, zero padded to Kpad. */

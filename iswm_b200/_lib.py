@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS), ("phase", C.c_int8 * MAX_TAPS),
         ("coff", C.c_int16 * MAX_TAPS), ("wtap", C.c_int8 * MAX_TAPS),
         ("flags", C.c_int32), ("out_ws", C.c_int32), ("out_hs", C.c_int32), ("out_bs", C.c_int64),
-        ("w_ntaps", C.c_int32), ("reserved_", C.c_int32),
+        ("w_ntaps", C.c_int32), ("stats_replicas", C.c_int32),
     ]
 
 
@@ -46,7 +46,8 @@ class BnSide(C.Structure):
     """Mirror of iswm_bn_side."""
 
     _fields_ = [("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
-                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p)]
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p),
+                ("stats_replicas", C.c_int32)]
 
 
 class PackJob(C.Structure):
@@ -118,7 +119,7 @@ SIGNATURES = {
     "iswm_pack_weights_batched": (_i, [_p, _i, _i, _p]),
     "iswm_unpack_wgrad": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
     "iswm_unpack_wgrad_batched": (_i, [_p, _i, _i, _p]),
-    "iswm_bn_train_apply": (_i, [_p, _i, _p, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _p, _i, _p, _p]),
+    "iswm_bn_train_apply": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _p, _i, _p, _p]),
     "iswm_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "iswm_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _p]),
     "iswm_bn_bwd_apply": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _i, _p, _i, _p, _p, _p]),
@@ -127,6 +128,8 @@ SIGNATURES = {
     "iswm_bn_dual_bwd_apply": (_i, [_p, _i, _p, _p, _i, C.POINTER(BnSide), _p, _p, _i, C.POINTER(BnSide), _p, _i64, _i, _p, _i, _p, _i,
                                     _p, _p, _p, _p, _p]),
     "iswm_bn_bwd": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _i, _p, _i, _p, _p, _p]),
+    "iswm_stem_rows": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "iswm_unpack_wgrad_stem": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),
     "iswm_stem_im2col": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_maxpool_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "iswm_maxpool_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),

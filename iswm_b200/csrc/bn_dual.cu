@@ -27,6 +27,7 @@ struct BnSide {                      // one BatchNorm's per-channel vectors
   long long* nbt;
   float* save_mean;                  // forward: written; backward: read
   float* save_invstd;
+  int stats_rep;                     // copies of the statistics vector to sum
 };
 
 // ------------------------------------------------------------------------------------------------------------- forward
@@ -59,9 +60,14 @@ bn_dual_train_apply_kernel(const __nv_bfloat16* __restrict__ xa, int xa_ld, cons
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int c = c0 + j;
-      const double mean_d = S.stats[c] * invM;
+      double s1 = S.stats[c], s2 = S.stats[C + c];
+      for (int r = 1; r < S.stats_rep; r++) {
+        s1 += S.stats[(size_t)r * 2 * C + c];
+        s2 += S.stats[(size_t)r * 2 * C + C + c];
+      }
+      const double mean_d = s1 * invM;
       const float mean = (float)mean_d;
-      const float var = fmaxf((float)(S.stats[C + c] * invM - mean_d * mean_d), 0.f);
+      const float var = fmaxf((float)(s2 * invM - mean_d * mean_d), 0.f);
       const float invstd = rsqrtf(var + eps);
       scv[j] = S.gamma[c] * invstd;
       shv[j] = fmaf(-mean, scv[j], S.beta[c]);
@@ -325,7 +331,7 @@ extern "C" int iswm_bn_dual_train_apply(const void* d_x, int x_ld, const iswm_bn
   int nx, ny, rpb, blocks;
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks, 2);          // 2 resident blocks per SM (launch bounds): one wave
   auto mk = [](const iswm_bn_side* s) {
-    return BnSide{s->stats, s->gamma, s->beta, s->running_mean, s->running_var, reinterpret_cast<long long*>(s->num_batches_tracked), s->save_mean, s->save_invstd};
+    return BnSide{s->stats, s->gamma, s->beta, s->running_mean, s->running_var, reinterpret_cast<long long*>(s->num_batches_tracked), s->save_mean, s->save_invstd, s->stats_replicas > 1 ? s->stats_replicas : 1};
   };
   launch_k(bn_dual_train_apply_kernel, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, BF(d_x_ds), x_ds_ld, mk(main_bn), mk(ds_bn),
            M, C, eps, momentum, BFW(d_out), out_ld, d_relu_bits, nx, ny, rpb);

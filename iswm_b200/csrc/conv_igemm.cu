@@ -59,6 +59,7 @@ struct ConvKParams {
   const __nv_bfloat16* res;
   const uint8_t* mask;           // ISWM_EPI_RES_MASK: ReLU sign bits [pixels][Cout/8] gating the residual (dz = dout . mask)
   double* stats;                 // fp64 accumulators: cross-CTA summation order no longer shows up in fp32 results
+  int stats_rep;                 // copies of the accumulator vector; this CTA adds into copy blockIdx.x % stats_rep
   // ISWM_EPI_BN_DZ: BatchNorm-backward pass 1 of the unit whose activation gradient this launch produces (res = its pre-BN output)
   const float* bn_mean;
   const float* bn_invstd;
@@ -323,6 +324,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // flush: the four quadrant warps of a warpgroup combine their partial sums through the (idle) staging tile in a
     // fixed order, then ONE fp64 atomic per channel and component leaves the CTA (fp64: the order in which CTAs
     // arrive does not show up in the fp32 mean / variance, so a training step is reproducible bit for bit)
+    double* const stats_mine = p.stats + (size_t)(blockIdx.x % (unsigned)p.stats_rep) * (size_t)(2 * p.Cout);
     auto flush_stats = [&](int n0f) {
       if (issuer) tc::tma_store_wait_read<0>();        // every warp's stores have left the staging tile
       asm volatile("bar.sync %0, 128;" ::"r"(bar_wg) : "memory");
@@ -357,19 +359,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int e = 0; e < 2; e++)
               if (col + e < p.Cout) {
-                atomicAdd(p.stats + col + e, (double)t[e]);
-                atomicAdd(p.stats + p.Cout + col + e,
+                atomicAdd(stats_mine + col + e, (double)t[e]);
+                atomicAdd(stats_mine + p.Cout + col + e,
                           (double)p.bn_invstd[col + e] * ((double)t[2 + e] - (double)p.bn_mean[col + e] * (double)t[e]));
               }
             continue;
           }
           if (col < p.Cout) {
-            atomicAdd(p.stats + col, (double)t[0]);
-            atomicAdd(p.stats + p.Cout + col, (double)t[2]);
+            atomicAdd(stats_mine + col, (double)t[0]);
+            atomicAdd(stats_mine + p.Cout + col, (double)t[2]);
           }
           if (col + 1 < p.Cout) {
-            atomicAdd(p.stats + col + 1, (double)t[1]);
-            atomicAdd(p.stats + p.Cout + col + 1, (double)t[3]);
+            atomicAdd(stats_mine + col + 1, (double)t[1]);
+            atomicAdd(stats_mine + p.Cout + col + 1, (double)t[3]);
           }
         }
       }
@@ -849,6 +851,8 @@ static int conv_igemm_launch(const iswm_conv_desc* d, const void* d_in, const vo
   p.res = static_cast<const __nv_bfloat16*>(d_res);
   p.mask = d_res_mask;
   p.stats = d_stats;
+  p.stats_rep = ((d->flags & ISWM_EPI_STATS) && d->stats_replicas > 1) ? d->stats_replicas : 1;
+  ISWM_REQUIRE(p.stats_rep <= 64, "conv_igemm: stats_replicas=%d (at most 64)", d->stats_replicas);
   if (bn) { p.bn_mean = bn->mean; p.bn_invstd = bn->invstd; p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; }
   p.abort_flag = abort_flag;
 

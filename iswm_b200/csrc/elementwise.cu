@@ -124,7 +124,7 @@ unpack_wgrad_batched_kernel(const UnpackJob* __restrict__ jobs, int n_jobs) {
 struct PackJob {
   const float* w;
   __nv_bfloat16* dst;
-  int Cout, Cin, RS, pad, row_ld, mode;   // mode 0: forward operand (pad = cin_pad), 1: dgrad operand (pad = cout_pad)
+  int Cout, Cin, RS, pad, row_ld, mode;   // mode 0: forward operand (pad = cin_pad), 1: dgrad operand (pad = cout_pad), 2: stem row taps
   int blk_begin, blk_count;               // this job owns blocks [blk_begin, blk_begin + blk_count)
 };
 __global__ void __launch_bounds__(kT)
@@ -183,8 +183,22 @@ pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
         store8(j.dst + (int64_t)o * j.row_ld + (int64_t)t * j.pad + c0 + c, f);
       }
     }
+  } else if (j.mode == 2) {
+    // stem, row-tap form: dst[o][r][q] with q = s*Cin + c (kernel column s, input channel c), zero padded to `pad` per kernel
+    // row r: the operand of the 7-tap convolution over the x-unrolled image rows (stem_rows_kernel)
+    int ks = 1;
+    while (ks * ks < j.RS) ks++;
+    const int64_t total = (int64_t)j.Cout * j.row_ld;
+    for (int64_t i = (int64_t)lb * kT + tid; i < total; i += (int64_t)nb * kT) {
+      const int o = (int)(i / j.row_ld), k = (int)(i % j.row_ld);
+      const int r = k / j.pad, q = k % j.pad;
+      const int sx = q / j.Cin, c = q % j.Cin;
+      float v = 0.f;
+      if (r < ks && sx < ks) v = j.w[((int64_t)o * j.Cin + c) * j.RS + r * ks + sx];
+      j.dst[i] = __float2bfloat16_rn(v);
+    }
   } else if (j.mode == 0) {
-    // anything else (the stem: pad = Cin = 3, RS = 49): element-wise
+    // anything else (the stem's im2col form: pad = Cin = 3, RS = 49): element-wise
     const int64_t total = (int64_t)j.Cout * j.row_ld;
     for (int64_t i = (int64_t)lb * kT + tid; i < total; i += (int64_t)nb * kT) {
       const int o = (int)(i / j.row_ld), k = (int)(i % j.row_ld);
@@ -246,7 +260,7 @@ struct DropSeed {
 // BatchNorm training forward: stats -> normalise (+residual, ReLU, dropout)
 template <bool RES, bool RELU, bool DROP>
 __global__ void __launch_bounds__(kT, 3)
-bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const double* __restrict__ stats,
+bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const double* __restrict__ stats, int stats_rep,
                       int64_t M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float eps, float momentum, float* running_mean, float* running_var,
                       long long* nbt, float* save_mean, float* save_invstd,
@@ -257,6 +271,18 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
   pdl_launch();
   const uint64_t drop_seed = DROP ? drop_seed_in.resolve() : 0ull;
   const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
+  // statistics spread over several copies (narrow convolutions, iswm_conv_desc.stats_replicas; C <= 128 there): the block folds
+  // them once into shared memory - one value per thread - instead of every thread summing the copies of its 8 channels
+  __shared__ double s_stat[256];
+  const bool folded = stats_rep > 1 && 2 * C <= 256;
+  if (folded) {
+    for (int i = threadIdx.x; i < 2 * C; i += kT) {
+      double a = stats[i];
+      for (int r = 1; r < stats_rep; r++) a += stats[(size_t)r * 2 * C + i];
+      s_stat[i] = a;
+    }
+    __syncthreads();
+  }
   if (ty >= ny) return;
   const int c0 = tx << 3;
   // the first U rows are requested BEFORE the per-channel constants (a chain of dependent global loads and fp64
@@ -281,9 +307,19 @@ bn_train_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const doubl
   for (int j = 0; j < 8; j++) {
     const int c = c0 + j;
     // fp64 sums (see conv_igemm.cu): E[x^2] - mean^2 without cancellation trouble, rounded to fp32 once
-    const double mean_d = stats[c] * invM;
+    double s1, s2;
+    if (folded) {
+      s1 = s_stat[c]; s2 = s_stat[C + c];
+    } else {
+      s1 = stats[c]; s2 = stats[C + c];
+      for (int r = 1; r < stats_rep; r++) {       // copies filled by different CTAs of the convolution (fixed order; fp64)
+        s1 += stats[(size_t)r * 2 * C + c];
+        s2 += stats[(size_t)r * 2 * C + C + c];
+      }
+    }
+    const double mean_d = s1 * invM;
     const float mean = (float)mean_d;
-    const float var = fmaxf((float)(stats[C + c] * invM - mean_d * mean_d), 0.f);
+    const float var = fmaxf((float)(s2 * invM - mean_d * mean_d), 0.f);
     const float invstd = rsqrtf(var + eps);
     sc[j] = gamma[c] * invstd;
     sh[j] = fmaf(-mean, sc[j], beta[c]);          // same expression in the backward kernels (mask recomputation)
@@ -801,6 +837,69 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld,
 // coalesced reads along W, then every thread emits 16-byte chunks of consecutive output rows.
 constexpr int kStemStrip = 64;
 constexpr int kStemPatchW = 2 * kStemStrip + 5;           // 133 input columns feed 64 stride-2 outputs
+// Stem, row-tap form (network/backbone/resnet.py:144: 7x7 / stride 2 / pad 3 on a 3-channel image). The image is unrolled
+// along x ONLY: out[p][b][hh][wo][s*Cin + c] = img[b][c][2*hh + p][2*wo + s - 3] (zero outside the image, kpitch - 7*Cin
+// zero channels of padding), p = row parity. The 7 kernel ROWS then run as 7 taps of the ordinary implicit GEMM over the two
+// parity phases (tap r reads phase (r+1)&1 at row offset (r-3-p)/2), so the matrix the GEMM reads is 48 bytes per output
+// pixel and row instead of the 320-byte rows of a full 7x7 im2col: 100 MB instead of 335 MB at cfg2, and the fill is a plain
+// streaming kernel. One thread = one (p, b, hh, wo) pixel = kpitch bf16.
+template <int CIN>
+__global__ void __launch_bounds__(kT)
+stem_rows_kernel(const float* __restrict__ img, int B, int H, int W, int Hh, int Wo, int kpitch,
+                 __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  const int64_t total = 2ll * B * Hh * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int wo = (int)(i % Wo);
+    int64_t r = i / Wo;
+    const int hh = (int)(r % Hh);
+    r /= Hh;
+    const int b = (int)(r % B), p = (int)(r / B);
+    const int h = 2 * hh + p;
+    float v[24];
+#pragma unroll
+    for (int k = 0; k < 24; k++) v[k] = 0.f;
+    if (h < H) {
+#pragma unroll
+      for (int c = 0; c < CIN; c++) {
+        const float* row = img + (((int64_t)b * CIN + c) * H + h) * W;
+#pragma unroll
+        for (int sx = 0; sx < 7; sx++) {
+          const int w = 2 * wo + sx - 3;
+          v[sx * CIN + c] = (w >= 0 && w < W) ? __ldg(row + w) : 0.f;
+        }
+      }
+    }
+    __nv_bfloat16* o = out + i * kpitch;
+#pragma unroll
+    for (int k = 0; k < 24; k += 8) {
+      F8 f;
+#pragma unroll
+      for (int e = 0; e < 8; e++) f.v[e] = v[k + e];
+      store8(o + k, f);
+    }
+    for (int k = 24; k < kpitch; k += 8) {
+      F8 f;
+#pragma unroll
+      for (int e = 0; e < 8; e++) f.v[e] = 0.f;
+      store8(o + k, f);
+    }
+  }
+}
+// weight-gradient accumulator of the row-tap stem [Cout][ks][kpitch] (q = s*Cin + c) -> fp32 OIHW gradient
+__global__ void unpack_wgrad_stem_kernel(const float* __restrict__ dw, int Cout, int Cin, int ks, int kpitch, float beta,
+                                         float* __restrict__ g) {
+  pdl_wait();
+  pdl_launch();
+  const int total = Cout * Cin * ks * ks;
+  for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
+    const int sx = i % ks, r = (i / ks) % ks, c = (i / (ks * ks)) % Cin, o = i / (ks * ks * Cin);
+    const float v = dw[((int64_t)o * ks + r) * kpitch + sx * Cin + c];
+    g[i] = (beta == 0.f) ? v : fmaf(beta, g[i], v);
+  }
+}
+
 __global__ void __launch_bounds__(kT)
 stem_im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int Ho, int Wo,
                    int Kpad, __nv_bfloat16* __restrict__ out) {
@@ -1620,7 +1719,7 @@ extern "C" int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, i
   return check_launch("unpack_wgrad");
 }
 
-extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int64_t M, int C,
+extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_stats, int stats_replicas, int64_t M, int C,
                                    const float* d_gamma, const float* d_beta, float eps, float momentum,
                                    float* d_running_mean, float* d_running_var, int64_t* d_nbt,
                                    float* d_save_mean, float* d_save_invstd, const void* d_res, int res_ld,
@@ -1639,7 +1738,7 @@ extern "C" int iswm_bn_train_apply(const void* d_x, int x_ld, const double* d_st
   bn_row_grid(C, M, 4, nx, ny, rpb, blocks, env_waves);
   const bool has_res = d_res != nullptr, has_drop = drop_p > 0.f;
 #define ISWM_BN_APPLY(R, L, D)                                                                                     \
-  launch_k(bn_train_apply_kernel<R, L, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, d_stats, M, C,    \
+  launch_k(bn_train_apply_kernel<R, L, D>, dim3(blocks), dim3(kT), 0, ST(stream), BF(d_x), x_ld, d_stats, std::max(1, stats_replicas), M, C,    \
            d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var, reinterpret_cast<long long*>(d_nbt),      \
            d_save_mean, d_save_invstd, BF(d_res), res_ld, drop_p, DropSeed{drop_seed, reinterpret_cast<const long long*>(d_drop_step)}, BFW(d_out), out_ld, nx, ny, rpb, relu ? d_relu_bits : nullptr)
   if (has_drop) {
@@ -1778,6 +1877,23 @@ extern "C" int iswm_stem_im2col(const float* d_img, int B, int Cin, int H, int W
   }
   launch_k(stem_im2col_kernel, dim3((unsigned)blocks), dim3(kT), smem, ST(stream), d_img, B, Cin, H, W, Ho, Wo, Kpad, BFW(d_out));
   return check_launch("stem_im2col");
+}
+extern "C" int iswm_stem_rows(const float* d_img, int B, int Cin, int H, int W, int Hh, int Wo, int kpitch, void* d_out, void* stream) {
+  ISWM_REQUIRE(d_img && d_out && B >= 1 && H >= 1 && W >= 1, "stem_rows: null/empty");
+  ISWM_REQUIRE(Cin >= 1 && Cin <= 3 && 7 * Cin <= 24 && kpitch >= 24 && (kpitch % 8) == 0 && kpitch <= 64,
+               "stem_rows: Cin=%d (1..3), kpitch=%d (a multiple of 8 in 24..64)", Cin, kpitch);
+  ISWM_REQUIRE(Hh == (H + 1) / 2 && Wo == (W + 1) / 2, "stem_rows: Hh / Wo must be ceil(H/2) / ceil(W/2)");
+  const int64_t total = 2ll * B * Hh * Wo;
+  const int grid = grid_for(total, kT, 16);
+  if (Cin == 3) launch_k(stem_rows_kernel<3>, dim3(grid), dim3(kT), 0, ST(stream), d_img, B, H, W, Hh, Wo, kpitch, BFW(d_out));
+  else if (Cin == 2) launch_k(stem_rows_kernel<2>, dim3(grid), dim3(kT), 0, ST(stream), d_img, B, H, W, Hh, Wo, kpitch, BFW(d_out));
+  else launch_k(stem_rows_kernel<1>, dim3(grid), dim3(kT), 0, ST(stream), d_img, B, H, W, Hh, Wo, kpitch, BFW(d_out));
+  return check_launch("stem_rows");
+}
+extern "C" int iswm_unpack_wgrad_stem(const float* d_dw, int Cout, int Cin, int ks, int kpitch, float beta, float* d_grad, void* stream) {
+  ISWM_REQUIRE(d_dw && d_grad && Cout >= 1 && Cin >= 1 && ks >= 1 && ks * Cin <= kpitch, "unpack_wgrad_stem: bad arguments");
+  launch_k(unpack_wgrad_stem_kernel, dim3(grid_for((int64_t)Cout * Cin * ks * ks)), dim3(kT), 0, ST(stream), d_dw, Cout, Cin, ks, kpitch, beta, d_grad);
+  return check_launch("unpack_wgrad_stem");
 }
 extern "C" int iswm_maxpool_fwd(const void* d_x, int B, int H, int W, int C, int Ho, int Wo,
                                 void* d_out, uint8_t* d_idx, void* stream) {

@@ -23,6 +23,9 @@ from ._lib import check
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+# channels per pixel of the x-unrolled stem rows (21 used): 32 = 64-byte pixels; 24 (48-byte, sector-straddling pixels) makes the
+# TMA loads of the 7-tap convolution 2.3x slower (tools/prof_stem.py: 231 vs 99 us)
+STEM_KPITCH = 32
 
 
 class _StreamCache:
@@ -152,6 +155,10 @@ class Engine:
         # blocks with a downsample branch: the closing BatchNorm and the downsample BatchNorm run as ONE kernel per pass
         # (csrc/bn_dual.cu; the normalised shortcut is never written, backward reads dout / sign bits once per pass for both)
         self.dual_bn = __import__("os").environ.get("ISWM_DUAL_BN", "1") != "0"
+        # stem 7x7/s2: the image unrolled along x only (iswm_stem_rows, 48 B per pixel row) + the 7 kernel rows as 7 taps of the
+        # implicit GEMM over the two row-parity phases, instead of a full im2col matrix (320 B per pixel) + one GEMM
+        # (ISWM_STEM_ROWS=0: the im2col form)
+        self.stem_rows = __import__("os").environ.get("ISWM_STEM_ROWS", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -217,21 +224,23 @@ class Engine:
         """Repack every convolution's weights (both operand layouts) in ONE kernel launch; called when the
         parameters changed (optimiser step, load_state_dict) instead of 2 small launches per layer."""
         import numpy as np
-        sig = tuple((s.conv.weight.data_ptr(), tuple(s.conv.weight.shape)) for s in self.specs) + (need_dgrad, str(self.device))
+        sig = tuple((s.conv.weight.data_ptr(), tuple(s.conv.weight.shape)) for s in self.specs) + (need_dgrad, str(self.device), self.stem_rows)
         if getattr(self, "_pack_sig", None) != sig:
             jobs = []
             for s in self.specs:
                 w = s.conv.weight
                 Cout, Cin, R, S = w.shape
                 RS = R * S
-                if s.is_stem:
+                if s.is_stem and self.stem_rows:
+                    cin_pad, row_ld = 64, 7 * 64              # [Cout][7 kernel rows][64]: (kernel column, channel) pairs inside a row
+                elif s.is_stem:
                     cin_pad, row_ld = Cin, ((RS * Cin + 63) // 64) * 64
                 else:
                     cin_pad = ((Cin + 63) // 64) * 64
                     row_ld = RS * cin_pad
                 if s.packed_fwd is None or s.packed_fwd.numel() != Cout * row_ld or s.packed_fwd.device != w.device:
                     s.packed_fwd = torch.empty(Cout * row_ld, dtype=torch.bfloat16, device=w.device)
-                jobs.append((w.data_ptr(), s.packed_fwd.data_ptr(), Cout, Cin, RS, cin_pad, row_ld, 0))
+                jobs.append((w.data_ptr(), s.packed_fwd.data_ptr(), Cout, Cin, RS, cin_pad, row_ld, 2 if (s.is_stem and self.stem_rows) else 0))
                 if need_dgrad and s.name in self._aspp_cat_slot():
                     # the four ASPP conv branches share ONE K-concatenated dgrad operand [Cfeat][28 taps][256]
                     # (iswm_aspp_bwd): each branch's taps are a slice of the concatenated row
@@ -281,6 +290,15 @@ class Engine:
         v = (w._version, self.weights_epoch, w.data_ptr())
         if self.batched_pack and (s.packed_fwd is None or s.version != v or (need_dgrad and not s.is_stem and not getattr(s, "has_dgrad", False))):
             self.pack_all(need_dgrad or self.model.training)
+            return
+        if s.is_stem and self.stem_rows:
+            if s.packed_fwd is None or s.version != v or s.packed_fwd.device != w.device or s.packed_fwd.numel() != s.cout * 448:
+                s.packed_fwd = torch.empty(s.cout * 448, dtype=torch.bfloat16, device=w.device)
+                arr, nblk = _lib.fill_pack_jobs([(w.data_ptr(), s.packed_fwd.data_ptr(), s.cout, s.cin, 49, 64, 448, 2)])
+                jobs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(w.device)
+                check(_lib.lib().iswm_pack_weights_batched(jobs.data_ptr(), 1, nblk, _st()), "pack stem")
+                self._stem_job_keep = jobs
+                s.version = v
             return
         if s.packed_fwd is None or s.version != v or s.packed_fwd.device != w.device:
             s.packed_fwd = ops.pack_weight_fwd(w.detach(), out=s.packed_fwd if (s.packed_fwd is not None and s.packed_fwd.device == w.device) else None, stem=s.is_stem)
@@ -342,7 +360,7 @@ class Engine:
             self.wacc_off = {}
             for s in self.specs:
                 if s.k > 1:
-                    n = s.cout * (160 if s.is_stem else s.k * s.k * s.cin)
+                    n = s.cout * (7 * STEM_KPITCH if s.is_stem else s.k * s.k * s.cin)   # stem: [Cout][7][kpitch] (row taps) or [Cout][160] (im2col)
                     self.wacc_off[s.name] = (wsz, n)
                     wsz += n
             self.wacc = torch.zeros(wsz, dtype=torch.float32, device=self.device)
@@ -354,6 +372,8 @@ class Engine:
         d = ops.make_conv_desc(B if B is not None else x.B, Hi if Hi is not None else x.H, Wi if Wi is not None else x.W,
                                cin if cin is not None else x.C, x.ld, n_img, Ho, Wo,
                                cout if cout is not None else s.cout, out_ld, taps, flags, res_ld)
+        if stats is not None:
+            d.stats_replicas = stats.numel() // (2 * d.Cout)
         ev = self._prof_begin()
         check(_lib.lib().iswm_conv_igemm(C.byref(d), x.ptr, (wgt if wgt is not None else s.packed_fwd).data_ptr(),
                                          out_t.data_ptr(), None if scale is None else scale.data_ptr(),
@@ -421,7 +441,8 @@ class Engine:
         M = B * Ho * Wo
         Cout = s.cout
         raw = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=self.device)
-        stats = self._stats_slot(2 * Cout)
+        rep = self._stats_rep(Cout)
+        stats = self._stats_slot(2 * Cout * rep)
         self._conv(s, xin, raw, Cout, Ho, Wo, taps, n_img, _lib.EPI_STATS, stats=stats)
         if out is None:
             out = Act.new(B, Ho, Wo, Cout, self.device)
@@ -435,7 +456,7 @@ class Engine:
         # instead of the block output (ISWM_RELU_BITS=0 restores the activation read)
         bits = torch.empty((M, Cout // 8), dtype=torch.uint8, device=self.device) if (relu and residual is not None and self.relu_bits) else None
         ev = self._prof_begin()
-        check(L.iswm_bn_train_apply(raw.data_ptr(), Cout, stats.data_ptr(), M, Cout, bn.weight.data_ptr(), bn.bias.data_ptr(),
+        check(L.iswm_bn_train_apply(raw.data_ptr(), Cout, stats.data_ptr(), rep, M, Cout, bn.weight.data_ptr(), bn.bias.data_ptr(),
                                     BN_EPS, BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                     bn.num_batches_tracked.data_ptr(), save.data_ptr(), save[Cout:].data_ptr(),
                                     None if residual is None else residual.ptr, 0 if residual is None else residual.ld,
@@ -537,14 +558,15 @@ class Engine:
         self._pack(s, True)
         xin, taps, n_img, Ho, Wo = self._prep_input(s, x)
         raw = torch.empty((x.B, Ho, Wo, s.cout), dtype=torch.bfloat16, device=self.device)
-        stats = self._stats_slot(2 * s.cout)
+        stats = self._stats_slot(2 * s.cout * self._stats_rep(s.cout))
         self._conv(s, xin, raw, s.cout, Ho, Wo, taps, n_img, _lib.EPI_STATS, stats=stats)
         return raw, stats, xin, taps, n_img, Ho, Wo
 
     def _bn_side(self, bn, stats, save, Cc, train_fwd: bool):
         return _lib.BnSide(stats.data_ptr() if stats is not None else None, bn.weight.data_ptr(), bn.bias.data_ptr(),
                            bn.running_mean.data_ptr() if train_fwd else None, bn.running_var.data_ptr() if train_fwd else None,
-                           bn.num_batches_tracked.data_ptr() if train_fwd else None, save.data_ptr(), save[Cc:].data_ptr())
+                           bn.num_batches_tracked.data_ptr() if train_fwd else None, save.data_ptr(), save[Cc:].data_ptr(),
+                           1 if stats is None else stats.numel() // (2 * Cc))
 
     def _unit_train_dual(self, s: ConvSpec, x: Act, sds: ConvSpec, xds: Act, dsc) -> Act:
         """Closing unit of a bottleneck block with a downsample branch (resnet.py:110-118): out = relu(bn3(conv3(x)) +
@@ -820,7 +842,7 @@ class Engine:
         need = 0
         for s in self.specs:
             if s.bn is not None:
-                need += 4 * s.cout + 192    # fwd stats + bwd sums and barrier counter (fp64); the same count covers mean/invstd (fp32)
+                need += 2 * s.cout * (self._stats_rep(s.cout) + 1) + 192    # fwd stats (x copies) + bwd sums and barrier counter (fp64); covers mean/invstd (fp32) too
         need += 4096
         if getattr(self, "_scratch64", None) is None or self._scratch64.numel() < need or self._scratch64.device != self.device:
             self._scratch64 = torch.empty(need, dtype=torch.float64, device=self.device)
@@ -828,6 +850,12 @@ class Engine:
         self._scratch64.zero_()
         self._scratch64_off = 0
         self._scratch32_off = 0
+
+    @staticmethod
+    def _stats_rep(cout: int) -> int:
+        """Copies of a convolution's statistics accumulator (iswm_conv_desc.stats_replicas): narrow layers end every CTA on the
+        same 2*Cout addresses, so their fp64 atomics are spread over 4 copies that the BatchNorm kernel folds (cfg2 same-box: 12.87 -> 12.65 ms/step; 8 copies: 12.73)."""
+        return int(__import__("os").environ.get("ISWM_STATS_REP", "4")) if cout <= 128 else 1
 
     def _stats_slot(self, n: int) -> torch.Tensor:
         """zeroed fp64 accumulator slot"""
@@ -880,11 +908,21 @@ class Engine:
 
         # ---- stem: 7x7/s2 conv as im2col GEMM -> BN -> ReLU -> maxpool 3x3/s2 (resnet.py:144-148)
         H1, W1 = (H + 1) // 2, (W + 1) // 2
-        Kp = 160
-        col = torch.empty((B * H1 * W1, Kp), dtype=torch.bfloat16, device=dev)
-        check(L.iswm_stem_im2col(x.data_ptr(), B, 3, H, W, H1, W1, Kp, col.data_ptr(), _st()), "stem_im2col")
-        colA = Act(col.view(1, 1, B * H1 * W1, Kp), 1, 1, B * H1 * W1, Kp, Kp)
-        stem_out = self._stem_unit(colA, B, H1, W1, train)
+        if self.stem_rows and self.stem.cin <= 3:
+            # x-unrolled rows, phase-major over the row parity: [2][B][H1][W1][kpitch]; the 7 kernel rows are the convolution's taps
+            rows = torch.empty((2 * B, H1, W1, STEM_KPITCH), dtype=torch.bfloat16, device=dev)
+            ev = self._prof_begin()
+            check(L.iswm_stem_rows(x.data_ptr(), B, self.stem.cin, H, W, H1, W1, STEM_KPITCH, rows.data_ptr(), _st()), "stem_rows")
+            self._prof_end(ev, "hbm:stem_rows", 4.0 * x.numel() + 2.0 * rows.numel(), "stem_rows")
+            colA = Act(rows, B, H1, W1, STEM_KPITCH, STEM_KPITCH)
+            stem_taps = [((r - 3 - ((r + 1) & 1)) // 2, 0, (r + 1) & 1) for r in range(7)]
+            stem_out = self._stem_unit(colA, B, H1, W1, train, stem_taps, 2 * B)
+        else:
+            Kp = 160
+            col = torch.empty((B * H1 * W1, Kp), dtype=torch.bfloat16, device=dev)
+            check(L.iswm_stem_im2col(x.data_ptr(), B, 3, H, W, H1, W1, Kp, col.data_ptr(), _st()), "stem_im2col")
+            colA = Act(col.view(1, 1, B * H1 * W1, Kp), 1, 1, B * H1 * W1, Kp, Kp)
+            stem_out = self._stem_unit(colA, B, H1, W1, train)
         H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
         pooled = Act.new(B, H2, W2, 64, dev)
         idx = torch.empty((B, H2, W2, 64), dtype=torch.uint8, device=dev) if train else None
@@ -1011,26 +1049,33 @@ class Engine:
             self._ones_t = t
         return t
 
-    def _stem_unit(self, colA: Act, B, H1, W1, train) -> Act:
-        """The stem conv runs as a 1-tap GEMM over the im2col matrix; output viewed as [B,H1,W1,64]."""
+    def _stem_unit(self, colA: Act, B, H1, W1, train, row_taps=None, n_img=1) -> Act:
+        """The stem conv: `row_taps` given = 7 row taps over the x-unrolled image rows (colA = [2B,H1,W1,24] phase-major);
+        else a 1-tap GEMM over the im2col matrix. Output [B,H1,W1,64]."""
         L = _lib.lib()
         s = self.stem
         self._pack(s, False)
         M = B * H1 * W1
         dev = self.device
         out = Act.new(B, H1, W1, 64, dev)
-        taps = [(0, 0, 0)]
+        if row_taps is not None:
+            taps, geo = row_taps, dict(Hi=H1, Wi=W1, B=B)
+            Ho_, Wo_ = H1, W1
+        else:
+            taps, geo = [(0, 0, 0)], {}
+            Ho_, Wo_ = 1, M
         if not train:
             self._fold(s)
-            self._conv(s, colA, out.t, 64, 1, M, taps, 1, _lib.EPI_AFFINE | _lib.EPI_RELU, s.fold_scale, s.fold_shift, cin=colA.C)
+            self._conv(s, colA, out.t, 64, Ho_, Wo_, taps, n_img, _lib.EPI_AFFINE | _lib.EPI_RELU, s.fold_scale, s.fold_shift, cin=colA.C, **geo)
             self._tap(s.name, out)
             return out
         raw = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
-        stats = self._stats_slot(128)
-        self._conv(s, colA, raw, 64, 1, M, taps, 1, _lib.EPI_STATS, stats=stats, cin=colA.C)
+        rep = self._stats_rep(64)
+        stats = self._stats_slot(128 * rep)
+        self._conv(s, colA, raw, 64, Ho_, Wo_, taps, n_img, _lib.EPI_STATS, stats=stats, cin=colA.C, **geo)
         save = self._save_slot(128)
         bn = s.bn
-        check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
+        check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), rep, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                     BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
                                     save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, None, out.ptr, 64, None, _st()), "bn_train_apply stem")
         self._tap(s.name, out)
@@ -1048,11 +1093,19 @@ class Engine:
             out.grad = None
             off, n = self.wacc_off[s.name]
             acc = self.wacc[off:off + n]
-            d = ops.make_conv_desc(1, 1, M, colA.C, colA.ld, 1, 1, M, 64, 64, taps)
+            if row_taps is not None:
+                d = ops.make_conv_desc(B, H1, W1, colA.C, colA.ld, n_img, H1, W1, 64, 64, taps)
+            else:
+                d = ops.make_conv_desc(1, 1, M, colA.C, colA.ld, 1, 1, M, 64, 64, taps)
             gview = self.grad_views[id(s.conv.weight)]
             with self._wgrad_ctx(dy, colA.t):
+                ev = self._prof_begin()
                 check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
-                check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
+                self._prof_end(ev, "conv_wgrad", 2.0 * M * 64 * 147, "wgrad " + s.name)
+                if row_taps is not None:
+                    check(L.iswm_unpack_wgrad_stem(acc.data_ptr(), 64, s.cin, 7, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad_stem")
+                else:
+                    check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
                 self._notify(s.conv.weight)
                 self._notify(bn.weight)
                 self._notify(bn.bias)

@@ -106,7 +106,7 @@ class DataParallel:
         self.model, self.criterion, self.group = model, criterion, group
         self.engine = model.engine()
         self.world = dist.get_world_size(group)
-        self.bucket_bytes = bucket_bytes
+        self.bucket_bytes = int(os.environ.get("ISWM_DP_BUCKET_MB", "0")) << 20 or bucket_bytes   # experiment knob
         self.bucketer: Optional[GradBucketer] = None
         self.comm_mode, self.peer = "nccl", None
         p0 = next(iter(model.parameters()))

@@ -332,3 +332,25 @@ def test_conv_dgrad_carrying_the_bn_backward_reduction(B, Cu, H, W, Cv, k, dil):
     assert float((dx.float() - dx_ref.float()).abs().max()) <= 8e-3 * amax      # one bf16 ulp where a sum's last bits moved
     np.testing.assert_allclose(dg2.cpu().numpy(), dg.cpu().numpy(), rtol=1e-4, atol=1e-4 * scale.max())
     np.testing.assert_allclose(db2.cpu().numpy(), db.cpu().numpy(), rtol=1e-4, atol=1e-4 * scale.max())
+
+
+@pytest.mark.parametrize("Cout,rep", [(64, 8), (48, 8), (128, 3), (256, 2)])
+def test_conv_stats_replicas_sum_to_the_single_accumulator(Cout, rep):
+    """iswm_conv_desc.stats_replicas: CTA i adds its per-channel sums into copy i % replicas of the fp64 accumulator; the copies
+    summed in fp64 give the fp32 statistics of the single-copy run bit for bit (what iswm_bn_train_apply reads)."""
+    B, Cin, H, W = 4, 64, 40, 40
+    x, w = _mk(B, Cin, H, W, Cout, 3, seed=31)
+    xd, wp = _nhwc(x).to(DEV), ops.pack_weight_fwd(w.to(DEV))
+    out_ld = ((Cout + 7) // 8) * 8
+    res = []
+    for r in (1, rep):
+        out = torch.zeros((B, H, W, out_ld), dtype=torch.bfloat16, device=DEV)
+        stats = torch.zeros(2 * Cout * r, dtype=torch.float64, device=DEV)
+        d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, out_ld, ops.conv_taps(3, 1), flags=_lib.EPI_STATS)
+        d.stats_replicas = r
+        ops.conv_igemm(d, xd, wp, out, stats=stats)
+        _assert_healthy()
+        res.append((out.clone(), stats.view(r, 2 * Cout)))
+    assert torch.equal(res[0][0], res[1][0])
+    assert float(res[1][1].abs().sum(1).min()) > 0            # every copy received something (50 tiles over `rep` copies)
+    assert torch.equal(res[0][1].sum(0).float(), res[1][1].sum(0).float())

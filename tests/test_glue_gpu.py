@@ -66,7 +66,7 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
     nbt = torch.zeros((), dtype=torch.long, device=DEV)
     gd, bd = gamma.to(DEV), beta.to(DEV)
     resd = nhwc(res).to(DEV) if with_res else None
-    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, rmd.data_ptr(), rvd.data_ptr(),
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), 1, M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, rmd.data_ptr(), rvd.data_ptr(),
                                   nbt.data_ptr(), save.data_ptr(), save[C:].data_ptr(), None if resd is None else resd.data_ptr(), C,
                                   1 if relu else 0, 0.0, 0, None, out.data_ptr(), C, None, st()))
     close(nchw(out), y.detach(), 1e-2, 2e-2)
@@ -100,7 +100,7 @@ def test_bn_train_apply_and_backward(B, C, H, W, relu, with_res):
         # packed ReLU sign bits (one byte per 8 channels) instead of the activation: identical sums and gradients
         bits = torch.zeros((M, C // 8), dtype=torch.uint8, device=DEV)
         out_b = torch.empty_like(out)
-        check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+        check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), 1, M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
                                       save.data_ptr(), save[C:].data_ptr(), resd.data_ptr(), C, 1, 0.0, 0, None, out_b.data_ptr(), C, bits.data_ptr(), st()))
         assert torch.equal(out_b, out)
         want = (out.float().reshape(M, C // 8, 8) > 0).to(torch.int32) * (2 ** torch.arange(8, device=DEV, dtype=torch.int32))
@@ -339,12 +339,12 @@ def test_bn_backward_with_dropout_against_torch_with_the_kernels_own_mask(B, C, 
     out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
     save = torch.empty(2 * C, dtype=torch.float32, device=DEV)
     gd, bd = gamma.to(DEV), beta.to(DEV)
-    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), 1, M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
                                   save.data_ptr(), save[C:].data_ptr(), None, C, 1, p, seed, step.data_ptr(), out.data_ptr(), C, None, st()))
     # the keep mask depends on (seed, step, element index) only: the same launch WITHOUT the ReLU leaves bn(x) * keep / (1 - p),
     # which is zero exactly where the element was dropped (bn(x) == 0 itself has measure zero)
     probe = torch.empty_like(out)
-    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), 1, M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
                                   save.data_ptr(), save[C:].data_ptr(), None, C, 0, p, seed, step.data_ptr(), probe.data_ptr(), C, None, st()))
     mask = (nchw(probe).float().cpu() != 0).float()
     frac = float(mask.mean())
@@ -374,7 +374,7 @@ def test_bn_backward_with_dropout_against_torch_with_the_kernels_own_mask(B, C, 
     # a different step counter draws a different mask (the graph-replayed step advances it on the device)
     out2 = torch.empty_like(out)
     step2 = torch.tensor([8], dtype=torch.int64, device=DEV)
-    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
+    check(L().iswm_bn_train_apply(xd.data_ptr(), C, stats.data_ptr(), 1, M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, None, None, None,
                                   save.data_ptr(), save[C:].data_ptr(), None, C, 1, p, seed, step2.data_ptr(), out2.data_ptr(), C, None, st()))
     assert not torch.equal(out2, out)
 
@@ -438,3 +438,59 @@ def test_dual_batchnorm_of_a_downsample_block_against_torch(B, C, H, W):
         close(nchw(dx), xr_.grad, 2e-2, 2e-2 * scale)
         close(dg, gr_.grad, 2e-2, 5e-2)
         close(db, br_.grad, 2e-2, 5e-2)
+
+
+@pytest.mark.parametrize("kp", [32, 24])
+@pytest.mark.parametrize("B,H,W", [(2, 18, 22), (1, 65, 49), (2, 200, 131), (1, 7, 9)])
+def test_stem_row_taps_forward_and_weight_gradient(B, H, W, kp):
+    """Stem 7x7 / stride 2 / pad 3 (network/backbone/resnet.py:144) in ROW-TAP form: iswm_stem_rows (image unrolled along x, two
+    row-parity phases, bit-exact against the padded image), then the 7 kernel rows as taps of iswm_conv_igemm / iswm_conv_wgrad
+    with the mode-2 packed weights and iswm_unpack_wgrad_stem, against F.conv2d and its autograd weight gradient. Odd sizes:
+    the odd phase has one row less (zero row), ragged edges."""
+    import ctypes as Ct
+    from iswm_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    img = torch.randn((B, 3, H, W), generator=g)
+    w = torch.randn((64, 3, 7, 7), generator=g) * 0.1
+    H1, W1 = (H + 1) // 2, (W + 1) // 2
+    rows = torch.full((2 * B, H1, W1, kp), 7.0, dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_stem_rows(img.to(DEV).data_ptr(), B, 3, H, W, H1, W1, kp, rows.data_ptr(), st()))
+    pad = F.pad(img, (3, 3 + 2, 0, 2))                                    # x: 3 left / right (+ slack for odd W), y: slack rows below
+    ref = torch.zeros((2, B, H1, W1, 24))
+    for p in range(2):
+        for hh in range(H1):
+            h = 2 * hh + p
+            if h >= H:
+                continue
+            for s_ in range(7):
+                # element [.., wo, s*3 + c] = img[b, c, h, 2*wo + s - 3]  (padded coordinates: 2*wo + s)
+                ref[p, :, hh, :, 3 * s_:3 * s_ + 3] = pad[:, :, h, s_:s_ + 2 * W1:2][:, :, :W1].permute(0, 2, 1)
+    assert torch.equal(rows.cpu().view(2, B, H1, W1, kp)[..., :24], ref.to(torch.bfloat16))
+    assert torch.count_nonzero(rows[..., 21:]).item() == 0
+    # forward: 7 row taps over the two phases
+    arr, nblk = _lib.fill_pack_jobs([(w.to(DEV).data_ptr(), 0, 64, 3, 49, 64, 448, 2)])
+    wd = w.to(DEV)
+    wp = torch.empty(64 * 448, dtype=torch.bfloat16, device=DEV)
+    arr, nblk = _lib.fill_pack_jobs([(wd.data_ptr(), wp.data_ptr(), 64, 3, 49, 64, 448, 2)])
+    jobs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(DEV)
+    check(L().iswm_pack_weights_batched(jobs.data_ptr(), 1, nblk, st()))
+    taps = [((r - 3 - ((r + 1) & 1)) // 2, 0, (r + 1) & 1) for r in range(7)]
+    out = torch.zeros((B, H1, W1, 64), dtype=torch.bfloat16, device=DEV)
+    d = ops.make_conv_desc(B, H1, W1, kp, kp, 2 * B, H1, W1, 64, 64, taps)
+    ops.conv_igemm(d, rows, wp, out)
+    torch.cuda.synchronize()
+    assert ops.abort_code() == 0
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    y = F.conv2d(img.to(torch.bfloat16).float(), wr, stride=2, padding=3)
+    close(nchw(out), y.detach(), 1e-2, 1e-2)
+    # weight gradient
+    dy = rnd((B, 64, H1, W1), 18)
+    y.backward(dy.float())
+    acc = torch.zeros((64, 7, kp), dtype=torch.float32, device=DEV)
+    ops.conv_wgrad(d, rows, nhwc(dy).to(DEV), acc)
+    grad = torch.zeros((64, 3, 7, 7), dtype=torch.float32, device=DEV)
+    check(L().iswm_unpack_wgrad_stem(acc.data_ptr(), 64, 3, 7, kp, 0.0, grad.data_ptr(), st()))
+    torch.cuda.synchronize()
+    assert ops.abort_code() == 0
+    assert float((grad.cpu() - wr.grad).abs().max()) <= 5e-3 * float(wr.grad.abs().max())
+    assert torch.count_nonzero(acc[:, :, 21:]).item() == 0

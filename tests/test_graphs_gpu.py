@@ -124,7 +124,7 @@ def test_dropout_mask_follows_device_step_counter():
     def run(seed, step):
         out = torch.empty_like(x)
         sp = None if step is None else torch.tensor([step], dtype=torch.int64, device=DEV)
-        _lib.check(_lib.lib().iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), M, C, gm.data_ptr(), bt.data_ptr(), 1e-5, 0.1, None, None, None,
+        _lib.check(_lib.lib().iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), 1, M, C, gm.data_ptr(), bt.data_ptr(), 1e-5, 0.1, None, None, None,
                                                   save.data_ptr(), save[C:].data_ptr(), None, C, 0, p, seed, None if sp is None else sp.data_ptr(),
                                                   out.data_ptr(), C, None, st), "bn_train_apply")
         torch.cuda.synchronize()

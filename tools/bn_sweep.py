@@ -31,7 +31,7 @@ for M, C in shapes:
     save = torch.empty(2 * C, device=dev); sums = torch.zeros(2 * C, dtype=torch.float64, device=dev); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
     for with_res in (False, True):
         rp = res.data_ptr() if with_res else None
-        t1 = timeit(lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), M, C, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),
+        t1 = timeit(lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), 1, M, C, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),
                                                              save.data_ptr(), save[C:].data_ptr(), rp, C, 1, 0.0, 0, None, out.data_ptr(), C, None, st())))
         ap = out.data_ptr() if with_res else None
         t2 = timeit(lambda: _lib.check(L.iswm_bn_bwd_reduce(dout.data_ptr(), C, x.data_ptr(), C, ap, C, M, C, save.data_ptr(), save[C:].data_ptr(), g.data_ptr(), b.data_ptr(), 1, 0.0, 0, None, sums.data_ptr(), st())))

@@ -42,7 +42,7 @@ for (M, C) in [(16, 256), (16384, 256), (16384, 1024), (65536, 512), (262144, 25
     gm = torch.ones(C, device=dev); bt = torch.zeros(C, device=dev); save = torch.empty(2 * C, device=dev)
     sums = torch.zeros(2 * C + 2, dtype=torch.float64, device=dev)
     dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
-    fa = lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), M, C, gm.data_ptr(), bt.data_ptr(), 1e-5, 0.1, None, None, None,
+    fa = lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), 1, M, C, gm.data_ptr(), bt.data_ptr(), 1e-5, 0.1, None, None, None,
                                                   save.data_ptr(), save[C:].data_ptr(), None, C, 1, 0.0, 0, None, out.data_ptr(), C, None, st()), "a")
     fr = lambda: _lib.check(L.iswm_bn_bwd_reduce(out.data_ptr(), C, x.data_ptr(), C, None, C, M, C, save.data_ptr(), save[C:].data_ptr(), gm.data_ptr(), bt.data_ptr(),
                                                  1, 0.0, 0, None, sums.data_ptr(), st()), "r")

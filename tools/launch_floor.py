@@ -31,6 +31,6 @@ for (M, C) in [(128, 64), (16384, 256), (16384, 1024)]:
     x = torch.randn((M, C), device=dev).to(torch.bfloat16); out = torch.empty_like(x)
     stats = torch.stack([x.double().sum(0), (x.double() ** 2).sum(0)]).reshape(-1).contiguous()
     g = torch.ones(C, device=dev); b = torch.zeros(C, device=dev); save = torch.empty(2 * C, device=dev)
-    t = bench(lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), M, C, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, None,
+    t = bench(lambda: _lib.check(L.iswm_bn_train_apply(x.data_ptr(), C, stats.data_ptr(), 1, M, C, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, None,
                                                        save.data_ptr(), save[C:].data_ptr(), None, C, 1, 0.0, 0, None, out.data_ptr(), C, None, st())))
     print(f"bn_train_apply M={M} C={C}: {t:6.2f} us/launch back-to-back ({M * C * 4 / t / 1e3:6.0f} GB/s)")
