@@ -815,6 +815,7 @@ def run_ours(args):
                "sample": f"1 warm-up + 2 timed steps of batch 2, {H}x{W}, R50-OS16 fwd+CE+bwd+SGD, fp32 torch oracle on the host"}
     gflop = TRAIN_GFLOP_PER_IMG.get((args.backbone, args.output_stride, H))
     extra = None
+    launch_mode = "one CUDA graph replay per step (GraphedTrainStep)" if stepper is not None else "eager launches"
     if world == 1 and not args.no_extras and (args.backbone, args.output_stride, H, B) == ("resnet50", 16, 512, 16):
         del model, opt, stepper, x_dev, y_dev
         torch.cuda.empty_cache()
@@ -828,7 +829,7 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": train_workload_name(args.backbone, args.output_stride, H, W, B),
                    "parallelism": f"dp{world}", "global_batch": B * world,
-                   "launch": "one CUDA graph replay per step (GraphedTrainStep)" if stepper is not None else "eager launches",
+                   "launch": launch_mode,
                    "comm": None if dp is None else ("peer-memory kernels over NVLink (iswm_b200.peer): histogram / gradient buckets / loss, captured in the graph"
                                                     if dp.comm_mode == "peer" else "torch.distributed NCCL collectives"),
                    "l2": "no explicit flush: each step streams > 2 GB of activations (>> 126 MB L2)",
