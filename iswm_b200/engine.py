@@ -621,16 +621,13 @@ class Engine:
         d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps)
         with self._wgrad_ctx(dy, xin.t):
             ev = self._prof_begin()
-            if s.k == 1:
-                check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), gview.data_ptr(), _st()), "conv_wgrad " + s.name)
-                self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin, "wgrad " + s.name)
-            else:
-                off, n = self.wacc_off[s.name]
-                acc = self.wacc[off:off + n]
-                check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad " + s.name)
-                self._prof_end(ev, "conv_wgrad", 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k, "wgrad " + s.name)
+            dst = gview if s.k == 1 else self.wacc[self.wacc_off[s.name][0]:self.wacc_off[s.name][0] + self.wacc_off[s.name][1]]
+            flops = 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k
+            check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), dst.data_ptr(), _st()), "conv_wgrad " + s.name)
+            self._prof_end(ev, "conv_wgrad", flops, "wgrad " + s.name)
+            if s.k != 1:
                 if not self._batched_unpack():
-                    check(L.iswm_unpack_wgrad(acc.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
+                    check(L.iswm_unpack_wgrad(dst.data_ptr(), Cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
             # notifications are issued in the same context: a bucket all-reduce launched from here orders itself after
             # this stream, which has seen everything the main stream produced up to this unit (BatchNorm gradients too)
             self._notify(s.conv.weight)
@@ -766,7 +763,7 @@ class Engine:
         if not self.async_wgrad or self.debug_units is not None:      # the unit-replay recorder reads dW right away
             return Engine._NullCtx()
         if self._wstream is None or self._wstream.device != self.device:
-            self._wstream = torch.cuda.Stream(self.device)
+            self._wstream = torch.cuda.Stream(self.device, priority=int(__import__("os").environ.get("ISWM_WSTREAM_PRIO", "0")))
         main = torch.cuda.current_stream(self.device)
         self._wstream.wait_event(main.record_event())
         # held until the join below: their memory returns to the (main-stream) allocator pool only after the main
@@ -798,7 +795,7 @@ class Engine:
         if not (self.async_wgrad and self.fwd_overlap) or self.profile is not None or self.debug_units is not None or self.debug_taps is not None:
             return Engine._NullCtx()
         if self._wstream is None or self._wstream.device != self.device:
-            self._wstream = torch.cuda.Stream(self.device)
+            self._wstream = torch.cuda.Stream(self.device, priority=int(__import__("os").environ.get("ISWM_WSTREAM_PRIO", "0")))
         self._wstream.wait_event(torch.cuda.current_stream(self.device).record_event())
         self._fwd_forked = True
         return Engine._HandleCtx(self._wstream)
