@@ -1779,11 +1779,13 @@ extern "C" int iswm_bn_bwd_reduce(const void* d_dout, int dout_ld, const void* d
     nx = 32; ny = kT / nx;
     groups = (C / 8 + nx - 1) / nx;
     int64_t want = (M + (int64_t)ny * 8 - 1) / ((int64_t)ny * 8);
-    want = std::max<int64_t>(1, std::min<int64_t>(want, std::max(1, num_sms() * 3 / groups)));
+    static const int env_rw0 = [] { const char* e = getenv("ISWM_BN_RED_WAVES"); return e ? atoi(e) : 3; }();
+    want = std::max<int64_t>(1, std::min<int64_t>(want, std::max(1, num_sms() * env_rw0 / groups)));
     rows_per_block = (int)((M + want - 1) / want);
     blocks = (int)((M + rows_per_block - 1) / rows_per_block);
   } else {
-    bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, 3);   // one wave: every block ends with fp64 atomics on the same 2C addresses
+    static const int env_rw = [] { const char* e = getenv("ISWM_BN_RED_WAVES"); return e ? atoi(e) : 3; }();
+    bn_row_grid(C, M, 8, nx, ny, rows_per_block, blocks, env_rw);   // one wave: every block ends with fp64 atomics on the same 2C addresses
   }
   const int mask = !relu ? 0 : (relu == 2 ? 3 : (d_out_act ? 1 : 2));
   const bool has_drop = drop_p > 0.f;
