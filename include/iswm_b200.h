@@ -361,6 +361,20 @@ int iswm_bn_dual_bwd_apply(const void* d_dout, int dout_ld, const uint8_t* d_rel
                            int64_t M, int C, void* d_dx, int dx_ld, void* d_dx_ds, int dx_ds_ld,
                            float* d_dgamma, float* d_dbeta, float* d_dgamma_ds, float* d_dbeta_ds, void* stream);
 
+/* ---- stem tail: BatchNorm + ReLU + 3x3/s2/p1 max pooling in ONE pass (csrc/stem_pool.cu; network/backbone/resnet.py:145-147) ----
+ * forward: d_raw bf16 [B,H,W,64] = the stem convolution's pre-BN output (with its statistics in bn->stats); writes the pooled
+ * bf16 [B,Ho,Wo,64] tensor and, per pooled element, which of the 9 window positions won (uint8 [B,Ho,Wo,64], first maximum in
+ * window order) - the normalised half-resolution activation is never written. bn: stats / gamma / beta read, running statistics
+ * updated, save_mean / save_invstd written. */
+int iswm_stem_pool_fwd(const void* d_raw, const iswm_bn_side* bn, int B, int H, int W, int C, int Ho, int Wo,
+                       float eps, float momentum, void* d_out, uint8_t* d_idx, void* stream);
+/* backward (two launches inside): d_dpool bf16 [B,Ho,Wo,64] gradient of the pooled tensor -> d_dy bf16 [B,H,W,64] gradient of the
+ * pre-BN tensor; both BatchNorm-backward passes gather the activation gradient through the argmax codes and recompute the ReLU
+ * mask from d_raw, so that gradient is never written either. d_sums double[128], zeroed by the caller; dgamma / dbeta ACCUMULATE. */
+int iswm_stem_pool_bwd(const void* d_dpool, const uint8_t* d_idx, const void* d_raw, const iswm_bn_side* bn,
+                       int B, int H, int W, int C, int Ho, int Wo, double* d_sums, void* d_dy,
+                       float* d_dgamma, float* d_dbeta, void* stream);
+
 /* Both passes in ONE launch (what the engine uses): pass 1, a grid-wide barrier, pass 2 over the same rows (served
  * from L2 for all but the largest tensors). d_sums: double[2*C + 1], zeroed by the caller; the extra cell is the
  * barrier's arrival counter. The grid is sized to be co-resident; the barrier wait is bounded

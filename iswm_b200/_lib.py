@@ -127,6 +127,8 @@ SIGNATURES = {
     "iswm_bn_dual_bwd_reduce": (_i, [_p, _i, _p, _p, _i, C.POINTER(BnSide), _p, _i, C.POINTER(BnSide), _i64, _i, _p, _p, _p]),
     "iswm_bn_dual_bwd_apply": (_i, [_p, _i, _p, _p, _i, C.POINTER(BnSide), _p, _p, _i, C.POINTER(BnSide), _p, _i64, _i, _p, _i, _p, _i,
                                     _p, _p, _p, _p, _p]),
+    "iswm_stem_pool_fwd": (_i, [_p, C.POINTER(BnSide), _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p]),
+    "iswm_stem_pool_bwd": (_i, [_p, _p, _p, C.POINTER(BnSide), _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "iswm_bn_bwd": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _u64, _p, _p, _i, _p, _i, _p, _p, _p]),
     "iswm_stem_rows": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_unpack_wgrad_stem": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),

@@ -159,6 +159,9 @@ class Engine:
         # implicit GEMM over the two row-parity phases, instead of a full im2col matrix (320 B per pixel) + one GEMM
         # (ISWM_STEM_ROWS=0: the im2col form)
         self.stem_rows = __import__("os").environ.get("ISWM_STEM_ROWS", "1") != "0"
+        # stem tail (train): BatchNorm + ReLU + maxpool as one pass forward and one reduce / apply pair backward
+        # (csrc/stem_pool.cu: neither the half-resolution activation nor its gradient is written); ISWM_STEM_POOL=0: separate kernels
+        self.stem_pool = __import__("os").environ.get("ISWM_STEM_POOL", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -921,10 +924,14 @@ class Engine:
             colA = Act(col.view(1, 1, B * H1 * W1, Kp), 1, 1, B * H1 * W1, Kp, Kp)
             stem_out = self._stem_unit(colA, B, H1, W1, train)
         H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
-        pooled = Act.new(B, H2, W2, 64, dev)
-        idx = torch.empty((B, H2, W2, 64), dtype=torch.uint8, device=dev) if train else None
-        check(L.iswm_maxpool_fwd(stem_out.ptr, B, H1, W1, 64, H2, W2, pooled.ptr, None if idx is None else idx.data_ptr(), _st()), "maxpool_fwd")
-        if train:
+        if isinstance(stem_out, tuple):                  # fused stem tail: (pooled activation) came out of _stem_unit directly
+            pooled = stem_out[0]
+            stem_out = None
+        else:
+            pooled = Act.new(B, H2, W2, 64, dev)
+            idx = torch.empty((B, H2, W2, 64), dtype=torch.uint8, device=dev) if train else None
+            check(L.iswm_maxpool_fwd(stem_out.ptr, B, H1, W1, 64, H2, W2, pooled.ptr, None if idx is None else idx.data_ptr(), _st()), "maxpool_fwd")
+        if train and stem_out is not None:
             def pool_bwd():
                 g = pooled.grad
                 assert g.ld == 64
@@ -1072,6 +1079,31 @@ class Engine:
         self._conv(s, colA, raw, 64, Ho_, Wo_, taps, n_img, _lib.EPI_STATS, stats=stats, cin=colA.C, **geo)
         save = self._save_slot(128)
         bn = s.bn
+        fused_tail = self.stem_pool and self.debug_units is None and self.debug_taps is None
+        if fused_tail:
+            H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
+            pooled = Act.new(B, H2, W2, 64, dev)
+            idx = torch.empty((B, H2, W2, 64), dtype=torch.uint8, device=dev)
+            side = self._bn_side(bn, stats, save, 64, True)
+            ev = self._prof_begin()
+            check(L.iswm_stem_pool_fwd(raw.data_ptr(), C.byref(side), B, H1, W1, 64, H2, W2, BN_EPS, BN_MOMENTUM, pooled.ptr, idx.data_ptr(), _st()), "stem_pool_fwd")
+            self._prof_end(ev, "hbm:stem_pool_fwd", 2.0 * M * 64 + 3.0 * B * H2 * W2 * 64, "stem_pool_fwd")
+
+            def backward_fused():
+                g = pooled.grad
+                assert g is not None and g.ld == 64
+                sums = self._stats_slot(130)
+                dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
+                side_b = self._bn_side(bn, None, save, 64, False)
+                ev = self._prof_begin()
+                check(L.iswm_stem_pool_bwd(g.ptr, idx.data_ptr(), raw.data_ptr(), C.byref(side_b), B, H1, W1, 64, H2, W2, sums.data_ptr(), dy.data_ptr(),
+                                           self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "stem_pool_bwd")
+                self._prof_end(ev, "hbm:stem_pool_bwd", 2.0 * (2.0 * M * 64 + 3.0 * B * H2 * W2 * 64) + 2.0 * M * 64, "stem_pool_bwd")
+                pooled.grad = None
+                self._stem_wgrad(s, bn, colA, dy, B, H1, W1, M, taps, row_taps, n_img)
+
+            self.tape.append(backward_fused)
+            return (pooled,)
         check(L.iswm_bn_train_apply(raw.data_ptr(), 64, stats.data_ptr(), rep, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                     BN_MOMENTUM, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
                                     save.data_ptr(), save[64:].data_ptr(), None, 0, 1, 0.0, 0, None, out.ptr, 64, None, _st()), "bn_train_apply stem")
@@ -1088,24 +1120,8 @@ class Engine:
                                       save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, None, dy.data_ptr(), 64, None, 0,
                                       self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd_apply stem")
             out.grad = None
-            off, n = self.wacc_off[s.name]
-            acc = self.wacc[off:off + n]
-            if row_taps is not None:
-                d = ops.make_conv_desc(B, H1, W1, colA.C, colA.ld, n_img, H1, W1, 64, 64, taps)
-            else:
-                d = ops.make_conv_desc(1, 1, M, colA.C, colA.ld, 1, 1, M, 64, 64, taps)
             gview = self.grad_views[id(s.conv.weight)]
-            with self._wgrad_ctx(dy, colA.t):
-                ev = self._prof_begin()
-                check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
-                self._prof_end(ev, "conv_wgrad", 2.0 * M * 64 * 147, "wgrad " + s.name)
-                if row_taps is not None:
-                    check(L.iswm_unpack_wgrad_stem(acc.data_ptr(), 64, s.cin, 7, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad_stem")
-                else:
-                    check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
-                self._notify(s.conv.weight)
-                self._notify(bn.weight)
-                self._notify(bn.bias)
+            self._stem_wgrad(s, bn, colA, dy, B, H1, W1, M, taps, row_taps, n_img)
             if self.debug_units is not None:
                 self.debug_units.append(dict(name=s.name, k=7, stride=2, dilation=1, relu=True, x=None, image=self._image, raw=raw.view(B, H1, W1, 64).clone(),
                                              out=out.t.clone(), dout=dout.t.clone(), mean=save[:64].clone(), invstd=save[64:128].clone(),
@@ -1116,6 +1132,28 @@ class Engine:
 
         self.tape.append(backward)
         return out
+
+    def _stem_wgrad(self, s, bn, colA: Act, dy: torch.Tensor, B, H1, W1, M, taps, row_taps, n_img):
+        """Weight gradient of the stem convolution from dy (gradient of its pre-BN output) on the weight-gradient stream."""
+        L = _lib.lib()
+        off, n = self.wacc_off[s.name]
+        acc = self.wacc[off:off + n]
+        if row_taps is not None:
+            d = ops.make_conv_desc(B, H1, W1, colA.C, colA.ld, n_img, H1, W1, 64, 64, taps)
+        else:
+            d = ops.make_conv_desc(1, 1, M, colA.C, colA.ld, 1, 1, M, 64, 64, taps)
+        gview = self.grad_views[id(s.conv.weight)]
+        with self._wgrad_ctx(dy, colA.t):
+            ev = self._prof_begin()
+            check(L.iswm_conv_wgrad(C.byref(d), colA.ptr, dy.data_ptr(), acc.data_ptr(), _st()), "conv_wgrad stem")
+            self._prof_end(ev, "conv_wgrad", 2.0 * M * 64 * 147, "wgrad " + s.name)
+            if row_taps is not None:
+                check(L.iswm_unpack_wgrad_stem(acc.data_ptr(), 64, s.cin, 7, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad_stem")
+            else:
+                check(L.iswm_unpack_wgrad(acc.data_ptr(), 64, s.cin, 49, s.cin, colA.C, 1.0, gview.data_ptr(), _st()), "unpack_wgrad stem")
+            self._notify(s.conv.weight)
+            self._notify(bn.weight)
+            self._notify(bn.bias)
 
     def _aspp_pool(self, feat: Act, dst: Act, train: bool):
         """ASPPPooling (_deeplab.py:130-141): GAP -> 1x1 -> BN -> ReLU -> broadcast (bilinear from 1x1)."""

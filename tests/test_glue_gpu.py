@@ -494,3 +494,67 @@ def test_stem_row_taps_forward_and_weight_gradient(B, H, W, kp):
     assert ops.abort_code() == 0
     assert float((grad.cpu() - wr.grad).abs().max()) <= 5e-3 * float(wr.grad.abs().max())
     assert torch.count_nonzero(acc[:, :, 21:]).item() == 0
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 33, 47), (3, 64, 40), (1, 9, 7)])
+def test_stem_bn_relu_maxpool_fused_against_the_separate_kernels(B, H, W):
+    """csrc/stem_pool.cu (resnet.py:145-147): BatchNorm + ReLU + maxpool in one pass / its backward without the activation
+    gradient tensor, against bn_train_apply -> maxpool_fwd and maxpool_bwd -> bn_bwd_reduce -> bn_bwd_apply. Pooled values,
+    argmax codes, saved statistics: bit-identical. Backward: same summands in a different fp32 order."""
+    import ctypes as Ct
+    C = 64
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    M = B * H * W
+    raw = rnd((B, C, H, W), 41, 2.0)
+    rawd = nhwc(raw).to(DEV)
+    g = torch.Generator().manual_seed(42)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.randn(C, generator=g) * 0.3).to(DEV)
+    rep = 4
+    st1 = torch.stack([raw.double().sum((0, 2, 3)), (raw.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    stats = torch.zeros(rep * 2 * C, dtype=torch.float64, device=DEV)
+    stats.view(rep, 2 * C)[0] = st1 * 0.25
+    stats.view(rep, 2 * C)[1] = st1 * 0.5
+    stats.view(rep, 2 * C)[3] = st1 * 0.25                       # copies that sum to the statistics (copy 2 stays empty)
+    dpool = nhwc(rnd((B, C, Ho, Wo), 43)).to(DEV)
+    # separate kernels
+    rm1, rv1 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt1 = torch.zeros((), dtype=torch.long, device=DEV)
+    save1 = torch.empty(2 * C, device=DEV)
+    act = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    check(L().iswm_bn_train_apply(rawd.data_ptr(), C, stats.data_ptr(), rep, M, C, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm1.data_ptr(), rv1.data_ptr(),
+                                  nbt1.data_ptr(), save1.data_ptr(), save1[C:].data_ptr(), None, 0, 1, 0.0, 0, None, act.data_ptr(), C, None, st()))
+    pooled1 = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=DEV)
+    idx1 = torch.empty((B, Ho, Wo, C), dtype=torch.uint8, device=DEV)
+    check(L().iswm_maxpool_fwd(act.data_ptr(), B, H, W, C, Ho, Wo, pooled1.data_ptr(), idx1.data_ptr(), st()))
+    dact = torch.empty_like(act)
+    check(L().iswm_maxpool_bwd(dpool.data_ptr(), idx1.data_ptr(), B, H, W, C, Ho, Wo, dact.data_ptr(), st()))
+    sums1 = torch.zeros(2 * C + 2, dtype=torch.float64, device=DEV)
+    check(L().iswm_bn_bwd_reduce(dact.data_ptr(), C, rawd.data_ptr(), C, None, C, M, C, save1.data_ptr(), save1[C:].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                 1, 0.0, 0, None, sums1.data_ptr(), st()))
+    dy1 = torch.empty_like(act)
+    dg1, db1 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    check(L().iswm_bn_bwd_apply(dact.data_ptr(), C, rawd.data_ptr(), C, None, C, M, C, gamma.data_ptr(), beta.data_ptr(), save1.data_ptr(), save1[C:].data_ptr(),
+                                sums1.data_ptr(), 1, 0.0, 0, None, dy1.data_ptr(), C, None, 0, dg1.data_ptr(), db1.data_ptr(), st()))
+    # fused
+    rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt2 = torch.zeros((), dtype=torch.long, device=DEV)
+    save2 = torch.empty(2 * C, device=DEV)
+    side = _lib.BnSide(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(), rv2.data_ptr(), nbt2.data_ptr(), save2.data_ptr(), save2[C:].data_ptr(), rep)
+    pooled2 = torch.full((B, Ho, Wo, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    idx2 = torch.full((B, Ho, Wo, C), 77, dtype=torch.uint8, device=DEV)
+    check(L().iswm_stem_pool_fwd(rawd.data_ptr(), Ct.byref(side), B, H, W, C, Ho, Wo, 1e-5, 0.1, pooled2.data_ptr(), idx2.data_ptr(), st()))
+    assert torch.equal(pooled2, pooled1) and torch.equal(idx2, idx1)
+    assert torch.equal(save2, save1) and torch.equal(rm2, rm1) and torch.equal(rv2, rv1) and nbt2.item() == 1
+    sums2 = torch.zeros(2 * C + 2, dtype=torch.float64, device=DEV)
+    dy2 = torch.full((B, H, W, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    check(L().iswm_stem_pool_bwd(dpool.data_ptr(), idx2.data_ptr(), rawd.data_ptr(), Ct.byref(side), B, H, W, C, Ho, Wo, sums2.data_ptr(), dy2.data_ptr(),
+                                 dg2.data_ptr(), db2.data_ptr(), st()))
+    torch.cuda.synchronize()
+    mag = float(sums1.abs().max()) + 1.0
+    np.testing.assert_allclose(sums2[:2 * C].cpu().numpy(), sums1[:2 * C].cpu().numpy(), rtol=1e-5, atol=1e-5 * mag)
+    amax = float(dy1.float().abs().max())
+    assert float((dy2.float() - dy1.float()).abs().max()) <= 8e-3 * amax
+    assert float((dy2.float() != dy1.float()).float().mean()) < 0.02       # all but the odd rounding flip are identical
+    close(dg2, dg1, 1e-4, 1e-4 * mag)
+    close(db2, db1, 1e-4, 1e-4 * mag)

@@ -510,3 +510,34 @@ def test_dual_batchnorm_blocks_match_the_two_kernel_form():
     for k in d["bufs"]:                                   # running statistics / step counters of the downsample BatchNorms keep moving
         a, b = d["bufs"][k].float(), s_["bufs"][k].float()
         assert rel_l2(a, b) <= 2e-2, (k, rel_l2(a, b))
+
+
+def test_fused_stem_tail_matches_the_separate_kernels():
+    """Stem BatchNorm + ReLU + maxpool as one pass (csrc/stem_pool.cu, the default) against bn_train_apply + maxpool_fwd and
+    their three backward kernels: the forward is bit-identical (same logits, same loss); gradients differ by the fp32 order of
+    the stem BatchNorm's two reduction sums only."""
+    x = torch.randn((4, 3, 96, 96), generator=torch.Generator().manual_seed(45))
+    y = synth_labels((4, 96, 96), seed=46, fg=0.2, ign=0.05)
+    w = torch.tensor([1.0, 3.0])
+    res = []
+    for fused in (True, False):
+        m, _ = build("resnet50", 16, seed=81)
+        m.to(DEV).train()
+        eng = m.engine()
+        eng.dropout_p = 0.0
+        eng.stem_pool = fused
+        crit = CrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
+        n0 = _lib.launch_count()
+        logits = m(x.to(DEV))
+        loss = crit(logits, y.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((float(loss.detach()), eng.flat_g.clone(), _lib.launch_count() - n0, logits.detach().clone(),
+                    m.backbone.bn1.running_var.clone(), m.backbone.conv1.weight.grad.clone(), m.backbone.bn1.weight.grad.clone()))
+    assert torch.equal(res[0][3], res[1][3]) and res[0][0] == res[1][0]
+    assert torch.equal(res[0][4], res[1][4])
+    assert res[1][2] - res[0][2] == 2                    # (apply + maxpool) -> 1, (maxpool_bwd + reduce + apply) -> 2
+    rel = rel_l2(res[0][1], res[1][1])
+    report("fused_stem_tail_vs_separate", flat_grad_rel_l2=rel, stem_weight_grad_rel_l2=rel_l2(res[0][5], res[1][5]),
+           bn1_weight_grad_rel_l2=rel_l2(res[0][6], res[1][6]))
+    assert rel <= 1e-4 and rel_l2(res[0][5], res[1][5]) <= 2e-3 and rel_l2(res[0][6], res[1][6]) <= 1e-4
