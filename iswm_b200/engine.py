@@ -159,9 +159,10 @@ class Engine:
         # implicit GEMM over the two row-parity phases, instead of a full im2col matrix (320 B per pixel) + one GEMM
         # (ISWM_STEM_ROWS=0: the im2col form)
         self.stem_rows = __import__("os").environ.get("ISWM_STEM_ROWS", "1") != "0"
-        # stem tail (train): BatchNorm + ReLU + maxpool as one pass forward and one reduce / apply pair backward
-        # (csrc/stem_pool.cu: neither the half-resolution activation nor its gradient is written); ISWM_STEM_POOL=0: separate kernels
+        # stem tail (train): BatchNorm + ReLU + maxpool as one forward pass (csrc/stem_pool.cu: the half-resolution activation is
+        # never written; ISWM_STEM_POOL=0: separate kernels). The fused backward (ISWM_STEM_POOL_BWD=1) exists and is tested but loses
         self.stem_pool = __import__("os").environ.get("ISWM_STEM_POOL", "1") != "0"
+        self.stem_pool_bwd = __import__("os").environ.get("ISWM_STEM_POOL_BWD", "0") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -1094,11 +1095,22 @@ class Engine:
                 assert g is not None and g.ld == 64
                 sums = self._stats_slot(130)
                 dy = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
-                side_b = self._bn_side(bn, None, save, 64, False)
-                ev = self._prof_begin()
-                check(L.iswm_stem_pool_bwd(g.ptr, idx.data_ptr(), raw.data_ptr(), C.byref(side_b), B, H1, W1, 64, H2, W2, sums.data_ptr(), dy.data_ptr(),
-                                           self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "stem_pool_bwd")
-                self._prof_end(ev, "hbm:stem_pool_bwd", 2.0 * (2.0 * M * 64 + 3.0 * B * H2 * W2 * 64) + 2.0 * M * 64, "stem_pool_bwd")
+                if self.stem_pool_bwd:
+                    # both BatchNorm-backward passes gather the activation gradient through the argmax codes: measured SLOWER than
+                    # the three separate kernels (281 vs 178 us at cfg2: the gather runs twice), so off by default
+                    side_b = self._bn_side(bn, None, save, 64, False)
+                    ev = self._prof_begin()
+                    check(L.iswm_stem_pool_bwd(g.ptr, idx.data_ptr(), raw.data_ptr(), C.byref(side_b), B, H1, W1, 64, H2, W2, sums.data_ptr(), dy.data_ptr(),
+                                               self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "stem_pool_bwd")
+                    self._prof_end(ev, "hbm:stem_pool_bwd", 2.0 * (2.0 * M * 64 + 3.0 * B * H2 * W2 * 64) + 2.0 * M * 64, "stem_pool_bwd")
+                else:
+                    dact = torch.empty((M, 64), dtype=torch.bfloat16, device=dev)
+                    check(L.iswm_maxpool_bwd(g.ptr, idx.data_ptr(), B, H1, W1, 64, H2, W2, dact.data_ptr(), _st()), "maxpool_bwd")
+                    check(L.iswm_bn_bwd_reduce(dact.data_ptr(), 64, raw.data_ptr(), 64, None, 64, M, 64, save.data_ptr(), save[64:].data_ptr(),
+                                               bn.weight.data_ptr(), bn.bias.data_ptr(), 1, 0.0, 0, None, sums.data_ptr(), _st()), "bn_bwd_reduce stem")
+                    check(L.iswm_bn_bwd_apply(dact.data_ptr(), 64, raw.data_ptr(), 64, None, 64, M, 64, bn.weight.data_ptr(), bn.bias.data_ptr(), save.data_ptr(),
+                                              save[64:].data_ptr(), sums.data_ptr(), 1, 0.0, 0, None, dy.data_ptr(), 64, None, 0,
+                                              self.grad_views[id(bn.weight)].data_ptr(), self.grad_views[id(bn.bias)].data_ptr(), _st()), "bn_bwd_apply stem")
                 pooled.grad = None
                 self._stem_wgrad(s, bn, colA, dy, B, H1, W1, M, taps, row_taps, n_img)
 

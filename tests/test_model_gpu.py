@@ -526,6 +526,7 @@ def test_fused_stem_tail_matches_the_separate_kernels():
         eng = m.engine()
         eng.dropout_p = 0.0
         eng.stem_pool = fused
+        eng.stem_pool_bwd = fused                       # the fused backward too (off by default: it is slower)
         crit = CrossEntropyLoss(weight=w, ignore_index=255).to(DEV)
         n0 = _lib.launch_count()
         logits = m(x.to(DEV))
