@@ -48,6 +48,7 @@ struct ConvKParams {
   int out_ld, res_ld;
   int use_tma_out;               // bf16 output through smem staging + TMA store
   int res_prefetch;              // residual rows prefetched into shared memory one chunk ahead (short-K convolutions)
+  int narrow_tail;               // BN is not a multiple of 64: a tile's last chunk is written with plain stores, not the TMA box
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   int16_t coff[ISWM_MAX_TAPS];   // per-tap channel offset into the input buffer (K-concatenated convolutions)
   int8_t wtap[ISWM_MAX_TAPS];    // weight tap each tap reads (a subset of a packed tensor's taps)
@@ -557,7 +558,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 64; j++) f[j] = fmaxf(f[j], 0.f);
         }
-        if (tma_out) {
+        if (tma_out && !(p.narrow_tail && p.BN - c64 * 64 < 64)) {
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 32; j++) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -667,9 +668,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix + nc;
+            if ((ncols & 7) == 0 && (p.out_ld & 7) == 0 && (nc & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+              // narrow last chunk of a channel tile that is not a multiple of 64 wide (304 = 2 x 160): 16-byte stores
 #pragma unroll
-            for (int j = 0; j < 64; j++)
-              if (j < ncols) op[j] = __float2bfloat16_rn(f[j]);
+              for (int j = 0; j < 8; j++)
+                if (8 * j < ncols)
+                  *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; j++)
+                if (j < ncols) op[j] = __float2bfloat16_rn(f[j]);
+            }
           }
         }
       }
@@ -789,6 +799,12 @@ static int conv_igemm_launch(const iswm_conv_desc* d, const void* d_in, const vo
   } else {
     const int nt = (d->Cout + 255) / 256;
     BN = std::min(256, (((d->Cout + nt - 1) / nt + 63) / 64) * 64);
+    // without statistics / residual the tile's last 64-channel chunk may be narrow (written with plain 16-byte stores instead of
+    // the TMA box): 304 channels run as 2 x 160 columns instead of 2 x 192 - a sixth less MMA work on the decoder's data gradient
+    static const int env_nt = [] { const char* e = getenv("ISWM_CONV_NARROW_TAIL"); return e ? atoi(e) : 1; }();
+    if (env_nt && !(d->flags & (ISWM_EPI_STATS | ISWM_EPI_RESIDUAL | ISWM_EPI_BN_DZ)) && (d->Cout % 8) == 0)
+      BN = std::min(BN, (((d->Cout + nt - 1) / nt + 31) / 32) * 32);
+    p.narrow_tail = (BN % 64) != 0 ? 1 : 0;
   }
   p.BN = BN;
   p.tiles_n = (d->Cout + BN - 1) / BN;

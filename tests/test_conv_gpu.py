@@ -130,7 +130,10 @@ def test_conv_stride2_via_phases():
 
 @pytest.mark.parametrize("B,Cin,H,W,Cout,k,dil", [(2, 64, 16, 16, 128, 3, 1), (1, 256, 8, 8, 512, 3, 2), (2, 256, 16, 16, 64, 1, 1), (2, 256, 9, 11, 2, 1, 1),
                                                    (1, 128, 48, 48, 64, 3, 18), (1, 128, 80, 80, 64, 3, 24), (1, 128, 80, 80, 64, 3, 36),
-                                                   (2, 64, 50, 77, 64, 3, 36)])
+                                                   (2, 64, 50, 77, 64, 3, 36),
+                                                   # 304 gradient channels (the decoder's first 3x3): 2 x 160-column tiles, the narrow last chunk of
+                                                   # each tile written with plain stores; odd spatial size -> rows outside the image
+                                                   (2, 304, 16, 16, 256, 3, 1), (1, 304, 13, 21, 64, 1, 1), (1, 328, 9, 9, 64, 1, 1)])
 def test_conv_dgrad(B, Cin, H, W, Cout, k, dil):
     x, w = _mk(B, Cin, H, W, Cout, k, seed=7)
     g = torch.Generator().manual_seed(8)
