@@ -172,6 +172,11 @@ typedef struct {
                                  i % replicas and the consumer (iswm_bn_train_apply) sums the copies. With one copy every CTA of a
                                  narrow layer ends on the same 2*Cout addresses: 296 same-address fp64 atomics per channel cost a
                                  64-channel 3x3 convolution 14 of its 51 us (tools/prof_conv.py) */
+  int32_t in_phase_view;      /* != 0: d_in is a DENSE bf16 [B, 2*Hi, 2*Wi, in_ld] tensor and the convolution reads its four stride-2 parity
+                                 phases in place (phase[t] = 2*row parity + column parity, as for the phase-major copy, but n_img = B):
+                                 the stride-2 3x3 / 1x1 convolutions of resnet.py:104,183 without iswm_phase_split / iswm_subsample2
+                                 copies. The tensor map is 5-D {(column parity, channel), w, row parity, h, image}. Needs Cin %% 64 == 0. */
+  int32_t reserved2_;
 } iswm_conv_desc;
 
 /* d_in: bf16 activations; d_wgt: packed bf16 [Cout][ntaps][Cin_pad] (Cin_pad =

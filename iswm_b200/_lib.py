@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS), ("phase", C.c_int8 * MAX_TAPS),
         ("coff", C.c_int16 * MAX_TAPS), ("wtap", C.c_int8 * MAX_TAPS),
         ("flags", C.c_int32), ("out_ws", C.c_int32), ("out_hs", C.c_int32), ("out_bs", C.c_int64),
-        ("w_ntaps", C.c_int32), ("stats_replicas", C.c_int32),
+        ("w_ntaps", C.c_int32), ("stats_replicas", C.c_int32), ("in_phase_view", C.c_int32), ("reserved2_", C.c_int32),
     ]
 
 

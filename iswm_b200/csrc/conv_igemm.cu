@@ -48,6 +48,7 @@ struct ConvKParams {
   int out_ld, res_ld;
   int use_tma_out;               // bf16 output through smem staging + TMA store
   int res_prefetch;              // residual rows prefetched into shared memory one chunk ahead (short-K convolutions)
+  int phase_view, pv_ld;         // input read as the four parity phases of a dense tensor through a 5-D tensor map (pv_ld = its pixel pitch)
   int narrow_tail;               // BN is not a multiple of 64: a tile's last chunk is written with plain stores, not the TMA box
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   int16_t coff[ISWM_MAX_TAPS];   // per-tap channel offset into the input buffer (K-concatenated convolutions)
@@ -216,7 +217,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int cw = w0 + p.dw[t], ch = h0 + p.dh[t], cb = p.phase[t] * p.n_img_per_phase + b0;
           const uint32_t a_dst = ring + stage * stage_bytes;
           tc::mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
-          tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, p.coff[t] + kc * kKBlock, cw, ch, cb);
+          if (p.phase_view)
+            tc::tma_load_5d(a_dst, &tmap_a, bar_full + 8 * stage, (p.phase[t] & 1) * p.pv_ld + p.coff[t] + kc * kKBlock, cw, p.phase[t] >> 1, ch, b0);
+          else
+            tc::tma_load_4d(a_dst, &tmap_a, bar_full + 8 * stage, p.coff[t] + kc * kKBlock, cw, ch, cb);
           tc::tma_load_2d(a_dst + kABytes, &tmap_b, bar_full + 8 * stage, p.wtap[t] * p.cin_pad + kc * kKBlock, n0);
           stage += np;
           if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
@@ -774,8 +778,10 @@ static int conv_igemm_launch(const iswm_conv_desc* d, const void* d_in, const vo
   memset(&p, 0, sizeof(p));
   int B = d->B, Hi = d->Hi, Wi = d->Wi, Ho = d->Ho, Wo = d->Wo, n_img = d->n_img;
   const bool strided_out = d->out_ws != 0 || d->out_hs != 0 || d->out_bs != 0;
+  const bool phase_view = d->in_phase_view != 0;
+  ISWM_REQUIRE(!phase_view || ((d->Cin % kKBlock) == 0 && n_img == B), "conv_igemm: in_phase_view needs Cin %% 64 == 0 and n_img == B (Cin=%d n_img=%d B=%d)", d->Cin, n_img, B);
   bool pointwise = (d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->phase[0] == 0 &&
-                    Hi == Ho && Wi == Wo && n_img == B && !strided_out);
+                    Hi == Ho && Wi == Wo && n_img == B && !strided_out && !phase_view);
   if (pointwise) {  // a 1x1 convolution is a plain GEMM over all pixels: no tile-edge waste
     const int64_t M = (int64_t)B * Ho * Wo;
     if (M < (1ll << 31)) {
@@ -873,7 +879,16 @@ static int conv_igemm_launch(const iswm_conv_desc* d, const void* d_in, const vo
   p.abort_flag = abort_flag;
 
   CUtensorMap tmap_a, tmap_b;
-  {
+  if (phase_view) {
+    // dense [B, 2Hi, 2Wi, ld] read as four parity phases: {column parity * ld + channel, w, row parity, h, image}
+    const uint64_t ld = (uint64_t)d->in_ld, Wf = 2ull * Wi, Hf = 2ull * Hi;
+    const uint64_t dims[5] = {ld + (uint64_t)in_c, (uint64_t)Wi, 2, (uint64_t)Hi, (uint64_t)B};
+    const uint64_t str[5] = {1, 2 * ld, Wf * ld, 2 * Wf * ld, Hf * Wf * ld};
+    const uint32_t box[5] = {(uint32_t)kKBlock, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BB};
+    if (int rc = encode_tmap_bf16(&tmap_a, d_in, 5, dims, str, box)) return rc;
+    p.phase_view = 1;
+    p.pv_ld = d->in_ld;
+  } else {
     const uint64_t dims[4] = {(uint64_t)in_c, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)n_img};
     const uint64_t str[4] = {1, (uint64_t)d->in_ld, (uint64_t)Wi * d->in_ld, (uint64_t)Hi * Wi * d->in_ld};
     const uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};

@@ -48,6 +48,7 @@ struct WgradKParams {
   int vec_red;
   int nprod;                      // producer warps (1 or 2) taking alternate pixel blocks
   int n_img_per_phase;
+  int phase_view, pv_ld;          // x read as the four parity phases of a dense tensor through a 5-D tensor map
   int8_t dh[ISWM_MAX_TAPS], dw[ISWM_MAX_TAPS], phase[ISWM_MAX_TAPS];
   float* dwgt;
   int* abort_flag;
@@ -157,7 +158,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
 #pragma unroll
           for (int j = 0; j < kMaxG; j++) {
             const int t_ = min(tap, p.ntaps - 1);
-            c_dw[j] = p.dw[t_]; c_dh[j] = p.dh[t_]; c_db[j] = p.phase[t_] * p.n_img_per_phase; c_ch[j] = cc * 64;
+            c_dw[j] = p.dw[t_]; c_dh[j] = p.dh[t_]; c_ch[j] = cc * 64;
+            if (p.phase_view) { c_db[j] = p.phase[t_] >> 1; c_ch[j] += (p.phase[t_] & 1) * p.pv_ld; }   // row parity; column parity in the channel coordinate
+            else c_db[j] = p.phase[t_] * p.n_img_per_phase;
             if (++cc == p.cchunks) { cc = 0; tap++; }
           }
         }
@@ -177,7 +180,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
           tc::tma_load_4d(dst + kChunkBytes, &tmap_dy, bar, m0 + 64, w0, h0, b0);
 #pragma unroll
           for (int j = 0; j < kMaxG; j++)
-            if (j < gc) tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, c_ch[j], w0 + c_dw[j], h0 + c_dh[j], b0 + c_db[j]);
+            if (j < gc) {
+              if (p.phase_view) tc::tma_load_5d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, c_ch[j], w0 + c_dw[j], c_db[j], h0 + c_dh[j], b0);
+              else tc::tma_load_4d(dst + a_bytes + j * kChunkBytes, &tmap_x, bar, c_ch[j], w0 + c_dw[j], h0 + c_dh[j], b0 + c_db[j]);
+            }
           stage += np;
           if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
           tw += np;
@@ -316,8 +322,10 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
   WgradKParams p;
   memset(&p, 0, sizeof(p));
   int B = d->B, Hi = d->Hi, Wi = d->Wi, Ho = d->Ho, Wo = d->Wo, n_img = d->n_img;
+  const bool phase_view = d->in_phase_view != 0;
+  ISWM_REQUIRE(!phase_view || ((d->Cin % 64) == 0 && n_img == B), "conv_wgrad: in_phase_view needs Cin %% 64 == 0 and n_img == B");
   bool pointwise = (d->ntaps == 1 && d->dh[0] == 0 && d->dw[0] == 0 && d->phase[0] == 0 &&
-                    Hi == Ho && Wi == Wo && n_img == B);
+                    Hi == Ho && Wi == Wo && n_img == B && !phase_view);
   if (pointwise) {
     const int64_t M = (int64_t)B * Ho * Wo;
     if (M < (1ll << 31)) {
@@ -415,7 +423,15 @@ extern "C" int iswm_conv_wgrad(const iswm_conv_desc* d, const void* d_in, const 
     const uint32_t box[4] = {64u, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};
     if (int rc = encode_tmap_bf16(&tmap_dy, d_dy, 4, dims, str, box)) return rc;
   }
-  {
+  if (phase_view) {
+    const uint64_t ld = (uint64_t)d->in_ld, Wf = 2ull * Wi, Hf = 2ull * Hi;
+    const uint64_t dims[5] = {ld + (uint64_t)d->Cin, (uint64_t)Wi, 2, (uint64_t)Hi, (uint64_t)B};
+    const uint64_t str[5] = {1, 2 * ld, Wf * ld, 2 * Wf * ld, Hf * Wf * ld};
+    const uint32_t box[5] = {64u, (uint32_t)BW, 1, (uint32_t)BH, (uint32_t)BB};
+    if (int rc = encode_tmap_bf16(&tmap_x, d_in, 5, dims, str, box)) return rc;
+    p.phase_view = 1;
+    p.pv_ld = d->in_ld;
+  } else {
     const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)n_img};
     const uint64_t str[4] = {1, (uint64_t)d->in_ld, (uint64_t)Wi * d->in_ld, (uint64_t)Hi * Wi * d->in_ld};
     const uint32_t box[4] = {64u, (uint32_t)BW, (uint32_t)BH, (uint32_t)BB};

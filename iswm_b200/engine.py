@@ -56,7 +56,7 @@ class _StreamScope:
 class Act:
     """NHWC bf16 activation: `t` is a [B,H,W,C] view whose row pitch is `ld` elements."""
 
-    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad", "pending", "masked_ok", "bn_fold", "bn_sums")
+    __slots__ = ("t", "B", "H", "W", "C", "ld", "grad", "pending", "masked_ok", "bn_fold", "bn_sums", "phase_view")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, Cc: int, ld: int):
         self.t, self.B, self.H, self.W, self.C, self.ld = t, B, H, W, Cc, ld
@@ -70,6 +70,7 @@ class Act:
         # `bn_sums` by that consumer's data gradient once it has written dz (not dout) into `grad` and accumulated the sums
         self.bn_fold = None
         self.bn_sums = None
+        self.phase_view = False                       # (H, W) are per-phase dims of a dense [B, 2H, 2W, ld] tensor read in place (stride-2 convs)
 
     @property
     def M(self) -> int:
@@ -163,6 +164,9 @@ class Engine:
         # never written; ISWM_STEM_POOL=0: separate kernels). The fused backward (ISWM_STEM_POOL_BWD=1) exists and is tested but loses
         self.stem_pool = __import__("os").environ.get("ISWM_STEM_POOL", "1") != "0"
         self.stem_pool_bwd = __import__("os").environ.get("ISWM_STEM_POOL_BWD", "0") != "0"
+        # stride-2 convolutions read the parity phases of their dense input in place through a 5-D tensor map
+        # (iswm_conv_desc.in_phase_view) instead of phase_split / subsample2 copies (ISWM_PHASE_VIEW=0: the copies)
+        self.phase_view = __import__("os").environ.get("ISWM_PHASE_VIEW", "1") != "0"
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -375,7 +379,7 @@ class Engine:
               stats=None, wgt=None, cin=None, cout=None, Hi=None, Wi=None, B=None):
         d = ops.make_conv_desc(B if B is not None else x.B, Hi if Hi is not None else x.H, Wi if Wi is not None else x.W,
                                cin if cin is not None else x.C, x.ld, n_img, Ho, Wo,
-                               cout if cout is not None else s.cout, out_ld, taps, flags, res_ld)
+                               cout if cout is not None else s.cout, out_ld, taps, flags, res_ld, phase_view=x.phase_view)
         if stats is not None:
             d.stats_replicas = stats.numel() // (2 * d.Cout)
         ev = self._prof_begin()
@@ -393,6 +397,10 @@ class Engine:
             return x, ops.conv_taps(s.k, s.dilation), x.B, x.H, x.W
         assert s.stride == 2 and s.dilation == 1
         Ho, Wo = (x.H + 1) // 2, (x.W + 1) // 2
+        if self.phase_view and x.H % 2 == 0 and x.W % 2 == 0 and x.C % 64 == 0 and x.ld % 8 == 0:
+            xv = Act(x.t, x.B, Ho, Wo, x.C, x.ld)
+            xv.phase_view = True
+            return xv, (ops.conv_taps(1, 1) if s.k == 1 else ops.conv_taps_s2_3x3()), x.B, Ho, Wo
         if s.k == 1:
             xs = Act.new(x.B, Ho, Wo, x.C, self.device)
             check(L.iswm_subsample2(x.ptr, x.ld, x.B, x.H, x.W, x.C, xs.ptr, _st()), "subsample2")
@@ -622,7 +630,7 @@ class Engine:
         B, Cout = x.B, s.cout
         dy_ld = dy.stride(-2) if dy.dim() >= 2 else dy.shape[-1]          # a channel slice of a wider buffer keeps that buffer's pitch
         gview = self.grad_views[id(s.conv.weight)]
-        d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps)
+        d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps, phase_view=xin.phase_view)
         with self._wgrad_ctx(dy, xin.t):
             ev = self._prof_begin()
             dst = gview if s.k == 1 else self.wacc[self.wacc_off[s.name][0]:self.wacc_off[s.name][0] + self.wacc_off[s.name][1]]

@@ -190,7 +190,7 @@ def crop_flip_u8(src: torch.Tensor, size: Optional[Tuple[int, int]] = None, orig
 def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,
                    Cout: int, out_ld: int, taps: Sequence[Tuple[int, int, int]], flags: int = 0,
                    res_ld: int = 0, wtaps: Optional[Sequence[int]] = None,
-                   out_strides: Optional[Tuple[int, int, int]] = None, w_ntaps: int = 0) -> ConvDesc:
+                   out_strides: Optional[Tuple[int, int, int]] = None, w_ntaps: int = 0, phase_view: bool = False) -> ConvDesc:
     d = ConvDesc()
     d.B, d.Hi, d.Wi, d.Cin, d.in_ld, d.n_img = B, Hi, Wi, Cin, in_ld, n_img
     d.Ho, d.Wo, d.Cout, d.out_ld, d.res_ld = Ho, Wo, Cout, out_ld, res_ld
@@ -203,6 +203,7 @@ def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, H
         d.wtap[i] = 0 if wtaps is None else wtaps[i] + 1
     d.flags = flags
     d.w_ntaps = w_ntaps
+    d.in_phase_view = 1 if phase_view else 0         # x is the dense [B, 2Hi, 2Wi, ld] tensor, read as its four parity phases in place
     if out_strides is not None:                      # (w, h, image) element strides of a strided output view
         d.out_ws, d.out_hs, d.out_bs = out_strides
     return d

@@ -357,3 +357,31 @@ def test_conv_stats_replicas_sum_to_the_single_accumulator(Cout, rep):
     assert torch.equal(res[0][0], res[1][0])
     assert float(res[1][1].abs().sum(1).min()) > 0            # every copy received something (50 tiles over `rep` copies)
     assert torch.equal(res[0][1].sum(0).float(), res[1][1].sum(0).float())
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k", [(2, 128, 16, 16, 128, 3), (1, 64, 24, 40, 64, 3), (2, 256, 16, 16, 512, 1), (3, 64, 8, 8, 96, 1), (1, 128, 130, 128, 64, 3)])
+def test_stride2_convs_read_the_parity_phases_in_place(B, Cin, H, W, Cout, k):
+    """iswm_conv_desc.in_phase_view: the stride-2 3x3 (resnet.py:104 with stride 2) and the stride-2 1x1 downsample (:183) read
+    the dense input through a 5-D tensor map {(column parity, channel), w, row parity, h, image} - no phase_split / subsample2
+    copy - in the forward convolution and in the weight gradient. Against F.conv2d and its autograd weight gradient."""
+    x, w = _mk(B, Cin, H, W, Cout, k, seed=51)
+    g = torch.Generator().manual_seed(52)
+    Ho, Wo = H // 2, W // 2
+    dy = torch.randn((B, Cout, Ho, Wo), generator=g).to(torch.bfloat16)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    y = F.conv2d(x.float(), wr, stride=2, padding=k // 2)
+    y.backward(dy.float())
+    xd = _nhwc(x).to(DEV)
+    taps = ops.conv_taps(1, 1) if k == 1 else ops.conv_taps_s2_3x3()
+    out = torch.zeros((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=DEV)
+    d = ops.make_conv_desc(B, Ho, Wo, Cin, Cin, B, Ho, Wo, Cout, Cout, taps, phase_view=True)
+    ops.conv_igemm(d, xd, ops.pack_weight_fwd(w.to(DEV)), out)
+    _assert_healthy()
+    assert _rel_err(out.float().cpu().permute(0, 3, 1, 2), y.detach()) < 1e-2
+    dw = torch.zeros((Cout, k * k, Cin), dtype=torch.float32, device=DEV)
+    ops.conv_wgrad(d, xd, _nhwc(dy).to(DEV), dw)
+    _assert_healthy()
+    grad = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=DEV)
+    ops.unpack_wgrad(dw, grad)
+    torch.cuda.synchronize()
+    assert _rel_err(grad.cpu(), wr.grad) < 5e-3
