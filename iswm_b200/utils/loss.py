@@ -49,8 +49,13 @@ class CrossEntropyLoss(nn.Module):
     normaliser is the GLOBAL batch's, as under the reference's nn.DataParallel (train.py:970,1046).
     """
 
-    def __init__(self, weight: Optional[torch.Tensor] = None, ignore_index: int = 255, reduction: str = "mean"):
+    def __init__(self, weight: Optional[torch.Tensor] = None, ignore_index: int = 255, reduction: str = "mean",
+                 check_labels: bool = False):
+        """`check_labels`: labels outside [0, C) other than `ignore_index` are treated as ignored by the kernels (torch raises a
+        device-side assert for them); with check_labels=True every call verifies the labels first and raises ValueError - a
+        debugging aid that costs a pass over the labels and a host synchronisation."""
         super().__init__()
+        self.check_labels = check_labels
         if reduction != "mean":
             raise NotImplementedError("the reference only uses reduction='mean' (train.py:457-459)")
         self.register_buffer("weight", None if weight is None else weight.detach().float().clone())
@@ -65,6 +70,12 @@ class CrossEntropyLoss(nn.Module):
         w = self.weight
         if w is not None and w.device != logits.device:
             w = w.to(logits.device)
+        if self.check_labels:
+            bad = ((labels < 0) | (labels >= logits.shape[1])) & (labels != self.ignore_index)
+            n_bad = int(bad.sum())
+            if n_bad:
+                raise ValueError(f"CrossEntropyLoss: {n_bad} label values outside [0, {logits.shape[1]}) that are not ignore_index={self.ignore_index} "
+                                 f"(first: {int(labels[bad][0])})")
         return _WeightedCEFn.apply(logits, labels, w, self.ignore_index, self.hist_hook, None)
 
 

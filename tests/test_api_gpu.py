@@ -143,3 +143,25 @@ def test_setup_criterion_dispatch_and_kat2(lm):
     loss.backward()
     assert abs(loss.item() - float(lm["kat2_loss"])) < 1e-6
     np.testing.assert_allclose(x.grad.cpu().numpy(), lm["kat2_grad"], rtol=1e-5, atol=1e-8)
+
+
+def test_cross_entropy_check_labels_flags_out_of_range_values():
+    """Labels outside [0, C) other than ignore_index: the kernels treat them as ignored (torch asserts on the device); the
+    opt-in check raises instead, and leaves a clean batch alone."""
+    from iswm_b200.utils.loss import CrossEntropyLoss
+    logits = torch.randn((2, 2, 16, 16), device=DEV)
+    y = torch.randint(0, 2, (2, 16, 16), device=DEV)
+    y[0, 0, 0] = 255
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 2.0]), ignore_index=255, check_labels=True).to(DEV)
+    ok = crit(logits, y)
+    y2 = y.clone()
+    y2[1, 3, 3] = 2
+    y2[1, 4, 4] = 128
+    with pytest.raises(ValueError, match="2 label values outside"):
+        crit(logits, y2)
+    silent = CrossEntropyLoss(weight=torch.tensor([1.0, 2.0]), ignore_index=255).to(DEV)
+    y3 = y.clone()
+    y3[1, 3, 3] = 255
+    y3[1, 4, 4] = 255
+    assert torch.equal(silent(logits, y2), silent(logits, y3))       # out-of-range == ignored, as documented
+    assert torch.isfinite(ok)
