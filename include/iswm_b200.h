@@ -270,6 +270,26 @@ typedef struct {
 } iswm_pack_job;
 int iswm_pack_weights_batched(const void* d_jobs, int n_jobs, int total_blocks, void* stream);
 
+/* Optimiser step + operand repack in ONE pass (csrc/sgd_pack.cu; train.py:421-431 torch.optim.SGD and :1049 optimizer.step()):
+ * the job table covers the flat parameter buffer - convolution weights (mode 1: update, then both packed bf16 layouts from the
+ * same shared-memory tile; mode 2: the stem, update + row-tap forward operand) and the ranges between them (mode 0: update only).
+ * Same arithmetic as iswm_sgd_step followed by iswm_pack_weights_batched: bit-identical weights, momentum and operands.
+ * Padding elements of the packed buffers (Cin / Cout rounded up to 64) are NOT written: pack once with
+ * iswm_pack_weights_batched before the first fused step. Job j owns thread blocks [blk_begin, blk_begin + blk_count). */
+typedef struct {
+  float* w; const float* g; float* m;          /* fp32 master weights / gradient / momentum (m NULL: no momentum) */
+  void* dst_f; void* dst_d;                    /* packed bf16 forward / data-gradient operands (NULL: none) */
+  int64_t n;                                   /* element count (modes 0 and 2) */
+  int32_t Cout, Cin, RS;
+  int32_t pad_f, row_ld_f;                     /* forward: channels per tap, elements per output channel */
+  int32_t pad_d, row_ld_d;                     /* dgrad: Cout padded to 64; taps per row of a K-concatenated operand (0 = RS) */
+  int32_t mode;                                /* 0 plain, 1 convolution, 2 stem */
+  int32_t TC;                                  /* input channels per tile (mode 1): a multiple of 8 with 16 * TC * RS <= 2304 */
+  int32_t blk_begin, blk_count;
+} iswm_sgd_pack_job;
+int iswm_sgd_pack_batched(const void* d_jobs, int n_jobs, int total_blocks, float lr, float momentum, float weight_decay,
+                          int nesterov, int first_step, const float* d_lr, void* stream);
+
 /* wgrad accumulator (fp32 rows of row_ld, element t*cin_stride + c) -> fp32 OIHW grad,
  * dst = beta*dst + src. Normal: cin_stride = Cin, row_ld = R*S*Cin. */
 int iswm_unpack_wgrad(const float* d_dw, int Cout, int Cin, int RS, int cin_stride, int row_ld,

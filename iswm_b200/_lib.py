@@ -57,6 +57,15 @@ class PackJob(C.Structure):
                 ("pad", C.c_int32), ("row_ld", C.c_int32), ("mode", C.c_int32), ("blk_begin", C.c_int32), ("blk_count", C.c_int32)]
 
 
+class SgdPackJob(C.Structure):
+    """Mirror of iswm_sgd_pack_job."""
+
+    _fields_ = [("w", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("dst_f", C.c_void_p), ("dst_d", C.c_void_p), ("n", C.c_int64),
+                ("Cout", C.c_int32), ("Cin", C.c_int32), ("RS", C.c_int32), ("pad_f", C.c_int32), ("row_ld_f", C.c_int32),
+                ("pad_d", C.c_int32), ("row_ld_d", C.c_int32), ("mode", C.c_int32), ("TC", C.c_int32),
+                ("blk_begin", C.c_int32), ("blk_count", C.c_int32)]
+
+
 class UnpackJob(C.Structure):
     """Mirror of iswm_unpack_job."""
 
@@ -117,6 +126,7 @@ SIGNATURES = {
     "iswm_pack_weight_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weight_dgrad": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weights_batched": (_i, [_p, _i, _i, _p]),
+    "iswm_sgd_pack_batched": (_i, [_p, _i, _i, _f, _f, _f, _i, _i, _p, _p]),
     "iswm_unpack_wgrad": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
     "iswm_unpack_wgrad_batched": (_i, [_p, _i, _i, _p]),
     "iswm_bn_train_apply": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _p, _p, _i, _p, _p]),

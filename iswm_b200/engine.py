@@ -275,6 +275,93 @@ class Engine:
             s.version = (w._version, self.weights_epoch, w.data_ptr())
             s.has_dgrad = need_dgrad and not s.is_stem
 
+    # ------------------------------------------------------------------ optimiser step fused with the repack
+    def packed_is_fresh(self) -> bool:
+        """True when every convolution's packed bf16 operands (both layouts) match the current master weights."""
+        for s in self.specs:
+            w = s.conv.weight
+            if s.packed_fwd is None or s.version != (w._version, self.weights_epoch, w.data_ptr()) or not (s.is_stem or getattr(s, "has_dgrad", False)):
+                return False
+        return True
+
+    def mark_packed_fresh(self):
+        """The packed operands were just rewritten from the master weights by a kernel (iswm_sgd_pack_batched): advance the
+        weights epoch (BatchNorm folds etc. refresh) and record that no repack is due."""
+        self.weights_epoch += 1
+        for s in self.specs:
+            w = s.conv.weight
+            s.version = (w._version, self.weights_epoch, w.data_ptr())
+
+    def sgd_pack_jobs(self, flat_w: torch.Tensor, flat_g: torch.Tensor, mom: Optional[torch.Tensor]):
+        """Job table of iswm_sgd_pack_batched over the flat parameter buffer, or None when the fused step does not apply
+        (operands not packed yet, per-layer packing, im2col stem). Cached on the buffers' addresses."""
+        if not (self.batched_pack and self.stem_rows) or not self.packed_is_fresh():
+            return None
+        params = self._param_list()
+        sig = (flat_w.data_ptr(), flat_g.data_ptr(), 0 if mom is None else mom.data_ptr(), getattr(self, "_pack_sig", None),
+               tuple(s.packed_fwd.data_ptr() for s in self.specs))
+        if getattr(self, "_sgd_pack_sig", None) == sig:
+            return self._sgd_pack_cache
+        spec_of = {id(s.conv.weight): s for s in self.specs}
+        slots = self._aspp_cat_slot()
+        rows, off, run = [], 0, None                       # run = [start, end) of consecutive non-convolution parameters
+        def flush():
+            nonlocal run
+            if run is not None:
+                rows.append(dict(mode=0, off=run[0], n=run[1] - run[0]))
+                run = None
+        for p in params:
+            n = p.numel()
+            if p.data_ptr() != flat_w.data_ptr() + 4 * off:
+                return None                                # parameters are not views of the flat buffer (flatten_parameters first)
+            s = spec_of.get(id(p))
+            if s is None:
+                run = [off, off + n] if run is None else [run[0], off + n]
+            else:
+                flush()
+                Cout, Cin, R, S_ = p.shape
+                RS = R * S_
+                if s.is_stem:
+                    rows.append(dict(mode=2, off=off, n=n, Cout=Cout, Cin=Cin, RS=RS, dst_f=s.packed_fwd.data_ptr(), dst_d=0, pad_f=64, row_ld_f=7 * 64,
+                                     pad_d=0, row_ld_d=0, TC=0))
+                else:
+                    cin_pad, cout_pad = ((Cin + 63) // 64) * 64, ((Cout + 63) // 64) * 64
+                    if s.name in slots:
+                        tap_off, taps_total = slots[s.name]
+                        dst_d, row_ld_d = self.aspp_wcat.data_ptr() + 2 * tap_off * cout_pad, taps_total
+                    else:
+                        if s.packed_dgrad is None:
+                            return None
+                        dst_d, row_ld_d = s.packed_dgrad.data_ptr(), 0
+                    TC = 128 if RS == 1 else max(8, (144 // RS) // 8 * 8)
+                    rows.append(dict(mode=1, off=off, n=n, Cout=Cout, Cin=Cin, RS=RS, dst_f=s.packed_fwd.data_ptr(), dst_d=dst_d, pad_f=cin_pad,
+                                     row_ld_f=RS * cin_pad, pad_d=cout_pad, row_ld_d=row_ld_d, TC=TC))
+            off += n
+        flush()
+        arr = (_lib.SgdPackJob * len(rows))()
+        begin = 0
+        for i, r in enumerate(rows):
+            j = arr[i]
+            j.w, j.g = flat_w.data_ptr() + 4 * r["off"], flat_g.data_ptr() + 4 * r["off"]
+            j.m = None if mom is None else mom.data_ptr() + 4 * r["off"]
+            j.n, j.mode = r["n"], r["mode"]
+            if r["mode"] == 0:
+                j.blk_count = max(1, min(64, (r["n"] + 4095) // 4096))
+            else:
+                j.dst_f, j.dst_d = r["dst_f"], r["dst_d"] or None
+                j.Cout, j.Cin, j.RS, j.pad_f, j.row_ld_f, j.pad_d, j.row_ld_d, j.TC = (r["Cout"], r["Cin"], r["RS"], r["pad_f"], r["row_ld_f"],
+                                                                                          r["pad_d"], r["row_ld_d"], r["TC"])
+                if r["mode"] == 2:
+                    j.blk_count = max(1, min(64, (r["n"] + 1023) // 1024))
+                else:
+                    tiles = ((r["Cout"] + 15) // 16) * ((r["Cin"] + r["TC"] - 1) // r["TC"])
+                    j.blk_count = max(1, min(512, tiles // 2))
+            j.blk_begin = begin
+            begin += j.blk_count
+        dev_jobs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(flat_w.device)
+        self._sgd_pack_sig, self._sgd_pack_cache = sig, (dev_jobs, len(rows), begin)
+        return self._sgd_pack_cache
+
     def _aspp_cat_slot(self):
         """name -> (first tap, total taps) of the ASPP conv branches inside the concatenated dgrad operand; empty when the
         fused ASPP backward is off (ISWM_ASPP_FUSED_BWD=0) or the branch widths do not allow it."""

@@ -38,6 +38,7 @@ class GraphedTrainStep:
         self.engine = self.model.engine()
         self.warmup_steps = max(1, warmup_steps)
         self.graph = None
+        self._fused_pack = False
         self.images = self.labels = self.loss = None
         self.dp = dp
         if dp is not None and getattr(dp, "comm_mode", "nccl") != "peer":
@@ -86,6 +87,9 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph, stream=cap):
             self.loss = self._eager(self.images, self.labels)
         self.launches_per_replay = _lib.launch_count() - n0      # library kernels recorded in the graph
+        # did the captured optimiser step repack the operands itself (FusedSGD with iswm_sgd_pack_batched)? then the graph holds no
+        # pack launch at its start and __call__ keeps the bookkeeping
+        self._fused_pack = self.engine.packed_is_fresh()
         self._restore(snap)
         self.engine.invalidate_packed()
 
@@ -123,8 +127,15 @@ class GraphedTrainStep:
         if labels.data_ptr() != self.labels.data_ptr():
             self.labels.copy_(labels, non_blocking=True)
         self.optimizer.sync_device_state()
+        if self._fused_pack and not self.engine.packed_is_fresh():
+            # the captured step does not repack at its start (its optimiser kernel leaves the operands fresh): weights changed from
+            # outside since the last replay (snapshot restore after the capture, load_state_dict, manual edits) are packed here
+            self.engine.pack_all(True)
         self.graph.replay()
-        self.engine.invalidate_packed()                  # the replay changed the weights behind Python's back
+        if self._fused_pack:
+            self.engine.mark_packed_fresh()              # weights AND packed operands moved together inside the replay
+        else:
+            self.engine.invalidate_packed()              # the replay changed the weights behind Python's back
         self.optimizer._steps += 1
         self.engine.step += 1
         return self.loss

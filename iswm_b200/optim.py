@@ -21,6 +21,9 @@ class FusedSGD:
         self.param_groups = [{"lr": lr, "momentum": momentum, "weight_decay": weight_decay, "nesterov": nesterov}]
         self._mom = None
         self._steps = 0
+        # the step also rewrites the packed bf16 convolution operands (one pass over the weights instead of two; ISWM_SGD_PACK=0:
+        # iswm_sgd_step, and the next forward repacks)
+        self.fuse_pack = __import__("os").environ.get("ISWM_SGD_PACK", "1") != "0"
         self.lr_dev = None                 # device copy of the learning rate (enable_device_state: CUDA-graph replays)
         self.step_dev = None
 
@@ -59,6 +62,18 @@ class FusedSGD:
             self._mom = torch.zeros_like(flat_w)
             self._steps = 0
         lr = self.param_groups[0]["lr"]
+        jobs = eng.sgd_pack_jobs(flat_w, flat_g, self._mom) if self.fuse_pack else None
+        if jobs is not None:
+            # update + both bf16 operand packings of every convolution in ONE pass over the weights (csrc/sgd_pack.cu); the next
+            # forward finds its operands fresh
+            dev_jobs, n_jobs, n_blocks = jobs
+            _lib.check(_lib.lib().iswm_sgd_pack_batched(dev_jobs.data_ptr(), n_jobs, n_blocks, lr, self.momentum, self.weight_decay,
+                                                        1 if self.nesterov else 0, 1 if self._steps == 0 else 0,
+                                                        None if self.lr_dev is None else self.lr_dev.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream), "sgd_pack_batched")
+            self._steps += 1
+            eng.mark_packed_fresh()
+            return
         _lib.check(_lib.lib().iswm_sgd_step(flat_w.data_ptr(), flat_g.data_ptr(), self._mom.data_ptr(), flat_w.numel(),
                                             lr, self.momentum, self.weight_decay, 1 if self.nesterov else 0,
                                             1 if self._steps == 0 else 0, None if self.lr_dev is None else self.lr_dev.data_ptr(),

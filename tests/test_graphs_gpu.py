@@ -206,3 +206,105 @@ def test_eval_forward_between_forward_and_backward_keeps_the_tape():
     crit(mb(x2), y)
     with pytest.raises(RuntimeError, match="superseded"):
         stale.backward()
+
+
+def test_fused_sgd_repack_is_bit_identical_to_step_then_pack():
+    """FusedSGD with iswm_sgd_pack_batched (update + both bf16 operand packings in one pass, csrc/sgd_pack.cu) against
+    iswm_sgd_step followed by iswm_pack_weights_batched: master weights, momentum and every packed operand bit-identical after
+    three steps (weight decay, nesterov, the ASPP K-concatenated dgrad operand, the stem's row-tap operand, Cout = 2 / 48 tails)."""
+    batches = _batches(3)
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    res = []
+    for fuse in (True, False):
+        m = _model()
+        m.engine().dropout_p = 0.0
+        opt = FusedSGD(m, lr=5e-2, momentum=0.9, weight_decay=1e-4, nesterov=True)
+        opt.fuse_pack = fuse
+        n_pack = 0
+        for x, y in batches:
+            loss = crit(m(x), y)
+            opt.zero_grad()
+            loss.backward()
+            n0 = _lib.launch_count()
+            opt.step()
+            n_pack += _lib.launch_count() - n0
+        eng = m.engine()
+        if not fuse:
+            eng.pack_all(True)
+        assert eng.packed_is_fresh()
+        torch.cuda.synchronize()
+        packed = {s.name: (s.packed_fwd.clone(), None if s.packed_dgrad is None else s.packed_dgrad.clone()) for s in eng.specs}
+        res.append((eng.flat_w.clone(), opt._mom.clone(), packed, eng.aspp_wcat.clone(), float(loss.detach()), n_pack))
+    a, b = res
+    assert a[5] == 3 and b[5] == 3                              # one launch per step either way (the repack is the unfused path's extra one)
+    # (three steps at this learning rate amplify the weight-gradient kernels' fp32 atomics order chaotically - DESIGN 2 - so the two
+    # RUNS are not compared with each other; the update arithmetic is pinned by the test below, the packings here)
+    # the fused path's operands equal a fresh pack of ITS OWN weights, bit for bit
+    m2 = _model()
+    e2 = m2.engine()
+    crit(m2(batches[0][0]), batches[0][1]).backward()            # engine bound to the device, operand buffers allocated
+    with torch.no_grad():
+        e2.flatten_parameters().copy_(a[0])
+    e2.invalidate_packed()
+    e2.pack_all(True)
+    torch.cuda.synchronize()
+    for s in e2.specs:
+        f, d = a[2][s.name]
+        assert torch.equal(s.packed_fwd, f), s.name
+        if d is not None and s.packed_dgrad is not None:
+            assert torch.equal(s.packed_dgrad, d), s.name
+    assert torch.equal(e2.aspp_wcat, a[3])
+
+
+def test_fused_sgd_update_matches_sgd_step_kernel_exactly():
+    """Same gradients in, same weights / momentum out: the fused kernel's update arithmetic is iswm_sgd_step's."""
+    m = _model()
+    crit = CrossEntropyLoss().to(DEV)
+    (x, y), = _batches(1)
+    opt = FusedSGD(m, lr=5e-2, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    eng = m.engine()
+    eng.flatten_parameters()                                     # before the first pack: the very first step is fused already
+    loss = crit(m(x), y)
+    opt.zero_grad()
+    loss.backward()
+    w0, g0 = eng.flat_w.clone(), eng.flat_g.clone()
+    n0 = _lib.launch_count()
+    opt.step()                                                   # fused (first step: momentum buffer = gradient)
+    assert _lib.launch_count() - n0 == 1 and eng.packed_is_fresh()
+    loss = crit(m(x), y)
+    opt.zero_grad()
+    loss.backward()
+    w1, g1, m1 = eng.flat_w.clone(), eng.flat_g.clone(), opt._mom.clone()
+    opt.step()                                                   # fused, momentum in play
+    torch.cuda.synchronize()
+    # replay both updates with the plain kernel on copies
+    L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    wa, ma = w0.clone(), torch.zeros_like(w0)
+    _lib.check(L.iswm_sgd_step(wa.data_ptr(), g0.data_ptr(), ma.data_ptr(), wa.numel(), 5e-2, 0.9, 1e-4, 1, 1, None, st))
+    assert torch.equal(wa, w1) and torch.equal(ma, m1)
+    _lib.check(L.iswm_sgd_step(wa.data_ptr(), g1.data_ptr(), ma.data_ptr(), wa.numel(), 5e-2, 0.9, 1e-4, 1, 0, None, st))
+    torch.cuda.synchronize()
+    assert torch.equal(wa, eng.flat_w) and torch.equal(ma, opt._mom)
+
+
+def test_graph_replay_repacks_after_weights_were_loaded_from_outside():
+    """The captured step holds no repack at its start when FusedSGD repacks inside its own kernel; weights written from outside
+    between replays (load_state_dict) must still reach the bf16 operands before the next replay."""
+    crit = CrossEntropyLoss(weight=torch.tensor([1.0, 3.0])).to(DEV)
+    (x, y), (x2, y2) = _batches(2)
+    mg = _model()
+    mg.engine().dropout_p = 0.0
+    og = FusedSGD(mg, lr=1e-2, momentum=0.0, nesterov=False)
+    stepper = GraphedTrainStep(mg, crit, og)
+    stepper(x, y)
+    assert stepper._fused_pack
+    torch.manual_seed(123)
+    donor = modeling.deeplabv3plus_resnet50(num_classes=2, output_stride=16, pretrained_backbone=False).to(DEV).train()
+    sd = {k: v.clone() for k, v in donor.state_dict().items()}
+    mg.load_state_dict(sd)
+    lg = float(stepper(x2, y2))
+    me = _model()
+    me.engine().dropout_p = 0.0
+    me.load_state_dict(sd)
+    le = float(crit(me(x2), y2).detach())
+    assert abs(lg - le) <= 1e-6 * max(1.0, abs(le)), (lg, le)
