@@ -51,7 +51,7 @@ __device__ __forceinline__ float sgd_update(float w, float grad, float* mom_slot
 constexpr int kTO = 16;                 // output channels per tile
 constexpr int kTileMax = 16 * 144;      // floats of shared memory per tile
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 4)
 sgd_pack_kernel(const SgdPackJob* __restrict__ jobs, int n_jobs, SgdHyper h) {
   pdl_wait();
   pdl_launch();
@@ -98,16 +98,21 @@ sgd_pack_kernel(const SgdPackJob* __restrict__ jobs, int n_jobs, SgdHyper h) {
       // costs nine dependent memory round trips
       constexpr int kIter = kTileMax / kT;
       float wv[kIter], gv[kIter], mv[kIter];
-      long long gidx[kIter];
+      int gidx[kIter];                                    // offsets from the tile's first element (16 output channels: fits 31 bits)
+      const long long base = ((long long)o0 * j.Cin + c0) * RS;
+      float* const wb = j.w + base;
+      const float* const gb = j.g + base;
+      float* const mb = j.m ? j.m + base : nullptr;
+      const int ostride = j.Cin * RS;
 #pragma unroll
       for (int k = 0; k < kIter; k++) {
         const int i = tid + k * kT;
         const int o = i / F, f = i - o * F;
         const bool ok = (i < no * F) && (f < nf);
-        gidx[k] = ok ? ((long long)(o0 + o) * j.Cin + c0) * RS + f : -1;
-        wv[k] = ok ? j.w[gidx[k]] : 0.f;
-        gv[k] = ok ? j.g[gidx[k]] : 0.f;
-        mv[k] = (ok && j.m && !h.first) ? j.m[gidx[k]] : 0.f;
+        gidx[k] = ok ? o * ostride + f : -1;
+        wv[k] = ok ? wb[gidx[k]] : 0.f;
+        gv[k] = ok ? gb[gidx[k]] : 0.f;
+        mv[k] = (ok && mb && !h.first) ? mb[gidx[k]] : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < kIter; k++) {
@@ -115,8 +120,8 @@ sgd_pack_kernel(const SgdPackJob* __restrict__ jobs, int n_jobs, SgdHyper h) {
         const int i = tid + k * kT;
         float mslot = mv[k];
         const float wn = sgd_update(wv[k], gv[k], &mslot, h, lr);
-        j.w[gidx[k]] = wn;
-        if (j.m && h.momentum != 0.f) j.m[gidx[k]] = mslot;
+        wb[gidx[k]] = wn;
+        if (mb && h.momentum != 0.f) mb[gidx[k]] = mslot;
         tile[i] = wn;                                     // tile[o][c * RS + t] (i = o * F + f)
       }
     }
