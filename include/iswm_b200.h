@@ -246,6 +246,18 @@ int iswm_peer_small_sum(const void* const* slot_ptrs, int world, void* d_dst, in
  * ACCUMULATED into with fp32 reductions (zero it first). dy row pitch = out_ld. */
 int iswm_conv_wgrad(const iswm_conv_desc* desc, const void* d_in, const void* d_dy,
                     float* d_dw, void* stream);
+/* The weight gradients of SEVERAL convolutions in ONE launch (csrc/conv_wgrad.cu, grouped kernel): descs[n_jobs] with the
+ * per-job device pointers d_in[j] / d_dy[j] / d_dw[j] (host arrays). Work units (job, output tile, pixel-block range) are
+ * dealt to the CTAs on the host - a layer's worth of small GEMMs has enough tiles to fill the SMs with few pixel-range splits,
+ * so almost no partial-tile reductions remain. Results as n_jobs calls of iswm_conv_wgrad (accumulated into d_dw[j]). The
+ * plan is cached per set of shapes; the first call of a shape set allocates device memory (not inside a stream capture). */
+int iswm_conv_wgrad_grouped(const iswm_conv_desc* descs, const void* const* d_in, const void* const* d_dy,
+                            float* const* d_dw, int n_jobs, void* stream);
+/* Same with a CTA budget: the launch plans its tiles x splits for max_ctas SMs instead of all of them (0 = all), so that several
+ * small weight gradients launched on different streams run next to each other, each with few splits - a split costs a whole
+ * partial-tile fp32 reduction, and a 1x1 layer at 32x32 spread over 148 SMs is mostly that. */
+int iswm_conv_wgrad_ex(const iswm_conv_desc* desc, const void* d_in, const void* d_dy,
+                       float* d_dw, int max_ctas, void* stream);
 
 /* fp32 OIHW [Cout][Cin][R*S] -> bf16 rows of row_ld elements, element (t*cin_pad + c) = w[o][c][t],
  * zero elsewhere. Forward operand: cin_pad = Cin rounded up to 64, row_ld = R*S*cin_pad.

@@ -123,6 +123,8 @@ SIGNATURES = {
     "iswm_peer_small_publish": (_i, [C.POINTER(_p), _i, _i, _p, _i, _i, _i, _p]),
     "iswm_peer_small_sum": (_i, [C.POINTER(_p), _i, _p, _i, _i, _i, _p]),
     "iswm_conv_wgrad": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _p]),
+    "iswm_conv_wgrad_grouped": (_i, [C.POINTER(ConvDesc), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _i, _p]),
+    "iswm_conv_wgrad_ex": (_i, [C.POINTER(ConvDesc), _p, _p, _p, _i, _p]),
     "iswm_pack_weight_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weight_dgrad": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "iswm_pack_weights_batched": (_i, [_p, _i, _i, _p]),

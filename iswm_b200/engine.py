@@ -167,6 +167,13 @@ class Engine:
         # stride-2 convolutions read the parity phases of their dense input in place through a 5-D tensor map
         # (iswm_conv_desc.in_phase_view) instead of phase_split / subsample2 copies (ISWM_PHASE_VIEW=0: the copies)
         self.phase_view = __import__("os").environ.get("ISWM_PHASE_VIEW", "1") != "0"
+        # weight gradients of these backbone layers are collected while the layer's backward runs and launched as ONE grouped
+        # kernel when it ends (iswm_conv_wgrad_grouped: a layer's 13-19 small GEMMs side by side need almost no pixel-range
+        # splits, i.e. almost no partial-tile reductions; layer3 325 -> 192 us, layer2 282 -> 230 us, tools/prof_wgrad_group.py).
+        # layer1 (operands far larger than L2: every tile would stream them from HBM again: 319 -> 374 us)
+        # keeps one launch per convolution. conv_wgrad 2.63 -> 2.28 ms/step, step 12.50 -> 12.42. ISWM_WGRAD_GROUP="" turns it off.
+        self.group_wgrad = tuple(x for x in __import__("os").environ.get("ISWM_WGRAD_GROUP", "layer2,layer3,layer4").split(",") if x)
+        self._wq, self._wq_layer = [], None
         self._fwd_keep = []
         self._wstream = None
         self._wgrad_keep = []
@@ -718,10 +725,19 @@ class Engine:
         dy_ld = dy.stride(-2) if dy.dim() >= 2 else dy.shape[-1]          # a channel slice of a wider buffer keeps that buffer's pitch
         gview = self.grad_views[id(s.conv.weight)]
         d = ops.make_conv_desc(B, xin.H, xin.W, xin.C, xin.ld, n_img, Ho, Wo, Cout, dy_ld, taps, phase_view=xin.phase_view)
+        dst = gview if s.k == 1 else self.wacc[self.wacc_off[s.name][0]:self.wacc_off[s.name][0] + self.wacc_off[s.name][1]]
+        flops = 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k
+        layer = s.name.split(".")[1] if s.name.startswith("backbone.layer") else None
+        if layer in self.group_wgrad and self.debug_units is None:
+            if self._wq and self._wq_layer != layer:
+                self._flush_wgrad_group()
+            self._wq_layer = layer
+            self._wq.append((d, xin.t, dy, dst, s, flops, gview))
+            return self._conv_backward_dx(s, x, dy, dy_ld, taps, Ho, Wo, need_dx)
+        if self._wq:
+            self._flush_wgrad_group()
         with self._wgrad_ctx(dy, xin.t):
             ev = self._prof_begin()
-            dst = gview if s.k == 1 else self.wacc[self.wacc_off[s.name][0]:self.wacc_off[s.name][0] + self.wacc_off[s.name][1]]
-            flops = 2.0 * B * Ho * Wo * Cout * s.cin * s.k * s.k
             check(L.iswm_conv_wgrad(C.byref(d), xin.ptr, dy.data_ptr(), dst.data_ptr(), _st()), "conv_wgrad " + s.name)
             self._prof_end(ev, "conv_wgrad", flops, "wgrad " + s.name)
             if s.k != 1:
@@ -733,6 +749,32 @@ class Engine:
             if s.bn is not None:
                 self._notify(s.bn.weight)
                 self._notify(s.bn.bias)
+        self._conv_backward_dx(s, x, dy, dy_ld, taps, Ho, Wo, need_dx)
+
+    def _flush_wgrad_group(self):
+        """One grouped launch for the queued weight gradients of a layer (side stream, after everything the main stream has
+        produced so far), then their unpack / gradient-ready notifications."""
+        q, self._wq, self._wq_layer = self._wq, [], None
+        if not q:
+            return
+        L = _lib.lib()
+        keep = [t for job in q for t in (job[1], job[2])]
+        with self._wgrad_ctx(*keep):
+            ev = self._prof_begin()
+            ops.conv_wgrad_grouped([(d, xt, dy, dst) for (d, xt, dy, dst, _, _, _) in q], _st())
+            self._prof_end(ev, "conv_wgrad", sum(job[5] for job in q), "wgrad group " + q[0][4].name.split(".")[1])
+            for (d, xt, dy, dst, s, _, gview) in q:
+                if s.k != 1 and not self._batched_unpack():
+                    check(L.iswm_unpack_wgrad(dst.data_ptr(), s.cout, s.cin, s.k * s.k, s.cin, s.k * s.k * s.cin, 1.0, gview.data_ptr(), _st()), "unpack_wgrad")
+                self._notify(s.conv.weight)
+                if s.bn is not None:
+                    self._notify(s.bn.weight)
+                    self._notify(s.bn.bias)
+
+    def _conv_backward_dx(self, s: ConvSpec, x: Act, dy: torch.Tensor, dy_ld: int, taps, Ho, Wo, need_dx: bool):
+        """Data gradient into x.grad (assign or accumulate)."""
+        L = _lib.lib()
+        B, Cout = x.B, s.cout
         if not need_dx:
             return
         Cin = s.cin
@@ -1326,6 +1368,7 @@ class Engine:
                 elif p.grad.data_ptr() != self.grad_views[id(p)].data_ptr():
                     raise RuntimeError("parameter .grad was replaced by a foreign tensor; call optimizer.zero_grad(set_to_none=True)")
         self.wacc.zero_()
+        self._wq, self._wq_layer = [], None
         # classifier: bias grad, low-res logits gradient, weight grad, data grad
         cls = self.cls
         ldp = 8 * ((ncls + 7) // 8)
@@ -1346,6 +1389,8 @@ class Engine:
         # reverse sweep
         for fn in reversed(self.tape):
             fn()
+        if self._wq:
+            self._flush_wgrad_group()
         if self._batched_unpack():
             with self._wgrad_ctx():              # after every weight-gradient kernel of the sweep, on their stream
                 self._unpack_all()

@@ -225,6 +225,15 @@ def aspp_bwd(dycat: torch.Tensor, wcat: torch.Tensor, rates: Sequence[int], dfea
                                    dfeat.stride(2), 1 if accumulate else 0, _stream()), "aspp_bwd")
 
 
+def conv_wgrad_grouped(jobs, stream: Optional[int] = None) -> None:
+    """jobs: sequence of (ConvDesc, x, dy, dw) - the weight gradients of several convolutions in ONE launch (iswm_conv_wgrad_grouped)."""
+    n = len(jobs)
+    descs = (ConvDesc * n)(*[j[0] for j in jobs])
+    P = C.c_void_p * n
+    xin, dys, dws = P(*[j[1].data_ptr() for j in jobs]), P(*[j[2].data_ptr() for j in jobs]), P(*[j[3].data_ptr() for j in jobs])
+    check(_lib.lib().iswm_conv_wgrad_grouped(descs, xin, dys, dws, n, _stream() if stream is None else stream), "conv_wgrad_grouped")
+
+
 def conv_wgrad(desc: ConvDesc, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor) -> None:
     check(_lib.lib().iswm_conv_wgrad(C.byref(desc), _ptr(x), _ptr(dy), _ptr(dw), _stream()), "conv_wgrad")
 

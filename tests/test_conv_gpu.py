@@ -385,3 +385,37 @@ def test_stride2_convs_read_the_parity_phases_in_place(B, Cin, H, W, Cout, k):
     ops.unpack_wgrad(dw, grad)
     torch.cuda.synchronize()
     assert _rel_err(grad.cpu(), wr.grad) < 5e-3
+
+
+def test_grouped_weight_gradients_equal_the_single_launches():
+    """iswm_conv_wgrad_grouped: one launch for a layer's worth of convolutions (work units dealt to the CTAs on the host) against
+    one iswm_conv_wgrad per convolution: 1x1 / 3x3 / dilated, Cin tails, Cout below and above one M tile, a stride-2 job reading
+    its input as parity phases in place, and more jobs than one launch holds (26 > 24). fp32 split order differs: 1e-5."""
+    g = torch.Generator().manual_seed(61)
+    shapes = [(2, 256, 16, 16, 64, 1, 1, False), (2, 64, 16, 16, 64, 3, 1, False), (2, 64, 16, 16, 256, 1, 1, False),
+              (1, 128, 24, 24, 128, 3, 2, False), (2, 96, 12, 12, 72, 3, 1, False), (2, 304, 16, 16, 256, 3, 1, False),
+              (2, 128, 16, 16, 128, 3, 1, True), (2, 256, 16, 16, 512, 1, 1, True), (3, 1024, 8, 8, 256, 1, 1, False)]
+    shapes = shapes * 3                                         # 27 jobs -> two launches
+    jobs, singles = [], []
+    for (B, Cin, H, W, Cout, k, dil, s2) in shapes:
+        x = torch.randn((B, H, W, Cin), generator=g).to(torch.bfloat16).to(DEV)
+        if s2:
+            Ho, Wo = H // 2, W // 2
+            taps = ops.conv_taps(1, 1) if k == 1 else ops.conv_taps_s2_3x3()
+            d = ops.make_conv_desc(B, Ho, Wo, Cin, Cin, B, Ho, Wo, Cout, Cout, taps, phase_view=True)
+        else:
+            Ho, Wo = H, W
+            d = ops.make_conv_desc(B, H, W, Cin, Cin, B, H, W, Cout, Cout, ops.conv_taps(k, dil))
+        dy = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).to(DEV)
+        dw_g = torch.zeros((Cout, k * k, Cin), dtype=torch.float32, device=DEV)
+        dw_s = torch.zeros_like(dw_g)
+        jobs.append((d, x, dy, dw_g))
+        singles.append((d, x, dy, dw_s))
+    for (d, x, dy, dw) in singles:
+        ops.conv_wgrad(d, x, dy, dw)
+    ops.conv_wgrad_grouped(jobs)
+    ops.conv_wgrad_grouped(jobs)                                # accumulates: twice the gradient
+    _assert_healthy()
+    for i, ((_, _, _, a), (_, _, _, b)) in enumerate(zip(jobs, singles)):
+        scale = float(b.abs().max()) + 1e-6
+        assert float((a - 2.0 * b).abs().max()) <= 2e-5 * scale * 2, (i, shapes[i])
