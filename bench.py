@@ -472,7 +472,7 @@ def run_lossmetric(args, dev, world, rank, local):
         "e2e": {"value": N / e2e_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": lh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "wce2_kernel (fused weighted softmax-CE forward + backward)", "achieved": res[k]["GB/s"], "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": res[k]["frac_of_hbm_peak"], "traffic": traffic_from_profiles("wce2_kernel"), "peak_source": pk["_source"] + " hbm_gbs"},
+                     "unit": "GB/s", "frac": res[k]["frac_of_hbm_peak"], "traffic": traffic_from_profiles("cfg5:wce_fwd_bwd"), "peak_source": pk["_source"] + " hbm_gbs"},
         "cpu_baseline": cpu}))
 
 

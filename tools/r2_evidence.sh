@@ -22,6 +22,8 @@ ncu --set full --clock-control none --import-source on -k regex:'conv_igemm|conv
 tail -n 1 gpurun_out/${tag}_ncu2.log
 unset ISWM_BENCH_GRAPH
 python bench.py --workload lossmetric --steps 2 > /dev/null 2>&1 &&
-ncu --set full --clock-control none -k regex:'class_hist|wce2|argmax_confusion' -c 3 -o gpurun_out/${tag}_lossmetric python bench.py --workload lossmetric --steps 1 > gpurun_out/${tag}_ncu3.log 2>&1
-tail -n 1 gpurun_out/${tag}_ncu3.log
+for k in class_hist wce2 argmax_confusion; do
+  ncu --set full --clock-control none -k regex:$k -c 1 -o gpurun_out/${tag}_lossmetric_$k python bench.py --workload lossmetric --steps 1 > gpurun_out/${tag}_ncu3_$k.log 2>&1
+  tail -n 1 gpurun_out/${tag}_ncu3_$k.log
+done
 cuobjdump -sass iswm_b200/libiswm_b200.so > /tmp/sass.txt 2>/dev/null; python tools/sass_summary.py /tmp/sass.txt > gpurun_out/${tag}_sass.txt 2>&1; head -30 gpurun_out/${tag}_sass.txt
