@@ -156,6 +156,7 @@ class Engine:
         # blocks with a downsample branch: the closing BatchNorm and the downsample BatchNorm run as ONE kernel per pass
         # (csrc/bn_dual.cu; the normalised shortcut is never written, backward reads dout / sign bits once per pass for both)
         self.dual_bn = __import__("os").environ.get("ISWM_DUAL_BN", "1") != "0"
+        self.ds_bwd_late = __import__("os").environ.get("ISWM_DS_BWD_LATE", "1") != "0"
         # stem 7x7/s2: the image unrolled along x only (iswm_stem_rows, 48 B per pixel row) + the 7 kernel rows as 7 taps of the
         # implicit GEMM over the two row-parity phases, instead of a full im2col matrix (320 B per pixel) + one GEMM
         # (ISWM_STEM_ROWS=0: the im2col form)
@@ -679,7 +680,7 @@ class Engine:
         bn_ds(conv_ds(xds))), both BatchNorms in one kernel per pass (csrc/bn_dual.cu). `dsc` = _conv_raw(sds, xds)."""
         L = _lib.lib()
         raw, stats, xin, taps, n_img, Ho, Wo = self._conv_raw(s, x)
-        raw_ds, stats_ds, xin_ds, taps_ds, n_img_ds, Ho_ds, Wo_ds = dsc
+        raw_ds, stats_ds, xin_ds, taps_ds, n_img_ds, Ho_ds, Wo_ds, ds_dy = dsc
         assert (Ho, Wo) == (Ho_ds, Wo_ds) and s.cout == sds.cout
         B, Cout = x.B, s.cout
         M = B * Ho * Wo
@@ -713,7 +714,10 @@ class Engine:
             self._prof_end(ev, "hbm:bn_bwd_apply", 2.0 * M * Cout * 5 + M * Cout / 8, "bn_bwd_apply " + s.name + "+ds")
             out.grad = None
             self._conv_backward(s, x, xin, taps, n_img, Ho, Wo, dy, True)
-            self._conv_backward(sds, xds, xin_ds, taps_ds, n_img_ds, Ho, Wo, dy_ds, True)
+            if self.ds_bwd_late:
+                ds_dy.append(dy_ds)                   # the downsample convolution's backward runs after conv1's (taped in forward())
+            else:
+                self._conv_backward(sds, xds, xin_ds, taps_ds, n_img_ds, Ho, Wo, dy_ds, True)
 
         self.tape.append(backward)
         return out
@@ -1090,6 +1094,12 @@ class Engine:
                 if (ds is not None and train and self.dual_bn and self.relu_bits and self.debug_units is None and self.debug_taps is None
                         and c3.cout % 8 == 0):
                     dsc = self._conv_raw(ds, a)   # downsample convolution now; its BatchNorm rides on the block's closing one
+                    # its backward is taped HERE, i.e. it runs after conv1's: conv1's data gradient then writes the block input's
+                    # gradient fresh and the (strided, for stride 2) downsample gradient accumulates into a quarter of it - the other
+                    # order needs a zero fill of the whole tensor and a full read-modify-write by conv1
+                    ds_dy = []
+                    self.tape.append(lambda ds=ds, a=a, dsc=dsc, ds_dy=ds_dy: ds_dy and self._conv_backward(ds, a, dsc[2], dsc[3], dsc[4], dsc[5], dsc[6], ds_dy.pop(), True))
+                    dsc = dsc + (ds_dy,)
                     y = unit(c1, a, **kw)
                     y = unit(c2, y, **kw)
                     a = self._unit_train_dual(c3, y, ds, a, dsc)
