@@ -1942,10 +1942,84 @@ extern "C" int iswm_gap_bwd_add(const void* d_dpool, int B, int64_t HW, int C, v
   launch_k(broadcast_hw_kernel, dim3(grid_for((int64_t)B * HW * (C / 8))), dim3(kT), 0, ST(stream), BF(d_dpool), B, HW, C, BFW(d_dx), dx_ld, 1.0f / (float)HW, 1);
   return check_launch("gap_bwd_add");
 }
+namespace iswm {
+// x4 upsampling (the decoder's interpolate of the ASPP output, network/_deeplab.py:58, and every size the model is used at):
+// a thread owns a 4 x 4 block of output pixels of one 8-channel group. Output rows 4r, 4r+1 share their two source rows, so do
+// 4r+2, 4r+3 (only the weights differ) - borders included, because bil_src clamps both the same way - and likewise for columns:
+// per row pair 2 x 4 source pixels are loaded for 2 x 4 outputs, 16 loads per 16 stores instead of the generic kernel's 64 (it is
+// bound by L2 reads: 4 x 16 B per 16 B written, 11 TB/s of L2 traffic at cfg2). Same weights (bil_src per output) and the
+// same expression as the generic kernel: bit-identical results; all register indices are static.
+__global__ void __launch_bounds__(kT, 2)
+bilinear_up4_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int B, int Hi, int Wi, int C,
+                        __nv_bfloat16* __restrict__ out, int out_ld) {
+  pdl_wait();
+  pdl_launch();
+  const int nvec = C >> 3;
+  const int Ho = 4 * Hi, Wo = 4 * Wi;
+  const int64_t total = (int64_t)B * Hi * Wi * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int c8 = (int)(i % nvec) << 3;
+    int64_t m = i / nvec;
+    const int k = (int)(m % Wi), r = (int)((m / Wi) % Hi), b = (int)(m / ((int64_t)Wi * Hi));
+    int xc[4];                                           // source columns of output columns {4k, 4k+1} and {4k+2, 4k+3}
+    float lxs[4];
+    {
+      float t;
+      bil_src(4 * k, 0.25f, Wi, xc[0], xc[1], t);
+      bil_src(4 * k + 2, 0.25f, Wi, xc[2], xc[3], t);
+#pragma unroll
+      for (int dx = 0; dx < 4; dx++) {
+        int a0, a1;
+        bil_src(4 * k + dx, 0.25f, Wi, a0, a1, lxs[dx]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 2; g++) {                        // row pair {4r + 2g, 4r + 2g + 1}
+      int y0, y1;
+      float t;
+      bil_src(4 * r + 2 * g, 0.25f, Hi, y0, y1, t);
+      F8 v[2][4];
+      const __nv_bfloat16* r0 = x + ((int64_t)b * Hi + y0) * Wi * x_ld + c8;
+      const __nv_bfloat16* r1 = x + ((int64_t)b * Hi + y1) * Wi * x_ld + c8;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        v[0][c] = load8(r0 + (int64_t)xc[c] * x_ld);
+        v[1][c] = load8(r1 + (int64_t)xc[c] * x_ld);
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++) {
+        const int ho = 4 * r + 2 * g + dy;
+        int a0, a1;
+        float ly;
+        bil_src(ho, 0.25f, Hi, a0, a1, ly);
+#pragma unroll
+        for (int dx = 0; dx < 4; dx++) {
+          const float lx = lxs[dx];
+          const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+          const int c0 = (dx < 2) ? 0 : 2;               // static after unrolling
+          F8 o;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            o.v[j] = w00 * v[0][c0].v[j] + w01 * v[0][c0 + 1].v[j] + w10 * v[1][c0].v[j] + w11 * v[1][c0 + 1].v[j];
+          store8(out + (((int64_t)b * Ho + ho) * Wo + 4 * k + dx) * out_ld + c8, o);
+        }
+      }
+    }
+  }
+}
+}  // namespace iswm
+
 extern "C" int iswm_bilinear_fwd(const void* d_x, int x_ld, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                  void* d_out, int out_ld, void* stream) {
   REQ_C8(C, "bilinear_fwd"); REQ_LD8(x_ld, "bilinear_fwd"); REQ_LD8(out_ld, "bilinear_fwd");
   ISWM_REQUIRE(d_x && d_out, "bilinear_fwd: null");
+  if (Ho == 4 * Hi && Wo == 4 * Wi) {
+    const char* e = getenv("ISWM_BILINEAR_UP4");         // "0": the generic kernel (tests compare the two bit for bit)
+    if (!(e && e[0] == '0')) {
+      launch_k(bilinear_up4_fwd_kernel, dim3(grid_for((int64_t)B * Hi * Wi * (C / 8), kT, 16)), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, Hi, Wi, C, BFW(d_out), out_ld);
+      return check_launch("bilinear_fwd (x4)");
+    }
+  }
   launch_k(bilinear_fwd_kernel, dim3((unsigned)(B * Ho), (unsigned)std::min(8, (Wo * (C / 8) + kT - 1) / kT)), dim3(kT), 0, ST(stream), BF(d_x), x_ld, B, Hi, Wi, C, Ho, Wo, BFW(d_out), out_ld);
   return check_launch("bilinear_fwd");
 }

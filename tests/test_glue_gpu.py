@@ -558,3 +558,26 @@ def test_stem_bn_relu_maxpool_fused_against_the_separate_kernels(B, H, W):
     assert float((dy2.float() != dy1.float()).float().mean()) < 0.02       # all but the odd rounding flip are identical
     close(dg2, dg1, 1e-4, 1e-4 * mag)
     close(db2, db1, 1e-4, 1e-4 * mag)
+
+
+@pytest.mark.parametrize("B,C,Hi,Wi,ld", [(2, 256, 8, 8, 304), (1, 16, 5, 7, 24), (2, 64, 1, 3, 64), (1, 256, 32, 32, 256)])
+def test_bilinear_up4_fast_path_is_bit_identical_to_the_generic_kernel(B, C, Hi, Wi, ld):
+    """x4 upsampling (the decoder's interpolate, _deeplab.py:58): the 4x4-output-block kernel (9 loads per 16 stores) against the
+    generic one-output-per-thread kernel - same weights, same expression: bit-equal, into a channel slice of a wider buffer."""
+    import os
+    x = rnd((B, C, Hi, Wi), 71)
+    xd = nhwc(x).to(DEV)
+    Ho, Wo = 4 * Hi, 4 * Wi
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["ISWM_BILINEAR_UP4"] = flag
+        out = torch.full((B, Ho, Wo, ld), 3.0, dtype=torch.bfloat16, device=DEV)
+        check(L().iswm_bilinear_fwd(xd.data_ptr(), C, B, Hi, Wi, C, Ho, Wo, out[..., ld - C:].data_ptr(), ld, st()))
+        outs.append(out)
+    os.environ.pop("ISWM_BILINEAR_UP4")
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    ref = F.interpolate(x.float(), size=(Ho, Wo), mode="bilinear", align_corners=False)
+    close(nchw(outs[0][..., ld - C:]), ref, 1e-2, 1e-2)
+    if ld > C:
+        assert float(outs[0][..., :ld - C].float().min()) == 3.0
