@@ -505,6 +505,25 @@ int iswm_u8_to_f32_norm(const uint8_t* d_src, int B, int Hs, int Ws, int C, cons
 int iswm_crop_flip_u8(const uint8_t* d_src, int B, int Hs, int Ws, const int32_t* d_origin_xy,
                       const uint8_t* d_flip, int H, int W, uint8_t* d_out, void* stream);
 
+/* The reference's whole TRAIN transform (train.py:355-362) on uint8 tiles, one call:
+ *   ExtRandomScale (utils/ext_transforms.py:94-111: F.resize to (int(h*s), int(w*s)), bilinear for the image, nearest for the label)
+ *   -> ExtRandomCrop(pad_if_needed=True) (:366-393: zero padding on all four sides when the scaled tile is smaller than the crop, then
+ *   F.crop) -> ExtRandomHorizontalFlip (:94-111 of the flip class) -> ExtToTensor -> ExtNormalize (:273-324).
+ * The resampling arithmetic is Pillow's (Resample.c two-pass 8 bpc fixed point; Geometry.c ImagingScaleAffine), restated in
+ * iswm_b200/csrc/scale_math.h: images and labels are BIT-IDENTICAL to the PIL pipeline for the same random draws.
+ *   d_img      uint8 [B,Hs,Ws,C] (C = 1..4), device;  d_lbl uint8 [B,Hs,Ws] or NULL (then d_lbl_out NULL too)
+ *   d_geom     int32 [B,8] device, one record per sample, written by the host that drew the random numbers:
+ *              {sh, sw = scaled size; pad = zero padding per side; y0, x0 = crop origin in the padded tile; flip; 0; 0}
+ *   kmax       taps per coefficient row, >= ceil(max(Hs/sh, Ws/sw, 1)) * 2 + 1 over the batch (3..16)
+ *   tab_w/h    table capacity: >= max sw / max sh over the batch
+ *   d_tables   int32 workspace, B * iswm_random_scale_table_words(tab_w, tab_h, kmax) words (coefficient rows + index tables)
+ *   mean, stdv HOST float[C];  d_out float32 NCHW [B,C,H,W];  d_lbl_out uint8 [B,H,W] (padding = 0, like F.pad's default fill)
+ * Three launches (plan, image, label) on `stream`. */
+int64_t iswm_random_scale_table_words(int tab_w, int tab_h, int kmax);
+int iswm_random_scale_crop(const uint8_t* d_img, const uint8_t* d_lbl, int B, int Hs, int Ws, int C, const int32_t* d_geom,
+                           int kmax, int tab_w, int tab_h, int32_t* d_tables, const float* mean, const float* stdv,
+                           int H, int W, float* d_out, uint8_t* d_lbl_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,8 @@ SIGNATURES = {
     "iswm_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _i64, _p, _p, _p]),
     "iswm_u8_to_f32_norm": (_i, [_p, _i, _i, _i, _i, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _p, _p]),
     "iswm_crop_flip_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "iswm_random_scale_table_words": (_i64, [_i, _i, _i]),
+    "iswm_random_scale_crop": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _p, _p, _p]),
 }
 
 _lib = None

@@ -86,15 +86,70 @@ class DeviceTransform:
     labels stay uint8 (the criterion and the metric read them as they are). Crop origins and flip decisions are drawn
     on the host from `generator` (one origin / one coin per image, as ExtRandomCrop.get_params and
     ExtRandomHorizontalFlip do per sample, utils/ext_transforms.py:350-365, :94-111). Normalisation is bit-identical
-    to torchvision's to_tensor + normalize. ExtRandomScale (PIL bilinear / nearest resampling) and the pad_if_needed
-    branch stay on the host: tiles must be at least crop_size."""
+    to torchvision's to_tensor + normalize.
+
+    The FULL train pipeline of train.py:355-362 - ExtRandomScale((0.5, 2.0)) first, ExtRandomCrop(pad_if_needed=True) -
+    is `DeviceTransform(mean, std, crop_size=S, hflip=True, scale_range=(0.5, 2.0), pad_if_needed=True)`: one
+    `ops.random_scale_crop` call (3 launches) that resamples ONLY the crop window of the scaled tile, bit-identical to
+    Pillow's bilinear (image) / nearest (label) resize, zero padding included (utils/ext_transforms.py:94-111, :377-391).
+    `draw_scaled` makes the per-sample records on the host (scale ~ U(lo, hi), target = (int(h*s), int(w*s)), padding,
+    crop origin in the padded tile, flip) exactly as the reference's classes derive them from their random numbers."""
 
     def __init__(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), crop_size=None, hflip: bool = False,
-                 p_flip: float = 0.5, generator: torch.Generator = None):
+                 p_flip: float = 0.5, generator: torch.Generator = None, scale_range=None, pad_if_needed: bool = False):
         self.mean, self.std = tuple(mean), tuple(std)
         self.crop_size = (crop_size, crop_size) if isinstance(crop_size, int) else crop_size
         self.hflip, self.p_flip = hflip, p_flip
         self.generator = generator
+        self.scale_range, self.pad_if_needed = scale_range, pad_if_needed
+        if scale_range is not None and self.crop_size is None:
+            raise ValueError("scale_range needs crop_size: scaled tiles of one batch differ in size (the reference crops them too)")
+        self._tables = None
+
+    @staticmethod
+    def scaled_geometry(Hs: int, Ws: int, scale: float, crop_hw, pad_if_needed: bool = True):
+        """(sh, sw, pad, Hp, Wp) of one sample: ExtRandomScale's target size (utils/ext_transforms.py:107) and the padding
+        ExtRandomCrop(pad_if_needed) adds on EVERY side (:377-385: width first, then height on the already padded tile)."""
+        sh, sw = int(Hs * scale), int(Ws * scale)
+        th, tw = crop_hw
+        pad = 0
+        if pad_if_needed and sw + 2 * pad < tw:
+            pad += int((1 + tw - (sw + 2 * pad)) / 2)
+        if pad_if_needed and sh + 2 * pad < th:
+            pad += int((1 + th - (sh + 2 * pad)) / 2)
+        return sh, sw, pad, sh + 2 * pad, sw + 2 * pad
+
+    def draw_scaled(self, B: int, Hs: int, Ws: int, scales=None) -> torch.Tensor:
+        """Host-side records of one batch for the scaled pipeline: int32 [B,8] = (sh, sw, pad, y0, x0, flip, 0, 0).
+        `scales` overrides the uniform draw (tests)."""
+        H, W = self.crop_size
+        lo, hi = self.scale_range
+        geom = torch.zeros((B, 8), dtype=torch.int32)
+        for b in range(B):
+            s = float(scales[b]) if scales is not None else lo + (hi - lo) * float(torch.rand((), generator=self.generator, dtype=torch.float64))
+            sh, sw, pad, Hp, Wp = self.scaled_geometry(Hs, Ws, s, (H, W), self.pad_if_needed)
+            if sh < 1 or sw < 1:
+                raise ValueError(f"scale {s} collapses the {Hs}x{Ws} tile")
+            if Hp < H or Wp < W:
+                raise ValueError(f"scaled tile {sh}x{sw} smaller than the {H}x{W} crop (pad_if_needed=False)")
+            if Hp == H and Wp == W:
+                y0 = x0 = 0                                    # ExtRandomCrop.get_params returns the origin without drawing
+            else:
+                y0 = int(torch.randint(0, Hp - H + 1, (), generator=self.generator))
+                x0 = int(torch.randint(0, Wp - W + 1, (), generator=self.generator))
+            fl = int(float(torch.rand((), generator=self.generator)) < self.p_flip) if self.hflip else 0
+            geom[b, 0], geom[b, 1], geom[b, 2], geom[b, 3], geom[b, 4], geom[b, 5] = sh, sw, pad, y0, x0, fl
+        return geom
+
+    def _call_scaled(self, images, labels, geom):
+        from . import ops
+        B, Hs, Ws, _ = images.shape
+        geom = geom if geom is not None else self.draw_scaled(B, Hs, Ws)
+        kmax = ops.random_scale_kmax(Hs, Ws, geom.tolist())
+        tab_hw = (int(geom[:, 0].max()), int(geom[:, 1].max()))
+        x, y, self._tables = ops.random_scale_crop(images, labels, geom.to(images.device, non_blocking=True), self.crop_size, self.mean, self.std,
+                                                   kmax, tab_hw, self._tables)
+        return x if labels is None else (x, y)
 
     def draw(self, B: int, Hs: int, Ws: int):
         """Host-side random parameters of one batch: (origin_xy int32 [B,2] or None, flip uint8 [B] or None)."""
@@ -114,6 +169,8 @@ class DeviceTransform:
         from . import ops
         if not images.is_cuda:
             raise RuntimeError("DeviceTransform runs on CUDA tensors (iswm_b200 has no CPU path)")
+        if self.scale_range is not None:
+            return self._call_scaled(images, labels, params)
         B, Hs, Ws, _ = images.shape
         org, flip = params if params is not None else self.draw(B, Hs, Ws)
         dev = images.device

@@ -185,6 +185,53 @@ def crop_flip_u8(src: torch.Tensor, size: Optional[Tuple[int, int]] = None, orig
     return out
 
 
+def random_scale_kmax(Hs: int, Ws: int, geom) -> int:
+    """Taps per coefficient row iswm_random_scale_crop needs for a batch of geometry records (host int array [B,8]):
+    Pillow's ksize = ceil(max(in / out, 1)) * 2 + 1, the largest over both axes and all samples."""
+    k = 3
+    for g in geom:
+        sh, sw = int(g[0]), int(g[1])
+        if sh < 1 or sw < 1:
+            raise ValueError(f"scaled size {sh}x{sw}: the scale collapses the tile")
+        for n_in, n_out in ((Hs, sh), (Ws, sw)):
+            fs = max(float(n_in) / n_out, 1.0)
+            c = int(fs)
+            k = max(k, (c + (1 if c < fs else 0)) * 2 + 1)
+    return k
+
+
+def random_scale_crop(img: torch.Tensor, lbl: Optional[torch.Tensor], geom: torch.Tensor, size: Tuple[int, int],
+                      mean: Sequence[float], std: Sequence[float], kmax: int, tab_hw: Tuple[int, int],
+                      tables: Optional[torch.Tensor] = None):
+    """ExtRandomScale -> ExtRandomCrop(pad_if_needed) -> ExtRandomHorizontalFlip -> ExtToTensor -> ExtNormalize
+    (train.py:355-362) on uint8 tiles [B,Hs,Ws,C] (+ uint8 labels [B,Hs,Ws]): float32 [B,C,H,W] and uint8 [B,H,W],
+    bit-identical to the PIL pipeline for the draws in `geom` (int32 [B,8] on the device, see include/iswm_b200.h)."""
+    if img.dtype != torch.uint8 or img.dim() != 4:
+        raise TypeError("random_scale_crop wants uint8 [B,H,W,C] tiles")
+    if lbl is not None and (lbl.dtype != torch.uint8 or lbl.dim() != 3 or lbl.shape != img.shape[:3]):
+        raise TypeError("random_scale_crop wants uint8 [B,H,W] labels of the image's size")
+    if geom.dtype != torch.int32 or geom.dim() != 2 or geom.shape[1] != 8 or geom.shape[0] != img.shape[0] or not geom.is_cuda:
+        raise TypeError("random_scale_crop wants an int32 [B,8] device geometry tensor")
+    img = img.contiguous()
+    lbl = None if lbl is None else lbl.contiguous()
+    geom = geom.contiguous()
+    B, Hs, Ws, Cc = img.shape
+    H, W = size
+    if len(mean) != Cc or len(std) != Cc:
+        raise ValueError("mean / std need one value per channel")
+    tab_h, tab_w = tab_hw
+    words = int(_lib.lib().iswm_random_scale_table_words(tab_w, tab_h, kmax)) * max(B, 1)
+    if tables is None or tables.numel() < words:
+        tables = torch.empty(words, dtype=torch.int32, device=img.device)
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=img.device)
+    lout = None if lbl is None else torch.empty((B, H, W), dtype=torch.uint8, device=img.device)
+    mu = (C.c_float * Cc)(*[float(v) for v in mean])
+    sd = (C.c_float * Cc)(*[float(v) for v in std])
+    check(_lib.lib().iswm_random_scale_crop(_ptr(img), _ptr(lbl), B, Hs, Ws, Cc, _ptr(geom), kmax, tab_w, tab_h, _ptr(tables), mu, sd,
+                                            H, W, _ptr(out), _ptr(lout), _stream()), "random_scale_crop")
+    return out, lout, tables
+
+
 # ----------------------------------------------------------------------------- convolution
 
 def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,

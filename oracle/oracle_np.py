@@ -199,3 +199,125 @@ def upsample_bilinear_nchw(x: np.ndarray, H: int, W: int) -> np.ndarray:
     c = x[..., y1, :][..., :, x0]
     d = x[..., y1, :][..., :, x1]
     return ((1 - ly) * (1 - lx) * a + (1 - ly) * lx * b + ly * (1 - lx) * c + ly * lx * d).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# ExtRandomScale / ExtRandomCrop(pad_if_needed). The arithmetic lives in a third-party
+# dependency: Pillow (requirements.txt pins 10.x; 12.2 here - src/libImaging/Resample.c and Geometry.c are unchanged
+# between them for this path), reached through torchvision's F.resize -> PIL.Image.resize. Restated from the
+# published algorithm and pinned against PIL itself in tests/test_scale_oracle.py (PIL is importable on the build
+# container AND on the GPU box) plus the reference-generated fixtures tests/golden/scale_rows.npz.
+
+_PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (support 1.0) over the full box
+    (0, in_size): returns (ksize, bounds int32 [out,2] = (xmin, count), kk int32 [out, ksize] fixed point 2^-22)."""
+    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    xx = np.arange(out_size, dtype=np.float64)
+    center = 0.0 + (xx + 0.5) * scale
+    ss = 1.0 / filterscale
+    xmin = (center - support + 0.5).astype(np.int64)            # C (int) cast: truncation toward zero
+    xmin = np.maximum(xmin, 0)
+    xmax = (center + support + 0.5).astype(np.int64)
+    xmax = np.minimum(xmax, in_size) - xmin
+    x = np.arange(ksize, dtype=np.int64)[None, :]
+    arg = ((x + xmin[:, None]).astype(np.float64) - center[:, None] + 0.5) * ss
+    arg = np.abs(arg)
+    w = np.where(arg < 1.0, 1.0 - arg, 0.0)
+    w = np.where(x < xmax[:, None], w, 0.0)
+    # the C loop adds the weights one by one, left to right (np.sum would pair them)
+    acc = np.zeros(out_size, dtype=np.float64)
+    for k in range(ksize):
+        acc = acc + w[:, k]
+    ww = acc[:, None]
+    kd = np.where(ww != 0.0, w / np.where(ww != 0.0, ww, 1.0), w)
+    kd = np.where(x < xmax[:, None], kd, 0.0)
+    kk = np.where(kd < 0, (-0.5 + kd * (1 << _PIL_PRECISION_BITS)), (0.5 + kd * (1 << _PIL_PRECISION_BITS))).astype(np.int64).astype(np.int32)
+    bounds = np.stack([xmin, xmax], axis=1).astype(np.int32)
+    return ksize, bounds, kk
+
+
+def _pil_clip8(v: np.ndarray) -> np.ndarray:
+    return np.clip(v >> _PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+
+
+def pil_resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """PIL.Image.resize((out_w, out_h), BILINEAR) on a uint8 HWC (or HW) array: Resample.c ImagingResampleInner - the
+    horizontal pass into a uint8 intermediate, then the vertical pass, each `clip8((1 << 21) + sum(px * k))`."""
+    a = np.asarray(img)
+    squeeze = a.ndim == 2
+    if squeeze:
+        a = a[:, :, None]
+    H, W, _ = a.shape
+    if (out_h, out_w) == (H, W):
+        return np.asarray(img).copy()
+    half = 1 << (_PIL_PRECISION_BITS - 1)
+    cur = a
+    if out_w != W:
+        ks, b, kk = pil_bilinear_coeffs(W, out_w)
+        idx = np.minimum(b[:, 0:1] + np.arange(ks)[None, :], W - 1)          # taps beyond the count carry k = 0
+        g = cur[:, idx, :].astype(np.int64)                                   # [H, out_w, ks, C]
+        cur = _pil_clip8(half + (g * kk[None, :, :, None].astype(np.int64)).sum(axis=2))
+    if out_h != H:
+        ks, b, kk = pil_bilinear_coeffs(H, out_h)
+        idx = np.minimum(b[:, 0:1] + np.arange(ks)[None, :], H - 1)
+        g = cur[idx, :, :].astype(np.int64)                                   # [out_h, ks, W', C]
+        cur = _pil_clip8(half + (g * kk[:, :, None, None].astype(np.int64)).sum(axis=1))
+    return cur[:, :, 0] if squeeze else cur
+
+
+def pil_nearest_table(in_size: int, out_size: int) -> np.ndarray:
+    """Geometry.c ImagingScaleAffine: xo = a*0.5, then `xin = (int) xo; xo += a` - the source index of every output
+    pixel comes from a RUNNING double sum (not from (x + 0.5) * a), which decides exact-boundary cases."""
+    a = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    steps = np.full(out_size, a, dtype=np.float64)
+    steps[0] = 0.0 + a * 0.5
+    xo = np.cumsum(steps)                                                     # sequential adds, like the C loop
+    xin = np.where(xo < 0.0, -1, xo.astype(np.int64))
+    return xin.astype(np.int32)
+
+
+def pil_resize_nearest(lbl: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """PIL.Image.resize((out_w, out_h), NEAREST) on an HW array (labels, utils/ext_transforms.py:109)."""
+    a = np.asarray(lbl)
+    H, W = a.shape[:2]
+    if (out_h, out_w) == (H, W):
+        return a.copy()
+    yt, xt = pil_nearest_table(H, out_h), pil_nearest_table(W, out_w)
+    out = np.zeros((out_h, out_w) + a.shape[2:], dtype=a.dtype)
+    oky, okx = (yt >= 0) & (yt < H), (xt >= 0) & (xt < W)
+    out[np.ix_(oky, okx)] = a[np.ix_(yt[oky], xt[okx])]
+    return out
+
+
+def random_scale_geometry(Hs: int, Ws: int, scale: float, crop_hw, pad_if_needed: bool = True):
+    """Sizes the reference's train pipeline goes through for one sample: ExtRandomScale (utils/ext_transforms.py:107:
+    target = (int(h*scale), int(w*scale))), then ExtRandomCrop's pad_if_needed (:377-385: F.pad on ALL four sides by
+    int((1 + tw - w) / 2) when too narrow, then by int((1 + th - h) / 2) when still too low, fill 0).
+    Returns (sh, sw, pad, Hp, Wp): scaled size, total padding per side, padded size."""
+    sh, sw = int(Hs * scale), int(Ws * scale)
+    th, tw = crop_hw
+    pad = 0
+    if pad_if_needed and sw + 2 * pad < tw:
+        pad += int((1 + tw - (sw + 2 * pad)) / 2)
+    if pad_if_needed and sh + 2 * pad < th:
+        pad += int((1 + th - (sh + 2 * pad)) / 2)
+    return sh, sw, pad, sh + 2 * pad, sw + 2 * pad
+
+
+def random_scale_crop(img_u8: np.ndarray, lbl_u8: np.ndarray, sh: int, sw: int, pad: int, y0: int, x0: int, H: int, W: int,
+                      flip: bool, mean, std):
+    """ExtRandomScale -> ExtRandomCrop(pad_if_needed) -> ExtRandomHorizontalFlip -> ExtToTensor -> ExtNormalize
+    (train.py:355-362) for one sample with the random draws given: float32 [3,H,W] image, uint8 [H,W] label."""
+    si = pil_resize_bilinear_u8(img_u8, sh, sw)
+    sl = pil_resize_nearest(lbl_u8, sh, sw)
+    if pad:
+        si = np.pad(si, ((pad, pad), (pad, pad), (0, 0)))
+        sl = np.pad(sl, ((pad, pad), (pad, pad)))
+    ci, cl = crop_flip(si, x0, y0, H, W, flip), crop_flip(sl, x0, y0, H, W, flip)
+    return to_tensor_normalize(ci, mean, std), np.ascontiguousarray(cl)
