@@ -524,6 +524,36 @@ int iswm_random_scale_crop(const uint8_t* d_img, const uint8_t* d_lbl, int B, in
                            int kmax, int tab_w, int tab_h, int32_t* d_tables, const float* mean, const float* stdv,
                            int H, int W, float* d_out, uint8_t* d_lbl_out, void* stream);
 
+/* ---- the per-frame evaluators beside the confusion matrix: image-processing half on the device ---------
+ * Integer / byte work, bit-exact against OpenCV / SciPy as the reference calls them; the float64 scalar arithmetic on top
+ * (a few hundred numbers per frame) runs on the host in iswm_b200/metrics/shape_metrics.py in the reference's operation order.
+ * Masks are [N,H,W] device arrays of `dtype` (ISWM_U8 / ISWM_I32 / ISWM_I64), foreground = value > 0 (mask_utils.py:14).
+ * d_work: iswm_mask_work_bytes(N, H, W) bytes of device scratch. */
+int64_t iswm_mask_work_bytes(int N, int H, int W);
+/* MaskUtils.preprocess_mask (metrics/utils/mask_utils.py:7-52) + find_front_positions' row scan (:66-74):
+ *   3x3 close, 3x3 open (cv2.morphologyEx, default border), 8-connected components with areas
+ *   (cv2.connectedComponentsWithStats), largest component among those with area >= min_valid_area (the caller passes
+ *   H*W*0.001 as the reference computes it), area ties to the first label in OpenCV's numbering.
+ *   d_support uint8 [N,H,W]  the chosen component (all zero when there is none)
+ *   d_front   int32 [N,H]    its leftmost column per row, -1 = row empty
+ *   d_info    int32 [N,8]    {components, valid components, area of the chosen one, support pixels, its root pixel index, 0, 0, 0}
+ * The reference's return value is support * weight with weight = 1 for <= 1 valid component, else max(0.4, 1 - 0.2 (valid - 1)). */
+int iswm_mask_preprocess(const void* d_mask, int dtype, int N, int H, int W, double min_valid_area, uint8_t* d_support,
+                         int32_t* d_front, int32_t* d_info, void* d_work, void* stream);
+/* RegionMetrics.calculate_region_metrics (metrics/region_metrics.py:6-12 repair_small_gaps = dilate x3, erode x2 with a 3x3 box;
+ * :74-92 intersection / union with the ground truth; :44-61 scipy.ndimage.label with the 8-connected structure, areas >= min_area):
+ *   d_counts int32 [N,8]   {sum(pred > 0), sum(gt > 0), |repaired & gt|, |repaired | gt|, regions with area >= min_area, components, 0, 0}
+ *   d_areas  int32 [N,cap] the areas of those regions, unordered (at most cap are stored; counts[4] still counts all) */
+int iswm_region_components(const void* d_pred, int pred_dtype, const void* d_gt, int gt_dtype, int N, int H, int W, int min_area,
+                           int cap, int32_t* d_counts, int32_t* d_areas, void* d_work, void* stream);
+/* FrontTrackingMetrics.calculate_error's two nearest-point loops (metrics/front_tracking_metrics.py:48-63, :72-85): for every row i
+ * with a front point (i, a[i]) the FIRST closest point (j, b[j]) in row order: d2 = squared distance (-1 = no point in this row or B is
+ * empty), dx = |a[i] - b[j]|. d_front_a / d_front_b / d_d2 / d_dx int32 [N,H]. */
+int iswm_front_nearest(const int32_t* d_front_a, const int32_t* d_front_b, int N, int H, int32_t* d_d2, int32_t* d_dx, void* stream);
+/* MaskUtils.calculate_stability's row loop (metrics/utils/mask_utils.py:117-133): |front - x| of the first set pixel x of `d_other`
+ * (uint8 [N,H,W]) inside [front - window, front + window) clipped to the row; -1 = no front in this row or nothing in the window. */
+int iswm_front_window_diff(const int32_t* d_front, const uint8_t* d_other, int N, int H, int W, int window, int32_t* d_diff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,13 +5,15 @@ arithmetic follow the reference exactly (integer counts bit-exact, ratios in flo
 eps=1e-7); counts are produced by the CUDA confusion kernel and kept ON DEVICE as int64 until
 a result is read. The per-image shape / temporal / front-tracking evaluators of the reference
 (metrics/region_metrics.py, temporal_metrics.py, front_tracking_metrics.py — cv2/scipy CPU
-heuristics) are outside the accelerated hot path. They are PLUG-INS
-here: assign objects with the reference's evaluator interface (`update(pred, gt)`, `reset()`,
-`get_mean_score()` / `get_mean_error()`) to `temporal_evaluator`, `region_evaluator`,
-`front_tracking_evaluator` (the reference's own classes work unchanged) and `update()` feeds them
-exactly as stream_metrics.py:104-118 does. While a slot is empty its result key is NaN ("not
-measured") and the weighted score is taken over the measured terms with the reference's weights
-renormalised - a constant 0.0 would read as a perfect Front Tracking Error and add +0.25 to every score.
+heuristics) are the device-backed classes of `iswm_b200.metrics.shape_metrics`
+(bit-identical scores, tests/test_shape_gpu.py), created by default as stream_metrics.py:16-22 does.
+They are also PLUG-IN slots: any object with the reference's evaluator interface (`update(pred, gt)`,
+`reset()`, `get_mean_score()` / `get_mean_error()`) can be assigned to `temporal_evaluator`,
+`region_evaluator`, `front_tracking_evaluator` (the reference's own classes work unchanged) and
+`update()` feeds them exactly as stream_metrics.py:104-118 does. With `shape_metrics=False` the
+slots start empty: an empty slot's result key is NaN ("not measured") and the weighted score is taken
+over the measured terms with the reference's weights renormalised - a constant 0.0 would read as a
+perfect Front Tracking Error and add +0.25 to every score.
 """
 from __future__ import annotations
 
@@ -41,15 +43,20 @@ def _to_device_labels(a, device):
 
 
 class StreamMetrics:
-    def __init__(self, n_classes, sequence_length=7, temporal_stride=1, threshold=0.005, device=None):
+    def __init__(self, n_classes, sequence_length=7, temporal_stride=1, threshold=0.005, device=None, shape_metrics=True):
         self.n_classes = n_classes
         self.FOREGROUND_CLASS = 1
         self.sequence_length, self.temporal_stride, self.threshold = sequence_length, temporal_stride, threshold
         self.best_score = {"weighted_score": 0.0}
-        # optional CPU evaluators with the reference's interface (stream_metrics.py:16-22); None = not measured
+        # evaluators with the reference's interface (stream_metrics.py:16-22); None = not measured
         self.temporal_evaluator = None
         self.region_evaluator = None
         self.front_tracking_evaluator = None
+        if shape_metrics:
+            from .shape_metrics import FrontTrackingMetrics, RegionMetrics, TemporalMetrics
+            self.temporal_evaluator = TemporalMetrics(sequence_length=sequence_length, threshold=threshold)
+            self.region_evaluator = RegionMetrics()
+            self.front_tracking_evaluator = FrontTrackingMetrics()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         self._cm_dev: Optional[torch.Tensor] = None
         self.process_group = None          # set by iswm_b200.parallel to all-reduce counts in get_results
@@ -91,10 +98,12 @@ class StreamMetrics:
             t, p = label_trues[-1], label_preds[-1]
         else:
             t, p = label_trues, label_preds
-        if self.region_evaluator is not None:
-            self.region_evaluator.update(_to_host(p), _to_host(t))
-        if self.front_tracking_evaluator is not None:
-            self.front_tracking_evaluator.update(_to_host(p), _to_host(t))
+        for ev in (self.region_evaluator, self.front_tracking_evaluator):
+            if ev is not None:
+                if getattr(ev, "accepts_device", False):
+                    ev.update(p, t)
+                else:
+                    ev.update(_to_host(p), _to_host(t))
         t = _to_device_labels(t, self.device).reshape(-1)
         p = _to_device_labels(p, self.device).reshape(-1)
         ops.confusion(t, p, self.n_classes, out=self._cm())

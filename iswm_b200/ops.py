@@ -232,6 +232,75 @@ def random_scale_crop(img: torch.Tensor, lbl: Optional[torch.Tensor], geom: torc
     return out, lout, tables
 
 
+# ----------------------------------------------------------------------------- shape / front evaluators
+
+_MASK_DTYPES = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64}
+
+
+def _mask3(m: torch.Tensor) -> torch.Tensor:
+    if m.dtype not in _MASK_DTYPES:
+        raise TypeError(f"mask dtype {m.dtype}: uint8, int32 or int64")
+    if m.dim() == 2:
+        m = m.unsqueeze(0)
+    if m.dim() != 3:
+        raise TypeError("masks are [H,W] or [N,H,W]")
+    return m.contiguous()
+
+
+def _mask_work(N: int, H: int, W: int, device) -> torch.Tensor:
+    return torch.empty(int(_lib.lib().iswm_mask_work_bytes(N, H, W)), dtype=torch.uint8, device=device)
+
+
+def mask_preprocess(mask: torch.Tensor, min_valid_area: Optional[float] = None):
+    """MaskUtils.preprocess_mask + the front scan (metrics/utils/mask_utils.py:7-76) for [N,H,W] masks: returns
+    (support uint8 [N,H,W], front int32 [N,H], info int32 [N,8]) on the device, see include/iswm_b200.h."""
+    m = _mask3(mask)
+    N, H, W = m.shape
+    support = torch.empty((N, H, W), dtype=torch.uint8, device=m.device)
+    front = torch.empty((N, H), dtype=torch.int32, device=m.device)
+    info = torch.empty((N, 8), dtype=torch.int32, device=m.device)
+    thr = (H * W) * 0.001 if min_valid_area is None else float(min_valid_area)
+    check(_lib.lib().iswm_mask_preprocess(_ptr(m), _MASK_DTYPES[m.dtype], N, H, W, thr, _ptr(support), _ptr(front), _ptr(info),
+                                          _ptr(_mask_work(N, H, W, m.device)), _stream()), "mask_preprocess")
+    return support, front, info
+
+
+def region_components(pred: torch.Tensor, gt: torch.Tensor, min_area: int = 50, cap: int = 1024):
+    """RegionMetrics' image half (metrics/region_metrics.py:6-12, :44-61, :74-92): (counts int32 [N,8], areas int32 [N,cap])."""
+    p, g = _mask3(pred), _mask3(gt)
+    if p.shape != g.shape:
+        raise ValueError("prediction and ground truth differ in shape")
+    if g.dtype != p.dtype:
+        g = g.to(p.dtype)
+    N, H, W = p.shape
+    counts = torch.empty((N, 8), dtype=torch.int32, device=p.device)
+    areas = torch.zeros((N, cap), dtype=torch.int32, device=p.device)
+    check(_lib.lib().iswm_region_components(_ptr(p), _MASK_DTYPES[p.dtype], _ptr(g), _MASK_DTYPES[g.dtype], N, H, W, int(min_area), cap,
+                                            _ptr(counts), _ptr(areas), _ptr(_mask_work(N, H, W, p.device)), _stream()), "region_components")
+    return counts, areas
+
+
+def front_nearest(front_a: torch.Tensor, front_b: torch.Tensor):
+    """First closest front point of B for every front point of A (metrics/front_tracking_metrics.py:48-63): (d2, dx) int32 [N,H]."""
+    a, b = front_a.contiguous(), front_b.contiguous()
+    if a.dtype != torch.int32 or b.dtype != torch.int32 or a.shape != b.shape or a.dim() != 2:
+        raise TypeError("front_nearest wants two int32 [N,H] front tables")
+    d2, dx = torch.empty_like(a), torch.empty_like(a)
+    check(_lib.lib().iswm_front_nearest(_ptr(a), _ptr(b), a.shape[0], a.shape[1], _ptr(d2), _ptr(dx), _stream()), "front_nearest")
+    return d2, dx
+
+
+def front_window_diff(front: torch.Tensor, other: torch.Tensor, window: int) -> torch.Tensor:
+    """Row loop of MaskUtils.calculate_stability (metrics/utils/mask_utils.py:117-133): int32 [N,H], -1 = no score for the row."""
+    f, o = front.contiguous(), other.contiguous()
+    if f.dtype != torch.int32 or o.dtype != torch.uint8 or o.dim() != 3 or f.shape != o.shape[:2]:
+        raise TypeError("front_window_diff wants int32 [N,H] fronts and uint8 [N,H,W] masks")
+    diff = torch.empty_like(f)
+    check(_lib.lib().iswm_front_window_diff(_ptr(f), _ptr(o), o.shape[0], o.shape[1], o.shape[2], int(window), _ptr(diff), _stream()),
+          "front_window_diff")
+    return diff
+
+
 # ----------------------------------------------------------------------------- convolution
 
 def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,

@@ -28,7 +28,7 @@ def test_streammetrics_update_matches_reference_accumulation(lm):
     """Same call sequence as the golden generator: update(seq, sequence_data=True) uses the LAST frame only
     (stream_metrics.py:113-114), then update(frame, sequence_data=False); confusion matrix bit-exact, ratios to 1e-12."""
     assert StreamSegMetrics is StreamMetrics and metrics.StreamMetrics is StreamMetrics
-    sm = StreamMetrics(2)
+    sm = StreamMetrics(2, shape_metrics=False)               # the confusion-matrix path alone; the evaluators: tests/test_shape_gpu.py
     t, p = lm["upd_true"], lm["upd_pred"]
     sm.update(t, p, sequence_data=True)
     sm.update(t[0], p[0], sequence_data=False)
@@ -52,7 +52,7 @@ def test_streammetrics_update_matches_reference_accumulation(lm):
 def test_streammetrics_update_refreshes_best_score_every_call(lm):
     """stream_metrics.py:124-137: update() itself re-evaluates the running results and keeps the best weighted score and
     its components, without any get_results() call from the user."""
-    sm = StreamMetrics(2)
+    sm = StreamMetrics(2, shape_metrics=False)
     t, p = lm["upd_true"], lm["upd_pred"]
     sm.update(t[0], t[0], sequence_data=False)                   # perfect prediction first
     first = dict(sm.best_score)
@@ -80,7 +80,7 @@ def test_streammetrics_plugin_evaluators_follow_the_reference_formula(lm):
     r = sm.get_results()
     want = 0.05 * r["MIoU"] + 0.25 * r["Foreground IoU"] + 0.25 * r["Foreground F1"] + 0.25 * (1 - 2.5 / 10) + 0.10 * 0.6 + 0.10 * 0.7
     assert abs(sm._calculate_weighted_score(r) - want) < 1e-12 and abs(r["Best Score"] - want) < 1e-12
-    bare = StreamMetrics(2)
+    bare = StreamMetrics(2, shape_metrics=False)
     bare.update(t, p, sequence_data=True)
     rb = bare.get_results()
     assert math.isnan(rb["Front Tracking Error"]) and math.isnan(rb["Temporal Consistency"]) and math.isnan(rb["Region Continuity"])
