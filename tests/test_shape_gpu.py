@@ -54,15 +54,15 @@ def test_mask_preprocess_on_the_fixture_frames_and_a_full_size_frame():
 
 
 def test_equal_areas_go_to_the_first_label_in_opencv_order():
-    """Two 6x6 squares: raster-first is the right one (row 0), block-raster-first (cv2's numbering) is the left one (row 1, same
+    """Two 6x6 squares: raster-first is the right one (row 4), block-raster-first (cv2's numbering) is the left one (row 5, same
     block row) - np.argmax over equal areas picks cv2's label 1."""
     from iswm_b200 import ops
     m = np.zeros((1, 40, 64), np.uint8)
-    m[0, 0:6, 40:46] = 1
-    m[0, 1:7, 10:16] = 1
+    m[0, 4:10, 40:46] = 1
+    m[0, 5:11, 10:16] = 1
     s, f, i = ops.mask_preprocess(torch.from_numpy(m).to(DEV), min_valid_area=4.0)
     assert int(i[0, 1]) == 2 and int(i[0, 2]) == 36
-    assert int(s[0, 1:7, 10:16].sum()) == 36 and int(s.sum()) == 36
+    assert int(s[0, 5:11, 10:16].sum()) == 36 and int(s.sum()) == 36
     rs, _, _ = F.mask_preprocess(torch.from_numpy(m), min_valid_area=4.0)
     assert torch.equal(s.cpu(), rs)
 
