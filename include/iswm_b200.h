@@ -554,6 +554,25 @@ int iswm_front_nearest(const int32_t* d_front_a, const int32_t* d_front_b, int N
  * (uint8 [N,H,W]) inside [front - window, front + window) clipped to the row; -1 = no front in this row or nothing in the window. */
 int iswm_front_window_diff(const int32_t* d_front, const uint8_t* d_other, int N, int H, int W, int window, int32_t* d_diff, void* stream);
 
+/* ---- the train-mode tail without its full-resolution tensors (SURVEY kernels K11 + K12 + K13) ------------------------------
+ * network/utils.py:22 (F.interpolate of the classifier output to the input size) + train.py:1046 (weighted CE, ignore_index,
+ * mean) + train.py:1048 (their backward down to the classifier output), for 2 classes and an exact x4 upsample:
+ *   iswm_tail_fwd   d_lo fp32 NHWC [B,h,w,2] low-res logits, labels [B,4h,4w] of `label_dtype` ->
+ *                   d_dlo_acc fp32 [B,h,w,2] = adjoint of the upsample applied to w_y (softmax - onehot), NOT yet divided by
+ *                   the normaliser; d_hist int64[2] += class counts; d_loss_num double += sum_i w_{y_i} nll_i
+ *                   (the caller zeroes hist and loss_num; a data-parallel caller all-reduces d_hist before the next two calls)
+ *   iswm_tail_loss  d_loss = loss_num / sum_c w_c hist_c (nan for an all-ignored batch, like torch)
+ *   iswm_tail_bwd   d_dlo bf16 [B,h,w,dx_ld] = dlo_acc * (*d_gscale or 1) / sum_c w_c hist_c, channels >= 2 zero;
+ *                   d_bias_grad[0] += sum, [1] -= sum (classifier bias gradient; may be NULL); d_scratch: 8200 bytes of device
+ *                   memory, zero before the first call, owned by the caller (per-block partials + a self-resetting counter)
+ * Same per-pixel arithmetic as iswm_logits_up_fwd + iswm_wce_fwd_bwd (identical logits and nll); the gradient differs from the
+ * unfused chain only in where the 1/normaliser is applied (after the adjoint instead of before): fp32 rounding, below bf16. */
+int iswm_tail_fwd(const float* d_lo, int B, int h, int w, const void* d_labels, int label_dtype, int H, int W, const float* d_weight,
+                  int ignore_index, float* d_dlo_acc, int64_t* d_hist, double* d_loss_num, void* stream);
+int iswm_tail_loss(const double* d_loss_num, const float* d_weight, const int64_t* d_hist, int ignore_index, float* d_loss, void* stream);
+int iswm_tail_bwd(const float* d_dlo_acc, int B, int h, int w, const float* d_weight, const int64_t* d_hist, int ignore_index,
+                  const float* d_gscale, void* d_dlo, int dx_ld, float* d_bias_grad, void* d_scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

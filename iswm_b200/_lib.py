@@ -169,6 +169,9 @@ SIGNATURES = {
     "iswm_u8_to_f32_norm": (_i, [_p, _i, _i, _i, _i, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _p, _p]),
     "iswm_crop_flip_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     "iswm_random_scale_table_words": (_i64, [_i, _i, _i]),
+    "iswm_tail_fwd": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "iswm_tail_loss": (_i, [_p, _p, _p, _i, _p, _p]),
+    "iswm_tail_bwd": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
     "iswm_mask_work_bytes": (_i64, [_i, _i, _i]),
     "iswm_mask_preprocess": (_i, [_p, _i, _i, _i, _i, C.c_double, _p, _p, _p, _p, _p]),
     "iswm_region_components": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -1016,16 +1016,16 @@ class Engine:
         return t
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, train: bool, lowres: bool = False) -> torch.Tensor:
-        """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]; with `lowres` (eval only) the
-        classifier's fp32 NHWC [B,H/4,W/4,num_classes] output, for consumers that fuse the final upsample
-        (ops.predict_epilogue)."""
+    def forward(self, x: torch.Tensor, train: bool, lowres: bool = False, fused_tail: bool = False) -> torch.Tensor:
+        """x: fp32 NCHW [B,3,H,W] on CUDA -> fp32 NCHW logits [B,num_classes,H,W]; with `lowres` the classifier's fp32 NHWC
+        [B,H/4,W/4,num_classes] output, for consumers that fuse the final upsample: ops.predict_epilogue in eval mode, and in
+        train mode (`fused_tail=True`, then backward_tail() instead of backward()) the fused upsample + criterion + adjoint."""
         if not x.is_cuda:                    # before any CUDA call: the message must be ours, not the driver's
             raise RuntimeError("iswm_b200 runs on CUDA only: move the model and the input to a B200 (no CPU fallback)")
         with _StreamScope():
-            return self._forward(x, train, lowres)
+            return self._forward(x, train, lowres, fused_tail)
 
-    def _forward(self, x: torch.Tensor, train: bool, lowres: bool = False) -> torch.Tensor:
+    def _forward(self, x: torch.Tensor, train: bool, lowres: bool = False, fused_tail: bool = False) -> torch.Tensor:
         self._check_device(x)
         if x.dim() != 4 or x.shape[1] != self.stem.cin:
             raise ValueError(f"expected [B,{self.stem.cin},H,W] input, got {tuple(x.shape)}")
@@ -1185,8 +1185,10 @@ class Engine:
         lo = torch.empty((B, h4, w4, ncls), dtype=torch.float32, device=dev)
         self._conv(self.cls, y, lo, ncls, h4, w4, ops.conv_taps(1, 1), B, _lib.EPI_AFFINE | _lib.EPI_OUT_F32, ones, bias.detach())
         if lowres:
+            if train and not fused_tail:
+                raise RuntimeError("low-resolution logits are an inference-only output (or the fused train tail's: fused_tail=True)")
             if train:
-                raise RuntimeError("low-resolution logits are an inference-only output")
+                self._saved = (y, B, h4, w4, H, W, ncls)
             return lo
         logits = torch.empty((B, ncls, H, W), dtype=torch.float32, device=dev)
         check(L.iswm_logits_up_fwd(lo.data_ptr(), B, h4, w4, ncls, H, W, logits.data_ptr(), _st()), "logits_up_fwd")
@@ -1359,11 +1361,19 @@ class Engine:
         with _StreamScope():
             self._backward(dlogits)
 
-    def _backward(self, dlogits: torch.Tensor):
+    def backward_tail(self, fill_dlo):
+        """Backward of a forward(train=True, lowres=True, fused_tail=True): `fill_dlo(dlo bf16 [B,h,w,ldp], bias_grad fp32 [ncls])`
+        writes the gradient w.r.t. the classifier's output (all ldp channels) and ADDS the classifier bias gradient - the fused
+        tail's iswm_tail_bwd - in place of the adjoint of the full-resolution upsample."""
+        with _StreamScope():
+            self._backward(None, fill_dlo)
+
+    def _backward(self, dlogits, fill_dlo=None):
         L = _lib.lib()
         y, B, h4, w4, H, W, ncls = self._saved
         dev = self.device
-        dlogits = dlogits.contiguous().float()
+        if fill_dlo is None:
+            dlogits = dlogits.contiguous().float()
         params = self._param_list()
         fresh = all(p.grad is None for p in params)
         if fresh:
@@ -1383,9 +1393,12 @@ class Engine:
         cls = self.cls
         ldp = 8 * ((ncls + 7) // 8)
         dlo = torch.empty((B, h4, w4, ldp), dtype=torch.bfloat16, device=dev)
-        # adjoint of the final upsample; the classifier bias gradient (sum of dlogits per class) rides on the same sweep
-        check(L.iswm_logits_up_bwd(dlogits.data_ptr(), B, h4, w4, ncls, H, W, dlo.data_ptr(), ldp,
-                                   self.grad_views[id(cls.conv.bias)].data_ptr(), _st()), "logits_up_bwd")
+        if fill_dlo is not None:
+            fill_dlo(dlo, self.grad_views[id(cls.conv.bias)])
+        else:
+            # adjoint of the final upsample; the classifier bias gradient (sum of dlogits per class) rides on the same sweep
+            check(L.iswm_logits_up_bwd(dlogits.data_ptr(), B, h4, w4, ncls, H, W, dlo.data_ptr(), ldp,
+                                       self.grad_views[id(cls.conv.bias)].data_ptr(), _st()), "logits_up_bwd")
         d = ops.make_conv_desc(B, h4, w4, y.C, y.ld, B, h4, w4, ncls, ldp, [(0, 0, 0)])
         with self._wgrad_ctx(dlo, y.t):
             check(L.iswm_conv_wgrad(C.byref(d), y.ptr, dlo.data_ptr(), self.grad_views[id(cls.conv.weight)].data_ptr(), _st()), "conv_wgrad cls")
@@ -1393,7 +1406,7 @@ class Engine:
             self._notify(cls.conv.weight)
         self._dgrad_into(cls, y, dlo, ldp, h4, w4, [(0, 0, 0)], h4, w4)
         if self.debug_units is not None:
-            self.debug_units.append(dict(name=cls.name, kind="cls", x=y.t.clone(), dlogits=dlogits.clone(), dlo=dlo.clone(),
+            self.debug_units.append(dict(name=cls.name, kind="cls", x=y.t.clone(), dlogits=None if dlogits is None else dlogits.clone(), dlo=dlo.clone(),
                                          w=cls.conv.weight.detach().clone(), dW=self.grad_views[id(cls.conv.weight)].clone(),
                                          dbias=self.grad_views[id(cls.conv.bias)].clone(), xgrad_after=y.grad.t.clone()))
         # reverse sweep

@@ -28,8 +28,13 @@ from __future__ import annotations
 import torch
 
 
+def _fused_tail_default() -> bool:
+    import os
+    return os.environ.get("ISWM_FUSED_TAIL", "1") != "0"
+
+
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, warmup_steps: int = 2, dp=None):
+    def __init__(self, model, criterion, optimizer, warmup_steps: int = 2, dp=None, fused_tail=None):
         """`dp`: an iswm_b200.parallel.DataParallel on the peer-memory transport - its step (histogram / gradient-bucket /
         loss exchanges are plain kernels on event-ordered streams) is captured like the single-GPU one; the returned loss is
         then the GLOBAL loss. Every rank must construct and call the stepper in lockstep."""
@@ -41,6 +46,11 @@ class GraphedTrainStep:
         self._fused_pack = False
         self.images = self.labels = self.loss = None
         self.dp = dp
+        # fused train tail (model.forward_loss: upsample + criterion + their backward without full-resolution tensors);
+        # None = the ISWM_FUSED_TAIL environment switch
+        self.fused_tail = _fused_tail_default() if fused_tail is None else bool(fused_tail)
+        if dp is not None:
+            dp.fused_tail = self.fused_tail
         if dp is not None and getattr(dp, "comm_mode", "nccl") != "peer":
             raise RuntimeError("GraphedTrainStep(dp=...) needs the peer-memory transport (torch.distributed collectives issued from "
                                "Python hooks are not captured); construct DataParallel(..., comm='peer')")
@@ -50,8 +60,11 @@ class GraphedTrainStep:
     def _eager(self, x, y):
         if self.dp is not None:
             return self.dp.train_step(x, y, self.optimizer).detach()
-        logits = self.model(x)
-        loss = self.criterion(logits, y)
+        if self.fused_tail:
+            loss = self.model.forward_loss(x, y, self.criterion)
+        else:
+            logits = self.model(x)
+            loss = self.criterion(logits, y)
         self.optimizer.zero_grad()
         loss.backward()
         self.optimizer.step()

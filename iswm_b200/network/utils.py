@@ -32,6 +32,43 @@ class _EngineFn(torch.autograd.Function):
         return (None, None, None) + (None,) * ctx.n_params
 
 
+class _EngineTailFn(torch.autograd.Function):
+    """forward + criterion as ONE autograd node with the fused tail (csrc/tail_fused.cu): the full-resolution logits and their
+    gradient never exist; backward hands the classifier-output gradient straight to the engine."""
+
+    @staticmethod
+    def forward(ctx, x, labels, engine, criterion, anchor, *params):
+        from .. import ops
+        ctx.engine, ctx.n_params = engine, len(params)
+        lo = engine.forward(x, train=True, lowres=True, fused_tail=True)
+        ctx.generation = engine.generation
+        w = criterion.weight
+        if w is not None and w.device != lo.device:
+            w = w.to(lo.device)
+        dlo_acc, hist, num = ops.tail_fwd(lo, labels, w, criterion.ignore_index)
+        if criterion.hist_hook is not None:
+            criterion.hist_hook(hist)                  # data parallel: SUM over ranks -> global-batch denominator
+        criterion.last_hist = hist
+        ctx.tail = (dlo_acc, hist, w, criterion.ignore_index)
+        return ops.tail_loss(num, w, hist, criterion.ignore_index)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import ops
+        eng = ctx.engine
+        if ctx.generation != eng.generation:
+            raise RuntimeError("backward() of a forward pass that a later train-mode forward superseded: the engine keeps "
+                               "ONE pending tape (no gradient accumulation over several forwards, like the reference loop)")
+        dlo_acc, hist, w, ignore = ctx.tail
+        ctx.tail = None
+        g = g.to(device=dlo_acc.device, dtype=torch.float32).contiguous()
+        scratch = getattr(eng, "_tail_scratch", None)
+        if scratch is None or scratch.device != dlo_acc.device:
+            scratch = eng._tail_scratch = torch.zeros(8200, dtype=torch.uint8, device=dlo_acc.device)
+        eng.backward_tail(lambda dlo, bias_grad: ops.tail_bwd(dlo_acc, w, hist, ignore, g, dlo, bias_grad, scratch))
+        return (None, None, None, None, None) + (None,) * ctx.n_params
+
+
 class _SimpleSegmentationModel(nn.Module):
     def __init__(self, backbone, classifier):
         super().__init__()
@@ -55,6 +92,22 @@ class _SimpleSegmentationModel(nn.Module):
             return eng.forward(x, train=True)          # BN batch statistics, no tape kept for backward
         with torch.no_grad():                          # eval: BatchNorm folded into the conv epilogues
             return eng.forward(x, train=False)
+
+    def forward_loss(self, x, labels, criterion):
+        """`criterion(model(x), labels)` for the training loop (train.py:1045-1046) with the tail fused: final x4 upsample, weighted
+        cross entropy and their backward run as three small kernels over the LOW-RES classifier output and the labels; the
+        full-resolution logits and their gradient are never written. Falls back to the plain composition whenever the fused
+        kernels do not apply (eval mode, no gradient, another criterion, more than two classes, sizes not divisible by 4)."""
+        from ..utils.loss import CrossEntropyLoss
+        eng = self.engine()
+        params = eng._param_list()
+        fusable = (self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+                   and type(criterion) is CrossEntropyLoss and not criterion.check_labels and eng.cls.cout == 2
+                   and x.dim() == 4 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
+                   and labels.dim() == 3 and labels.dtype in (torch.uint8, torch.int32, torch.int64))
+        if not fusable:
+            return criterion(self(x), labels)
+        return _EngineTailFn.apply(x, labels, eng, criterion, params[0], *params)
 
     @torch.no_grad()
     def forward_lowres(self, x):

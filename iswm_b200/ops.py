@@ -301,6 +301,41 @@ def front_window_diff(front: torch.Tensor, other: torch.Tensor, window: int) -> 
     return diff
 
 
+# ----------------------------------------------------------------------------- fused train tail (K11 + K12 + K13)
+
+def tail_fwd(lo: torch.Tensor, labels: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int = 255):
+    """Upsample x4 + weighted CE + adjoint of the upsample from the classifier's fp32 NHWC [B,h,w,2] output (network/utils.py:22,
+    train.py:1046-1048): returns (dlo_acc fp32 [B,h,w,2] - unnormalised -, hist int64 [2], loss_num float64 [1])."""
+    if lo.dtype != torch.float32 or lo.dim() != 4 or lo.shape[3] != 2:
+        raise TypeError("tail_fwd wants fp32 NHWC [B,h,w,2] low-resolution logits")
+    B, h, w, _ = lo.shape
+    if labels.dim() != 3 or tuple(labels.shape) != (B, 4 * h, 4 * w):
+        raise ValueError(f"tail_fwd: labels {tuple(labels.shape)} are not the x4 grid of {tuple(lo.shape)}")
+    lo, labels = lo.contiguous(), labels.contiguous()
+    dlo_acc = torch.empty_like(lo)
+    hist = torch.zeros(2, dtype=torch.int64, device=lo.device)
+    num = torch.zeros(1, dtype=torch.float64, device=lo.device)
+    check(_lib.lib().iswm_tail_fwd(_ptr(lo), B, h, w, _ptr(labels), _label_code(labels), 4 * h, 4 * w, _ptr(weight), int(ignore_index),
+                                   _ptr(dlo_acc), _ptr(hist), _ptr(num), _stream()), "tail_fwd")
+    return dlo_acc, hist, num
+
+
+def tail_loss(loss_num: torch.Tensor, weight: Optional[torch.Tensor], hist: torch.Tensor, ignore_index: int = 255) -> torch.Tensor:
+    loss = torch.empty((), dtype=torch.float32, device=hist.device)
+    check(_lib.lib().iswm_tail_loss(_ptr(loss_num), _ptr(weight), _ptr(hist), int(ignore_index), _ptr(loss), _stream()), "tail_loss")
+    return loss
+
+
+def tail_bwd(dlo_acc: torch.Tensor, weight: Optional[torch.Tensor], hist: torch.Tensor, ignore_index: int, gscale: Optional[torch.Tensor],
+             dlo: torch.Tensor, bias_grad: Optional[torch.Tensor], scratch: torch.Tensor) -> None:
+    """dlo (bf16 [B,h,w,ldp]) = dlo_acc * gscale / sum_c w_c hist_c, bias_grad[0] += sum, [1] -= sum; `scratch`: >= 8200 zeroed bytes."""
+    B, h, w, _ = dlo_acc.shape
+    if dlo.dtype != torch.bfloat16 or tuple(dlo.shape[:3]) != (B, h, w) or not dlo.is_contiguous() or scratch.numel() * scratch.element_size() < 8200:
+        raise TypeError("tail_bwd: bad dlo / scratch")
+    check(_lib.lib().iswm_tail_bwd(_ptr(dlo_acc), B, h, w, _ptr(weight), _ptr(hist), int(ignore_index), _ptr(gscale), _ptr(dlo), dlo.shape[3],
+                                   _ptr(bias_grad), _ptr(scratch), _stream()), "tail_bwd")
+
+
 # ----------------------------------------------------------------------------- convolution
 
 def make_conv_desc(B: int, Hi: int, Wi: int, Cin: int, in_ld: int, n_img: int, Ho: int, Wo: int,

@@ -189,8 +189,11 @@ class DataParallel:
     def train_step(self, images, labels, optimizer=None):
         """forward -> global-batch weighted CE -> backward with overlapped bucketed all-reduce -> step.
         Returns the GLOBAL loss (sum over ranks of local numerators / global denominator)."""
-        logits = self.model(images)
-        loss = self.criterion(logits, labels)
+        if getattr(self, "fused_tail", False):
+            loss = getattr(self.model, "module", self.model).forward_loss(images, labels, self.criterion)
+        else:
+            logits = self.model(images)
+            loss = self.criterion(logits, labels)
         if optimizer is not None:
             optimizer.zero_grad()
         loss.backward()
