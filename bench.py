@@ -618,7 +618,81 @@ def run_extras(dev):
                      "whole_step_tensor_frac": FWD_GFLOP_PER_IMG[("resnet50", 16, 2048)] * 8e9 / (ms * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", 1400.0)}
     del model, x, y
     torch.cuda.empty_cache()
+    extra["next_rows"] = run_next_rows(dev, pk)
     return extra
+
+
+def run_next_rows(dev, pk):
+    """The rows either side of the hot path, timed in the driver's own run at cfg2's geometry: the device train
+    transform (uint8 tiles -> scaled / cropped / flipped / normalised fp32 batch), the fused train tail against the unfused kernel
+    chain, and the image half of the per-frame evaluators. Median of 10 launches, L2 flushed between them."""
+    from iswm_b200 import _lib, ops
+    from iswm_b200.data import DeviceTransform
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def med_us(fn, reps=10):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e3
+
+    g = torch.Generator().manual_seed(0)
+    B, S = 16, 512
+    tiles = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).to(dev)
+    lbl8 = (torch.rand((B, S, S), generator=g) < 0.05).to(torch.uint8).to(dev)
+    tf = DeviceTransform(crop_size=S, hflip=True, scale_range=(0.5, 2.0), pad_if_needed=True, generator=torch.Generator().manual_seed(1))
+    geom = tf.draw_scaled(B, S, S)
+    us = med_us(lambda: tf(tiles, lbl8, params=geom))
+    nbytes = B * S * S * (3 * 4 + 1)                      # fp32 image + uint8 label written; the uint8 taps come through L1 / L2
+    out["device_transform"] = {"workload": f"ExtRandomScale(0.5-2) + RandomCrop(pad) + flip + ToTensor + Normalize, {B} x {S}x{S} uint8 tiles, 3 launches",
+                               "us": us, "img_per_s": B / (us * 1e-6), "written_GB/s": nbytes / (us * 1e-6) / 1e9}
+    # fused tail vs the unfused chain (cfg2: 16 x 128x128 low-res logits, int64 labels)
+    h = S // 4
+    lo = torch.randn((B, h, h, 2), generator=g).to(dev)
+    y = (torch.rand((B, S, S), generator=g) < 0.05).long().to(dev)
+    wts = torch.tensor([1.0, 7.0], device=dev)
+    L = _lib.lib()
+    st = lambda: torch.cuda.current_stream().cuda_stream   # noqa: E731
+    logits = torch.empty((B, 2, S, S), dtype=torch.float32, device=dev)
+    dlo = torch.empty((B, h, h, 8), dtype=torch.bfloat16, device=dev)
+    bias = torch.zeros(2, dtype=torch.float32, device=dev)
+    scratch = torch.zeros(8200, dtype=torch.uint8, device=dev)
+
+    def unfused():
+        _lib.check(L.iswm_logits_up_fwd(lo.data_ptr(), B, h, h, 2, S, S, logits.data_ptr(), st()))
+        hist = ops.class_hist(y, 2)
+        _, grad = ops.wce_fwd_bwd(logits, y, wts, hist, 255, 1.0, True)
+        _lib.check(L.iswm_logits_up_bwd(grad.data_ptr(), B, h, h, 2, S, S, dlo.data_ptr(), 8, bias.data_ptr(), st()))
+
+    def fused():
+        acc, hist, num = ops.tail_fwd(lo, y, wts, 255)
+        ops.tail_loss(num, wts, hist, 255)
+        ops.tail_bwd(acc, wts, hist, 255, None, dlo, bias, scratch)
+
+    uu, fu = med_us(unfused), med_us(fused)
+    alg = B * S * S * 8 + 3 * B * h * h * 8 + B * h * h * 16
+    out["train_tail"] = {"workload": f"x4 upsample + weighted CE + backward to the classifier output, {B} x {S}x{S}, int64 labels",
+                         "unfused_us": uu, "fused_us": fu, "fused_algorithmic_bytes": alg,
+                         "fused_frac_of_hbm_peak": alg / (fu * 1e-6) / 1e9 / pk["hbm_gbs"]}
+    masks = (torch.rand((8, S, S), generator=g) < 0.02).to(torch.uint8)
+    masks[:, 100:400, 200:260] = 1
+    masks = masks.to(dev)
+    out["shape_metrics"] = {"workload": f"MaskUtils.preprocess_mask image half (close, open, 8-connected components, largest region, fronts), 8 x {S}x{S} masks, 8 launches",
+                            "us": med_us(lambda: ops.mask_preprocess(masks)),
+                            "region_us": med_us(lambda: ops.region_components(masks, masks))}
+    del flush
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm

@@ -204,13 +204,22 @@ tail_bwd_kernel(const float* __restrict__ dlo_acc, int64_t n_px, const float* __
     s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {                                                 // the last block to finish adds the partials up, in a fixed order
     __threadfence();
     double t = 0.0;
-    for (unsigned i = 0; i < gridDim.x; i++) t += *reinterpret_cast<volatile double*>(partials + i);
-    bias_grad[0] += (float)t;
-    bias_grad[1] -= (float)t;
-    *counter = 0;                                               // ready for the next launch (graph replays included)
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += kTT) t += *reinterpret_cast<volatile double*>(partials + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();                                            // s_red is reused
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int i = 0; i < kTT / 32; i++) sum += s_red[i];
+      bias_grad[0] += (float)sum;
+      bias_grad[1] -= (float)sum;
+      *counter = 0;                                             // ready for the next launch (graph replays included)
+    }
   }
 }
 

@@ -60,9 +60,10 @@ def test_fused_tail_equals_the_unfused_chain(B, h, w, dtype, weighted):
     assert abs(float(l1) - float(l0)) <= 2e-6 * abs(float(l0)), (float(l0), float(l1))
     a, b = d0.float(), d1.float()
     assert torch.equal(a[..., 2:], torch.zeros_like(a[..., 2:])) and torch.equal(b[..., 2:], torch.zeros_like(b[..., 2:]))
-    # the normaliser is applied after the adjoint instead of before it: fp32 rounding, visible as rare 1-ulp bf16 flips
+    # the normaliser is applied after the adjoint instead of before it (and the two adjoints add their <= 64 terms in different
+    # orders): fp32 rounding of the LARGEST term, visible as rare 1-ulp bf16 flips - more where positive and negative terms cancel
     diff = (a[..., :2] - b[..., :2]).abs()
-    ulp = a[..., :2].abs().clamp_min(1e-30) * 2.0 ** -7
+    ulp = a[..., :2].abs().clamp_min(1e-30) * 2.0 ** -7 + 1e-6 * float(a.abs().max())
     assert bool((diff <= ulp).all()), float((diff / ulp).max())
     assert float((diff > 0).float().mean()) < 0.02, float((diff > 0).float().mean())
     assert torch.allclose(b0, b1, rtol=2e-4, atol=1e-6), (b0, b1)
@@ -97,9 +98,9 @@ def test_fused_tail_all_ignored_batch_and_scratch_reuse():
     assert torch.isnan(l1).item() and h1.tolist() == [0, 0]             # torch: nan for an all-ignored batch
     assert torch.count_nonzero(d1.float()).item() == 0 and torch.count_nonzero(b1).item() == 0
     assert int(scratch.view(torch.int32)[2048]) == 0                     # the block counter re-armed itself
-    with pytest.raises(RuntimeError):
+    with pytest.raises(ValueError):
         ops.tail_fwd(lo, y[:, :16], None)                               # labels must be the x4 grid
-    with pytest.raises((RuntimeError, ValueError)):
+    with pytest.raises(ValueError):
         ops.tail_fwd(lo, y[:, :16, :16].contiguous(), None)
 
 
