@@ -49,6 +49,16 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
   const int b = blockIdx.z, I0 = blockIdx.y * TL, J0 = blockIdx.x * TL;
   const int ybase = 4 * I0 - 2, xbase = 4 * J0 - 2;
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  // every label this thread will need, requested up front: NIT loads in flight instead of a chain of NIT cold misses
+  constexpr int NIT = (TF * TF + kTT - 1) / kTT;
+  YT yv[NIT];
+#pragma unroll
+  for (int k = 0; k < NIT; k++) {
+    const int t = threadIdx.x + k * kTT;
+    const int py = t / TF, px = t - py * TF;
+    const int y = ybase + py, x = xbase + px;
+    yv[k] = (t < TF * TF && y >= 0 && y < H && x >= 0 && x < W) ? labels[((int64_t)b * H + y) * W + x] : (YT)0;
+  }
   for (int t = threadIdx.x; t < (TL + 2) * (TL + 2); t += kTT) {
     const int r = t / (TL + 2), c = t % (TL + 2);
     const int ii = min(max(I0 - 1 + r, 0), h - 1), jj = min(max(J0 - 1 + c, 0), w - 1);
@@ -71,8 +81,11 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
   const float w0 = weight ? weight[0] : 1.0f, w1 = weight ? weight[1] : 1.0f;
   float acc = 0.f;
   unsigned c0 = 0, c1 = 0;
-  for (int t = threadIdx.x; t < TF * TF; t += kTT) {
-    const int py = t / TF, px = t % TF;
+#pragma unroll
+  for (int k = 0; k < NIT; k++) {
+    const int t = threadIdx.x + k * kTT;
+    if (t >= TF * TF) break;
+    const int py = t / TF, px = t - py * TF;
     const int y = ybase + py, x = xbase + px;
     float g = 0.f;
     if (y >= 0 && y < H && x >= 0 && x < W) {
@@ -81,7 +94,7 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
       const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
       const float a0 = bil_mix(w00, s_lo[y0][x0][0], w01, s_lo[y0][x1][0], w10, s_lo[y1][x0][0], w11, s_lo[y1][x1][0]);
       const float a1 = bil_mix(w00, s_lo[y0][x0][1], w01, s_lo[y0][x1][1], w10, s_lo[y1][x0][1], w11, s_lo[y1][x1][1]);
-      const long long yy = (long long)labels[((int64_t)b * H + y) * W + x];
+      const long long yy = (long long)yv[k];
       const bool valid = (yy == 0 || yy == 1) && yy != ignore_index;
       // the arithmetic of wce2_kernel: d = x_other - x_target, nll = softplus(d), p_other = sigmoid(d)
       const float d = (yy == 1) ? (a0 - a1) : (a1 - a0);
