@@ -756,14 +756,19 @@ def run_ours(args):
         # batch host -> prefetch buffer -> static buffer
         x_dev, y_dev = stepper.images, stepper.labels
     eager_only = [False]
+    from iswm_b200.graphs import _fused_tail_default
+    fused_tail = _fused_tail_default()
 
     def step(x, y):
         if stepper is not None and not eager_only[0]:
             return stepper(x, y)
         if dp is not None:
             return dp.train_step(x, y, opt)
-        logits = model(x)
-        loss = crit(logits, y)
+        if fused_tail:                      # the same tail kernels as the captured step (model.forward_loss)
+            loss = model.forward_loss(x, y, crit)
+        else:
+            logits = model(x)
+            loss = crit(logits, y)
         opt.zero_grad()
         loss.backward()
         opt.step()

@@ -45,7 +45,9 @@ class _EngineTailFn(torch.autograd.Function):
         w = criterion.weight
         if w is not None and w.device != lo.device:
             w = w.to(lo.device)
+        ev = engine._prof_begin()
         dlo_acc, hist, num = ops.tail_fwd(lo, labels, w, criterion.ignore_index)
+        engine._prof_end(ev, "hbm:tail_fwd", float(labels.numel() * labels.element_size() + 2 * lo.numel() * 4), "tail_fwd")
         if criterion.hist_hook is not None:
             criterion.hist_hook(hist)                  # data parallel: SUM over ranks -> global-batch denominator
         criterion.last_hist = hist
@@ -65,7 +67,12 @@ class _EngineTailFn(torch.autograd.Function):
         scratch = getattr(eng, "_tail_scratch", None)
         if scratch is None or scratch.device != dlo_acc.device:
             scratch = eng._tail_scratch = torch.zeros(8200, dtype=torch.uint8, device=dlo_acc.device)
-        eng.backward_tail(lambda dlo, bias_grad: ops.tail_bwd(dlo_acc, w, hist, ignore, g, dlo, bias_grad, scratch))
+        def fill(dlo, bias_grad):
+            ev = eng._prof_begin()
+            ops.tail_bwd(dlo_acc, w, hist, ignore, g, dlo, bias_grad, scratch)
+            eng._prof_end(ev, "hbm:tail_bwd", float(dlo_acc.numel() * 4 + dlo.numel() * 2), "tail_bwd")
+
+        eng.backward_tail(fill)
         return (None, None, None, None, None) + (None,) * ctx.n_params
 
 
