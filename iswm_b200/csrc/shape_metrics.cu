@@ -83,11 +83,14 @@ ccl_union_kernel(const uint8_t* __restrict__ m, int N, int H, int W, int* __rest
   for (int64_t g = (int64_t)blockIdx.x * kT + threadIdx.x; g < total; g += (int64_t)gridDim.x * kT) {
     if (!m[g]) continue;
     const int x = (int)(g % W), y = (int)((g / W) % H);
-    if (x > 0 && m[g - 1]) unite(L, (int)g, (int)(g - 1));
-    if (y > 0) {
-      if (m[g - W]) unite(L, (int)g, (int)(g - W));
-      if (x > 0 && m[g - W - 1]) unite(L, (int)g, (int)(g - W - 1));
-      if (x < W - 1 && m[g - W + 1]) unite(L, (int)g, (int)(g - W + 1));
+    // decision tree over the scan mask (W, NW, N, NE): a set N already holds W, NW and NE together (they are its row
+    // neighbours, joined when their own pixels were visited); without N, W stands for NW (NW is W's N) and NE is on its own
+    if (y > 0 && m[g - W]) {
+      unite(L, (int)g, (int)(g - W));
+    } else {
+      if (x > 0 && m[g - 1]) unite(L, (int)g, (int)(g - 1));
+      else if (y > 0 && x > 0 && m[g - W - 1]) unite(L, (int)g, (int)(g - W - 1));
+      if (y > 0 && x < W - 1 && m[g - W + 1]) unite(L, (int)g, (int)(g - W + 1));
     }
   }
 }
