@@ -39,10 +39,11 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
                   unsigned long long* __restrict__ hist, double* __restrict__ loss_num) {
   pdl_wait();
   pdl_launch();
-  __shared__ float s_lo[TL + 2][TL + 2][2];
+  __shared__ float2 s_lo[(TL + 2) * (TL + 2)];     // (class 0, class 1) of the low-res logits around the tile
   __shared__ float s_g[TF][TF + 1];
   __shared__ float s_t[TL][TF + 1];
-  __shared__ int s_i0[2][TF], s_i1[2][TF];
+  __shared__ int s_i0[2][TF], s_i1[2][TF];         // low-res tap indices of every full-resolution row / column (-1000 = outside the image)
+  __shared__ int s_o0[2][TF], s_o1[2][TF];         // the same as element offsets into s_lo (rows pre-multiplied by the tile pitch)
   __shared__ float s_l1[2][TF];
   __shared__ float s_red[kTT / 32];
   __shared__ unsigned s_cnt[kTT / 32][2];
@@ -62,9 +63,7 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
   for (int t = threadIdx.x; t < (TL + 2) * (TL + 2); t += kTT) {
     const int r = t / (TL + 2), c = t % (TL + 2);
     const int ii = min(max(I0 - 1 + r, 0), h - 1), jj = min(max(J0 - 1 + c, 0), w - 1);
-    const float2 v = *reinterpret_cast<const float2*>(lo + (((int64_t)b * h + ii) * w + jj) * 2);
-    s_lo[r][c][0] = v.x;
-    s_lo[r][c][1] = v.y;
+    s_lo[t] = *reinterpret_cast<const float2*>(lo + (((int64_t)b * h + ii) * w + jj) * 2);
   }
   if (threadIdx.x < 2 * TF) {
     const int axis = threadIdx.x / TF, k = threadIdx.x % TF;
@@ -76,6 +75,9 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
     s_i0[axis][k] = i0;
     s_i1[axis][k] = i1;
     s_l1[axis][k] = l1;
+    const int org = (axis == 0 ? I0 : J0) - 1, pitch = axis == 0 ? (TL + 2) : 1;
+    s_o0[axis][k] = i0 < 0 ? -1 : (i0 - org) * pitch;
+    s_o1[axis][k] = i0 < 0 ? -1 : (i1 - org) * pitch;
   }
   __syncthreads();
   const float w0 = weight ? weight[0] : 1.0f, w1 = weight ? weight[1] : 1.0f;
@@ -86,14 +88,15 @@ tail_fused_kernel(const float* __restrict__ lo, int h, int w, const YT* __restri
     const int t = threadIdx.x + k * kTT;
     if (t >= TF * TF) break;
     const int py = t / TF, px = t - py * TF;
-    const int y = ybase + py, x = xbase + px;
+    const int ry0 = s_o0[0][py], cx0 = s_o0[1][px];
     float g = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) {
-      const int y0 = s_i0[0][py] - (I0 - 1), y1 = s_i1[0][py] - (I0 - 1), x0 = s_i0[1][px] - (J0 - 1), x1 = s_i1[1][px] - (J0 - 1);
+    if ((ry0 | cx0) >= 0) {                                      // inside the image on both axes
+      const int ry1 = s_o1[0][py], cx1 = s_o1[1][px];
       const float ly = s_l1[0][py], lx = s_l1[1][px];
       const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-      const float a0 = bil_mix(w00, s_lo[y0][x0][0], w01, s_lo[y0][x1][0], w10, s_lo[y1][x0][0], w11, s_lo[y1][x1][0]);
-      const float a1 = bil_mix(w00, s_lo[y0][x0][1], w01, s_lo[y0][x1][1], w10, s_lo[y1][x0][1], w11, s_lo[y1][x1][1]);
+      const float2 v00 = s_lo[ry0 + cx0], v01 = s_lo[ry0 + cx1], v10 = s_lo[ry1 + cx0], v11 = s_lo[ry1 + cx1];
+      const float a0 = bil_mix(w00, v00.x, w01, v01.x, w10, v10.x, w11, v11.x);
+      const float a1 = bil_mix(w00, v00.y, w01, v01.y, w10, v10.y, w11, v11.y);
       const long long yy = (long long)yv[k];
       const bool valid = (yy == 0 || yy == 1) && yy != ignore_index;
       // the arithmetic of wce2_kernel: d = x_other - x_target, nll = softplus(d), p_other = sigmoid(d)
