@@ -117,6 +117,106 @@ stem_pool_fwd_kernel(const __nv_bfloat16* __restrict__ raw, StemBn bn, int B, in
   }
 }
 
+// Tiled form of the forward (what iswm_stem_pool_fwd launches; ISWM_STEM_POOL_TILED=0 keeps the gather form above): a block
+// normalises the (2 TPH + 1) x (2 TPW + 1) input pixels under a TPH x TPW tile of pooled outputs ONCE into shared memory
+// (bf16, what bn_train_apply would have stored; positions outside the image hold -inf, which never wins a strict `>`), then
+// every pooled output takes its nine candidates from there in window order. The gather form normalised every input element
+// 2.25 times and was bound by its nine scattered 16-byte loads per output (90 us at cfg2 for 168 MB: 0.31 of the HBM peak);
+// here an input element is loaded and normalised 1.16 times, with coalesced 128-byte pixel rows. Pooled values and argmax
+// codes are bit-identical (same bn_relu_bf16, same first-maximum rule).
+constexpr int TPH = 4, TPW = 16;
+constexpr int TIH = 2 * TPH + 1, TIW = 2 * TPW + 1;
+
+__global__ void __launch_bounds__(kT)
+stem_pool_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ raw, StemBn bn, int B, int H, int W, int Ho, int Wo, int64_t M,
+                           float eps, float momentum, int tiles_h, int tiles_w, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ double s_stat[2 * kC];
+  __shared__ uint4 s_act[TIH * TIW * 8];                // [input row][input column][channel group of 8] bf16
+  for (int i = threadIdx.x; i < 2 * kC; i += kT) {
+    double a = bn.stats[i];
+    for (int r = 1; r < bn.stats_rep; r++) a += bn.stats[(size_t)r * 2 * kC + i];
+    s_stat[i] = a;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7;                       // kT is a multiple of 8: a thread keeps its channel group in both phases
+  const int c0 = cg << 3;
+  const double invM = 1.0 / (double)M;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = c0 + j;
+    const double mean_d = s_stat[c] * invM;
+    const float mean = (float)mean_d;
+    const float var = fmaxf((float)(s_stat[kC + c] * invM - mean_d * mean_d), 0.f);
+    const float invstd = rsqrtf(var + eps);
+    sc[j] = bn.gamma[c] * invstd;
+    sh[j] = fmaf(-mean, sc[j], bn.beta[c]);
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+      bn.save_mean[c] = mean;
+      bn.save_invstd[c] = invstd;
+      if (bn.running_mean) {
+        const float unbiased = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
+        bn.running_mean[c] = (1.f - momentum) * bn.running_mean[c] + momentum * mean;
+        bn.running_var[c] = (1.f - momentum) * bn.running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bn.nbt) *bn.nbt += 1;
+  const int tiles_per_img = tiles_h * tiles_w;
+  const int total_tiles = B * tiles_per_img;
+  const uint32_t ninf2 = 0xFF80FF80u;                   // two bf16 -inf
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+    const int ho0 = (tr / tiles_w) * TPH, wo0 = (tr % tiles_w) * TPW;
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+    const __nv_bfloat16* img = raw + (int64_t)b * H * W * kC + c0;
+    __syncthreads();                                    // the previous tile's readers are done with s_act
+    for (int it = threadIdx.x; it < TIH * TIW * 8; it += kT) {
+      const int px = it >> 3;
+      const int r = px / TIW, c = px - r * TIW;
+      const int hi = hi0 + r, wi = wi0 + c;
+      uint4 v = make_uint4(ninf2, ninf2, ninf2, ninf2);
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const F8 x = unpack8(load_raw(img + ((int64_t)hi * W + wi) * kC));
+        v.x = pack_bf16x2(fmaxf(fmaf(x.v[0], sc[0], sh[0]), 0.f), fmaxf(fmaf(x.v[1], sc[1], sh[1]), 0.f));
+        v.y = pack_bf16x2(fmaxf(fmaf(x.v[2], sc[2], sh[2]), 0.f), fmaxf(fmaf(x.v[3], sc[3], sh[3]), 0.f));
+        v.z = pack_bf16x2(fmaxf(fmaf(x.v[4], sc[4], sh[4]), 0.f), fmaxf(fmaf(x.v[5], sc[5], sh[5]), 0.f));
+        v.w = pack_bf16x2(fmaxf(fmaf(x.v[6], sc[6], sh[6]), 0.f), fmaxf(fmaf(x.v[7], sc[7], sh[7]), 0.f));
+      }
+      s_act[it] = v;
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < TPH * TPW * 8; it += kT) {
+      const int po = it >> 3;
+      const int pr = po / TPW, pc = po - pr * TPW;
+      const int ho = ho0 + pr, wo = wo0 + pc;
+      if (ho >= Ho || wo >= Wo) continue;
+      float best[8];
+      int arg[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const F8 v = unpack8(s_act[((2 * pr + t / 3) * TIW + 2 * pc + t % 3) * 8 + cg]);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (v.v[j] > best[j]) { best[j] = v.v[j]; arg[j] = t; }
+      }
+      const int64_t m = ((int64_t)b * Ho + ho) * Wo + wo;
+      F8 o;
+#pragma unroll
+      for (int j = 0; j < 8; j++) o.v[j] = best[j];
+      store8(out + m * kC + c0, o);
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(idx + m * kC + c0) = pk;
+    }
+  }
+}
+
 // gradient of the (never stored) stem activation for the 2x2 pixel block (i, j) of image b, channels [c0, c0+8): sum of the
 // pooled gradients whose argmax code points at each pixel (the loop of maxpool_bwd_kernel)
 __device__ __forceinline__ void gather_block(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx, int b, int i, int j,
@@ -295,8 +395,21 @@ extern "C" int iswm_stem_pool_fwd(const void* d_raw, const iswm_bn_side* bn, int
   ISWM_REQUIRE(Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1 && B >= 1, "stem_pool_fwd: 3x3 / stride 2 / pad 1 geometry expected");
   const StemBn sb{bn->stats, bn->stats_replicas > 1 ? bn->stats_replicas : 1, bn->gamma, bn->beta, bn->running_mean, bn->running_var,
                   reinterpret_cast<long long*>(bn->num_batches_tracked), bn->save_mean, bn->save_invstd};
-  launch_k(stem_pool_fwd_kernel, dim3(stem_grid((int64_t)B * Ho * Wo * 8)), dim3(kT), 0, ST(stream), BF(d_raw), sb, B, H, W, Ho, Wo,
-           (int64_t)B * H * W, eps, momentum, BFW(d_out), d_idx);
+  static const bool tiled = [] {
+    const char* e = getenv("ISWM_STEM_POOL_TILED");
+    return !(e && e[0] == '0');
+  }();
+  if (tiled) {
+    const int tiles_h = (Ho + TPH - 1) / TPH, tiles_w = (Wo + TPW - 1) / TPW;
+    const int64_t tiles = (int64_t)B * tiles_h * tiles_w;
+    ISWM_REQUIRE(tiles < (1ll << 31), "stem_pool_fwd: too many tiles");
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)resident_grid(stem_pool_fwd_tiled_kernel, kT));
+    launch_k(stem_pool_fwd_tiled_kernel, dim3((unsigned)grid), dim3(kT), 0, ST(stream), BF(d_raw), sb, B, H, W, Ho, Wo, (int64_t)B * H * W, eps,
+             momentum, tiles_h, tiles_w, BFW(d_out), d_idx);
+  } else {
+    launch_k(stem_pool_fwd_kernel, dim3(stem_grid((int64_t)B * Ho * Wo * 8)), dim3(kT), 0, ST(stream), BF(d_raw), sb, B, H, W, Ho, Wo,
+             (int64_t)B * H * W, eps, momentum, BFW(d_out), d_idx);
+  }
   return check_launch("stem_pool_fwd");
 }
 

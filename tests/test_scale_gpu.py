@@ -72,3 +72,29 @@ def test_scaled_pipeline_draws_are_reproducible_and_refuse_bad_input():
         ops.random_scale_crop(img.float(), lbl, torch.zeros((4, 8), dtype=torch.int32, device=dev), (32, 32), MEAN, STD, 5, (96, 128))
     with pytest.raises(TypeError):
         ops.random_scale_crop(img, lbl, torch.zeros((4, 8), dtype=torch.int32), (32, 32), MEAN, STD, 5, (96, 128))
+
+
+def test_full_size_properties_of_the_scaled_pipeline():
+    """Size-independent properties at cfg2's geometry (16 x 512^2): scale 1 with a full-size crop IS the unscaled pipeline
+    (Pillow returns a copy; the coefficient rows degenerate to one tap of 2^22), and an exact x2 nearest upscale of the labels
+    repeats every pixel twice along both axes."""
+    from iswm_b200 import ops
+    from iswm_b200.data import DeviceTransform
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    B, S = 16, 512
+    img = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).to(dev)
+    lbl = torch.randint(0, 2, (B, S, S), generator=g, dtype=torch.uint8).to(dev)
+    tf1 = DeviceTransform(MEAN, STD, crop_size=S, hflip=True, scale_range=(1.0, 1.0), pad_if_needed=True, generator=torch.Generator().manual_seed(4))
+    geom = tf1.draw_scaled(B, S, S)
+    assert geom[:, :5].tolist() == [[S, S, 0, 0, 0]] * B and 0 < int(geom[:, 5].sum()) < B
+    x1, y1 = tf1(img, lbl, params=geom)
+    x0 = ops.u8_to_f32_norm(img, MEAN, STD, (S, S), None, geom[:, 5].to(torch.uint8).to(dev))
+    y0 = ops.crop_flip_u8(lbl, (S, S), None, geom[:, 5].to(torch.uint8).to(dev))
+    assert torch.equal(x1, x0) and torch.equal(y1, y0)
+    tf2 = DeviceTransform(MEAN, STD, crop_size=S, hflip=False, scale_range=(2.0, 2.0), pad_if_needed=True)
+    geom2 = tf2.draw_scaled(B, S, S, scales=[2.0] * B)
+    geom2[:, 3], geom2[:, 4] = 256, 128                       # crop origin (y0, x0) in the 1024^2 upscaled tile
+    _, y2 = tf2(img, lbl, params=geom2)
+    want = lbl[:, 128:384, 64:320].repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert torch.equal(y2, want)

@@ -119,3 +119,22 @@ def test_streammetrics_default_evaluators_take_device_tensors():
     want = dict(zip(keys, G[f"sm_results_{k}"]))
     for key in ("Temporal Consistency", "Front Tracking Error", "Region Continuity", "MIoU", "Best Score"):
         assert float(res[key]) == float(want[key]), key
+
+
+def test_full_size_properties_of_the_preprocessing():
+    """At 512^2: a solid rectangle away from the border survives close / open / labelling unchanged and preprocessing is idempotent
+    on its own output; speckle below the 0.1 % area bar leaves an empty support."""
+    from iswm_b200 import ops
+    m = torch.zeros((3, 512, 512), dtype=torch.uint8)
+    m[0, 100:400, 200:260] = 1
+    m[1, 100:400, 200:260] = 1
+    m[1, 50:60, 30:45] = 1                                    # a second region below the bar (150 px < 262 px): not "valid"
+    g = torch.Generator().manual_seed(1)
+    m[2] = (torch.rand((512, 512), generator=g) < 0.002).to(torch.uint8)
+    s, f, i = ops.mask_preprocess(m.to(DEV))
+    assert torch.equal(s[0].cpu(), m[0]) and torch.equal(s[1].cpu(), m[0])
+    assert i[:, :4].cpu().tolist()[0] == [1, 1, 18000, 18000] and i[1, :4].cpu().tolist() == [2, 1, 18000, 18000]
+    assert int(s[2].sum()) == 0 and int(i[2, 1]) == 0
+    assert f[0, 100:400].cpu().tolist() == [200] * 300 and int(f[0, :100].max()) == -1 and int(f[0, 400:].max()) == -1
+    s2, f2, i2 = ops.mask_preprocess(s)
+    assert torch.equal(s2, s) and torch.equal(f2, f) and torch.equal(i2[:2, 1:4], i[:2, 1:4])
