@@ -117,13 +117,15 @@ stem_pool_fwd_kernel(const __nv_bfloat16* __restrict__ raw, StemBn bn, int B, in
   }
 }
 
-// Tiled form of the forward (what iswm_stem_pool_fwd launches; ISWM_STEM_POOL_TILED=0 keeps the gather form above): a block
+// Tiled form of the forward (ISWM_STEM_POOL_TILED=1; measured SLOWER than the gather form above, which stays the default): a block
 // normalises the (2 TPH + 1) x (2 TPW + 1) input pixels under a TPH x TPW tile of pooled outputs ONCE into shared memory
 // (bf16, what bn_train_apply would have stored; positions outside the image hold -inf, which never wins a strict `>`), then
 // every pooled output takes its nine candidates from there in window order. The gather form normalised every input element
-// 2.25 times and was bound by its nine scattered 16-byte loads per output (90 us at cfg2 for 168 MB: 0.31 of the HBM peak);
-// here an input element is loaded and normalised 1.16 times, with coalesced 128-byte pixel rows. Pooled values and argmax
-// codes are bit-identical (same bn_relu_bf16, same first-maximum rule).
+// 2.25 times with nine scattered 16-byte loads per output (92 us at cfg2 for 168 MB: 0.31 of the HBM peak); here an input
+// element is loaded and normalised 1.16 times, with coalesced 128-byte pixel rows - and the kernel takes 105 us: three
+// 40 KB blocks per SM, two block barriers per tile and a fill loop of dependent loads hide less latency than the gather
+// form's nine independent loads per thread at 75 registers. Pooled values and argmax codes are bit-identical (same
+// bn_relu_bf16, same first-maximum rule); kept as a tested alternative.
 constexpr int TPH = 4, TPW = 16;
 constexpr int TIH = 2 * TPH + 1, TIW = 2 * TPW + 1;
 
@@ -396,8 +398,8 @@ extern "C" int iswm_stem_pool_fwd(const void* d_raw, const iswm_bn_side* bn, int
   const StemBn sb{bn->stats, bn->stats_replicas > 1 ? bn->stats_replicas : 1, bn->gamma, bn->beta, bn->running_mean, bn->running_var,
                   reinterpret_cast<long long*>(bn->num_batches_tracked), bn->save_mean, bn->save_invstd};
   static const bool tiled = [] {
-    const char* e = getenv("ISWM_STEM_POOL_TILED");
-    return !(e && e[0] == '0');
+    const char* e = getenv("ISWM_STEM_POOL_TILED");      // measured slower than the gather form: off unless asked for
+    return e && e[0] == '1';
   }();
   if (tiled) {
     const int tiles_h = (Ho + TPH - 1) / TPH, tiles_w = (Wo + TPW - 1) / TPW;
