@@ -622,6 +622,50 @@ def run_extras(dev):
     return extra
 
 
+def run_e2e_u8(model, crit, opt, dev, B, H, W, steps):
+    """The same train step fed the way SURVEY 8f rank 2 intends: the host ships uint8 HWC tiles and uint8 labels from pinned memory
+    (1/4 and 1/8 of the fp32 / int64 bytes of the headline e2e), `DeviceTransform` (flip + ToTensor + Normalize on the device, straight
+    into the captured step's input buffer) precedes one graph replay per step, every step's loss is read back on the host."""
+    from iswm_b200.data import DeviceTransform, HostBatchPrefetcher
+    from iswm_b200.graphs import GraphedTrainStep
+    from iswm_b200.train_utils import DeferredLoss
+    from iswm_b200 import ops
+    g = torch.Generator().manual_seed(123)
+    tiles = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+    lab = (torch.rand((B, H, W), generator=g) < 0.02).to(torch.uint8)
+    lab[torch.rand((B, H, W), generator=g) < 0.01] = 255
+    lab = lab.pin_memory()
+    tf = DeviceTransform(crop_size=(H, W), hflip=True, generator=torch.Generator().manual_seed(5))
+    stepper = GraphedTrainStep(model, crit, opt)
+    x0, y0 = tf(tiles.to(dev), lab.to(dev))
+    stepper(x0, y0)                                      # capture for uint8 labels
+    torch.cuda.synchronize()
+
+    def run(n):
+        pre = HostBatchPrefetcher(((tiles, lab) for _ in range(n)), dev, image_dtype=torch.uint8)
+        dl = DeferredLoss()
+        for xs, ys in pre:
+            org, flip = tf.draw(B, H, W)
+            flip_d = flip.to(dev, non_blocking=True)
+            ops.u8_to_f32_norm(xs, tf.mean, tf.std, (H, W), None, flip_d, out=stepper.images)     # no staging copy: the graph reads this buffer
+            ops.crop_flip_u8(ys, (H, W), None, flip_d, out=stepper.labels)
+            dl.push(stepper(stepper.images, stepper.labels))
+        return dl.flush()
+
+    run(3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del stepper
+    return {"workload": "cfg2 train step from uint8 HWC tiles + uint8 labels in pinned host memory: H2D, flip + ToTensor + Normalize on the device (DeviceTransform kernels writing the captured step's input buffers), one graph replay, loss read back",
+            "value": B * steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / steps, "h2d_bytes_per_step": tiles.numel() + lab.numel(), "d2h_bytes_per_step": 4,
+            "loss": float(last)}
+
+
 def run_next_rows(dev, pk):
     """The rows either side of the hot path, timed in the driver's own run at cfg2's geometry: the device train
     transform (uint8 tiles -> scaled / cropped / flipped / normalised fp32 batch), the fused train tail against the unfused kernel
@@ -901,12 +945,18 @@ def run_ours(args):
     extra = None
     launch_mode = "one CUDA graph replay per step (GraphedTrainStep)" if stepper is not None else "eager launches"
     if world == 1 and not args.no_extras and (args.backbone, args.output_stride, H, B) == ("resnet50", 16, 512, 16):
+        e2e_u8 = None
+        try:
+            e2e_u8 = run_e2e_u8(model, crit, opt, dev, B, H, W, args.steps)
+        except Exception as e:
+            e2e_u8 = {"error": repr(e)}
         del model, opt, stepper, x_dev, y_dev
         torch.cuda.empty_cache()
         try:
             extra = run_extras(dev)
         except Exception as e:                           # the headline must survive a failure of the side measurements
             extra = {"error": repr(e)}
+        extra["e2e_u8"] = e2e_u8
     line = {
         "metric": f"train img/s DeepLabV3+ {'R50' if args.backbone == 'resnet50' else 'R101'} {H}^2", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
