@@ -126,3 +126,31 @@ def test_kernel_arithmetic_host_emulation_equals_the_oracle_on_random_batches(em
             sh, sw, pad, y0, x0, fl = [int(v) for v in geom[b, :6]]
             ri, rl = O.random_scale_crop(img[b], lbl[b], sh, sw, pad, y0, x0, H, W, bool(fl), MEAN, STD)
             assert np.array_equal(ri, out[b]) and np.array_equal(rl, lo[b]), (trial, b)
+
+
+def test_kernel_arithmetic_host_emulation_equals_pillow_over_the_whole_scale_domain(emul):
+    """Scales from 1/6.5 to 3 (coefficient rows of 3 .. 15 taps, the library's limit is 16): the kernels' arithmetic against Pillow
+    ITSELF (resize, then numpy pad / crop / flip and the fp32 normalisation), not only against the restatement."""
+    Image = pytest.importorskip("PIL.Image")
+    from iswm_b200 import ops
+    rng = np.random.RandomState(17)
+    Hs, Ws, H, W = 53, 67, 24, 40
+    img = rng.randint(0, 256, (1, Hs, Ws, 3), dtype=np.uint8)
+    lbl = rng.randint(0, 4, (1, Hs, Ws)).astype(np.uint8)
+    seen = set()
+    for s in [1 / 6.5, 0.2, 0.26, 1 / 3.0, 0.41, 0.5, 0.66, 0.75, 0.99, 1.0, 1.01, 1.25, 1.5, 2.0, 2.37, 3.0]:
+        sh, sw, pad, Hp, Wp = O.random_scale_geometry(Hs, Ws, s, (H, W))
+        y0, x0, fl = rng.randint(0, Hp - H + 1), rng.randint(0, Wp - W + 1), rng.randint(0, 2)
+        geom = np.array([[sh, sw, pad, y0, x0, fl, 0, 0]], np.int32)
+        kmax = ops.random_scale_kmax(Hs, Ws, geom.tolist())
+        seen.add(kmax)
+        out, lo = _emul_run(emul, img, lbl, geom, H, W, kmax)
+        ri = np.asarray(Image.fromarray(img[0]).resize((sw, sh), Image.BILINEAR))
+        rl = np.asarray(Image.fromarray(lbl[0]).resize((sw, sh), Image.NEAREST))
+        ri = np.pad(ri, ((pad, pad), (pad, pad), (0, 0)))[y0:y0 + H, x0:x0 + W]
+        rl = np.pad(rl, ((pad, pad), (pad, pad)))[y0:y0 + H, x0:x0 + W]
+        if fl:
+            ri, rl = ri[:, ::-1], rl[:, ::-1]
+        assert np.array_equal(O.to_tensor_normalize(ri, MEAN, STD), out[0]), (s, sh, sw, pad)
+        assert np.array_equal(rl, lo[0]), (s, sh, sw, pad)
+    assert min(seen) == 3 and max(seen) == 15, seen
