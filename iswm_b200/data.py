@@ -143,7 +143,11 @@ class DeviceTransform:
 
     def _call_scaled(self, images, labels, geom):
         from . import ops
-        B, Hs, Ws, _ = images.shape
+        B, Hs, Ws, Cc = images.shape
+        if B == 0:                                             # an empty batch (drop_last=False loaders can end on one): nothing to launch
+            H, W = self.crop_size
+            x = torch.empty((0, Cc, H, W), dtype=torch.float32, device=images.device)
+            return x if labels is None else (x, torch.empty((0, H, W), dtype=torch.uint8, device=images.device))
         geom = geom if geom is not None else self.draw_scaled(B, Hs, Ws)
         kmax = ops.random_scale_kmax(Hs, Ws, geom.tolist())
         tab_hw = (int(geom[:, 0].max()), int(geom[:, 1].max()))

@@ -68,6 +68,8 @@ def test_scaled_pipeline_draws_are_reproducible_and_refuse_bad_input():
     a = DeviceTransform(MEAN, STD, crop_size=32, hflip=True, scale_range=(0.5, 2.0), pad_if_needed=True, generator=torch.Generator().manual_seed(9))(img, lbl)
     b = DeviceTransform(MEAN, STD, crop_size=32, hflip=True, scale_range=(0.5, 2.0), pad_if_needed=True, generator=torch.Generator().manual_seed(9))(img, lbl)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[0].shape == (4, 3, 32, 32)
+    e = DeviceTransform(MEAN, STD, crop_size=32, hflip=True, scale_range=(0.5, 2.0), pad_if_needed=True)(img[:0], lbl[:0])     # empty batch
+    assert e[0].shape == (0, 3, 32, 32) and e[1].shape == (0, 32, 32)
     with pytest.raises(TypeError):
         ops.random_scale_crop(img.float(), lbl, torch.zeros((4, 8), dtype=torch.int32, device=dev), (32, 32), MEAN, STD, 5, (96, 128))
     with pytest.raises(TypeError):
