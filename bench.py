@@ -774,6 +774,10 @@ def run_ours(args):
         dp = DataParallel(model, crit)
     x_dev, y_dev = synth_batch(B, H, W, rank, device=dev)
     x_host, y_host = synth_batch(B, H, W, rank, pinned=True)
+    # host labels in the form the reference's loader yields them: uint8 (ExtToTensor(target_type='uint8'), utils/ext_transforms.py:273-293);
+    # train.py:1040 widens them with labels.to(device, dtype=torch.long) - here the widening happens on the device, in the copy into the
+    # captured step's int64 label buffer
+    y_host = y_host.to(torch.uint8).pin_memory()
 
     # the step is captured once and replayed as ONE CUDA graph launch (iswm_b200.graphs.GraphedTrainStep, the recommended
     # API; ISWM_BENCH_GRAPH=0 times the eager ~430-launch step instead). Data-parallel steps are captured too when the
@@ -967,11 +971,11 @@ def run_ours(args):
                    "comm": None if dp is None else ("peer-memory kernels over NVLink (iswm_b200.peer): histogram / gradient buckets / loss, captured in the graph"
                                                     if dp.comm_mode == "peer" else "torch.distributed NCCL collectives"),
                    "l2": "no explicit flush: each step streams > 2 GB of activations (>> 126 MB L2)",
-                   "e2e_note": "per step: images+labels H2D from pinned memory (HostBatchPrefetcher, copy of batch i+1 under step i) and the loss D2H (DeferredLoss: read on the host one step later, last one before the timer stops)",
+                   "e2e_note": "per step: fp32 images + uint8 labels (what the reference's loader yields; widened to int64 on the device as train.py:1040 does) H2D from pinned memory (HostBatchPrefetcher, copy of batch i+1 under step i) and the loss D2H (DeferredLoss: read on the host one step later, last one before the timer stops)",
                    "whole_step_tensor_frac": (gflop * 1e9 * B * world * args.steps / (ms * 1e-3) / 1e12 / world / peaks().get("bf16_tflops_sustained", 1400.0)) if gflop else None,
                    "loss": last, "dp_parity": dp_parity, "extra": extra},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8) * world, "d2h_bytes_per_step": 4 * world,
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * y_host.element_size()) * world, "d2h_bytes_per_step": 4 * world,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roof,

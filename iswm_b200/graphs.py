@@ -133,8 +133,12 @@ class GraphedTrainStep:
     def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         if self.graph is None:
             self._capture(images, labels)                # the capture itself does not execute: fall through and replay
-        elif images.shape != self.images.shape or labels.shape != self.labels.shape or labels.dtype != self.labels.dtype:
+        elif images.shape != self.images.shape or labels.shape != self.labels.shape:
             raise ValueError("GraphedTrainStep was captured for a fixed batch geometry; build another one for this shape")
+        elif labels.dtype != self.labels.dtype and (labels.is_floating_point() or labels.dtype == torch.bool):
+            raise ValueError(f"labels of dtype {labels.dtype}: integer class indices expected")
+        # integer labels of another width (the reference's loader yields uint8, train.py:1040 widens them with .to(device, dtype=torch.long))
+        # are widened / narrowed by the copy into the captured step's label buffer
         if images.data_ptr() != self.images.data_ptr():
             self.images.copy_(images, non_blocking=True)
         if labels.data_ptr() != self.labels.data_ptr():

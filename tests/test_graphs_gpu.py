@@ -108,6 +108,12 @@ def test_graphed_step_then_eval_uses_fresh_weights():
     assert stepper.launches_per_replay > 300
     with pytest.raises(ValueError):
         stepper(x[:1], y[:1])
+    # integer labels of another width (the reference's loader yields uint8; train.py:1040 widens them) are widened by the copy into the
+    # captured step's buffer; floating-point "labels" are refused
+    stepper(x, y.to(torch.uint8))
+    assert stepper.labels.dtype == y.dtype and torch.equal(stepper.labels, y)
+    with pytest.raises(ValueError):
+        stepper(x, y.float())
 
 
 def test_dropout_mask_follows_device_step_counter():
