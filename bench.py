@@ -307,6 +307,7 @@ def run_predict(args, dev, world, rank, local):
     metrics = StreamMetrics(2, device=dev)
     x_dev, y_dev = synth_batch(B, H, W, rank, device=dev)
     x_host, y_host = synth_batch(B, H, W, rank, pinned=True)
+    y_host = y_host.to(torch.uint8).pin_memory()        # the loader's label format (ExtToTensor(target_type='uint8'), utils/ext_transforms.py:273-293)
 
     def barrier():
         if world > 1:
@@ -391,7 +392,7 @@ def run_predict(args, dev, world, rank, local):
         "config": {"workload": f"cfg4: predict.py path, DeepLabV3+ ResNet-50 OS16 eval forward on synthetic {H}x{W} tiles, batch {B} per GPU, softmax[:,1] > 0.5 fused with the confusion matrix, mIoU read per step (e2e)",
                    "parallelism": f"dp{world}", "global_batch": B * world, "l2": "inputs and activations >> 126 MB L2", "miou": miou},
         "clocks": clocks,
-        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8) * world,
+        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * y_host.element_size()) * world,
                 "d2h_bytes_per_step": 8 * 5 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}))
 
