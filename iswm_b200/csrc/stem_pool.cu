@@ -397,10 +397,8 @@ extern "C" int iswm_stem_pool_fwd(const void* d_raw, const iswm_bn_side* bn, int
   ISWM_REQUIRE(Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1 && B >= 1, "stem_pool_fwd: 3x3 / stride 2 / pad 1 geometry expected");
   const StemBn sb{bn->stats, bn->stats_replicas > 1 ? bn->stats_replicas : 1, bn->gamma, bn->beta, bn->running_mean, bn->running_var,
                   reinterpret_cast<long long*>(bn->num_batches_tracked), bn->save_mean, bn->save_invstd};
-  static const bool tiled = [] {
-    const char* e = getenv("ISWM_STEM_POOL_TILED");      // measured slower than the gather form: off unless asked for
-    return e && e[0] == '1';
-  }();
+  const char* tiled_env = getenv("ISWM_STEM_POOL_TILED"); // measured slower than the gather form: off unless asked for;
+  const bool tiled = tiled_env && tiled_env[0] == '1';    // read per call (one launch per step) so that a test can switch it in-process
   if (tiled) {
     const int tiles_h = (Ho + TPH - 1) / TPH, tiles_w = (Wo + TPW - 1) / TPW;
     const int64_t tiles = (int64_t)B * tiles_h * tiles_w;
