@@ -87,3 +87,35 @@ def test_weighted_masks_hold_no_pixel_equal_to_one(fakes):
     pre = MaskUtils.preprocess(G[f"pred_{k}"][0])
     assert pre.valid == 2 and pre.weight == 0.8 and pre.count > 0 and pre.front_positions() == []
     assert set(np.unique(pre.numpy()).tolist()) == {0.0, 0.8}
+
+
+def test_host_half_equals_the_real_reference_classes_at_the_default_window(fakes):
+    """Build-container only (skipped where /root/reference or cv2 is absent): StreamMetrics with the DEFAULT sequence_length=7 over
+    20 frames of every kind, driven exactly as train.py:676-681 does - the product's evaluators (on the numpy stand-ins for the
+    kernels) against the reference's own classes running here, every reported number bit for bit."""
+    import contextlib
+    import io
+    pytest.importorskip("cv2")
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    from oracle.gen_golden_shape import make_frames
+    _, ref_metrics = ref_import.reference_modules()
+    from iswm_b200.metrics import StreamMetrics
+    L, Tn = 7, 20
+    for k, kind in enumerate(KINDS):
+        preds, gts = make_frames(300 + k, Tn, 48, 80, kind)
+        ref = ref_metrics.StreamMetrics(2, sequence_length=L)
+        mine = StreamMetrics(2, sequence_length=L, device="cpu")
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i in range(Tn - L + 1):
+                ref.update(gts[i:i + L].astype(np.int64), preds[i:i + L].astype(np.int64), sequence_data=True)
+                mine.update(gts[i:i + L].astype(np.int64), preds[i:i + L].astype(np.int64), sequence_data=True)
+                assert same([ref.temporal_evaluator.get_latest_score()], [mine.temporal_evaluator.get_latest_score()]), (kind, i)
+            a, b = ref.get_results(), mine.get_results()
+        assert set(a) == set(b), (kind, set(a) ^ set(b))
+        for key in a:
+            assert same([float(a[key])], [float(b[key])]), (kind, key, a[key], b[key])
+        assert np.array_equal(ref.confusion_matrix, mine.confusion_matrix)
+        assert same(ref.front_tracking_evaluator.tracking_errors, mine.front_tracking_evaluator.tracking_errors), kind
+        assert same(ref.region_evaluator.valid_scores, mine.region_evaluator.valid_scores), kind
