@@ -154,3 +154,41 @@ def test_kernel_arithmetic_host_emulation_equals_pillow_over_the_whole_scale_dom
         assert np.array_equal(O.to_tensor_normalize(ri, MEAN, STD), out[0]), (s, sh, sw, pad)
         assert np.array_equal(rl, lo[0]), (s, sh, sw, pad)
     assert min(seen) == 3 and max(seen) == 15, seen
+
+
+def test_kernel_arithmetic_host_emulation_equals_the_real_reference_pipeline_on_random_draws(emul):
+    """Build-container only (skipped where /root/reference is absent): 40 random draws through the reference's own
+    ExtCompose([ExtRandomScale, ExtRandomCrop(pad_if_needed), ExtRandomHorizontalFlip, ExtToTensor, ExtNormalize]) (train.py:355-362)
+    against the kernels' arithmetic, image and label bit for bit."""
+    import sys
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    from iswm_b200 import ops
+    from oracle.gen_golden_scale import ScriptedRandom
+    ref_import.install_stubs()
+    m = sys.modules.get("utils")
+    if m is not None and not getattr(m, "__file__", "").startswith(ref_import.REF_ROOT):
+        del sys.modules["utils"]
+    import utils.ext_transforms as et  # type: ignore
+    sr = ScriptedRandom()
+    saved = et.random
+    et.random = sr
+    try:
+        rng = np.random.RandomState(23)
+        Hs, Ws, crop = 45, 61, (28, 36)
+        img = rng.randint(0, 256, (Hs, Ws, 3), dtype=np.uint8)
+        lbl = rng.randint(0, 2, (Hs, Ws)).astype(np.uint8)
+        pipeline = et.ExtCompose([et.ExtRandomScale((0.5, 2.0)), et.ExtRandomCrop(size=crop, pad_if_needed=True), et.ExtRandomHorizontalFlip(),
+                                  et.ExtToTensor(), et.ExtNormalize(mean=[float(v) for v in MEAN], std=[float(v) for v in STD])])
+        for _ in range(40):
+            sr.scale, sr.frac_i, sr.frac_j, sr.coin, sr.log = float(rng.uniform(0.5, 2.0)), float(rng.rand()), float(rng.rand()), float(rng.rand()), {}
+            ti, tl = pipeline(Image.fromarray(img), Image.fromarray(lbl))
+            sh, sw, pad, Hp, Wp = O.random_scale_geometry(Hs, Ws, sr.scale, crop)
+            geom = np.array([[sh, sw, pad, sr.log.get("i", 0), sr.log.get("j", 0), int(sr.coin < 0.5), 0, 0]], np.int32)
+            out, lo = _emul_run(emul, img[None], lbl[None], geom, crop[0], crop[1], ops.random_scale_kmax(Hs, Ws, geom.tolist()))
+            assert np.array_equal(out[0], ti.numpy()), (sr.scale, geom)
+            assert np.array_equal(lo[0], tl.numpy().astype(np.uint8)), (sr.scale, geom)
+    finally:
+        et.random = saved
