@@ -171,8 +171,17 @@ class MaskUtils:
 
     @staticmethod
     def _presence(p: Pre, threshold: float) -> bool:
+        """np.sum(mask) / mask.size >= threshold (mask_utils.py:139-142). For an unweighted mask the sum is the integer pixel count; a
+        weighted mask (several valid regions) is summed by numpy in its pairwise order, which `count * weight` reproduces to ~1e-13
+        relative - when the ratio sits that close to the threshold the mask itself is fetched and summed exactly as the reference does."""
         H, W = p.shape
-        return bool((p.count * p.weight if p.valid > 1 else p.count) / (H * W) >= threshold)
+        if p.valid <= 1:
+            return bool(p.count / (H * W) >= threshold)
+        ratio = p.count * p.weight / (H * W)
+        if abs(ratio - threshold) <= 1e-9 * max(abs(threshold), 1e-30):
+            m = p.numpy()
+            ratio = np.sum(m) / m.size
+        return bool(ratio >= threshold)
 
     @staticmethod
     def check_wave_presence(mask, threshold=0.005):

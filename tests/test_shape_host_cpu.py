@@ -119,3 +119,18 @@ def test_host_half_equals_the_real_reference_classes_at_the_default_window(fakes
         assert np.array_equal(ref.confusion_matrix, mine.confusion_matrix)
         assert same(ref.front_tracking_evaluator.tracking_errors, mine.front_tracking_evaluator.tracking_errors), kind
         assert same(ref.region_evaluator.valid_scores, mine.region_evaluator.valid_scores), kind
+
+
+def test_wave_presence_of_a_weighted_mask_at_the_threshold(fakes):
+    """A weighted mask whose ratio sits ON the threshold: the decision is numpy's own sum of the float mask (mask_utils.py:139-142)."""
+    from iswm_b200.metrics.shape_metrics import MaskUtils
+    from oracle import shape_np as S
+    m = np.zeros((100, 100), np.uint8)
+    m[10:40, 10:31] = 1                                      # 630 px, the largest region
+    m[60:80, 60:80] = 1                                      # 400 px: a second valid region -> weight 0.8
+    pre = MaskUtils.preprocess(m)
+    assert pre.valid == 2 and pre.count == 630
+    ref_mask = S.preprocess_mask(m)
+    exact = float(np.sum(ref_mask) / ref_mask.size)
+    for thr in (exact, np.nextafter(exact, 1.0), np.nextafter(exact, 0.0), 0.8 * 630 / 10000, 0.05, 0.051):
+        assert MaskUtils.check_wave_presence(m, thr) == bool(S.check_wave_presence(m, thr)), thr
